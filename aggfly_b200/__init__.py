@@ -1,0 +1,22 @@
+"""aggfly_b200 -- a B200-native (sm_100a) engine for aggfly's ``aggregate_dataset`` hot path.
+
+Drop-in surface (same names as ``import aggfly as af``): ``aggregate_dataset``,
+``aggregate_time``, ``aggregate_space``, ``TemporalAggregator``, ``SpatialAggregator``, ``Dataset``,
+``Grid``, ``GridWeights``, ``GeoRegions``, ``weights_from_objects``.  Everything numeric runs in
+hand-written CUDA kernels behind the C-ABI in ``include/aggfly_b200.h``; there is no CPU fallback.
+"""
+from .aggregate import (ALLOWED_ENGINE, SpatialAggregator, aggregate_dataset, aggregate_space,
+                        aggregate_time, resolve_engine)
+from .dataset import Dataset, Grid, RasterArray, lon_to_180, lon_to_360
+from .spec import TemporalAggregator
+from .timeaxis import CalendarIndex, CFDate, group_bounds, translate_groupby
+from .weights import GeoRegions, GridWeights, lower_to_csr, weights_from_objects
+
+__version__ = "0.1.0"
+
+__all__ = [
+    "aggregate_dataset", "aggregate_time", "aggregate_space", "TemporalAggregator", "SpatialAggregator",
+    "resolve_engine", "ALLOWED_ENGINE", "Dataset", "Grid", "RasterArray", "GridWeights", "GeoRegions",
+    "weights_from_objects", "lower_to_csr", "CalendarIndex", "CFDate", "group_bounds", "translate_groupby",
+    "lon_to_180", "lon_to_360",
+]

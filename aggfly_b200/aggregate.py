@@ -1,0 +1,212 @@
+"""The reference's public aggregation API on the CUDA engine.
+
+Same names, signatures, return types and error behaviour as ``aggfly/aggregate/aggregate.py``
+(``aggregate_dataset`` :210-282, ``aggregate_time`` :101-162, ``aggregate_space`` :165-198) and
+``aggfly/aggregate/spatial.py`` (``SpatialAggregator``); the only API addition is the engine value
+``"cuda"`` (what ``"auto"`` resolves to here).  ``"dask"`` / ``"numba"`` are accepted so existing
+scripts keep running, and are served by the same CUDA path -- there is no CPU engine in this
+package.
+"""
+from __future__ import annotations
+
+import warnings
+from typing import Dict, List, Optional, Union
+
+import numpy as np
+import pandas as pd
+
+from . import engine as _engine
+from .dataset import Dataset
+from .spec import Graph, Planner, TemporalAggregator, compile_spec
+from .timeaxis import CalendarIndex, label_values, labels_equal
+from .weights import GridWeights, lower_to_csr
+
+ALLOWED_ENGINE = ("auto", "cuda", "dask", "numba")          # reference: cli/config.py:27 + "cuda"
+
+_DEPRECATED_CLUSTER_KWARGS = ("n_workers", "threads_per_worker", "processes", "memory_limit", "cluster_args")
+
+
+def resolve_engine(engine: str, da=None, calc: str = None) -> str:
+    """aggfly/aggregate/nb_kernels.py:59-74 -- every known engine resolves to "cuda" here."""
+    if engine not in ALLOWED_ENGINE:
+        raise ValueError(f"engine must be 'cuda', 'dask', 'numba', or 'auto', got {engine!r}")
+    return "cuda"
+
+
+# ---------------------------------------------------------------------------------------------
+# temporal
+# ---------------------------------------------------------------------------------------------
+class _DeviceRaster:
+    """The call's raster on the device, flattened to [T, cells]."""
+
+    def __init__(self, dataset: Dataset):
+        self.tensor = _engine.to_device(dataset.values)
+        T = self.tensor.shape[0]
+        self.n_lat, self.n_lon = len(dataset.latitude), len(dataset.longitude)
+        self.n_cells = self.n_lat * self.n_lon
+        self.flat = self.tensor.reshape(T, self.n_cells)
+
+
+def _plan(dataset: Dataset, aggregator_dict: Optional[Dict[str, list]]):
+    graph = Graph(dataset.dtype, dataset.time)
+    if aggregator_dict is None:
+        outputs = {"variable": graph.raw}                               # aggregate.py:269-270
+    else:
+        outputs = compile_spec(graph, aggregator_dict)
+    names = list(outputs.keys())
+    nodes = [outputs[n] for n in names]
+    first = graph.labels(nodes[0])
+    for n, node in zip(names, nodes):
+        if not labels_equal(graph.labels(node), first):
+            # the reference would union the axes and NaN-fill (xr.combine_by_coords, spatial.py:90-92)
+            raise ValueError(f"output {n!r} ends on a different time axis than {names[0]!r}; all outputs "
+                             "of one call must share one output time axis")
+    stage = Planner(graph).plan(nodes)
+    return names, stage
+
+
+def _temporal_device(dataset: Dataset, aggregator_dict, target_stripes: int = 0):
+    names, stage = _plan(dataset, aggregator_dict)
+    raster = _DeviceRaster(dataset)
+    res = _engine.run_stage(stage, raster.flat, raster.n_cells, target_stripes=target_stripes)
+    return names, res, raster
+
+
+def aggregate_time(dataset: Dataset, weights: GridWeights = None,
+                   aggregator_dict: Dict[str, Union[list, TemporalAggregator]] = None,
+                   engine: str = "auto", **kwargs) -> Dict[str, Dataset]:
+    """Temporal chains only: {output name: Dataset with values[G, lat, lon]} (aggregate.py:101-162)."""
+    resolve_engine(engine)
+    if aggregator_dict is None:
+        if not kwargs:
+            raise ValueError("No arguments provided.")
+        aggregator_dict = kwargs
+    names, res, raster = _temporal_device(dataset, aggregator_dict)
+    X = res.X.cpu().numpy()                                             # [G, n_cols, cells]
+    out = {}
+    for c, name in enumerate(names):
+        vals = X[:, c, :].astype(res.nodes[c].dtype, copy=False)
+        vals = np.ascontiguousarray(vals).reshape(len(res.labels), raster.n_lat, raster.n_lon)
+        out[name] = Dataset.from_arrays(vals, res.labels, dataset.latitude, dataset.longitude,
+                                        lon_is_360=dataset.lon_is_360, name=name)
+    return out
+
+
+def _execute_single_step(agg: TemporalAggregator, dataset: Dataset):
+    """TemporalAggregator.execute (temporal.py:165-263): a Dataset, or a list for multi-ddargs."""
+    out = aggregate_time(dataset, None, {"_step": [("aggregate", agg)]})
+    vals = list(out.values())
+    return vals if agg.multi_dd else vals[0]
+
+
+# ---------------------------------------------------------------------------------------------
+# spatial
+# ---------------------------------------------------------------------------------------------
+def _device_csr(weights: GridWeights, dataset: Dataset) -> _engine.DeviceCSR:
+    import torch
+    lon_order = dataset.lon_sort_order() if dataset.lon_is_360 else None
+    key = (torch.cuda.current_device(), len(dataset.latitude), len(dataset.longitude),
+           None if lon_order is None else lon_order.tobytes(), id(weights.weights))
+    cache = getattr(weights, "_csr_cache", None)
+    if cache is None:
+        cache = {}
+        try:
+            weights._csr_cache = cache
+        except Exception:
+            pass
+    if key not in cache:
+        host = lower_to_csr(weights.weights, weights.grid.cell_id, len(dataset.latitude),
+                            len(dataset.longitude), lon_order)
+        cache[key] = _engine.DeviceCSR(host)
+    return cache[key]
+
+
+def _assemble_panel(panel: np.ndarray, names: List[str], labels, region_ids: np.ndarray,
+                    weights: GridWeights) -> pd.DataFrame:
+    """spatial.py:136-153: long frame, then the row-drop rules."""
+    R, G, NC = panel.shape
+    out = pd.DataFrame({"region_id": np.repeat(region_ids, G),
+                        "time": np.tile(label_values(labels), R)})
+    flat = panel.reshape(R * G, NC)
+    for c, nm in enumerate(names):
+        out[nm] = flat[:, c]
+    ok = ~np.isnan(flat).any(axis=1)
+    if getattr(weights, "zero_weight", "area") == "nan":
+        wsum = weights.weights.groupby("index_right")["weight"].sum()
+        zero_regions = np.asarray(wsum.index[~(wsum > 0)])
+        keep = np.isin(out["region_id"].to_numpy(), zero_regions) | ok
+    else:
+        keep = ok
+    return out.loc[keep].reset_index(drop=True)
+
+
+class SpatialAggregator:
+    """aggfly/aggregate/spatial.py:37-154 on the CUDA engine: takes temporally-reduced Datasets
+    (one per output name, dims time x lat x lon, sharing one time axis)."""
+
+    def __init__(self, dataset: Union[list, Dataset], weights: GridWeights, names: Union[str, List[str]] = "climate"):
+        self.dataset = dataset if isinstance(dataset, list) else [dataset]
+        self.weights_obj = weights
+        self.grid = weights.grid
+        self.weights = weights.weights
+        self.names = [names] if isinstance(names, str) else list(names)
+        self.zero_weight = getattr(weights, "zero_weight", "area")
+
+    def compute(self, npartitions: int = None) -> pd.DataFrame:
+        import torch
+        d0 = self.dataset[0]
+        for d in self.dataset[1:]:
+            if not labels_equal(d.time, d0.time):
+                raise ValueError("all outputs of one call must share one output time axis")
+        n_cells = len(d0.latitude) * len(d0.longitude)
+        G = len(d0.time)
+        dt = np.result_type(*[d.dtype for d in self.dataset])
+        X = torch.stack([_engine.to_device(d.values).reshape(G, n_cells).to(_engine._tdtype(dt))
+                         for d in self.dataset], dim=1).contiguous()
+        # validity mask = AND over names of ~isnan  (spatial.py:114-119), by the library's kernel
+        V = torch.empty((G, n_cells), dtype=torch.uint8, device=X.device)
+        _engine.valid_mask(X, dt, V)
+        res = _engine.StageResult(X, V, dt, d0.time, None)
+        csr = _device_csr(self.weights_obj, d0)
+        panel = _engine.run_spmm(csr, res).cpu().numpy()
+        return _assemble_panel(panel, self.names, d0.time, csr.host.region_ids, self.weights_obj)
+
+
+def aggregate_space(dataset_dict: Dict[str, Dataset], weights: GridWeights, npartitions=None, **kwargs) -> pd.DataFrame:
+    """aggregate.py:165-198."""
+    return SpatialAggregator(list(dataset_dict.values()), weights, names=list(dataset_dict.keys())).compute()
+
+
+# ---------------------------------------------------------------------------------------------
+# the hot path
+# ---------------------------------------------------------------------------------------------
+def aggregate_dataset(weights: GridWeights, dataset: Dataset = None,
+                      aggregator_dict: Dict[str, Union[list, TemporalAggregator]] = None,
+                      dataset_dict=None, engine: str = "auto", **kwargs) -> pd.DataFrame:
+    """Gridded raster -> region x period panel (aggregate.py:210-282).
+
+    One pass: fused temporal kernel(s) over the raster, CSR weighted average onto regions, panel
+    assembly.  Output frame: ``[regionid, "time", *names]``, regions in shapefile-row order, periods
+    ascending, rows with NaN dropped (except zero-weight regions under ``zero_weight="nan"``).
+    """
+    if dataset is None:
+        raise ValueError("No dataset provided.")
+    resolve_engine(engine)
+    stale = {k: kwargs.pop(k) for k in _DEPRECATED_CLUSTER_KWARGS if k in kwargs}
+    if stale:
+        warnings.warn(
+            f"aggregate_dataset no longer builds a Dask cluster; {sorted(stale)} is/are ignored. "
+            "aggfly_b200 runs on the CUDA engine of the current device.",
+            DeprecationWarning, stacklevel=2)
+    if aggregator_dict is None and kwargs:
+        aggregator_dict = kwargs
+    if aggregator_dict is None and dataset_dict is not None:
+        df = aggregate_space(dataset_dict, weights)
+    else:
+        names, res, raster = _temporal_device(dataset, aggregator_dict)
+        csr = _device_csr(weights, dataset)
+        panel = _engine.run_spmm(csr, res).cpu().numpy()
+        df = _assemble_panel(panel, names, res.labels, csr.host.region_ids, weights)
+    rid = weights.georegions.regionid
+    df = weights.georegions.shp[[rid]].merge(df, left_index=True, right_on="region_id").drop(columns="region_id")
+    return df

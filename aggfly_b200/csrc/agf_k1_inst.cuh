@@ -1,0 +1,126 @@
+// agf_k1_inst.cuh -- K1 launcher + instantiation list; included by the agf_k1_*.cu units with
+// AGF_T (float|double), AGF_FN (entry name) and AGF_PART (0: single-level, 1: two-level) defined.
+#include <cmath>
+#include <cstring>
+
+#include "agf_host.h"
+
+using namespace agf;
+
+static float f32_round_down(double t) {
+    float f = (float)t;
+    if ((double)f > t) f = nextafterf(f, -INFINITY);
+    return f;
+}
+static float f32_round_up(double t) {
+    float f = (float)t;
+    if ((double)f < t) f = nextafterf(f, INFINITY);
+    return f;
+}
+// v > t0 (fp64 compare, as the reference does) <=> v > lo for a float v when lo = largest float <= t0;
+// v < t1 <=> v < hi with hi = smallest float >= t1.  Keeps the hot loop in fp32 compares, bit-exact.
+static inline void set_thresholds(LaneP<float> &L, double t0, double t1) {
+    L.lo = f32_round_down(t0);
+    L.hi = f32_round_up(t1);
+}
+static inline void set_thresholds(LaneP<double> &L, double t0, double t1) {
+    L.lo = t0;
+    L.hi = t1;
+}
+
+template <typename T, int NL, int NS, bool DIAG>
+static int launch_k1(const K1Launch &a) {
+    const agf_program *p = a.p;
+    K1Params<T, NL, NS> kp;
+    memset(&kp, 0, sizeof(kp));
+    const agf_program_desc_t &d = p->desc;
+    kp.x = (const T *)a.d_x;
+    kp.ld = a.ld;
+    kp.row0 = a.row0;
+    kp.n_cells = (int)p->n_cells;
+    kp.stripe0 = a.s0;
+    kp.b1 = p->d_b1;
+    kp.b2 = p->d_b2;
+    kp.stripes = p->d_stripes;
+    kp.partial = a.d_partial;
+    kp.out = a.d_out;
+    kp.valid = a.d_valid;
+    kp.n_lanes = d.n_lanes;
+    kp.n_slots = d.n_slots;
+    kp.n_cols = d.n_cols;
+    kp.out_ncols = a.ncols;
+    kp.valid_and = a.vand;
+    kp.in_f64 = d.in_dtype == AGF_F64;
+    kp.out_f64 = d.out_dtype == AGF_F64;
+    kp.need_nan = p->need_nan;
+    kp.need_cnt = p->need_cnt;
+    kp.has_sine = p->has_sine;
+    kp.diag = DIAG;
+    for (int l = 0; l < d.n_lanes; ++l) {
+        LaneP<T> &L = kp.lanes[l];
+        L.calc = d.lanes[l].calc;
+        L.flag = d.lanes[l].flag;
+        L.t0 = d.lanes[l].t0;
+        L.t1 = d.lanes[l].t1;
+        L.base = (d.lanes[l].flag == 0) ? L.t0 : L.t1;  // nb_kernels.py:168
+        set_thresholds(L, L.t0, L.t1);
+    }
+    if (NS > 0) {
+        for (int j = 0; j < d.n_slots; ++j) {
+            SlotP &S = kp.slots[j];
+            S.src = d.slots[j].src;
+            S.xform = d.slots[j].xform;
+            S.xparam = d.slots[j].xparam;
+            S.x_f64 = d.slots[j].x_f64;
+            S.calc = d.slots[j].calc;
+            S.flag = d.slots[j].flag;
+            S.t0 = d.slots[j].t0;
+            S.t1 = d.slots[j].t1;
+            S.base = (S.flag == 0) ? S.t0 : S.t1;
+        }
+    } else {
+        for (int c = 0; c < d.n_cols; ++c) {
+            ColP &C = kp.cols[c];
+            C.src = d.cols[c].src;
+            C.xform = d.cols[c].xform;
+            C.xparam = d.cols[c].xparam;
+            C.x_f64 = d.cols[c].x_f64;
+            C.dst = d.cols[c].dst;
+        }
+    }
+    dim3 grid((unsigned)((p->n_cells + K1_THREADS - 1) / K1_THREADS), (unsigned)(a.s1 - a.s0));
+    agf_k1_ldg<T, NL, NS, DIAG><<<grid, K1_THREADS, 0, a.stream>>>(kp);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int AGF_FN(const K1Launch &a, int *rc) {
+    const agf_program *p = a.p;
+#define K1CASE(NL, NS, DG)                                                                  \
+    if (p->kernel_lanes == NL && p->kernel_slots == NS && p->kernel_diag == (DG ? 1 : 0)) { \
+        *rc = launch_k1<AGF_T, NL, NS, DG>(a);                                              \
+        return 0;                                                                           \
+    }
+#if AGF_PART == 0
+    K1CASE(1, 0, false)
+    K1CASE(1, 0, true)
+    K1CASE(4, 0, false)
+    K1CASE(4, 0, true)
+    K1CASE(16, 0, false)
+    K1CASE(16, 0, true)
+    K1CASE(32, 0, false)
+    K1CASE(32, 0, true)
+#else
+    K1CASE(1, 1, false)
+    K1CASE(1, 4, false)
+    K1CASE(1, 16, false)
+    K1CASE(1, 32, false)
+    K1CASE(4, 1, false)
+    K1CASE(4, 4, false)
+    K1CASE(4, 16, false)
+    K1CASE(4, 32, false)
+    K1CASE(16, 16, true)
+#endif
+#undef K1CASE
+    return 1;
+}

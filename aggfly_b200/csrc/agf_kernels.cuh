@@ -1,0 +1,480 @@
+// agf_kernels.cuh -- device code of libaggfly_b200 (sm_100a).
+//
+// K1  agf_k1_*      fused temporal kernel: one thread per grid cell walks the time axis of its
+//                   stripe once; level-1 reducers ("lanes": mean/sum/min/max/nanmean/dd/bins/
+//                   sine_dd per group of bounds1) live in registers, are flushed at every group
+//                   end into the level-2 reducers ("slots": sum/mean/min/max/dd/bins per group of
+//                   bounds2, after an optional power/spline transform), also in registers.
+//                   Semantics restate aggfly/aggregate/nb_kernels.py:121-251 (fp64 accumulation
+//                   in time order, result rounded to the raster dtype, NaN rules :15-25) and
+//                   aggfly/dataset/dataset.py:442-481,527-543 (power / spline).
+// K1f agf_finalize  merges the per-stripe partial records, mean division, dtype rounding,
+//                   trailing transforms, writes X[G, n_cols, cells] and the shared validity mask.
+// K2  agf_spmm      CSR weighted regional average, one warp per (region, period):
+//                   aggfly/aggregate/spatial.py:114-133, 181-186.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "aggfly_b200.h"
+
+namespace agf {
+
+constexpr int K1_THREADS = 256;  // cells per CTA (one cell per thread)
+constexpr int K1_U = 8;          // rows per register batch
+
+// ------------------------------------------------------------------------------------------
+// kernel parameter blocks (passed by value, live in the constant bank)
+// ------------------------------------------------------------------------------------------
+template <typename T>
+struct LaneP {
+    int calc;
+    int flag;
+    T lo, hi;  // v > t0  <=>  v > lo ;  v < t1  <=>  v < hi   (thresholds pre-rounded for float)
+    double t0, t1, base;
+};
+
+struct SlotP {
+    int src;
+    int xform;
+    double xparam;
+    int x_f64;
+    int calc;
+    int flag;
+    int pad_;
+    double t0, t1, base;
+};
+
+struct ColP {
+    int src;
+    int xform;
+    double xparam;
+    int x_f64;
+    int dst;  // column in the destination X
+};
+
+struct Stripe {  // one time stripe, cut at level-1 group boundaries
+    int g1_begin, g1_end;
+    int g2_first;  // level-2 group of g1_begin
+    int rec0;      // first partial record of this stripe
+};
+
+template <typename T, int NL, int NS>
+struct K1Params {
+    const T *x;
+    long long ld;
+    long long row0;
+    int n_cells;
+    int stripe0;
+    const int *b1;
+    const int *b2;
+    const Stripe *stripes;
+    double *partial;  // [n_recs, n_slots, n_cells]      (NS > 0)
+    void *out;        // X[G1, n_cols, n_cells]           (NS == 0)
+    unsigned char *valid;
+    int n_lanes, n_slots, n_cols;
+    int out_ncols, valid_and;  // column count of the (possibly shared) X; AND into V or overwrite
+    int in_f64, out_f64;
+    int need_nan, need_cnt, has_sine, diag;
+    LaneP<T> lanes[NL];
+    SlotP slots[NS > 0 ? NS : 1];
+    ColP cols[NS > 0 ? 1 : AGF_MAX_COLS];
+};
+
+// ------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double agf_nan() { return __longlong_as_double(0x7ff8000000000000LL); }
+__device__ __forceinline__ double agf_inf() { return __longlong_as_double(0x7ff0000000000000LL); }
+
+template <typename T>
+__device__ __forceinline__ double round_to(double v);
+template <>
+__device__ __forceinline__ double round_to<float>(double v) {
+    return (double)(float)v;
+}
+template <>
+__device__ __forceinline__ double round_to<double>(double v) {
+    return v;
+}
+
+__device__ __forceinline__ double ipow(double x, int p) {
+    double r = 1.0;
+    double b = x;
+    // square-and-multiply; for p <= 4 on f32-derived x every product is exact or a single
+    // rounding, i.e. correctly rounded like libm pow
+    while (p > 0) {
+        if (p & 1) r *= b;
+        p >>= 1;
+        if (p) b *= b;
+    }
+    return r;
+}
+
+// transform of a value whose dtype is the raster dtype T (dataset.py:442-481, 527-543)
+template <typename T>
+__device__ __forceinline__ double apply_xform(double x, int xform, double xparam, int x_f64) {
+    double r = x;
+    if (xform == AGF_XF_NONE) return x;
+    if (xform == AGF_XF_POWI) {
+        r = ipow(x, (int)xparam);
+    } else if (xform == AGF_XF_POW) {
+        r = pow(x, xparam);
+    } else {  // AGF_XF_SPLINE2: (x > 20) * (x - 20) in the value's own dtype
+        if (sizeof(T) == 4 && !x_f64) {
+            float xf = (float)x;
+            float d = xf - 20.0f;
+            r = (double)((xf > 20.0f) ? d : d * 0.0f);
+        } else {
+            double d = x - 20.0;
+            r = (x > 20.0) ? d : d * 0.0;
+        }
+        return r;
+    }
+    return x_f64 ? r : round_to<T>(r);
+}
+
+// transform of a value that is already float64-typed (only used for trailing transforms of f64 slots)
+__device__ __forceinline__ double apply_xform64(double x, int xform, double xparam) {
+    if (xform == AGF_XF_NONE) return x;
+    if (xform == AGF_XF_POWI) return ipow(x, (int)xparam);
+    if (xform == AGF_XF_POW) return pow(x, xparam);
+    double d = x - 20.0;
+    return (x > 20.0) ? d : d * 0.0;
+}
+
+template <int N>
+__device__ __forceinline__ double select_reg(const double (&v)[N], int idx) {
+    double r = v[0];
+#pragma unroll
+    for (int i = 1; i < N; ++i) r = (idx == i) ? v[i] : r;
+    return r;
+}
+
+// single-sine degree days from a group's mean / min / max (nb_kernels.py:211-251)
+__device__ __forceinline__ double sine_dd_value(double tavg, double tmin, double tmax, double t0,
+                                                double t1, int kind) {
+    const double PI = 3.141592653589793;
+    double val = 0.0;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        double thr = j == 0 ? t0 : t1;
+        double part;
+        if (kind == 0) {
+            if (thr <= tmin) {
+                part = tavg - thr;
+            } else if (thr < tmax && tmin < thr) {
+                double rng = tmax - tmin;
+                double a = acos((2.0 * thr - tmax - tmin) / rng);
+                part = ((tavg - thr) * a + rng * sin(a) / 2.0) / PI;
+            } else {
+                part = 0.0;
+            }
+            val += (j == 0) ? part : -part;
+        } else {
+            if (thr >= tmax) {
+                part = thr - tavg;
+            } else if (thr < tmax && tmin < thr) {
+                double alpha = (tmax - tmin) / 2.0;
+                double r = (thr - tavg) / alpha;
+                double at = atan(r / sqrt(1.0 - r * r));
+                part = (1.0 / PI) * ((thr - tavg) * (at + PI / 2.0) + alpha * cos(at));
+            } else {
+                part = 0.0;
+            }
+            val += (j == 0) ? -part : part;
+        }
+    }
+    return val;
+}
+
+// ------------------------------------------------------------------------------------------
+// per-thread reducer state (everything statically indexed -> registers)
+// ------------------------------------------------------------------------------------------
+template <typename T, int NL, int NS>
+struct CellState {
+    double a[NL];               // level-1 accumulators
+    double b[NS > 0 ? NS : 1];  // level-2 accumulators
+    int nn;                     // non-NaN values in the current level-1 group
+    bool nan;                   // NaN seen in the current level-1 group
+};
+
+template <typename T, int NL, int NS>
+__device__ __forceinline__ void l1_init(const K1Params<T, NL, NS> &p, CellState<T, NL, NS> &s) {
+#pragma unroll
+    for (int l = 0; l < NL; ++l) {
+        int c = (l < p.n_lanes) ? p.lanes[l].calc : AGF_CALC_SUM;
+        s.a[l] = (c == AGF_CALC_MIN || c == AGF_CALC_HIDDEN_MIN)   ? agf_inf()
+                 : (c == AGF_CALC_MAX || c == AGF_CALC_HIDDEN_MAX) ? -agf_inf()
+                                                                   : 0.0;
+    }
+    s.nn = 0;
+    s.nan = false;
+}
+
+template <typename T, int NL, int NS>
+__device__ __forceinline__ void l2_init(const K1Params<T, NL, NS> &p, CellState<T, NL, NS> &s) {
+    if (NS > 0) {
+#pragma unroll
+        for (int j = 0; j < NS; ++j) {
+            int c = (j < p.n_slots) ? p.slots[j].calc : AGF_CALC_SUM;
+            s.b[j] = (c == AGF_CALC_MIN) ? agf_inf() : (c == AGF_CALC_MAX) ? -agf_inf() : 0.0;
+        }
+    }
+}
+
+// one raster value into every level-1 lane (nb_kernels.py:134-141, 170-177, 193-196, 213-220)
+template <typename T, int NL, int NS>
+__device__ __forceinline__ void l1_acc(const K1Params<T, NL, NS> &p, CellState<T, NL, NS> &s, T v) {
+    const double vd = (double)v;
+    const bool isn = (v != v);
+    if (p.need_nan) s.nan |= isn;
+    if (p.need_cnt) s.nn += isn ? 0 : 1;
+#pragma unroll
+    for (int l = 0; l < NL; ++l) {
+        if (l < p.n_lanes) {
+            const LaneP<T> &L = p.lanes[l];
+            switch (L.calc) {
+                case AGF_CALC_MEAN:
+                case AGF_CALC_SUM:
+                    s.a[l] += vd;  // a NaN value poisons the sum == "any NaN -> NaN"
+                    break;
+                case AGF_CALC_NANMEAN:
+                case AGF_CALC_HIDDEN_SUM:
+                    if (!isn) s.a[l] += vd;
+                    break;
+                case AGF_CALC_MIN:
+                case AGF_CALC_HIDDEN_MIN:
+                    if (vd < s.a[l]) s.a[l] = vd;
+                    break;
+                case AGF_CALC_MAX:
+                case AGF_CALC_HIDDEN_MAX:
+                    if (vd > s.a[l]) s.a[l] = vd;
+                    break;
+                case AGF_CALC_DD:
+                    if (v > L.lo && v < L.hi) s.a[l] += fabs(vd - L.base);
+                    break;
+                case AGF_CALC_BINS:
+                    if (v > L.lo && v < L.hi) s.a[l] += 1.0;
+                    break;
+                default:
+                    break;
+            }
+        }
+    }
+}
+
+// value of lane l for a finished group of n_grp rows, rounded to the raster dtype (:143-155, :260)
+template <typename T, int NL, int NS>
+__device__ __forceinline__ double l1_value(const K1Params<T, NL, NS> &p,
+                                           const CellState<T, NL, NS> &s, int l, int n_grp) {
+    const LaneP<T> &L = p.lanes[l];
+    double r;
+    switch (L.calc) {
+        case AGF_CALC_MEAN:
+            r = s.a[l] / (double)n_grp;
+            break;
+        case AGF_CALC_NANMEAN:
+            r = (s.nn > 0) ? s.a[l] / (double)s.nn : agf_nan();
+            break;
+        case AGF_CALC_MIN:
+        case AGF_CALC_MAX:
+        case AGF_CALC_DD:
+            r = s.nan ? agf_nan() : s.a[l];
+            break;
+        case AGF_CALC_SINE_DD:
+            // lanes 0..2 are the hidden sum / min / max helpers (host guarantees it)
+            r = (s.nan || s.nn == 0)
+                    ? agf_nan()
+                    : sine_dd_value(s.a[0] / (double)s.nn, s.a[NL > 1 ? 1 : 0], s.a[NL > 2 ? 2 : 0],
+                                    L.t0, L.t1, L.flag);
+            break;
+        default:  // SUM, BINS, hidden helpers
+            r = s.a[l];
+            break;
+    }
+    if (n_grp == 0) r = agf_nan();  // empty resample bin -> NaN for every reducer
+    return round_to<T>(r);
+}
+
+// one level-1 group value into slot j (same arithmetic as the reference's second
+// numba_resample pass over the per-group series)
+__device__ __forceinline__ void l2_acc_one(const SlotP &S, double &b, double xt) {
+    switch (S.calc) {
+        case AGF_CALC_MEAN:
+        case AGF_CALC_SUM:
+            b += xt;
+            break;
+        case AGF_CALC_MIN:
+            b = (xt < b || xt != xt) ? xt : b;  // NaN is sticky: any NaN -> NaN
+            break;
+        case AGF_CALC_MAX:
+            b = (xt > b || xt != xt) ? xt : b;
+            break;
+        case AGF_CALC_DD:
+            if (xt > S.t0 && xt < S.t1) b += fabs(xt - S.base);
+            if (xt != xt) b = xt;
+            break;
+        case AGF_CALC_BINS:
+            if (xt > S.t0 && xt < S.t1) b += 1.0;
+            break;
+        default:
+            break;
+    }
+}
+
+// merge of two partial records of the same slot (stripe order)
+__device__ __forceinline__ double l2_merge(int calc, double acc, double part) {
+    switch (calc) {
+        case AGF_CALC_MIN:
+            return (part < acc || part != part) ? part : acc;
+        case AGF_CALC_MAX:
+            return (part > acc || part != part) ? part : acc;
+        default:
+            return acc + part;
+    }
+}
+
+template <typename T>
+__device__ __forceinline__ void store_col(void *out, int out_f64, size_t idx, double v) {
+    if (out_f64)
+        reinterpret_cast<double *>(out)[idx] = v;
+    else
+        reinterpret_cast<float *>(out)[idx] = (float)v;
+}
+
+// end of level-1 group g (n_grp rows): emit columns (single-level) or feed the slots
+template <typename T, int NL, int NS, bool DIAG>
+__device__ __forceinline__ void l1_flush(const K1Params<T, NL, NS> &p, CellState<T, NL, NS> &s,
+                                         int g, int n_grp, int cell) {
+    double val[NL];
+#pragma unroll
+    for (int l = 0; l < NL; ++l) val[l] = (l < p.n_lanes) ? l1_value(p, s, l, n_grp) : 0.0;
+
+    if (NS == 0) {
+        bool ok = true;
+        const size_t base = (size_t)g * p.out_ncols;
+        if (DIAG) {  // column c == lane c, no transform
+#pragma unroll
+            for (int l = 0; l < NL; ++l) {
+                if (l < p.n_cols) {
+                    ok &= (val[l] == val[l]);
+                    store_col<T>(p.out, p.out_f64, (base + p.cols[l].dst) * p.n_cells + cell, val[l]);
+                }
+            }
+        } else {
+            for (int c = 0; c < p.n_cols; ++c) {
+                const ColP &C = p.cols[c];
+                double x = apply_xform<T>(select_reg<NL>(val, C.src), C.xform, C.xparam, C.x_f64);
+                ok &= (x == x);
+                store_col<T>(p.out, p.out_f64, (base + C.dst) * p.n_cells + cell, x);
+            }
+        }
+        unsigned char *vp = p.valid + (size_t)g * p.n_cells + cell;
+        *vp = (p.valid_and ? (*vp != 0) && ok : ok) ? 1 : 0;
+    } else {
+#pragma unroll
+        for (int j = 0; j < NS; ++j) {
+            if (j < p.n_slots) {
+                const SlotP &S = p.slots[j];
+                double x = DIAG ? val[j < NL ? j : 0] : select_reg<NL>(val, S.src);
+                double xt = apply_xform<T>(x, S.xform, S.xparam, S.x_f64);
+                l2_acc_one(S, s.b[j], xt);
+            }
+        }
+    }
+}
+
+template <typename T, int NL, int NS>
+__device__ __forceinline__ void l2_write_rec(const K1Params<T, NL, NS> &p,
+                                             const CellState<T, NL, NS> &s, int rec, int cell) {
+    if (NS > 0) {
+#pragma unroll
+        for (int j = 0; j < NS; ++j)
+            if (j < p.n_slots)
+                p.partial[((size_t)rec * p.n_slots + j) * p.n_cells + cell] = s.b[j];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K1, direct-load variant: any shape / alignment.  Register double-buffered batches of K1_U
+// rows that never cross a level-1 group boundary; next batch's loads are issued before the
+// current batch is reduced.
+// ------------------------------------------------------------------------------------------
+template <typename T, int NL, int NS, bool DIAG>
+__global__ void __launch_bounds__(K1_THREADS)
+    agf_k1_ldg(const __grid_constant__ K1Params<T, NL, NS> p) {
+    const int cell = blockIdx.x * K1_THREADS + threadIdx.x;
+    if (cell >= p.n_cells) return;
+    const Stripe st = p.stripes[p.stripe0 + blockIdx.y];
+    int g = st.g1_begin;
+    const int g_end = st.g1_end;
+    if (g >= g_end) return;
+    int g2 = st.g2_first;
+    int rec = st.rec0;
+    int next_b2 = (NS > 0) ? p.b2[g2 + 1] : 0;
+
+    CellState<T, NL, NS> s;
+    l1_init(p, s);
+    l2_init(p, s);
+
+    const T *xc = p.x + cell;
+    int glo = p.b1[g];      // first row of the current group
+    int nb = p.b1[g + 1];   // one past its last row
+    int ck = glo;
+    int clen = min(K1_U, nb - ck);
+    T cur[K1_U], nxt[K1_U];
+#pragma unroll
+    for (int i = 0; i < K1_U; ++i)
+        cur[i] = (i < clen) ? __ldg(xc + (size_t)(ck + i - p.row0) * p.ld) : T(0);
+
+    while (g < g_end) {
+        // descriptor of the next batch
+        const int nk = ck + clen;
+        const bool ends = (nk == nb);
+        int ng = g, nnb = nb;
+        if (ends) {
+            ng = g + 1;
+            nnb = (ng < g_end) ? p.b1[ng + 1] : nk;
+        }
+        const int nlen = (ng < g_end) ? min(K1_U, nnb - nk) : 0;
+#pragma unroll
+        for (int i = 0; i < K1_U; ++i)
+            nxt[i] = (i < nlen) ? __ldg(xc + (size_t)(nk + i - p.row0) * p.ld) : T(0);
+
+        // reduce the current batch in time order
+#pragma unroll
+        for (int i = 0; i < K1_U; ++i)
+            if (i < clen) l1_acc(p, s, cur[i]);
+
+        if (ends) {
+            l1_flush<T, NL, NS, DIAG>(p, s, g, nb - glo, cell);
+            l1_init(p, s);
+            if (NS > 0) {
+                // close every level-2 group that ends with level-1 group g
+                if (g + 1 == next_b2 || g + 1 == g_end) {
+                    l2_write_rec(p, s, rec, cell);
+                    l2_init(p, s);
+                    ++rec;
+                    if (g + 1 == next_b2) {
+                        do {  // skip zero-width level-2 groups (they get no record -> NaN)
+                            ++g2;
+                            next_b2 = p.b2[g2 + 1];
+                        } while (next_b2 == g + 1 && g + 1 < g_end);
+                    }
+                }
+            }
+            glo = nb;
+        }
+#pragma unroll
+        for (int i = 0; i < K1_U; ++i) cur[i] = nxt[i];
+        ck = nk;
+        clen = nlen;
+        g = ng;
+        nb = nnb;
+    }
+}
+
+}  // namespace agf

@@ -1,0 +1,130 @@
+// agf_post.cuh -- kernels after the temporal pass: finalize (K1f), CSR regional average (K2),
+// validity mask.  Included by agf_api.cu only.
+#pragma once
+#include "agf_kernels.cuh"
+
+namespace agf {
+
+// ------------------------------------------------------------------------------------------
+// K1f: finalize (two-level programs)
+// ------------------------------------------------------------------------------------------
+struct FinParams {
+    const double *partial;
+    void *out;
+    unsigned char *valid;
+    const int *b2;
+    const int *g2_rec_ptr;  // [G2+1] -> range in g2_rec_idx
+    const int *g2_rec_idx;  // record ids of each level-2 group, in stripe order
+    int n_cells, n_slots, n_cols, in_f64, out_f64;
+    int out_ncols, valid_and;
+    SlotP slots[AGF_MAX_SLOTS];
+    ColP cols[AGF_MAX_COLS];
+};
+
+__global__ void __launch_bounds__(256) agf_finalize(const __grid_constant__ FinParams p) {
+    const int cell = blockIdx.x * 256 + threadIdx.x;
+    if (cell >= p.n_cells) return;
+    const int g2 = blockIdx.y;
+    const int r0 = p.g2_rec_ptr[g2], r1 = p.g2_rec_ptr[g2 + 1];
+    const int n2 = p.b2[g2 + 1] - p.b2[g2];
+    bool ok = true;
+    for (int c = 0; c < p.n_cols; ++c) {
+        const ColP &C = p.cols[c];
+        const SlotP &S = p.slots[C.src];
+        double v;
+        if (r1 == r0) {
+            v = agf_nan();  // empty level-2 group
+        } else {
+            v = p.partial[((size_t)p.g2_rec_idx[r0] * p.n_slots + C.src) * p.n_cells + cell];
+            for (int r = r0 + 1; r < r1; ++r)
+                v = l2_merge(S.calc, v,
+                             p.partial[((size_t)p.g2_rec_idx[r] * p.n_slots + C.src) * p.n_cells + cell]);
+            if (S.calc == AGF_CALC_MEAN) v = v / (double)n2;
+        }
+        const bool slot_f64 = S.x_f64 || p.in_f64;
+        if (!slot_f64) v = (double)(float)v;  // stored in the dtype of the slot's input series
+        if (C.xform != AGF_XF_NONE) {
+            if (slot_f64) {
+                v = apply_xform64(v, C.xform, C.xparam);
+            } else {
+                v = apply_xform<float>(v, C.xform, C.xparam, C.x_f64);
+            }
+        }
+        ok &= (v == v);
+        const size_t idx = ((size_t)g2 * p.out_ncols + C.dst) * p.n_cells + cell;
+        if (p.out_f64)
+            reinterpret_cast<double *>(p.out)[idx] = v;
+        else
+            reinterpret_cast<float *>(p.out)[idx] = (float)v;
+    }
+    unsigned char *vp = p.valid + (size_t)g2 * p.n_cells + cell;
+    *vp = (p.valid_and ? (*vp != 0) && ok : ok) ? 1 : 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// K2: CSR weighted regional average, one warp per (region, period)
+// ------------------------------------------------------------------------------------------
+constexpr int SPMM_NCB = 8;  // columns accumulated per pass over a region's entries
+
+template <typename TX>
+__global__ void __launch_bounds__(256)
+    agf_spmm(const int *__restrict__ row_ptr, const int *__restrict__ cell_idx,
+             const double *__restrict__ w, const TX *__restrict__ X,
+             const unsigned char *__restrict__ V, long long n_cells, long long G, int n_cols,
+             int n_regions, double *__restrict__ panel, double *__restrict__ den_out) {
+    const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (wid >= (long long)n_regions * G) return;
+    const int r = (int)(wid / G);
+    const long long g = wid % G;
+    const int e0 = row_ptr[r], e1 = row_ptr[r + 1];
+    const unsigned char *Vg = V + (size_t)g * n_cells;
+
+    for (int c0 = 0; c0 < n_cols; c0 += SPMM_NCB) {
+        double acc[SPMM_NCB];
+#pragma unroll
+        for (int c = 0; c < SPMM_NCB; ++c) acc[c] = 0.0;
+        double den = 0.0;
+        for (int e = e0 + lane; e < e1; e += 32) {
+            const int cell = cell_idx[e];
+            const double we = w[e];
+            if (Vg[cell]) {
+                den += we;
+#pragma unroll
+                for (int c = 0; c < SPMM_NCB; ++c)
+                    if (c0 + c < n_cols)
+                        acc[c] += we * (double)X[((size_t)g * n_cols + c0 + c) * n_cells + cell];
+            }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            den += __shfl_xor_sync(0xffffffffu, den, off);
+#pragma unroll
+            for (int c = 0; c < SPMM_NCB; ++c) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], off);
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int c = 0; c < SPMM_NCB; ++c)
+                if (c0 + c < n_cols)
+                    panel[((size_t)r * G + g) * n_cols + c0 + c] = (den != 0.0) ? acc[c] / den : agf_nan();
+            if (c0 == 0 && den_out) den_out[(size_t)r * G + g] = den;
+        }
+    }
+}
+
+// shared validity mask of an existing X: V[g, cell] = AND_c !isnan(X[g, c, cell])  (spatial.py:114-119)
+template <typename TX>
+__global__ void __launch_bounds__(256)
+    agf_valid_mask(const TX *__restrict__ X, long long n_cells, int n_cols, unsigned char *__restrict__ V) {
+    const long long cell = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (cell >= n_cells) return;
+    const size_t g = blockIdx.y;
+    bool ok = true;
+    for (int c = 0; c < n_cols; ++c) {
+        const TX v = X[(g * n_cols + c) * n_cells + cell];
+        ok &= (v == v);
+    }
+    V[g * n_cells + cell] = ok ? 1 : 0;
+}
+
+}  // namespace agf

@@ -1,0 +1,190 @@
+"""Light data model for the hot path: ``Dataset`` (raster + axes) and ``Grid`` (cell ids).
+
+The reference wraps an ``xarray.DataArray`` (aggfly/dataset/dataset.py:21-118) and only uses it,
+on this path, for: the values, the time index, the lat/lon vectors, ``lon_is_360`` /
+``rescale_longitude`` (:419-440) and ``grid.cell_id`` (aggfly/dataset/grid.py:74-80).  xarray is
+not a dependency here: a ``Dataset`` holds a time-major ``values[time, lat, lon]`` array (numpy,
+pinned/pageable torch CPU tensor, or torch CUDA tensor) plus plain axes.  If xarray is
+importable, a ``DataArray`` is accepted and unwrapped.
+"""
+from __future__ import annotations
+
+from copy import copy
+from typing import Any, Optional, Sequence
+
+import numpy as np
+import pandas as pd
+
+from .timeaxis import CalendarIndex
+
+
+def lon_to_180(longitude):
+    """aggfly/dataset/grid_utils.py:16-31."""
+    return (np.asarray(longitude, dtype=float) + 180) % 360 - 180
+
+
+def lon_to_360(longitude):
+    """aggfly/dataset/grid_utils.py:34-49."""
+    lon = np.asarray(longitude, dtype=float)
+    return (lon < 0) * (lon + 360) + (lon >= 0) * lon
+
+
+class Grid:
+    """Cell numbering of a lat x lon grid (aggfly/dataset/grid.py:56-87, 137-147):
+    ``cell_id = lat_index * n_lon + lon_index`` over the grid's own (lat, lon) order."""
+
+    def __init__(self, longitude, latitude, name=None, lon_is_360=False):
+        self.longitude = np.asarray(longitude, dtype=float)
+        self.latitude = np.asarray(latitude, dtype=float)
+        self.name = name
+        self.lon_is_360 = lon_is_360
+        self.index = np.arange(len(self.latitude) * len(self.longitude)).reshape(
+            len(self.latitude), len(self.longitude))
+        self.cell_id = self.index.flatten()
+        self.resolution_lon, self.resolution_lat = self.get_resolution()
+
+    def get_resolution(self):
+        res_lon = abs(np.diff(self.longitude).mean()) if len(self.longitude) > 1 else 0.0
+        res_lat = abs(np.diff(self.latitude).mean()) if len(self.latitude) > 1 else 0.0
+        if res_lon == 0.0:
+            res_lon = res_lat
+        if res_lat == 0.0:
+            res_lat = res_lon
+        return res_lon, res_lat
+
+    @property
+    def resolution(self):
+        return max(self.resolution_lon, self.resolution_lat)
+
+
+class RasterArray:
+    """Minimal stand-in for the ``xarray.DataArray`` the reference's ``Dataset`` wraps."""
+
+    def __init__(self, data, dims: Sequence[str], coords: dict):
+        self.data, self.dims, self.coords = data, tuple(dims), dict(coords)
+
+
+def _is_torch(x) -> bool:
+    return type(x).__module__.startswith("torch")
+
+
+class Dataset:
+    """Raster + axes.  ``Dataset(da, xycoords, timecoord, lon_is_360=True, preprocess=None, ...)``
+    keeps the reference's constructor (aggfly/dataset/dataset.py:47-118) for a ``RasterArray`` /
+    ``xarray.DataArray``; ``Dataset.from_arrays`` is the direct route."""
+
+    def __init__(self, da, xycoords=("longitude", "latitude"), timecoord="time", time_sel=None,
+                 lon_is_360=True, preprocess=None, georegions=None, time_fix=False, name=None):
+        if not isinstance(da, RasterArray):
+            da = _from_xarray(da)
+        xdim, ydim = xycoords
+        dims = list(da.dims)
+        for need in (xdim, ydim, timecoord):
+            if need not in dims:
+                raise ValueError(f"dimension {need!r} not found in {dims}")
+        values = da.data
+        order = [dims.index(timecoord), dims.index(ydim), dims.index(xdim)]
+        if order != [0, 1, 2]:
+            values = values.permute(*order).contiguous() if _is_torch(values) else np.transpose(values, order)
+        if preprocess is not None:
+            values = preprocess(values)
+        self._init(values, da.coords[timecoord], da.coords[ydim], da.coords[xdim], lon_is_360, name)
+        self.georegions = georegions
+
+    def _init(self, values, time, latitude, longitude, lon_is_360, name):
+        if not isinstance(time, CalendarIndex):
+            time = pd.DatetimeIndex(time)
+        if not time.is_monotonic_increasing:                          # da.sortby("time"), dataset.py:87
+            if isinstance(time, CalendarIndex):
+                order = np.argsort(time.ordinal_hours(), kind="stable")
+            else:
+                order = np.argsort(time.values, kind="stable")
+            time = time[order]
+            values = values[order] if not _is_torch(values) else values[list(order)]
+        if not _is_torch(values):
+            values = np.asarray(values)
+            if values.dtype not in (np.float32, np.float64):
+                values = values.astype(np.float64)
+        self.values = values
+        self.time = time
+        self.latitude = np.asarray(latitude, dtype=float)
+        self.longitude = np.asarray(longitude, dtype=float)
+        self.lon_is_360 = bool(lon_is_360)
+        self.name = name
+        self.history = []
+        self.georegions = None
+        if tuple(self.values.shape) != (len(self.time), len(self.latitude), len(self.longitude)):
+            raise ValueError(f"values shape {tuple(self.values.shape)} does not match axes "
+                             f"({len(self.time)}, {len(self.latitude)}, {len(self.longitude)})")
+        self.grid = Grid(self.longitude, self.latitude, name, self.lon_is_360)
+
+    @classmethod
+    def from_arrays(cls, values, time, latitude, longitude, lon_is_360=True, name=None) -> "Dataset":
+        """values[time, lat, lon] (numpy or torch, float32/float64), time = DatetimeIndex | CalendarIndex."""
+        self = cls.__new__(cls)
+        self._init(values, time, latitude, longitude, lon_is_360, name)
+        return self
+
+    # -- reference API surface used on the hot path ----------------------------------------------
+    @property
+    def da(self) -> RasterArray:
+        return RasterArray(self.values, ("time", "latitude", "longitude"),
+                           {"time": self.time, "latitude": self.latitude, "longitude": self.longitude})
+
+    @property
+    def dtype(self) -> np.dtype:
+        v = self.values
+        if _is_torch(v):
+            import torch
+            return np.dtype(np.float32 if v.dtype == torch.float32 else np.float64)
+        return v.dtype
+
+    @property
+    def shape(self):
+        return tuple(self.values.shape)
+
+    def deepcopy(self) -> "Dataset":
+        new = copy(self)                      # the raster itself is immutable on this path
+        new.history = list(self.history)
+        return new
+
+    def lon_sort_order(self) -> np.ndarray:
+        """Column order the reference's ``rescale_longitude`` puts a 0-360 raster in
+        (relabel to -180..180, then ``sortby('longitude')``; dataset.py:419-440,
+        grid_utils.py:52-73).  Identity for a -180..180 dataset."""
+        if not self.lon_is_360:
+            return np.arange(len(self.longitude))
+        return np.argsort(lon_to_180(self.longitude), kind="stable")
+
+    def rescale_longitude(self) -> None:
+        """Relabel + sort longitudes (a host-side, metadata + column permutation operation)."""
+        if self.lon_is_360:
+            order = np.argsort(lon_to_180(self.longitude), kind="stable")
+            self.longitude = lon_to_180(self.longitude)[order]
+            self.lon_is_360 = False
+        else:
+            order = np.argsort(lon_to_360(self.longitude), kind="stable")
+            self.longitude = lon_to_360(self.longitude)[order]
+            self.lon_is_360 = True
+        self.values = self.values[..., list(order)] if _is_torch(self.values) else self.values[..., order]
+        self.grid = Grid(self.longitude, self.latitude, self.name, self.lon_is_360)
+
+    def __repr__(self):
+        return (f"<aggfly_b200.Dataset {self.name or ''} time={len(self.time)} lat={len(self.latitude)} "
+                f"lon={len(self.longitude)} dtype={self.dtype} lon_is_360={self.lon_is_360}>")
+
+
+def _from_xarray(da: Any) -> RasterArray:
+    try:
+        import xarray as xr                                    # optional
+    except Exception as exc:                                   # pragma: no cover
+        raise TypeError("Dataset expects a RasterArray (xarray is not installed)") from exc
+    if not isinstance(da, xr.DataArray):
+        raise TypeError(f"Dataset expects a RasterArray or xarray.DataArray, got {type(da)}")
+    coords = {}
+    for d in da.dims:
+        idx = da.get_index(d)
+        if type(idx).__name__ == "CFTimeIndex":
+            idx = CalendarIndex(idx.calendar, idx.year, idx.month, idx.day, idx.hour)
+        coords[d] = idx
+    return RasterArray(da.values, da.dims, coords)

@@ -1,0 +1,193 @@
+"""Launcher: runs planned stages (spec.py) and the CSR regional average through the C-ABI.
+
+PyTorch is used for plumbing only -- device buffers, streams, host<->device copies; every
+number is produced by the kernels in ``csrc/`` (no torch math on the data path, no CPU path).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+
+from . import _lib
+from .spec import ProgramSpec, Stage, build_desc
+from .weights import HostCSR
+
+
+# Tunables (tests pin target_stripes to exercise the stripe/merge path; 0 = library heuristic).
+OPTIONS = {"target_stripes": 0}
+
+
+def _torch():
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError("aggfly_b200 needs a CUDA device (B200); there is no CPU fallback")
+    return torch
+
+
+def _tdtype(np_dtype):
+    torch = _torch()
+    return torch.float64 if np.dtype(np_dtype) == np.float64 else torch.float32
+
+
+def to_device(values, device=None):
+    """Raster -> contiguous device tensor [T, cells...] (numpy, CPU tensor or CUDA tensor)."""
+    torch = _torch()
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+    if isinstance(values, np.ndarray):
+        if values.dtype not in (np.float32, np.float64):
+            values = values.astype(np.float64)
+        values = torch.from_numpy(np.ascontiguousarray(values))
+    if values.dtype not in (torch.float32, torch.float64):
+        values = values.to(torch.float64)
+    return values.to(device, non_blocking=True).contiguous()
+
+
+class Program:
+    """RAII wrapper of an ``agf_program_t``."""
+
+    def __init__(self, spec: ProgramSpec, out_dtype, n_cells: int, target_stripes: int = 0):
+        self.spec = spec
+        desc, self._keep = build_desc(spec, out_dtype)
+        self.handle = C.c_void_p()
+        _lib.check(_lib.lib().agf_program_create(C.byref(self.handle), C.byref(desc), n_cells, target_stripes))
+        self.info = _lib.ProgramInfo()
+        _lib.check(_lib.lib().agf_program_info(self.handle, C.byref(self.info)))
+
+    def stripe_rows(self, s: int) -> Tuple[int, int]:
+        a, b = C.c_int64(), C.c_int64()
+        _lib.check(_lib.lib().agf_program_stripe_rows(self.handle, s, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def close(self):
+        if self.handle:
+            _lib.lib().agf_program_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class DeviceCSR:
+    """CSR arrays resident on the device + the ``agf_csr_t`` handle."""
+
+    def __init__(self, host: HostCSR, device=None):
+        torch = _torch()
+        device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+        self.host = host
+        self.row_ptr = torch.from_numpy(host.row_ptr).to(device)
+        self.cell_idx = torch.from_numpy(host.cell_idx).to(device)
+        self.w = torch.from_numpy(host.w).to(device)
+        self.handle = C.c_void_p()
+        _lib.check(_lib.lib().agf_csr_create(C.byref(self.handle), host.n_regions, host.n_cells, host.nnz,
+                                             self.row_ptr.data_ptr(), self.cell_idx.data_ptr(), self.w.data_ptr()))
+
+    def close(self):
+        if self.handle:
+            _lib.lib().agf_csr_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class StageResult:
+    """X[G, n_cols, cells] + V[G, cells] on the device."""
+
+    def __init__(self, X, V, dtype, labels, nodes):
+        self.X, self.V, self.dtype, self.labels, self.nodes = X, V, np.dtype(dtype), labels, nodes
+
+    @property
+    def n_groups(self) -> int:
+        return int(self.X.shape[0])
+
+    @property
+    def n_cols(self) -> int:
+        return int(self.X.shape[1])
+
+
+def run_stage(stage: Stage, raster, n_cells: int, stream=None, target_stripes: int = 0,
+              _cache: Optional[Dict[int, StageResult]] = None) -> StageResult:
+    """Execute a stage (and, first, the stages it reads from) on the current device.
+
+    ``raster`` is the device tensor of the call's dataset, shape [T, n_cells] (or [T, lat, lon]).
+    """
+    torch = _torch()
+    L = _lib.lib()
+    _cache = {} if _cache is None else _cache
+    target_stripes = target_stripes or OPTIONS["target_stripes"]
+    if id(stage) in _cache:
+        return _cache[id(stage)]
+    for sub in stage.inputs:
+        run_stage(sub, raster, n_cells, stream, target_stripes, _cache)
+
+    st = torch.cuda.current_stream() if stream is None else stream
+    sptr = st.cuda_stream
+    dev = raster.device
+    G = len(stage.labels)
+    n_cols = len(stage.nodes)
+    X = torch.empty((G, n_cols, n_cells), dtype=_tdtype(stage.dtype), device=dev)
+    V = torch.empty((G, n_cells), dtype=torch.uint8, device=dev)
+    first = True
+    for spec in stage.programs:
+        prog = Program(spec, stage.dtype, n_cells, target_stripes)
+        try:
+            src = getattr(spec, "_source", None)
+            if src is None:
+                x_ptr, ld = raster.data_ptr(), n_cells
+                assert raster.dtype == _tdtype(spec.in_dtype)
+            else:
+                sub_res = _cache[id(src[0])]
+                ld = sub_res.n_cols * n_cells
+                x_ptr = sub_res.X.data_ptr() + src[1] * n_cells * sub_res.X.element_size()
+                assert sub_res.dtype == np.dtype(spec.in_dtype)
+            partial = None
+            if prog.info.partial_bytes:
+                partial = torch.empty(prog.info.partial_bytes // 8, dtype=torch.float64, device=dev)
+            with torch.cuda.stream(st):
+                _lib.check(L.agf_temporal_run(prog.handle, x_ptr, ld, 0, 0, prog.info.n_stripes,
+                                              partial.data_ptr() if partial is not None else None,
+                                              X.data_ptr(), V.data_ptr(), n_cols, 0 if first else 1, sptr))
+                _lib.check(L.agf_temporal_finalize(prog.handle,
+                                                   partial.data_ptr() if partial is not None else None,
+                                                   X.data_ptr(), V.data_ptr(), n_cols, 0 if first else 1, sptr))
+            if partial is not None:
+                partial.record_stream(st)
+        finally:
+            prog.close()
+        first = False
+    res = StageResult(X, V, stage.dtype, stage.labels, stage.nodes)
+    _cache[id(stage)] = res
+    return res
+
+
+def run_spmm(csr: DeviceCSR, res: StageResult, stream=None, want_den: bool = False):
+    """panel[R, G, n_cols] (float64, device) = weighted regional average of a stage result."""
+    torch = _torch()
+    st = torch.cuda.current_stream() if stream is None else stream
+    R, G, NC = csr.host.n_regions, res.n_groups, res.n_cols
+    panel = torch.empty((R, G, NC), dtype=torch.float64, device=res.X.device)
+    den = torch.empty((R, G), dtype=torch.float64, device=res.X.device) if want_den else None
+    with torch.cuda.stream(st):
+        _lib.check(_lib.lib().agf_spmm_run(csr.handle, res.X.data_ptr(),
+                                           _lib.F64 if res.dtype == np.float64 else _lib.F32,
+                                           res.V.data_ptr(), G, NC, panel.data_ptr(),
+                                           den.data_ptr() if den is not None else None, st.cuda_stream))
+    return (panel, den) if want_den else panel
+
+
+def valid_mask(X, dtype, V, stream=None) -> None:
+    """V[g, cell] = AND over columns of ~isnan(X[g, c, cell]) (library kernel, no torch math)."""
+    torch = _torch()
+    st = torch.cuda.current_stream() if stream is None else stream
+    G, NC, n_cells = X.shape
+    with torch.cuda.stream(st):
+        _lib.check(_lib.lib().agf_valid_mask_run(X.data_ptr(), _lib.F64 if np.dtype(dtype) == np.float64 else _lib.F32,
+                                                 G, NC, n_cells, V.data_ptr(), st.cuda_stream))

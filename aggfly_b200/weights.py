@@ -1,0 +1,211 @@
+"""Weights side of the hot path: the ``weights`` frame contract and its lowering to a
+device-resident CSR.
+
+The reference's ``GridWeights`` (aggfly/weights/grid_weights.py) computes polygon / cell overlap
+with geopandas+shapely (out of scope here) and hands the aggregation a
+DataFrame with columns ``cell_id``, ``index_right``, ``weight`` (:379-521), a ``grid`` whose
+``cell_id`` numbers the -180..180-sorted grid (:614-648) and a ``zero_weight`` policy (:125).  This
+module keeps exactly that contract:
+
+* :class:`GeoRegions` / :class:`GridWeights` -- light containers with the attributes the hot path
+  reads (``weights.weights``, ``weights.grid.cell_id``, ``weights.zero_weight``,
+  ``weights.georegions.shp[[regionid]]``);
+* :func:`weights_from_objects` -- same name/signature as the reference; ``calculate_weights()``
+  supports axis-aligned rectangular regions exactly (rectangle / cell overlap x cos(lat) x
+  optional secondary raster, i.e. what ``get_area_weights`` / ``get_weighted_area_weights`` return
+  for such regions) -- enough for synthetic benchmarks; arbitrary polygons need the geometry
+  stack and are the "next" row f-2;
+* :func:`lower_to_csr` -- ``_weight_triplets`` (aggfly/aggregate/spatial.py:157-178) + the cell
+  re-ordering of ``rescale_longitude`` folded into ``cell_idx`` (raster memory order), so the
+  raster itself is never permuted on the device.
+"""
+from __future__ import annotations
+
+import warnings
+from copy import deepcopy
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+import pandas as pd
+
+from .dataset import Dataset, Grid, lon_to_180
+
+ZERO_WEIGHT_POLICIES = ("nan", "area", "drop")
+
+
+class GeoRegions:
+    """Region table: ``shp`` (one row per region, index = the ``index_right`` the weights frame
+    refers to) and the name of the id column (aggfly/regions/georegions.py:22-217)."""
+
+    def __init__(self, shp: pd.DataFrame, regionid: str = "geoid", region_list=None):
+        if regionid not in shp.columns:
+            raise ValueError(f"regionid column {regionid!r} not in {list(shp.columns)}")
+        if region_list is not None:
+            shp = shp[shp[regionid].isin(region_list)]
+        self.shp = shp
+        self.regionid = regionid
+
+    @property
+    def regions(self):
+        return self.shp[self.regionid]
+
+    @classmethod
+    def from_rectangles(cls, ids, lon_min, lon_max, lat_min, lat_max, regionid="geoid") -> "GeoRegions":
+        shp = pd.DataFrame({regionid: list(ids), "lon_min": np.asarray(lon_min, float),
+                            "lon_max": np.asarray(lon_max, float), "lat_min": np.asarray(lat_min, float),
+                            "lat_max": np.asarray(lat_max, float)})
+        return cls(shp, regionid)
+
+
+class GridWeights:
+    """Container with the reference's attribute names (aggfly/weights/grid_weights.py:103-138)."""
+
+    def __init__(self, grid: Grid, georegions: GeoRegions, raster_weights=None, chunks=30,
+                 project_dir: Optional[str] = None, simplify=None, zero_weight: str = "nan",
+                 default_to_area_weights: Optional[bool] = None, cosine_area: Optional[bool] = None,
+                 verbose: bool = True):
+        assert not grid.lon_is_360                                        # grid_weights.py:104
+        self.grid = grid
+        self.georegions = georegions
+        self.raster_weights = raster_weights
+        self.project_dir = project_dir
+        if default_to_area_weights is not None:                           # :112-119
+            warnings.warn('default_to_area_weights is deprecated; use zero_weight="area" (True) or '
+                          'zero_weight="drop" (False).', DeprecationWarning, stacklevel=2)
+            zero_weight = "area" if default_to_area_weights else "drop"
+        if zero_weight not in ZERO_WEIGHT_POLICIES:
+            raise ValueError(f"zero_weight must be one of {sorted(ZERO_WEIGHT_POLICIES)}, got {zero_weight!r}")
+        self.zero_weight = zero_weight
+        if cosine_area is None:
+            cosine_area = raster_weights is None                          # :133-135
+        self.cosine_area = cosine_area
+        self.weights: Optional[pd.DataFrame] = None
+        self._csr_cache = {}
+
+    @classmethod
+    def from_frame(cls, weights: pd.DataFrame, grid: Grid, georegions: GeoRegions,
+                   zero_weight: str = "nan") -> "GridWeights":
+        """Wrap a precomputed weights frame (e.g. the reference's cached ``.feather``)."""
+        for col in ("cell_id", "index_right", "weight"):
+            if col not in weights.columns:
+                raise ValueError(f"weights frame lacks column {col!r}")
+        self = cls(grid, georegions, zero_weight=zero_weight)
+        self.weights = weights
+        return self
+
+    def calculate_weights(self) -> None:
+        """Exact area (x cos(lat), x secondary raster) weights for rectangular regions."""
+        shp = self.georegions.shp
+        need = {"lon_min", "lon_max", "lat_min", "lat_max"}
+        if not need.issubset(shp.columns):
+            raise NotImplementedError(
+                "calculate_weights() here only handles axis-aligned rectangular regions "
+                "(GeoRegions.from_rectangles); for polygon regions compute the frame with the "
+                "reference and wrap it with GridWeights.from_frame (SURVEY.md section 8 f-2)")
+        lon, lat = self.grid.longitude, self.grid.latitude
+        dlon, dlat = self.grid.resolution_lon, self.grid.resolution_lat
+        rows = []
+        for ridx, r in zip(shp.index, shp.itertuples(index=False)):
+            ox = np.clip(np.minimum(lon + dlon / 2, r.lon_max) - np.maximum(lon - dlon / 2, r.lon_min), 0, None)
+            oy = np.clip(np.minimum(lat + dlat / 2, r.lat_max) - np.maximum(lat - dlat / 2, r.lat_min), 0, None)
+            jy, jx = np.nonzero(oy)[0], np.nonzero(ox)[0]
+            if len(jy) == 0 or len(jx) == 0:
+                continue
+            frac = np.outer(oy[jy], ox[jx]) / (dlon * dlat)               # cell area fraction inside
+            yy, xx = np.meshgrid(jy, jx, indexing="ij")
+            aw = frac * (np.cos(np.deg2rad(lat[yy])) if self.cosine_area else 1.0)
+            rows.append(pd.DataFrame({"cell_id": (yy * len(lon) + xx).ravel(), "index_right": ridx,
+                                      "area_weight": aw.ravel(), "longitude": lon[xx].ravel(),
+                                      "latitude": lat[yy].ravel()}))
+        w = pd.concat(rows, ignore_index=True)
+        if self.raster_weights is None:
+            w["weight"] = w["area_weight"]
+        else:
+            rw = np.asarray(self.raster_weights, dtype=float).reshape(-1)
+            w["raster_weight"] = np.nan_to_num(rw[w["cell_id"].to_numpy()], nan=0.0)
+            prod = w["area_weight"] * w["raster_weight"]
+            tot = prod.groupby(w["index_right"]).transform("sum")
+            with np.errstate(invalid="ignore", divide="ignore"):
+                w["weight"] = np.where(tot > 0, prod / tot, 0.0)          # per-region normalisation
+            empty = ~(tot > 0)
+            if empty.any():
+                if self.zero_weight == "area":
+                    warnings.warn("regions with no secondary weight fall back to AREA weights", UserWarning)
+                    w.loc[empty, "weight"] = w.loc[empty, "area_weight"]
+                elif self.zero_weight == "drop":
+                    warnings.warn("regions with no secondary weight are DROPPED", UserWarning)
+                    w = w.loc[~empty].reset_index(drop=True)
+        self.weights = shp[[self.georegions.regionid]].merge(w, right_on="index_right", left_index=True)
+        self._csr_cache.clear()
+
+
+def weights_from_objects(clim: Dataset, georegions: GeoRegions, secondary_weights=None,
+                         project_dir: Optional[str] = None, **kwargs) -> GridWeights:
+    """aggfly/weights/grid_weights.py:614-648: the weight grid is the dataset's grid after the
+    0-360 -> -180..180 relabel + sort."""
+    if clim.lon_is_360:
+        order = clim.lon_sort_order()
+        grid = Grid(lon_to_180(clim.longitude)[order], clim.latitude, clim.name, False)
+    else:
+        grid = Grid(clim.longitude, clim.latitude, clim.name, False)
+    return GridWeights(grid, georegions, secondary_weights, project_dir=project_dir, **kwargs)
+
+
+# ---------------------------------------------------------------------------------------------
+# CSR lowering
+# ---------------------------------------------------------------------------------------------
+@dataclass
+class HostCSR:
+    row_ptr: np.ndarray      # int32[R+1]
+    cell_idx: np.ndarray     # int32[nnz], raster memory order
+    w: np.ndarray            # float64[nnz]
+    region_ids: np.ndarray   # sorted unique index_right (row r <-> region_ids[r])
+    n_cells: int
+
+    @property
+    def n_regions(self) -> int:
+        return len(self.region_ids)
+
+    @property
+    def nnz(self) -> int:
+        return len(self.w)
+
+
+def lower_to_csr(wdf: pd.DataFrame, grid_cell_id: np.ndarray, n_lat: int, n_lon: int,
+                 lon_order: Optional[np.ndarray] = None) -> HostCSR:
+    """weights frame -> CSR over (region row, raster cell).
+
+    * rows: ``region_ids = sort(unique(index_right))``                       spatial.py:165-166
+    * cols: position of ``cell_id`` in ``grid.cell_id``; absent cells dropped  :168-172
+    * entries keep the frame's order inside each region (fp64 sum order of ``np.add.at``)
+    * ``lon_order`` (argsort of the relabelled longitudes) maps a position in the sorted grid
+      back to the raster's memory column: cell (i, j_sorted) -> i * n_lon + lon_order[j_sorted]
+    """
+    grid_cell_id = np.asarray(grid_cell_id)
+    n_cells = n_lat * n_lon
+    if len(grid_cell_id) != n_cells:
+        raise ValueError(f"weights grid has {len(grid_cell_id)} cells, the raster has {n_cells}")
+    region_ids = np.sort(pd.unique(wdf["index_right"]))
+    rows = np.searchsorted(region_ids, wdf["index_right"].to_numpy())
+    cid = wdf["cell_id"].to_numpy()
+    if np.array_equal(grid_cell_id, np.arange(n_cells)):
+        ok = (cid >= 0) & (cid < n_cells)
+        pos = np.where(ok, cid, 0).astype(np.int64)
+    else:
+        sorter = np.argsort(grid_cell_id, kind="stable")
+        loc = np.searchsorted(grid_cell_id, cid, sorter=sorter)
+        loc = np.clip(loc, 0, n_cells - 1)
+        pos = sorter[loc]
+        ok = grid_cell_id[pos] == cid
+    rows, pos = rows[ok], pos[ok]
+    w = wdf["weight"].to_numpy(dtype=np.float64)[ok]
+    if lon_order is not None:
+        lon_order = np.asarray(lon_order, dtype=np.int64)
+        pos = (pos // n_lon) * n_lon + lon_order[pos % n_lon]
+    order = np.argsort(rows, kind="stable")                      # group by region, keep frame order
+    rows, pos, w = rows[order], pos[order], w[order]
+    row_ptr = np.zeros(len(region_ids) + 1, dtype=np.int64)
+    np.cumsum(np.bincount(rows, minlength=len(region_ids)), out=row_ptr[1:])
+    return HostCSR(row_ptr.astype(np.int32), pos.astype(np.int32), np.ascontiguousarray(w),
+                   region_ids, n_cells)

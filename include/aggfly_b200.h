@@ -1,0 +1,210 @@
+/*
+ * aggfly_b200.h -- C-ABI of libaggfly_b200.so, the B200 (sm_100a) engine behind aggfly's
+ * `aggregate_dataset` hot path.
+ *
+ * The reference (dylanhogan/aggfly, pure Python) has no FFI; its backend seam for this path is
+ * the `engine=` string ("auto" | "dask" | "numba", aggfly/aggregate/aggregate.py:210-217,
+ * aggfly/aggregate/nb_kernels.py:59-74) and, underneath it, two operator-level functions:
+ *
+ *     numba_resample(da, freq, calc, ddargs, multi_dd)        aggfly/aggregate/nb_kernels.py:271-305
+ *         -> _block_stat / _block_dd / _block_bins / _block_sine_dd              :121-251
+ *     _scatter_block(block, region_idx, cell_idx, w_vals, n_regions)   aggfly/aggregate/spatial.py:181-186
+ *
+ * This header is what a maintainer would bind (ctypes) to add
+ * `engine="cuda"`:  a *program* is the lowered form of one aggregate_dataset spec (every
+ * `('aggregate', ...)` / `('transform', ...)` chain of the call, common prefixes shared, so the
+ * hourly raster is read once for all output names); a *CSR* is the lowered weights frame
+ * (aggfly/aggregate/spatial.py:157-178).
+ *
+ * Conventions
+ *   - plain C, no C++/torch types; every function returns int: 0 = ok, <0 = AGF_E_* library
+ *     error, >0 = cudaError_t.  agf_last_error() returns a thread-local message.
+ *   - the caller owns every data buffer (device pointers are e.g. torch tensors' data_ptr());
+ *     the library never allocates or frees caller-visible memory.  Opaque handles own only
+ *     small private tables (group bounds, stripe tables) and are destroyed explicitly.
+ *   - every launch takes a cudaStream_t (as uintptr_t) and is asynchronous; no hidden syncs.
+ *   - handles are bound to the device that was current at creation; distinct handles are
+ *     independent and may be used from different threads.
+ *   - there is no CPU fallback anywhere behind this header.
+ *
+ * Data layout
+ *   raster   x[T, n_cells]      time-major, cell = lat_index * n_lon + lon_index fastest
+ *                               (row stride `ld` elements), float32 or float64
+ *   columns  X[G, n_cols, n_cells]  per-cell temporal results, G = output periods
+ *   valid    V[G, n_cells] uint8    1 iff every column of the call is non-NaN there
+ *                                   (shared validity mask, aggfly/aggregate/spatial.py:114-119)
+ *   panel    P[n_regions, G, n_cols] float64
+ */
+#ifndef AGGFLY_B200_H
+#define AGGFLY_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AGF_ABI_VERSION 1
+
+#define AGF_MAX_LANES 32  /* level-1 reducers per program */
+#define AGF_MAX_SLOTS 32  /* level-2 reducers per program */
+#define AGF_MAX_COLS 64   /* output columns per program   */
+
+/* library error codes (negative) */
+#define AGF_E_INVALID (-1)      /* bad argument / descriptor */
+#define AGF_E_UNSUPPORTED (-2)  /* valid spec the fused kernels do not cover (host must split) */
+#define AGF_E_NOMEM (-3)
+#define AGF_E_STATE (-4)        /* handle used on the wrong device / after destroy */
+
+/* calc codes: aggfly/aggregate/temporal.py:98-134, aggfly/aggregate/nb_kernels.py:33 */
+enum {
+    AGF_CALC_MEAN = 0,
+    AGF_CALC_SUM = 1,
+    AGF_CALC_MIN = 2,
+    AGF_CALC_MAX = 3,
+    AGF_CALC_NANMEAN = 4,
+    AGF_CALC_DD = 5,       /* sum |v - base| over t0 < v < t1 (strict), nb_kernels.py:158-179 */
+    AGF_CALC_BINS = 6,     /* count of t0 < v < t1 (strict),           nb_kernels.py:182-199 */
+    AGF_CALC_SINE_DD = 7,  /* single-sine degree days,                 nb_kernels.py:202-251 */
+    AGF_CALC_HIDDEN_SUM = 8, /* helper lanes the host inserts in front of SINE_DD lanes */
+    AGF_CALC_HIDDEN_MIN = 9,
+    AGF_CALC_HIDDEN_MAX = 10
+};
+
+/* transforms between / after aggregate steps: aggfly/dataset/dataset.py:442-481, 527-543 */
+enum {
+    AGF_XF_NONE = 0,
+    AGF_XF_POWI = 1,    /* np.power(x, e), e a small non-negative integer (repeated multiply) */
+    AGF_XF_POW = 2,     /* np.power(x, e), general exponent */
+    AGF_XF_SPLINE2 = 3  /* (x > 20) * (x - 20), in the value's own dtype */
+};
+
+enum { AGF_F32 = 0, AGF_F64 = 1 };
+
+/* One level-1 reducer over the raw time axis (one `('aggregate', {...})` step applied to the
+ * raster; one lane per ddargs row for multi-ddargs). */
+typedef struct {
+    int32_t calc;
+    int32_t flag;  /* ddargs[2]: dd base selector (0 -> t0, else t1) / sine_dd kind */
+    double t0, t1; /* ddargs[0], ddargs[1] (compared in fp64, like the reference) */
+} agf_lane_t;
+
+/* One level-2 reducer: consumes the per-group values of lane `src` (rounded to the raster
+ * dtype, nb_kernels.py:260), optionally transformed, grouped by bounds2. */
+typedef struct {
+    int32_t src;    /* level-1 lane index */
+    int32_t xform;  /* AGF_XF_* applied to the lane value before reducing */
+    double xparam;  /* exponent for POWI / POW */
+    int32_t x_f64;  /* dtype of the transformed value (NumPy promotion decided by the host):
+                       0 = raster dtype, 1 = float64 */
+    int32_t calc;   /* MEAN, SUM, MIN, MAX, DD, BINS */
+    int32_t flag;
+    int32_t pad_;
+    double t0, t1;
+} agf_slot_t;
+
+/* One output column: value of a slot (or, when n_slots == 0, of a lane), optionally transformed
+ * after the last aggregate step. */
+typedef struct {
+    int32_t src;
+    int32_t xform;
+    double xparam;
+    int32_t x_f64; /* dtype of the column after the transform: 0 = raster dtype, 1 = float64 */
+    int32_t dst;   /* column index in the destination X (several programs may share one X) */
+} agf_col_t;
+
+typedef struct {
+    int32_t in_dtype;  /* AGF_F32 | AGF_F64: raster dtype */
+    int32_t out_dtype; /* dtype of X: AGF_F64 if any column is float64, else raster dtype */
+    int32_t n_lanes;
+    int32_t n_slots;   /* 0: single-level program, columns come straight from lanes */
+    int32_t n_cols;
+    int32_t pad_;
+    int64_t n_time;    /* T: rows of the whole time axis the bounds refer to */
+    int64_t n_groups1; /* G1 */
+    int64_t n_groups2; /* G2 (ignored when n_slots == 0) */
+    const int32_t *bounds1; /* host, int32[G1+1], row positions; nb_kernels.py:80-115 */
+    const int32_t *bounds2; /* host, int32[G2+1], positions on the level-1 group axis */
+    agf_lane_t lanes[AGF_MAX_LANES];
+    agf_slot_t slots[AGF_MAX_SLOTS];
+    agf_col_t cols[AGF_MAX_COLS];
+} agf_program_desc_t;
+
+typedef struct {
+    int32_t n_stripes;  /* time stripes (cut at level-1 group boundaries) */
+    int32_t n_recs;     /* partial records: one per (stripe, level-2 group it touches) */
+    int32_t n_cols;
+    int32_t out_dtype;
+    int64_t n_out_groups;   /* G of X / V / the panel: G2, or G1 when n_slots == 0 */
+    int64_t partial_bytes;  /* size of the partial buffer the caller must provide (0 if none) */
+    int64_t out_bytes;      /* size of X */
+    int64_t valid_bytes;    /* size of V */
+    int32_t kernel_lanes, kernel_slots, kernel_mode; /* which instantiation will run */
+    int32_t uses_tma;
+} agf_program_info_t;
+
+typedef struct agf_program agf_program_t;
+typedef struct agf_csr agf_csr_t;
+
+int agf_version(void);
+const char *agf_last_error(void);
+
+/* ---- programs (replace numba_resample + Dataset.power/spline chains) ------------------- */
+
+/* Lower a descriptor for a raster of n_cells cells on the current device.  `target_stripes`
+ * <= 0 lets the library choose how many time stripes to cut (enough CTAs to fill 148 SMs). */
+int agf_program_create(agf_program_t **out, const agf_program_desc_t *desc, int64_t n_cells,
+                       int32_t target_stripes);
+int agf_program_destroy(agf_program_t *prog);
+/* Host-only planning (no device needed): validates the descriptor, picks the kernel
+ * instantiation and cuts the time axis into stripes.  stripes_out (may be NULL) receives
+ * (g1_begin, g1_end, g2_first, rec0) per stripe.  Used by agf_program_create. */
+int agf_program_plan(const agf_program_desc_t *desc, int64_t n_cells, int32_t target_stripes,
+                     int32_t sm_count, int32_t *stripes_out, int32_t max_stripes,
+                     int32_t *n_stripes, int32_t *n_recs, int32_t *kernel_lanes,
+                     int32_t *kernel_slots, int32_t *kernel_diag);
+int agf_program_info(const agf_program_t *prog, agf_program_info_t *info);
+/* rows [row_begin, row_end) of the time axis covered by stripe s */
+int agf_program_stripe_rows(const agf_program_t *prog, int32_t stripe, int64_t *row_begin,
+                            int64_t *row_end);
+
+/* Run stripes [stripe_begin, stripe_end) of the fused temporal kernel.  d_x points at the
+ * raster row `row0` (so a streamed chunk can be passed on its own), `ld` is the row stride in
+ * elements.  Single-level programs write X / V directly; two-level programs write partial
+ * records that agf_temporal_finalize merges.
+ * Several programs of one call may share X / V: column c of this program goes to
+ * X[:, cols[c].dst, :] of an X with `out_ncols` columns, and with valid_and != 0 its validity
+ * is AND-ed into V instead of overwriting it. */
+int agf_temporal_run(const agf_program_t *prog, const void *d_x, int64_t ld, int64_t row0,
+                     int32_t stripe_begin, int32_t stripe_end, double *d_partial, void *d_out,
+                     uint8_t *d_valid, int32_t out_ncols, int32_t valid_and, uintptr_t stream);
+/* Merge partial records in stripe order, apply mean division / dtype rounding / trailing
+ * transforms, write X and V.  No-op for single-level programs. */
+int agf_temporal_finalize(const agf_program_t *prog, const double *d_partial, void *d_out,
+                          uint8_t *d_valid, int32_t out_ncols, int32_t valid_and, uintptr_t stream);
+
+/* ---- CSR weights + weighted regional average (replace _weight_triplets/_scatter_block) -- */
+
+/* d_row_ptr int32[n_regions+1], d_cell_idx int32[nnz] (raster memory order), d_w fp64[nnz]:
+ * caller-owned device arrays that must outlive the handle. */
+int agf_csr_create(agf_csr_t **out, int32_t n_regions, int64_t n_cells, int64_t nnz,
+                   const int32_t *d_row_ptr, const int32_t *d_cell_idx, const double *d_w);
+int agf_csr_destroy(agf_csr_t *csr);
+
+/* P[r, g, c] = sum_e w_e X[g, c, cell_e] V[g, cell_e] / sum_e w_e V[g, cell_e]  (NaN if the
+ * denominator is 0), aggfly/aggregate/spatial.py:114-133.  Also writes the denominators
+ * D[r, g] when d_den != NULL. */
+int agf_spmm_run(const agf_csr_t *csr, const void *d_x, int32_t x_dtype, const uint8_t *d_valid,
+                 int64_t n_groups, int32_t n_cols, double *d_panel, double *d_den,
+                 uintptr_t stream);
+
+/* V[g, cell] = 1 iff no column of X[g, :, cell] is NaN -- for callers that bring their own
+ * temporally-reduced X (aggregate_space / SpatialAggregator, aggfly/aggregate/spatial.py:114-119). */
+int agf_valid_mask_run(const void *d_x, int32_t x_dtype, int64_t n_groups, int32_t n_cols,
+                       int64_t n_cells, uint8_t *d_valid, uintptr_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AGGFLY_B200_H */

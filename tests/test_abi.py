@@ -1,0 +1,87 @@
+"""The C-ABI library loads and exports every symbol include/aggfly_b200.h declares (no compute
+calls: this runs without a GPU), and the host-only planner cuts stripes / records consistently."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from aggfly_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "aggfly_b200.h")).read()
+    declared = set(re.findall(r"^(?:int|const char \*)\s*\*?(agf_\w+)\(", hdr, flags=re.M))
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    L = _lib.lib()
+    for name in declared:
+        assert hasattr(L, name), name
+    assert L.agf_version() == 1
+
+
+def test_struct_sizes_match_the_header():
+    assert C.sizeof(_lib.Lane) == 24 and C.sizeof(_lib.Slot) == 48 and C.sizeof(_lib.Col) == 24
+    assert C.sizeof(_lib.ProgramDesc) == 64 + 32 * 24 + 32 * 48 + 64 * 24
+
+
+def _desc(b1, b2=None, n_lanes=1, n_slots=0, n_cols=1):
+    d = _lib.ProgramDesc()
+    d.in_dtype, d.out_dtype = _lib.F32, _lib.F32
+    d.n_lanes, d.n_slots, d.n_cols = n_lanes, n_slots, n_cols
+    b1 = np.ascontiguousarray(b1, dtype=np.int32)
+    d.n_time, d.n_groups1 = int(b1[-1]), len(b1) - 1
+    d.bounds1 = b1.ctypes.data_as(C.POINTER(C.c_int32))
+    keep = [b1]
+    if b2 is not None:
+        b2 = np.ascontiguousarray(b2, dtype=np.int32)
+        d.n_groups2 = len(b2) - 1
+        d.bounds2 = b2.ctypes.data_as(C.POINTER(C.c_int32))
+        keep.append(b2)
+    for c in range(n_cols):
+        d.cols[c].dst = c
+    return d, keep
+
+
+def _plan(d, n_cells, target):
+    buf = (C.c_int32 * (4 * 4096))()
+    n_str, n_rec, kl, ks, kd = (C.c_int32() for _ in range(5))
+    rc = _lib.lib().agf_program_plan(C.byref(d), n_cells, target, 148, buf, 4096, C.byref(n_str), C.byref(n_rec),
+                                     C.byref(kl), C.byref(ks), C.byref(kd))
+    _lib.check(rc)
+    s = np.array(buf[:4 * n_str.value]).reshape(-1, 4)
+    return s, n_rec.value, (kl.value, ks.value, kd.value)
+
+
+def test_planner_stripes_cover_groups_and_records_count_intersections():
+    b1 = np.arange(0, 24 * 365 + 1, 24)                       # 365 days
+    month_days = np.array([31, 28, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31])
+    b2 = np.concatenate([[0], np.cumsum(month_days)])
+    d, keep = _desc(b1, b2, n_slots=1)
+    for target in (1, 7, 12, 50, 365, 1000):
+        s, n_rec, kern = _plan(d, 24544, target)
+        assert s[0, 0] == 0 and s[-1, 1] == 365 and np.array_equal(s[1:, 0], s[:-1, 1])
+        want = 0
+        for g0, g1, g2_first, rec0 in s:
+            assert rec0 == want
+            assert b2[g2_first] <= g0 < b2[g2_first + 1]
+            want += len({int(np.searchsorted(b2, g, side="right") - 1) for g in range(g0, g1)})
+        assert n_rec == want and kern == (1, 1, 0)
+    s, n_rec, _ = _plan(d, 1038240, 0)                        # big grid: few stripes
+    assert len(s) <= 2
+    s, n_rec, _ = _plan(d, 24544, 0)                          # small grid: many stripes to fill 148 SMs
+    assert len(s) >= 12
+
+
+def test_planner_rejects_bad_descriptors():
+    d, keep = _desc([0, 5, 3])
+    with pytest.raises(_lib.AgfError, match="monotonic"):
+        _plan(d, 100, 1)
+    d, keep = _desc([0, 5, 9], [0, 1], n_slots=1)
+    with pytest.raises(_lib.AgfError, match="cover"):
+        _plan(d, 100, 1)
+    d, keep = _desc([0, 5, 9], [0, 2], n_lanes=9, n_slots=3)
+    with pytest.raises(_lib.AgfUnsupported):
+        _plan(d, 100, 1)

@@ -1,0 +1,299 @@
+"""Parity of the CUDA path (through the public API -> ctypes -> C-ABI -> kernels) against the
+CPU oracle on the same seeded inputs.  Bar: bit-exact for group indices, bin counts and every
+single-stripe result; rel 1e-12 where the stripe merge re-associates an fp64 sum (the
+north-star tolerance for weighted float outputs is rel 1e-5)."""
+import numpy as np
+import pandas as pd
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import aggfly_b200 as af
+from aggfly_b200 import engine
+from aggfly_b200.spec import ColSpec, LaneSpec, ProgramSpec, Stage
+from oracle import oracle as orc
+from tests import refcases as rc
+
+
+@pytest.fixture(autouse=True)
+def _need_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    engine.OPTIONS["target_stripes"] = 0
+    yield
+    engine.OPTIONS["target_stripes"] = 0
+
+
+def _exact(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    assert np.array_equal(np.isnan(a), np.isnan(b))
+    m = ~np.isnan(a)
+    assert np.array_equal(a[m], b[m]), np.abs(a[m] - b[m]).max()
+
+
+def _close(a, b, rtol):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    assert a.shape == b.shape
+    assert np.array_equal(np.isnan(a), np.isnan(b))
+    assert np.allclose(a, b, rtol=rtol, atol=0, equal_nan=True)
+
+
+# ---- kernel level: arbitrary bounds, every calc, both dtypes, NaNs, empty group --------------
+def _run_lanes(cube, bounds, lanes):
+    import torch
+    T, Y, X = cube.shape
+    prog = ProgramSpec(input=None, in_dtype=cube.dtype, bounds1=np.asarray(bounds), bounds2=None,
+                       lanes=[LaneSpec(c, dd) for c, dd in lanes], n_time=T)
+    prog._source = None
+    off = 3 if lanes[0][0] == "sine_dd" else 0
+    if off:
+        prog.lanes[:0] = [LaneSpec("_hidden_sum"), LaneSpec("_hidden_min"), LaneSpec("_hidden_max")]
+    prog.cols = [ColSpec(off + i, None, 0.0, cube.dtype == np.float64, out_col=i) for i in range(len(lanes))]
+    stage = Stage(programs=[prog], nodes=[None] * len(lanes), dtype=cube.dtype, labels=np.arange(len(bounds) - 1))
+    res = engine.run_stage(stage, engine.to_device(cube).reshape(T, Y * X), Y * X)
+    torch.cuda.synchronize()
+    return res.X.cpu().numpy().reshape(len(bounds) - 1, len(lanes), Y, X), res.V.cpu().numpy()
+
+
+@pytest.mark.parametrize("dt", ["float32", "float64"])
+@pytest.mark.parametrize("tag", ["clean", "nan"])
+def test_level1_kernels_match_reference_numba_outputs(golden, dt, tag):
+    cube, bounds, dda = golden[f"cube_{dt}_{tag}"], golden["bounds"], golden["ddargs"]
+    stats = ["mean", "sum", "min", "max", "nanmean"]
+    got, valid = _run_lanes(cube, bounds, [(c, None) for c in stats])
+    for i, c in enumerate(stats):
+        _exact(got[:, i], golden[f"stat_{c}_{dt}_{tag}"])
+    assert np.array_equal(valid.reshape(got[:, 0].shape), ~np.isnan(got).any(axis=1))
+    for calc in ("dd", "bins"):
+        got, _ = _run_lanes(cube, bounds, [(calc, tuple(r)) for r in dda])
+        _exact(np.moveaxis(got, 1, -1), golden[f"{calc}_{dt}_{tag}"])
+    got, _ = _run_lanes(cube, bounds, [("sine_dd", tuple(r)) for r in dda])
+    want = golden[f"sine_dd_{dt}_{tag}"]
+    assert np.array_equal(np.isnan(np.moveaxis(got, 1, -1)), np.isnan(want))
+    tol = 1e-5 if dt == "float32" else 1e-12                 # transcendental libm differences only
+    assert np.allclose(np.moveaxis(got, 1, -1), want, rtol=tol, atol=tol, equal_nan=True)
+
+
+# ---- reference test-suite goldens -------------------------------------------------------------
+def _ref_dataset():
+    arr, time, lat, lon = rc.dataset_360_arrays()
+    return af.Dataset.from_arrays(arr, time, lat, lon, lon_is_360=True)
+
+
+def _ref_weights(ds, zero_weight="nan"):
+    w = af.weights_from_objects(ds, af.GeoRegions(pd.DataFrame({"geoid": ["region_1"]}), "geoid"), zero_weight=zero_weight)
+    w.weights = rc.fixture_weights_frame()
+    return w
+
+
+def test_reference_golden_time_matrix():
+    out = af.aggregate_time(dataset=_ref_dataset(), weights=None, **rc.golden_time_spec())
+    cols = ["bins_-99_20", "bins_20_99", "cooling_dday", "tavg_1", "tavg_2"]
+    assert list(out) == cols
+    mat = np.stack([out[c].values.reshape(-1) for c in cols], axis=1)
+    assert np.allclose(mat, rc.GOLDEN_TIME_MATRIX)
+    assert list(out["tavg_1"].time) == [pd.Timestamp("2000-07-31")]
+
+
+def test_reference_golden_panel():
+    ds = _ref_dataset()
+    df = af.aggregate_dataset(dataset=ds, weights=_ref_weights(ds), **rc.golden_panel_spec())
+    assert list(df.columns) == ["geoid", "time", "tavg_1", "tavg_2"]
+    assert np.allclose(df[["tavg_1", "tavg_2"]].values, rc.GOLDEN_PANEL)
+    with pytest.warns(DeprecationWarning, match="no longer builds a Dask cluster"):
+        df2 = af.aggregate_dataset(dataset=ds, weights=_ref_weights(ds), n_workers=50, processes=True,
+                                   **rc.golden_panel_spec())
+    assert "n_workers" not in df2.columns and np.array_equal(df2["tavg_2"].values, df["tavg_2"].values)
+    with pytest.raises(ValueError, match="No dataset provided"):
+        af.aggregate_dataset(weights=_ref_weights(ds), **rc.golden_panel_spec())
+
+
+# ---- chains vs the oracle on seeded synthetic rasters --------------------------------------------
+BINS13 = [[-20 + 5 * i, -15 + 5 * i, 0] for i in range(13)]
+SPECS = {
+    "c1_tavg_poly": dict(tavg=[("aggregate", {"calc": "mean", "groupby": "date"}),
+                               ("transform", {"transform": "power", "exp": np.arange(1, 3)}),
+                               ("aggregate", {"calc": "sum", "groupby": "year"})]),
+    "c2_gdd": dict(gdd=[("aggregate", {"calc": "dd", "groupby": "date", "ddargs": [10, 30, 0]}),
+                        ("aggregate", {"calc": "sum", "groupby": "year"})]),
+    "c3_bins_and_poly": dict(
+        temp_bins=[("aggregate", {"calc": "mean", "groupby": "date"}),
+                   ("aggregate", {"calc": "bins", "groupby": "year", "ddargs": BINS13})],
+        tavg=[("aggregate", {"calc": "mean", "groupby": "date"}),
+              ("transform", {"transform": "power", "exp": np.arange(1, 3)}),
+              ("aggregate", {"calc": "sum", "groupby": "year"})]),
+    "c3b_daily": dict(hbins=[("aggregate", {"calc": "bins", "groupby": "date", "ddargs": BINS13})],
+                      tavg=[("aggregate", {"calc": "mean", "groupby": "date"})]),
+    "monthly_mix": dict(
+        tmax=[("aggregate", {"calc": "max", "groupby": "date"}), ("aggregate", {"calc": "mean", "groupby": "month"})],
+        tmin=[("aggregate", {"calc": "min", "groupby": "date"}), ("aggregate", {"calc": "min", "groupby": "month"})],
+        hdd=[("aggregate", {"calc": "dd", "groupby": "date", "ddargs": [-99, 18.3, 1]}),
+             ("aggregate", {"calc": "sum", "groupby": "month"})],
+        direct=[("aggregate", {"calc": "mean", "groupby": "month"})]),
+    "weekly": dict(w=[("aggregate", {"calc": "sum", "groupby": "date"}), ("aggregate", {"calc": "max", "groupby": "week"})]),
+    "spline_and_pow": dict(
+        s=[("aggregate", {"calc": "mean", "groupby": "date"}), ("transform", {"transform": "spline"}),
+           ("aggregate", {"calc": "sum", "groupby": "month"})],
+        p=[("aggregate", {"calc": "mean", "groupby": "date"}), ("transform", {"transform": "power", "exp": [[1, 3]]}),
+           ("aggregate", {"calc": "sum", "groupby": "month"})],
+        q=[("aggregate", {"calc": "mean", "groupby": "month"}), ("transform", {"transform": "power", "exp": np.arange(2, 4)})]),
+    "dd_bins_of_daily_dd": dict(x=[("aggregate", {"calc": "dd", "groupby": "date", "ddargs": [[10, 30, 0], [0.1, 17.3, 1]]}),
+                                   ("aggregate", {"calc": "sum", "groupby": "year"})]),
+    "three_levels": dict(a=[("aggregate", {"calc": "mean", "groupby": "date"}), ("aggregate", {"calc": "sum", "groupby": "month"}),
+                            ("aggregate", {"calc": "max", "groupby": "year"})]),
+    "nanmean_multipass": dict(a=[("aggregate", {"calc": "nanmean", "groupby": "date"}),
+                                 ("aggregate", {"calc": "nanmean", "groupby": "month"})]),
+    "sine": dict(s=[("aggregate", {"calc": "sine_dd", "groupby": "date", "ddargs": [10, 30, 0]}),
+                    ("aggregate", {"calc": "sum", "groupby": "month"})],
+                 h=[("aggregate", {"calc": "sine_dd", "groupby": "date", "ddargs": [[5, 18, 1], [12, 99, 0]]})]),
+}
+INEXACT = {"spline_and_pow": 1e-6, "sine": 1e-5}     # powf / libm transcendental differences only
+
+
+def _raster(dtype, nan, T=24 * 75 + 7, Y=5, X=9, seed=0):
+    rng = np.random.default_rng(seed)
+    t = pd.date_range("2001-11-20 03:00", periods=T, freq="h")
+    hours = np.arange(T)
+    base = 12 + 14 * np.sin(2 * np.pi * hours / (24 * 365))[:, None, None] + 5 * np.sin(2 * np.pi * hours / 24)[:, None, None]
+    arr = (base + rng.normal(0, 6, (T, Y, X))).astype(dtype)
+    if nan:
+        arr[:, 0, 0] = np.nan
+        arr[rng.random((T, Y, X)) < 0.001] = np.nan
+        arr[24 * 30: 24 * 31, 2, :] = np.nan
+    lat = np.linspace(49.75, 24.0, Y)
+    lon = np.linspace(235.0, 293.75, X)
+    return arr, t, lat, lon
+
+
+def _both_time(arr, t, lat, lon, spec):
+    want = orc.aggregate_time(orc.ODataset(arr, t, lat, lon, True), spec)
+    got = af.aggregate_time(dataset=af.Dataset.from_arrays(arr, t, lat, lon, True), weights=None, aggregator_dict=spec)
+    assert list(got) == list(want)
+    return got, want
+
+
+@pytest.mark.parametrize("name", list(SPECS))
+@pytest.mark.parametrize("dtype", ["float32", "float64"])
+@pytest.mark.parametrize("nan", [False, True])
+def test_chains_match_oracle_single_stripe(name, dtype, nan):
+    engine.OPTIONS["target_stripes"] = 1
+    arr, t, lat, lon = _raster(dtype, nan)
+    got, want = _both_time(arr, t, lat, lon, SPECS[name])
+    for k in want:
+        w_arr, w_lab = want[k]
+        assert got[k].values.dtype == w_arr.dtype, (k, got[k].values.dtype, w_arr.dtype)
+        assert np.array_equal(pd.DatetimeIndex(got[k].time).values, pd.DatetimeIndex(w_lab).values)
+        if name in INEXACT:
+            _close(got[k].values, w_arr, INEXACT[name])
+        else:
+            _exact(got[k].values, w_arr)
+
+
+@pytest.mark.parametrize("name", ["c1_tavg_poly", "c3_bins_and_poly", "monthly_mix", "weekly", "c3b_daily"])
+@pytest.mark.parametrize("stripes", [0, 3, 17, 1000])
+def test_chains_match_oracle_many_stripes(name, stripes):
+    engine.OPTIONS["target_stripes"] = stripes
+    arr, t, lat, lon = _raster("float32", True, seed=3)
+    got, want = _both_time(arr, t, lat, lon, SPECS[name])
+    for k in want:
+        if "bins" in k or "tmin" in k or "tmax" in k or k == "w":
+            _exact(got[k].values, want[k][0])              # counts / min / max do not depend on the split
+        else:
+            _close(got[k].values, want[k][0], 1e-12)
+
+
+def test_ragged_time_axis_with_gaps_and_tiny_grid():
+    arr, t, lat, lon = _raster("float32", True, T=24 * 20 + 5, Y=1, X=3, seed=9)
+    keep = np.ones(len(t), bool); keep[24 * 3 + 7: 24 * 6 + 2] = False; keep[-3:] = False
+    spec = dict(m=[("aggregate", {"calc": "mean", "groupby": "date"}), ("aggregate", {"calc": "sum", "groupby": "month"})],
+                b=[("aggregate", {"calc": "bins", "groupby": "date", "ddargs": [[0, 10, 0], [10, 99, 0]]}),
+                   ("aggregate", {"calc": "sum", "groupby": "month"})])
+    for stripes in (1, 5):
+        engine.OPTIONS["target_stripes"] = stripes
+        got, want = _both_time(arr[keep], t[keep], lat, lon, spec)
+        for k in want:
+            _close(got[k].values, want[k][0], 1e-12)
+    d = [("aggregate", {"calc": "mean", "groupby": "date"})]
+    got, want = _both_time(arr[keep], t[keep], lat, lon, dict(d=d))
+    _exact(got["d"].values, want["d"][0])                   # empty days -> NaN rows kept
+    assert np.isnan(want["d"][0][4]).all()
+
+
+def test_noleap_calendar_chain():
+    n = 365 * 3
+    arr = np.random.default_rng(4).normal(15, 12, (n, 3, 4)).astype(np.float32)
+    arr[100, 1, 1] = np.nan
+    spec = dict(gdd_m=[("aggregate", {"calc": "dd", "groupby": "date", "ddargs": [10, 30, 0]}),
+                       ("aggregate", {"calc": "sum", "groupby": "month"})])
+    want = orc.aggregate_time(orc.ODataset(arr, orc.cal_range("noleap", 2000, n), [0, 1, 2], [0, 1, 2, 3], False), spec)
+    got = af.aggregate_time(dataset=af.Dataset.from_arrays(arr, af.CalendarIndex.range("noleap", 2000, n),
+                                                          [0, 1, 2], [0, 1, 2, 3], False), weights=None, **spec)
+    _close(got["gdd_m"].values, want["gdd_m"][0], 1e-12)
+    assert len(got["gdd_m"].time) == 36 and got["gdd_m"].time.to_objects()[1].day == 28
+
+
+# ---- end to end vs the oracle ---------------------------------------------------------------------
+def _weights_case(lat, lon, rng, n_regions=7, zero_weight="nan", shuffle=True):
+    ny, nx = len(lat), len(lon)
+    rows = []
+    for r in range(n_regions):
+        cells = rng.choice(ny * nx + 4, size=rng.integers(1, 12), replace=False)   # a few ids off-grid
+        for c in cells:
+            rows.append((int(c), 10 + 3 * r, float(rng.random()) if r != 2 else 0.0))   # region row 2 has zero weight
+    wdf = pd.DataFrame(rows, columns=["cell_id", "index_right", "weight"])
+    if shuffle:
+        wdf = wdf.sample(frac=1.0, random_state=1).reset_index(drop=True)
+    shp = pd.DataFrame({"geoid": [f"r{r}" for r in range(n_regions + 1)]}, index=[10 + 3 * r for r in range(n_regions + 1)])
+    return wdf, shp
+
+
+@pytest.mark.parametrize("zero_weight", ["nan", "area", "drop"])
+@pytest.mark.parametrize("lon_is_360", [True, False])
+@pytest.mark.parametrize("name", ["c3_bins_and_poly", "c3b_daily", "monthly_mix"])
+def test_aggregate_dataset_matches_oracle(name, lon_is_360, zero_weight):
+    arr, t, lat, lon = _raster("float32", True, T=24 * 40, seed=11)
+    if not lon_is_360:
+        lon = lon - 360.0
+    else:
+        lon = np.concatenate([lon[4:], lon[:4] - 200.0])       # unsorted once relabelled: exercises the remap
+    rng = np.random.default_rng(2)
+    wdf, shp = _weights_case(lat, lon, rng)
+    want = orc.aggregate_dataset(orc.OWeights(wdf, np.arange(arr.shape[1] * arr.shape[2]), shp, "geoid", zero_weight),
+                                 orc.ODataset(arr, t, lat, lon, lon_is_360), aggregator_dict=SPECS[name])
+    ds = af.Dataset.from_arrays(arr, t, lat, lon, lon_is_360)
+    w = af.weights_from_objects(ds, af.GeoRegions(shp, "geoid"), zero_weight=zero_weight)
+    w.weights = wdf
+    got = af.aggregate_dataset(weights=w, dataset=ds, aggregator_dict=SPECS[name])
+    assert list(got.columns) == list(want.columns)
+    assert len(got) == len(want)
+    assert (got["geoid"].values == want["geoid"].values).all()
+    assert (got["time"].values == want["time"].values).all()
+    vals = [c for c in want.columns if c not in ("geoid", "time")]
+    _close(got[vals].values, want[vals].values, 1e-11)
+
+
+@pytest.mark.parametrize("case", [rc.spatial_case_multiregion_nan, rc.spatial_case_dropna_empty_group])
+def test_reference_spatial_scenarios(case):
+    vals, time, wdf = case()
+    n_t = vals.shape[0]
+    want = rc.wavg_loop_oracle({"v": vals.reshape(n_t, 4).T}, time.values, [0, 1, 2, 3], wdf, ["v"])
+    ds = af.Dataset.from_arrays(vals, time, [0.0, 1.0], [0.0, 1.0], lon_is_360=False)
+    w = af.GridWeights.from_frame(wdf, ds.grid, af.GeoRegions(pd.DataFrame({"id": ["a", "b"]}), "id"), zero_weight="area")
+    got = af.SpatialAggregator([ds], w, names=["v"]).compute()
+    assert got.shape == want.shape
+    assert (got[["region_id", "time"]].values == want[["region_id", "time"]].values).all()
+    assert np.allclose(got["v"].values, want["v"].values, rtol=1e-13)
+
+
+def test_no_spec_aggregates_the_raw_series():
+    arr, t, lat, lon = _raster("float32", True, T=30, seed=5)
+    rng = np.random.default_rng(8)
+    wdf, shp = _weights_case(lat, lon, rng)
+    want = orc.aggregate_dataset(orc.OWeights(wdf, np.arange(45), shp, "geoid", "area"), orc.ODataset(arr, t, lat, lon, True))
+    ds = af.Dataset.from_arrays(arr, t, lat, lon, True)
+    w = af.weights_from_objects(ds, af.GeoRegions(shp, "geoid"), zero_weight="area"); w.weights = wdf
+    got = af.aggregate_dataset(weights=w, dataset=ds)
+    assert list(got.columns) == ["geoid", "time", "variable"] and len(got) == len(want)
+    _close(got["variable"].values, want["variable"].values, 1e-12)

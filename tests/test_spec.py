@@ -1,0 +1,124 @@
+"""Host logic without a GPU: DSL -> symbolic series -> programs, key/dtype rules, error
+behaviour (reference: aggfly/aggregate/aggregate.py:36-162, 285-303; temporal.py:57-163)."""
+import ctypes as C
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from aggfly_b200 import _lib
+from aggfly_b200.spec import Graph, Planner, TemporalAggregator, build_desc, compile_spec
+from tests import refcases as rc
+
+T_HOURLY = pd.date_range("2001-01-01", periods=24 * 90, freq="h")
+
+
+def _plan(spec, dtype=np.float32, t=T_HOURLY):
+    g = Graph(dtype, t)
+    outs = compile_spec(g, spec)
+    return g, outs, Planner(g).plan(list(outs.values()))
+
+
+def test_keys_follow_reference_naming():
+    g, outs, _ = _plan(rc.golden_time_spec())
+    assert list(outs) == ["bins_-99_20", "bins_20_99", "cooling_dday", "tavg_1", "tavg_2"]
+    _, outs, _ = _plan(dict(t=[("aggregate", {"calc": "mean", "groupby": "date"}),
+                               ("transform", {"transform": "spline"}),
+                               ("aggregate", {"calc": "sum", "groupby": "year"})]))
+    assert list(outs) == ["t_spline1", "t_spline2"]
+    _, outs, _ = _plan(dict(b=[("aggregate", {"calc": "bins", "groupby": "date", "ddargs": [[0.5, 10, 0], [10, 20.25, 0]]})]))
+    assert list(outs) == ["b_0.5_10", "b_10_20.25"]
+
+
+def test_power_dtype_promotion_follows_numpy():
+    g, outs, _ = _plan(dict(a=[("aggregate", {"calc": "mean", "groupby": "date"}),
+                               ("transform", {"transform": "power", "exp": np.arange(1, 3)})]))
+    assert all(n.dtype == np.float64 for n in outs.values())            # numpy ints promote f32 -> f64
+    g, outs, _ = _plan(dict(a=[("aggregate", {"calc": "mean", "groupby": "date"}),
+                               ("transform", {"transform": "power", "exp": [[1, 2]]})]))
+    assert all(n.dtype == np.float32 for n in outs.values())            # python ints do not
+    g, outs, _ = _plan(dict(a=[("aggregate", {"calc": "dd", "groupby": "date", "ddargs": [10, 30, 0]}),
+                               ("aggregate", {"calc": "sum", "groupby": "year"})]))
+    assert outs["a"].dtype == np.float32                                # stays f32 end to end
+
+
+def test_shared_prefix_is_one_lane_and_one_program():
+    g, outs, stage = _plan(dict(
+        temp_bins=[("aggregate", {"calc": "mean", "groupby": "date"}),
+                   ("aggregate", {"calc": "bins", "groupby": "year",
+                                  "ddargs": [[-20 + 5 * i, -15 + 5 * i, 0] for i in range(13)]})],
+        tavg=[("aggregate", {"calc": "mean", "groupby": "date"}),
+              ("transform", {"transform": "power", "exp": np.arange(1, 3)}),
+              ("aggregate", {"calc": "sum", "groupby": "year"})]))
+    assert len(stage.programs) == 1
+    p = stage.programs[0]
+    assert len(p.lanes) == 1 and len(p.slots) == 15 and len(p.cols) == 15 and p.two_level
+    assert stage.dtype == np.float64
+    assert [c.out_col for c in p.cols] == list(range(15))
+    desc, keep = build_desc(p, stage.dtype)
+    n_str, n_rec, kl, ks, kd = (C.c_int32() for _ in range(5))
+    _lib.check(_lib.lib().agf_program_plan(C.byref(desc), 1038240, 0, 148, None, 0, C.byref(n_str), C.byref(n_rec),
+                                           C.byref(kl), C.byref(ks), C.byref(kd)))
+    assert (kl.value, ks.value, kd.value) == (1, 16, 0)
+
+
+def test_hourly_bins_plus_mean_is_single_level_diag():
+    g, outs, stage = _plan(dict(
+        hbins=[("aggregate", {"calc": "bins", "groupby": "date", "ddargs": [[i, i + 5, 0] for i in range(0, 65, 5)]})],
+        tavg=[("aggregate", {"calc": "mean", "groupby": "date"})]))
+    assert len(stage.programs) == 1 and not stage.programs[0].two_level
+    assert len(stage.programs[0].lanes) == 14 and stage.dtype == np.float32
+
+
+def test_mixed_depth_outputs_share_one_stage():
+    g, outs, stage = _plan(dict(
+        a=[("aggregate", {"calc": "mean", "groupby": "month"})],
+        b=[("aggregate", {"calc": "mean", "groupby": "date"}), ("aggregate", {"calc": "max", "groupby": "month"})]))
+    assert len(stage.programs) == 2
+    assert sorted(c.out_col for p in stage.programs for c in p.cols) == [0, 1]
+
+
+def test_three_levels_materialise_the_inner_series():
+    g, outs, stage = _plan(dict(
+        a=[("aggregate", {"calc": "mean", "groupby": "date"}), ("aggregate", {"calc": "sum", "groupby": "month"}),
+           ("aggregate", {"calc": "max", "groupby": "year"})]))
+    assert len(stage.inputs) == 1 and stage.inputs[0].programs[0].two_level
+    assert not stage.programs[0].two_level and stage.programs[0].input is not g.raw
+
+
+def test_unfusable_level2_calc_goes_multi_pass():
+    g, outs, stage = _plan(dict(a=[("aggregate", {"calc": "mean", "groupby": "date"}),
+                                   ("aggregate", {"calc": "nanmean", "groupby": "month"})]))
+    assert len(stage.inputs) == 1 and not stage.programs[0].two_level
+
+
+def test_many_lanes_split_into_several_programs():
+    dd = [[i, i + 1, 0] for i in range(40)]
+    g, outs, stage = _plan(dict(b=[("aggregate", {"calc": "bins", "groupby": "date", "ddargs": dd}),
+                                   ("aggregate", {"calc": "sum", "groupby": "year"})]))
+    assert len(outs) == 40 and len(stage.programs) == 3                 # 16 + 16 + 8 (diagonal form)
+    assert sorted(c.out_col for p in stage.programs for c in p.cols) == list(range(40))
+
+
+def test_errors_match_reference():
+    with pytest.raises(ValueError, match="multiple ddargs"):
+        _plan(dict(a=[("aggregate", {"calc": "mean", "groupby": "date"}),
+                      ("transform", {"transform": "power", "exp": np.arange(1, 3)}),
+                      ("aggregate", {"calc": "bins", "groupby": "month", "ddargs": [[0, 1, 0], [1, 2, 0]]})]))
+    with pytest.raises(ValueError, match="No valid transform"):
+        _plan(dict(a=[("aggregate", {"calc": "mean", "groupby": "date"}), ("transform", {"transform": "log"})]))
+    with pytest.raises(KeyError):
+        _plan(dict(a=[("aggregate", {"calc": "mean", "groupby": "decade"})]))
+    with pytest.raises(ValueError, match="unsupported calc"):
+        _plan(dict(a=[("aggregate", {"calc": "median", "groupby": "date"})]))
+    with pytest.raises(NotImplementedError, match="week"):
+        from aggfly_b200.timeaxis import CalendarIndex
+        g = Graph(np.float64, CalendarIndex.range("360_day", 2000, 60))
+        outs = compile_spec(g, dict(v=[("aggregate", {"calc": "mean", "groupby": "week"})]))
+        Planner(g).plan(list(outs.values()))
+
+
+def test_temporal_aggregator_attributes():
+    a = TemporalAggregator("dd", "date", ddargs=[10, 30, 0])
+    assert (a.calc, a.groupby, a.multi_dd, a.kwargs) == ("dd", "1D", False, {"ddargs": [10, 30, 0]})
+    assert TemporalAggregator("bins", "month", ddargs=[[0, 1, 0], [1, 2, 0]]).multi_dd
