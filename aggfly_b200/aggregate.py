@@ -47,22 +47,27 @@ class _DeviceRaster:
         self.flat = self.tensor.reshape(T, self.n_cells)
 
 
-def _plan(dataset: Dataset, aggregator_dict: Optional[Dict[str, list]]):
+def _compile(dataset: Dataset, aggregator_dict: Optional[Dict[str, list]]):
     graph = Graph(dataset.dtype, dataset.time)
     if aggregator_dict is None:
         outputs = {"variable": graph.raw}                               # aggregate.py:269-270
     else:
         outputs = compile_spec(graph, aggregator_dict)
+    return graph, outputs
+
+
+def _plan(dataset: Dataset, aggregator_dict: Optional[Dict[str, list]]):
+    """One stage for the whole call; every output must end on the same time axis (they are merged
+    into one panel -- the reference would union the axes and NaN-fill, spatial.py:90-92)."""
+    graph, outputs = _compile(dataset, aggregator_dict)
     names = list(outputs.keys())
     nodes = [outputs[n] for n in names]
     first = graph.labels(nodes[0])
     for n, node in zip(names, nodes):
         if not labels_equal(graph.labels(node), first):
-            # the reference would union the axes and NaN-fill (xr.combine_by_coords, spatial.py:90-92)
             raise ValueError(f"output {n!r} ends on a different time axis than {names[0]!r}; all outputs "
                              "of one call must share one output time axis")
-    stage = Planner(graph).plan(nodes)
-    return names, stage
+    return names, Planner(graph).plan(nodes)
 
 
 def _temporal_device(dataset: Dataset, aggregator_dict, target_stripes: int = 0):
@@ -75,21 +80,34 @@ def _temporal_device(dataset: Dataset, aggregator_dict, target_stripes: int = 0)
 def aggregate_time(dataset: Dataset, weights: GridWeights = None,
                    aggregator_dict: Dict[str, Union[list, TemporalAggregator]] = None,
                    engine: str = "auto", **kwargs) -> Dict[str, Dataset]:
-    """Temporal chains only: {output name: Dataset with values[G, lat, lon]} (aggregate.py:101-162)."""
+    """Temporal chains only: {output name: Dataset with values[G, lat, lon]} (aggregate.py:101-162).
+    Outputs may end on different time axes here (one stage per axis)."""
     resolve_engine(engine)
     if aggregator_dict is None:
         if not kwargs:
             raise ValueError("No arguments provided.")
         aggregator_dict = kwargs
-    names, res, raster = _temporal_device(dataset, aggregator_dict)
-    X = res.X.cpu().numpy()                                             # [G, n_cols, cells]
-    out = {}
-    for c, name in enumerate(names):
-        vals = X[:, c, :].astype(res.nodes[c].dtype, copy=False)
-        vals = np.ascontiguousarray(vals).reshape(len(res.labels), raster.n_lat, raster.n_lon)
-        out[name] = Dataset.from_arrays(vals, res.labels, dataset.latitude, dataset.longitude,
-                                        lon_is_360=dataset.lon_is_360, name=name)
-    return out
+    graph, outputs = _compile(dataset, aggregator_dict)
+    groups: List[List[str]] = []
+    for name, node in outputs.items():
+        for grp in groups:
+            if labels_equal(graph.labels(outputs[grp[0]]), graph.labels(node)):
+                grp.append(name)
+                break
+        else:
+            groups.append([name])
+    raster = _DeviceRaster(dataset)
+    planner = Planner(graph)
+    done: Dict[str, Dataset] = {}
+    for grp in groups:
+        res = _engine.run_stage(planner.plan([outputs[n] for n in grp]), raster.flat, raster.n_cells)
+        X = res.X.cpu().numpy()                                         # [G, n_cols, cells]
+        for c, name in enumerate(grp):
+            vals = X[:, c, :].astype(res.nodes[c].dtype, copy=False)
+            vals = np.ascontiguousarray(vals).reshape(len(res.labels), raster.n_lat, raster.n_lon)
+            done[name] = Dataset.from_arrays(vals, res.labels, dataset.latitude, dataset.longitude,
+                                             lon_is_360=dataset.lon_is_360, name=name)
+    return {name: done[name] for name in outputs}
 
 
 def _execute_single_step(agg: TemporalAggregator, dataset: Dataset):

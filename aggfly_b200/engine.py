@@ -113,59 +113,112 @@ class StageResult:
         return int(self.X.shape[1])
 
 
-def run_stage(stage: Stage, raster, n_cells: int, stream=None, target_stripes: int = 0,
-              _cache: Optional[Dict[int, StageResult]] = None) -> StageResult:
-    """Execute a stage (and, first, the stages it reads from) on the current device.
+class StageRunner:
+    """A planned stage made executable: program handles and device buffers are created once and
+    reused by every ``run`` (the yearly loop of a pipeline, benchmark steps)."""
 
-    ``raster`` is the device tensor of the call's dataset, shape [T, n_cells] (or [T, lat, lon]).
-    """
-    torch = _torch()
-    L = _lib.lib()
-    _cache = {} if _cache is None else _cache
-    target_stripes = target_stripes or OPTIONS["target_stripes"]
-    if id(stage) in _cache:
-        return _cache[id(stage)]
-    for sub in stage.inputs:
-        run_stage(sub, raster, n_cells, stream, target_stripes, _cache)
+    def __init__(self, stage: Stage, n_cells: int, device=None, target_stripes: int = 0, _shared=None):
+        torch = _torch()
+        self.stage, self.n_cells = stage, n_cells
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+        target_stripes = target_stripes or OPTIONS["target_stripes"]
+        shared = {} if _shared is None else _shared            # sub-stages shared between consumers
+        self.inputs: List[StageRunner] = []
+        for sub in stage.inputs:
+            if id(sub) not in shared:
+                shared[id(sub)] = StageRunner(sub, n_cells, self.device, target_stripes, shared)
+            self.inputs.append(shared[id(sub)])
+        self._by_stage = {id(r.stage): r for r in self.inputs}
+        G, n_cols = len(stage.labels), len(stage.nodes)
+        self.X = torch.empty((G, n_cols, n_cells), dtype=_tdtype(stage.dtype), device=self.device)
+        self.V = torch.empty((G, n_cells), dtype=torch.uint8, device=self.device)
+        self.programs: List[Program] = []
+        self.partials = []
+        for spec in stage.programs:
+            prog = Program(spec, stage.dtype, n_cells, target_stripes)
+            self.programs.append(prog)
+            self.partials.append(torch.empty(prog.info.partial_bytes // 8, dtype=torch.float64, device=self.device)
+                                 if prog.info.partial_bytes else None)
+        self.result = StageResult(self.X, self.V, stage.dtype, stage.labels, stage.nodes)
+        self._ran_token = None
 
-    st = torch.cuda.current_stream() if stream is None else stream
-    sptr = st.cuda_stream
-    dev = raster.device
-    G = len(stage.labels)
-    n_cols = len(stage.nodes)
-    X = torch.empty((G, n_cols, n_cells), dtype=_tdtype(stage.dtype), device=dev)
-    V = torch.empty((G, n_cells), dtype=torch.uint8, device=dev)
-    first = True
-    for spec in stage.programs:
-        prog = Program(spec, stage.dtype, n_cells, target_stripes)
-        try:
-            src = getattr(spec, "_source", None)
-            if src is None:
-                x_ptr, ld = raster.data_ptr(), n_cells
-                assert raster.dtype == _tdtype(spec.in_dtype)
-            else:
-                sub_res = _cache[id(src[0])]
-                ld = sub_res.n_cols * n_cells
-                x_ptr = sub_res.X.data_ptr() + src[1] * n_cells * sub_res.X.element_size()
-                assert sub_res.dtype == np.dtype(spec.in_dtype)
-            partial = None
-            if prog.info.partial_bytes:
-                partial = torch.empty(prog.info.partial_bytes // 8, dtype=torch.float64, device=dev)
-            with torch.cuda.stream(st):
-                _lib.check(L.agf_temporal_run(prog.handle, x_ptr, ld, 0, 0, prog.info.n_stripes,
-                                              partial.data_ptr() if partial is not None else None,
-                                              X.data_ptr(), V.data_ptr(), n_cols, 0 if first else 1, sptr))
-                _lib.check(L.agf_temporal_finalize(prog.handle,
-                                                   partial.data_ptr() if partial is not None else None,
-                                                   X.data_ptr(), V.data_ptr(), n_cols, 0 if first else 1, sptr))
-            if partial is not None:
-                partial.record_stream(st)
-        finally:
-            prog.close()
-        first = False
-    res = StageResult(X, V, stage.dtype, stage.labels, stage.nodes)
-    _cache[id(stage)] = res
-    return res
+    @property
+    def launches_per_run(self) -> int:
+        n = sum(r.launches_per_run for r in self.inputs)
+        return n + sum(2 if p.spec.two_level else 1 for p in self.programs)
+
+    def algorithmic_input_bytes(self) -> int:
+        """Bytes of raster the temporal kernels of this stage must read (each program reads its
+        input series once)."""
+        n = 0
+        for p in self.programs:
+            if getattr(p.spec, "_source", None) is None:
+                n += int(p.spec.bounds1[-1] - p.spec.bounds1[0]) * self.n_cells * np.dtype(p.spec.in_dtype).itemsize
+        return n
+
+    def run(self, raster, stream=None, token=None, k1_events=None) -> StageResult:
+        """Launch everything on ``stream`` (asynchronous).  ``raster``: device tensor [T, n_cells].
+        ``k1_events``: optional list that receives (start, end) CUDA event pairs bracketing each
+        temporal-kernel launch that reads the raster."""
+        torch = _torch()
+        L = _lib.lib()
+        token = object() if token is None else token
+        if self._ran_token is token:
+            return self.result
+        for sub in self.inputs:
+            sub.run(raster, stream, token, k1_events)
+        st = torch.cuda.current_stream() if stream is None else stream
+        sptr = st.cuda_stream
+        n_cols = len(self.stage.nodes)
+        first = True
+        with torch.cuda.stream(st):
+            for prog, partial in zip(self.programs, self.partials):
+                spec = prog.spec
+                src = getattr(spec, "_source", None)
+                if src is None:
+                    x_ptr, ld = raster.data_ptr(), self.n_cells
+                    if raster.dtype != _tdtype(spec.in_dtype):
+                        raise TypeError(f"raster dtype {raster.dtype} does not match the planned {spec.in_dtype}")
+                else:
+                    sub_res = self._by_stage[id(src[0])].result
+                    ld = sub_res.n_cols * self.n_cells
+                    x_ptr = sub_res.X.data_ptr() + src[1] * self.n_cells * sub_res.X.element_size()
+                    assert sub_res.dtype == np.dtype(spec.in_dtype)
+                pptr = partial.data_ptr() if partial is not None else None
+                ev = None
+                if k1_events is not None and src is None:
+                    ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                    ev[0].record(st)
+                _lib.check(L.agf_temporal_run(prog.handle, x_ptr, ld, 0, 0, prog.info.n_stripes, pptr,
+                                              self.X.data_ptr(), self.V.data_ptr(), n_cols, 0 if first else 1, sptr))
+                if ev is not None:
+                    ev[1].record(st)
+                    k1_events.append(ev)
+                _lib.check(L.agf_temporal_finalize(prog.handle, pptr, self.X.data_ptr(), self.V.data_ptr(),
+                                                   n_cols, 0 if first else 1, sptr))
+                first = False
+        self._ran_token = token
+        return self.result
+
+    def close(self):
+        for p in self.programs:
+            p.close()
+        for r in self.inputs:
+            r.close()
+
+
+def run_stage(stage: Stage, raster, n_cells: int, stream=None, target_stripes: int = 0) -> StageResult:
+    """Plan-and-run convenience: execute a stage (and the stages it reads from) once."""
+    runner = StageRunner(stage, n_cells, raster.device, target_stripes)
+    try:
+        return runner.run(raster, stream)
+    finally:
+        # handles own only small tables; X / V / partials are torch tensors kept alive by the result
+        if stream is None:
+            _torch().cuda.current_stream().synchronize()
+        else:
+            stream.synchronize()
+        runner.close()
 
 
 def run_spmm(csr: DeviceCSR, res: StageResult, stream=None, want_den: bool = False):

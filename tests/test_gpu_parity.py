@@ -161,7 +161,7 @@ def _raster(dtype, nan, T=24 * 75 + 7, Y=5, X=9, seed=0):
     if nan:
         arr[:, 0, 0] = np.nan
         arr[rng.random((T, Y, X)) < 0.001] = np.nan
-        arr[24 * 30: 24 * 31, 2, :] = np.nan
+        arr[24 * 30: 24 * 31, min(2, Y - 1), :] = np.nan
     lat = np.linspace(49.75, 24.0, Y)
     lon = np.linspace(235.0, 293.75, X)
     return arr, t, lat, lon
