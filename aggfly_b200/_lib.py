@@ -48,7 +48,8 @@ class ProgramInfo(C.Structure):
     _fields_ = [("n_stripes", C.c_int32), ("n_recs", C.c_int32), ("n_cols", C.c_int32),
                 ("out_dtype", C.c_int32), ("n_out_groups", C.c_int64), ("partial_bytes", C.c_int64),
                 ("out_bytes", C.c_int64), ("valid_bytes", C.c_int64), ("kernel_lanes", C.c_int32),
-                ("kernel_slots", C.c_int32), ("kernel_mode", C.c_int32), ("uses_tma", C.c_int32)]
+                ("kernel_slots", C.c_int32), ("kernel_mode", C.c_int32), ("uses_tma", C.c_int32),
+                ("kernel_kinds", C.c_int32), ("pad_", C.c_int32)]
 
 
 class AgfError(RuntimeError):

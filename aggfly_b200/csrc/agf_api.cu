@@ -4,9 +4,12 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
+
+#include <cuda.h>
 
 #include "agf_host.h"
 #include "agf_post.cuh"
@@ -42,6 +45,11 @@ int agf_fail(int code, const char *fmt, ...) {
     g_err = buf;
     return code;
 }
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn();
 
 extern "C" int agf_version(void) { return AGF_ABI_VERSION; }
 extern "C" const char *agf_last_error(void) { return g_err.c_str(); }
@@ -121,40 +129,57 @@ static int validate_desc(const agf_program_desc_t *d, int64_t n_cells) {
     return 0;
 }
 
-// choose the instantiation; returns 0 or AGF_E_UNSUPPORTED
-static int choose_kernel(const agf_program_desc_t *d, int *kl, int *ks, int *diag) {
-    auto fit = [](int n, std::initializer_list<int> sizes) {
-        for (int s : sizes)
-            if (n <= s) return s;
-        return -1;
-    };
+// lane kinds + 1:1 mapping flags of a descriptor
+static void analyse_desc(const agf_program_desc_t *d, unsigned *kinds, int *diag_ok) {
+    unsigned k = 0;
+    for (int l = 0; l < d->n_lanes; ++l) k |= kind_of_calc(d->lanes[l].calc);
+    *kinds = k;
+    bool dg;
     if (d->n_slots == 0) {
-        *kl = fit(d->n_lanes, {1, 4, 16, 32});
-        *ks = 0;
-        bool dg = d->n_cols <= d->n_lanes;
-        for (int c = 0; c < d->n_cols && dg; ++c)
-            dg = d->cols[c].src == c && d->cols[c].xform == AGF_XF_NONE;
-        *diag = dg ? 1 : 0;
-        return 0;
+        dg = d->n_cols <= d->n_lanes;
+        for (int c = 0; c < d->n_cols && dg; ++c) dg = d->cols[c].src == c && d->cols[c].xform == AGF_XF_NONE;
+    } else {
+        dg = d->n_slots <= d->n_lanes;
+        for (int j = 0; j < d->n_slots && dg; ++j) dg = d->slots[j].src == j;
     }
-    if (d->n_lanes <= 4) {
-        *kl = fit(d->n_lanes, {1, 4});
-        *ks = fit(d->n_slots, {1, 4, 16, 32});
-        *diag = 0;
-        return 0;
+    *diag_ok = dg ? 1 : 0;
+}
+
+// first-fit over the instantiation tables of the K1 units; returns 0 or AGF_E_UNSUPPORTED
+static int k1_select(const K1Launch &a, int mode, K1Choice *choice, int *rc) {
+    const bool f32 = a.p->desc.in_dtype == AGF_F32;
+    int miss;
+    if (a.use_tma) {
+        if (f32) {
+            miss = a.p->desc.n_slots > 0 ? agf_k1_f32_tma_two(a, mode, choice, rc) : agf_k1_f32_tma_single(a, mode, choice, rc);
+        } else {
+            miss = agf_k1_f64_tma(a, mode, choice, rc);
+        }
+    } else {
+        miss = f32 ? agf_k1_f32_ldg(a, mode, choice, rc) : agf_k1_f64_ldg(a, mode, choice, rc);
     }
-    bool dg = d->n_slots <= d->n_lanes && d->n_lanes <= 16;
-    for (int j = 0; j < d->n_slots && dg; ++j) dg = d->slots[j].src == j;
-    if (dg) {
-        *kl = 16;
-        *ks = 16;
-        *diag = 1;
-        return 0;
-    }
-    return fail(AGF_E_UNSUPPORTED,
-                "two-level program with %d lanes / %d slots has no fused instantiation "
-                "(split it: <=4 lanes, or <=16 lanes feeding one slot each)",
-                d->n_lanes, d->n_slots);
+    if (miss)
+        return fail(AGF_E_UNSUPPORTED,
+                    "program with %d lanes / %d slots has no fused instantiation (split it: <=4 lanes feeding "
+                    "<=32 slots, or <=16 lanes feeding one slot each; <=32 lanes single-level)",
+                    a.p->desc.n_lanes, a.p->desc.n_slots);
+    return 0;
+}
+
+static int choose_kernel(agf_program *p) {
+    analyse_desc(&p->desc, &p->kinds, &p->diag_ok);
+    K1Launch q{};
+    q.p = p;
+    q.use_tma = 1;
+    K1Choice ch{};
+    int rc = 0;
+    int r = k1_select(q, 1, &ch, &rc);
+    if (r) return r;
+    p->kernel_lanes = ch.lanes;
+    p->kernel_slots = ch.slots;
+    p->kernel_diag = ch.diag;
+    p->kernel_kinds = ch.kinds;
+    return 0;
 }
 
 struct Plan {
@@ -233,9 +258,11 @@ extern "C" int agf_program_plan(const agf_program_desc_t *desc, int64_t n_cells,
                                 int32_t *kernel_slots, int32_t *kernel_diag) {
     int rc = validate_desc(desc, n_cells);
     if (rc) return rc;
-    int kl, ks, dg;
-    rc = choose_kernel(desc, &kl, &ks, &dg);
+    agf_program tmp;
+    tmp.desc = *desc;
+    rc = choose_kernel(&tmp);
     if (rc) return rc;
+    const int kl = tmp.kernel_lanes, ks = tmp.kernel_slots, dg = tmp.kernel_diag;
     Plan plan;
     make_plan(desc, n_cells, target_stripes, sm_count, plan);
     if (n_stripes) *n_stripes = (int32_t)plan.stripes.size();
@@ -281,9 +308,6 @@ extern "C" int agf_program_create(agf_program_t **out, const agf_program_desc_t 
     *out = nullptr;
     int rc = validate_desc(desc, n_cells);
     if (rc) return rc;
-    int kl, ks, dg;
-    rc = choose_kernel(desc, &kl, &ks, &dg);
-    if (rc) return rc;
     int dev = -1, sms = 148;
     CU(cudaGetDevice(&dev));
     CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -296,9 +320,10 @@ extern "C" int agf_program_create(agf_program_t **out, const agf_program_desc_t 
     p->desc.bounds2 = nullptr;
     p->n_cells = n_cells;
     p->device = dev;
-    p->kernel_lanes = kl;
-    p->kernel_slots = ks;
-    p->kernel_diag = dg;
+    if ((rc = choose_kernel(p))) {
+        delete p;
+        return rc;
+    }
     for (int l = 0; l < desc->n_lanes; ++l) {
         const int c = desc->lanes[l].calc;
         if (c == AGF_CALC_MIN || c == AGF_CALC_MAX || c == AGF_CALC_DD || c == AGF_CALC_SINE_DD)
@@ -341,7 +366,8 @@ extern "C" int agf_program_info(const agf_program_t *p, agf_program_info_t *info
     info->kernel_lanes = p->kernel_lanes;
     info->kernel_slots = p->kernel_slots;
     info->kernel_mode = p->kernel_diag;
-    info->uses_tma = 0;
+    info->uses_tma = encode_tiled_fn() != nullptr && !getenv("AGF_DISABLE_TMA");
+    info->kernel_kinds = (int32_t)p->kernel_kinds;
     return 0;
 }
 
@@ -353,18 +379,41 @@ extern "C" int agf_program_stripe_rows(const agf_program_t *p, int32_t s, int64_
 }
 
 // ------------------------------------------------------------------------------------------
-// K1 dispatch (instantiations live in agf_k1_{f32,f64}_{single,two}.cu)
+// TMA tensor map (driver entry point fetched through the runtime: no link-time libcuda dependency)
 // ------------------------------------------------------------------------------------------
-static int dispatch_k1(const K1Launch &a) {
-    int rc = 0;
-    const bool f32 = a.p->desc.in_dtype == AGF_F32;
-    const bool two = a.p->desc.n_slots > 0;
-    int miss = f32 ? (two ? agf_k1_f32_two(a, &rc) : agf_k1_f32_single(a, &rc))
-                   : (two ? agf_k1_f64_two(a, &rc) : agf_k1_f64_single(a, &rc));
-    if (miss)
-        return fail(AGF_E_UNSUPPORTED, "no kernel instantiation for lanes=%d slots=%d diag=%d", a.p->kernel_lanes,
-                    a.p->kernel_slots, a.p->kernel_diag);
-    return rc;
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)ptr;
+    }
+    return fn;
+}
+
+bool agf_tma_eligible(const void *base, int elem_size, uint64_t ld) {
+    if (getenv("AGF_DISABLE_TMA")) return false;
+    return ((uintptr_t)base % 16 == 0) && ((ld * (uint64_t)elem_size) % 16 == 0) && encode_tiled_fn() != nullptr;
+}
+
+int agf_make_tensor_map(agf::TensorMap *out, const void *base, int elem_size, uint64_t n_cells, uint64_t n_rows,
+                        uint64_t ld, int box_rows) {
+    static_assert(sizeof(agf::TensorMap) == sizeof(CUtensorMap), "tensor map size");
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return fail(AGF_E_UNSUPPORTED, "cuTensorMapEncodeTiled not available");
+    cuuint64_t dims[2] = {n_cells, n_rows};
+    cuuint64_t strides[1] = {ld * (cuuint64_t)elem_size};
+    cuuint32_t box[2] = {(cuuint32_t)agf::TMA_CW, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn((CUtensorMap *)out, elem_size == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+                    2, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(AGF_E_UNSUPPORTED, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return 0;
 }
 
 static int check_device(int device) {
@@ -390,9 +439,12 @@ extern "C" int agf_temporal_run(const agf_program_t *p, const void *d_x, int64_t
         return fail(AGF_E_INVALID, "single-level program needs d_out and d_valid");
     for (int c = 0; c < p->desc.n_cols; ++c)
         if (p->desc.cols[c].dst >= out_ncols) return fail(AGF_E_INVALID, "col %d: dst outside X (out_ncols=%d)", c, out_ncols);
+    const int esz = p->desc.in_dtype == AGF_F64 ? 8 : 4;
     K1Launch a{p, d_x, ld, row0, stripe_begin, stripe_end, d_partial, d_out, d_valid, out_ncols, valid_and,
-               (cudaStream_t)stream};
-    return dispatch_k1(a);
+               (cudaStream_t)stream, agf_tma_eligible(d_x, esz, (uint64_t)ld) ? 1 : 0};
+    int krc = 0;
+    int sel = k1_select(a, 0, nullptr, &krc);
+    return sel ? sel : krc;
 }
 
 extern "C" int agf_temporal_finalize(const agf_program_t *p, const double *d_partial, void *d_out,

@@ -14,7 +14,10 @@ struct agf_program {
     int64_t n_cells = 0;
     int n_recs = 0;
     int device = -1;
-    int kernel_lanes = 0, kernel_slots = 0, kernel_diag = 0;
+    int kernel_lanes = 0, kernel_slots = 0, kernel_diag = 0;  // instantiation picked for the TMA variant
+    unsigned kernel_kinds = 0;
+    unsigned kinds = 0;  // lane kinds the program uses
+    int diag_ok = 0;     // columns (single-level) / slots (two-level) map 1:1 onto lanes
     int need_nan = 0, need_cnt = 0, has_sine = 0;
     // device copies
     int *d_b1 = nullptr, *d_b2 = nullptr, *d_g2_rec_ptr = nullptr, *d_g2_rec_idx = nullptr;
@@ -30,6 +33,13 @@ int agf_cuda_fail(cudaError_t e, const char *what);
         if (e_ != cudaSuccess) return agf_cuda_fail(e_, #call); \
     } while (0)
 
+// Encode a 2-D tiled tensor map over the raster view [n_rows, n_cells] (row stride ld elements),
+// box = [box_rows, TMA_CW].  Returns 0, or AGF_E_UNSUPPORTED when the view cannot be described
+// (alignment) -- the caller then uses the direct-load kernel.
+int agf_make_tensor_map(agf::TensorMap *out, const void *base, int elem_size, uint64_t n_cells, uint64_t n_rows,
+                        uint64_t ld, int box_rows);
+bool agf_tma_eligible(const void *base, int elem_size, uint64_t ld);
+
 struct K1Launch {
     const agf_program *p;
     const void *d_x;
@@ -40,10 +50,18 @@ struct K1Launch {
     uint8_t *d_valid;
     int ncols, vand;
     cudaStream_t stream;
+    int use_tma;
 };
 
-// one per (dtype, part) translation unit; return 1 if the instantiation is not in that unit
-int agf_k1_f32_single(const K1Launch &a, int *rc);
-int agf_k1_f32_two(const K1Launch &a, int *rc);
-int agf_k1_f64_single(const K1Launch &a, int *rc);
-int agf_k1_f64_two(const K1Launch &a, int *rc);
+struct K1Choice {
+    int lanes, slots, diag;
+    unsigned kinds;
+};
+
+// One per translation unit (agf_k1_*.cu).  mode 0: launch the first instantiation of that unit
+// that fits the program; mode 1: only report it in *choice.  Returns 1 if nothing in the unit fits.
+int agf_k1_f32_tma_single(const K1Launch &a, int mode, K1Choice *choice, int *rc);
+int agf_k1_f32_tma_two(const K1Launch &a, int mode, K1Choice *choice, int *rc);
+int agf_k1_f32_ldg(const K1Launch &a, int mode, K1Choice *choice, int *rc);
+int agf_k1_f64_tma(const K1Launch &a, int mode, K1Choice *choice, int *rc);
+int agf_k1_f64_ldg(const K1Launch &a, int mode, K1Choice *choice, int *rc);

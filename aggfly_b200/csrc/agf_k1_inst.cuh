@@ -1,5 +1,6 @@
-// agf_k1_inst.cuh -- K1 launcher + instantiation list; included by the agf_k1_*.cu units with
-// AGF_T (float|double), AGF_FN (entry name) and AGF_PART (0: single-level, 1: two-level) defined.
+// agf_k1_inst.cuh -- K1 launcher + first-fit instantiation table; included by the agf_k1_*.cu
+// units with AGF_T (float|double), AGF_TMA (0|1), AGF_FN (entry name) and AGF_LIST (the
+// K1CASE(NL, NS, DIAG, KINDS) rows of that unit, cheapest first) defined.
 #include <cmath>
 #include <cstring>
 
@@ -28,7 +29,7 @@ static inline void set_thresholds(LaneP<double> &L, double t0, double t1) {
     L.hi = t1;
 }
 
-template <typename T, int NL, int NS, bool DIAG>
+template <typename T, int NL, int NS, bool DIAG, unsigned KINDS, bool TMA>
 static int launch_k1(const K1Launch &a) {
     const agf_program *p = a.p;
     K1Params<T, NL, NS> kp;
@@ -88,39 +89,47 @@ static int launch_k1(const K1Launch &a) {
             C.dst = d.cols[c].dst;
         }
     }
-    dim3 grid((unsigned)((p->n_cells + K1_THREADS - 1) / K1_THREADS), (unsigned)(a.s1 - a.s0));
-    agf_k1_ldg<T, NL, NS, DIAG><<<grid, K1_THREADS, 0, a.stream>>>(kp);
+    if constexpr (TMA) {
+        // rows of the view the stripes of this launch can touch
+        const int64_t row_end = p->b1[p->stripes[a.s1 - 1].g1_end];
+        TensorMap tm;
+        int rc = agf_make_tensor_map(&tm, a.d_x, (int)sizeof(T), (uint64_t)p->n_cells, (uint64_t)(row_end - a.row0),
+                                     (uint64_t)a.ld, tma_rows<T>());
+        if (rc) return rc;
+        constexpr int smem = TMA_STAGES * TMA_TILE_BYTES + 2 * TMA_STAGES * 8;
+        static bool attr_set = false;  // per instantiation
+        if (!attr_set) {
+            CU(cudaFuncSetAttribute(agf_k1_tma<T, NL, NS, DIAG, KINDS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            attr_set = true;
+        }
+        dim3 grid((unsigned)((p->n_cells + TMA_CW - 1) / TMA_CW), (unsigned)(a.s1 - a.s0));
+        agf_k1_tma<T, NL, NS, DIAG, KINDS><<<grid, TMA_THREADS, smem, a.stream>>>(kp, tm);
+    } else {
+        dim3 grid((unsigned)((p->n_cells + K1_THREADS - 1) / K1_THREADS), (unsigned)(a.s1 - a.s0));
+        agf_k1_ldg<T, NL, NS, DIAG, KINDS><<<grid, K1_THREADS, 0, a.stream>>>(kp);
+    }
     CU(cudaGetLastError());
     return 0;
 }
 
-int AGF_FN(const K1Launch &a, int *rc) {
+static inline bool k1_fits(const agf_program *p, int NL, int NS, bool DG, unsigned KINDS) {
+    const agf_program_desc_t &d = p->desc;
+    if (d.n_lanes > NL) return false;
+    if ((NS == 0) != (d.n_slots == 0) || d.n_slots > NS) return false;
+    if (DG && !p->diag_ok) return false;
+    if (NS > 0 && NL > 4 && !DG) return false;  // select-chain form only for <= 4 lanes
+    return (p->kinds & ~KINDS) == 0;
+}
+
+int AGF_FN(const K1Launch &a, int mode, K1Choice *choice, int *rc) {
     const agf_program *p = a.p;
-#define K1CASE(NL, NS, DG)                                                                  \
-    if (p->kernel_lanes == NL && p->kernel_slots == NS && p->kernel_diag == (DG ? 1 : 0)) { \
-        *rc = launch_k1<AGF_T, NL, NS, DG>(a);                                              \
-        return 0;                                                                           \
+#define K1CASE(NL, NS, DG, KINDS)                                             \
+    if (k1_fits(p, NL, NS, DG, KINDS)) {                                      \
+        if (choice) *choice = K1Choice{NL, NS, DG ? 1 : 0, KINDS};            \
+        if (mode == 0) *rc = launch_k1<AGF_T, NL, NS, DG, KINDS, AGF_TMA>(a); \
+        return 0;                                                             \
     }
-#if AGF_PART == 0
-    K1CASE(1, 0, false)
-    K1CASE(1, 0, true)
-    K1CASE(4, 0, false)
-    K1CASE(4, 0, true)
-    K1CASE(16, 0, false)
-    K1CASE(16, 0, true)
-    K1CASE(32, 0, false)
-    K1CASE(32, 0, true)
-#else
-    K1CASE(1, 1, false)
-    K1CASE(1, 4, false)
-    K1CASE(1, 16, false)
-    K1CASE(1, 32, false)
-    K1CASE(4, 1, false)
-    K1CASE(4, 4, false)
-    K1CASE(4, 16, false)
-    K1CASE(4, 32, false)
-    K1CASE(16, 16, true)
-#endif
+    AGF_LIST
 #undef K1CASE
     return 1;
 }

@@ -25,6 +25,29 @@ namespace agf {
 constexpr int K1_THREADS = 256;  // cells per CTA (one cell per thread)
 constexpr int K1_U = 8;          // rows per register batch
 
+// Lane-kind sets.  The kinds a program uses are a COMPILE-TIME parameter of the temporal kernel:
+// with a single kind the per-element code is straight-line (e.g. LDS -> F2F -> DADD for
+// mean/sum); a runtime switch per element costs a branch tree per value and caps the kernel at
+// ~20% of the HBM roofline (measured, profiles/).
+enum : unsigned {
+    KIND_SUM = 1u,      // mean, sum (NaN-propagating add)
+    KIND_NANMEAN = 2u,  // nanmean
+    KIND_MINMAX = 4u,   // min, max
+    KIND_DD = 8u,       // degree days
+    KIND_BINS = 16u,    // bin counts
+    KIND_SINE = 32u,    // sine_dd + its hidden sum/min/max helper lanes
+    KIND_ALL = 63u
+};
+
+__host__ __device__ constexpr unsigned kind_of_calc(int calc) {
+    return (calc == AGF_CALC_MEAN || calc == AGF_CALC_SUM)  ? KIND_SUM
+           : (calc == AGF_CALC_NANMEAN)                      ? KIND_NANMEAN
+           : (calc == AGF_CALC_MIN || calc == AGF_CALC_MAX)  ? KIND_MINMAX
+           : (calc == AGF_CALC_DD)                           ? KIND_DD
+           : (calc == AGF_CALC_BINS)                         ? KIND_BINS
+                                                             : KIND_SINE;
+}
+
 // ------------------------------------------------------------------------------------------
 // kernel parameter blocks (passed by value, live in the constant bank)
 // ------------------------------------------------------------------------------------------
@@ -226,41 +249,64 @@ __device__ __forceinline__ void l2_init(const K1Params<T, NL, NS> &p, CellState<
 }
 
 // one raster value into every level-1 lane (nb_kernels.py:134-141, 170-177, 193-196, 213-220)
-template <typename T, int NL, int NS>
+template <unsigned KINDS, typename T, int NL, int NS>
 __device__ __forceinline__ void l1_acc(const K1Params<T, NL, NS> &p, CellState<T, NL, NS> &s, T v) {
     const double vd = (double)v;
-    const bool isn = (v != v);
-    if (p.need_nan) s.nan |= isn;
-    if (p.need_cnt) s.nn += isn ? 0 : 1;
+    bool isn = false;
+    if constexpr ((KINDS & (KIND_NANMEAN | KIND_MINMAX | KIND_DD | KIND_SINE)) != 0) isn = (v != v);
+    if constexpr ((KINDS & (KIND_MINMAX | KIND_DD | KIND_SINE)) != 0) s.nan |= isn;
+    if constexpr ((KINDS & (KIND_NANMEAN | KIND_SINE)) != 0) s.nn += isn ? 0 : 1;
 #pragma unroll
     for (int l = 0; l < NL; ++l) {
-        if (l < p.n_lanes) {
+        if (NL == 1 || l < p.n_lanes) {
             const LaneP<T> &L = p.lanes[l];
-            switch (L.calc) {
-                case AGF_CALC_MEAN:
-                case AGF_CALC_SUM:
-                    s.a[l] += vd;  // a NaN value poisons the sum == "any NaN -> NaN"
-                    break;
-                case AGF_CALC_NANMEAN:
-                case AGF_CALC_HIDDEN_SUM:
-                    if (!isn) s.a[l] += vd;
-                    break;
-                case AGF_CALC_MIN:
-                case AGF_CALC_HIDDEN_MIN:
-                    if (vd < s.a[l]) s.a[l] = vd;
-                    break;
-                case AGF_CALC_MAX:
-                case AGF_CALC_HIDDEN_MAX:
-                    if (vd > s.a[l]) s.a[l] = vd;
-                    break;
-                case AGF_CALC_DD:
-                    if (v > L.lo && v < L.hi) s.a[l] += fabs(vd - L.base);
-                    break;
-                case AGF_CALC_BINS:
-                    if (v > L.lo && v < L.hi) s.a[l] += 1.0;
-                    break;
-                default:
-                    break;
+            if constexpr (KINDS == KIND_SUM) {
+                s.a[l] += vd;  // a NaN value poisons the sum == "any NaN -> NaN"
+            } else if constexpr (KINDS == KIND_BINS) {
+                if (v > L.lo && v < L.hi) s.a[l] += 1.0;
+            } else if constexpr (KINDS == KIND_DD) {
+                if (v > L.lo && v < L.hi) s.a[l] += fabs(vd - L.base);
+            } else {
+                switch (L.calc) {
+                    case AGF_CALC_MEAN:
+                    case AGF_CALC_SUM:
+                        if constexpr ((KINDS & KIND_SUM) != 0) s.a[l] += vd;
+                        break;
+                    case AGF_CALC_NANMEAN:
+                        if constexpr ((KINDS & KIND_NANMEAN) != 0)
+                            if (!isn) s.a[l] += vd;
+                        break;
+                    case AGF_CALC_HIDDEN_SUM:
+                        if constexpr ((KINDS & KIND_SINE) != 0)
+                            if (!isn) s.a[l] += vd;
+                        break;
+                    case AGF_CALC_MIN:
+                        if constexpr ((KINDS & KIND_MINMAX) != 0)
+                            if (vd < s.a[l]) s.a[l] = vd;
+                        break;
+                    case AGF_CALC_HIDDEN_MIN:
+                        if constexpr ((KINDS & KIND_SINE) != 0)
+                            if (vd < s.a[l]) s.a[l] = vd;
+                        break;
+                    case AGF_CALC_MAX:
+                        if constexpr ((KINDS & KIND_MINMAX) != 0)
+                            if (vd > s.a[l]) s.a[l] = vd;
+                        break;
+                    case AGF_CALC_HIDDEN_MAX:
+                        if constexpr ((KINDS & KIND_SINE) != 0)
+                            if (vd > s.a[l]) s.a[l] = vd;
+                        break;
+                    case AGF_CALC_DD:
+                        if constexpr ((KINDS & KIND_DD) != 0)
+                            if (v > L.lo && v < L.hi) s.a[l] += fabs(vd - L.base);
+                        break;
+                    case AGF_CALC_BINS:
+                        if constexpr ((KINDS & KIND_BINS) != 0)
+                            if (v > L.lo && v < L.hi) s.a[l] += 1.0;
+                        break;
+                    default:
+                        break;
+                }
             }
         }
     }
@@ -403,7 +449,7 @@ __device__ __forceinline__ void l2_write_rec(const K1Params<T, NL, NS> &p,
 // rows that never cross a level-1 group boundary; next batch's loads are issued before the
 // current batch is reduced.
 // ------------------------------------------------------------------------------------------
-template <typename T, int NL, int NS, bool DIAG>
+template <typename T, int NL, int NS, bool DIAG, unsigned KINDS>
 __global__ void __launch_bounds__(K1_THREADS)
     agf_k1_ldg(const __grid_constant__ K1Params<T, NL, NS> p) {
     const int cell = blockIdx.x * K1_THREADS + threadIdx.x;
@@ -447,7 +493,7 @@ __global__ void __launch_bounds__(K1_THREADS)
         // reduce the current batch in time order
 #pragma unroll
         for (int i = 0; i < K1_U; ++i)
-            if (i < clen) l1_acc(p, s, cur[i]);
+            if (i < clen) l1_acc<KINDS>(p, s, cur[i]);
 
         if (ends) {
             l1_flush<T, NL, NS, DIAG>(p, s, g, nb - glo, cell);
@@ -458,11 +504,11 @@ __global__ void __launch_bounds__(K1_THREADS)
                     l2_write_rec(p, s, rec, cell);
                     l2_init(p, s);
                     ++rec;
-                    if (g + 1 == next_b2) {
+                    if (g + 1 < g_end && g + 1 == next_b2) {
                         do {  // skip zero-width level-2 groups (they get no record -> NaN)
                             ++g2;
                             next_b2 = p.b2[g2 + 1];
-                        } while (next_b2 == g + 1 && g + 1 < g_end);
+                        } while (next_b2 == g + 1);
                     }
                 }
             }
@@ -474,6 +520,163 @@ __global__ void __launch_bounds__(K1_THREADS)
         clen = nlen;
         g = ng;
         nb = nnb;
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------
+// K1, TMA variant (sm_100a): a producer warp streams [TT rows x 256 cells] tiles of the raster
+// into a shared-memory ring with cp.async.bulk.tensor (one elected thread, mbarrier
+// complete_tx), 8 consumer warps reduce straight out of shared memory (conflict-free: thread
+// t reads column t of every row).  Bytes in flight are set by the ring (STAGES x 24 KB per CTA,
+// two CTAs per SM), not by registers, which is what the HBM roofline needs.  Needs a 16-byte
+// aligned raster with a row stride that is a multiple of 16 bytes; otherwise the library runs
+// agf_k1_ldg.
+// ------------------------------------------------------------------------------------------
+constexpr int TMA_CW = 256;         // cells per tile row == consumer threads
+constexpr int TMA_TILE_BYTES = 24 * 1024;
+constexpr int TMA_STAGES = 4;
+constexpr int TMA_THREADS = TMA_CW + 32;
+
+template <typename T>
+__host__ __device__ constexpr int tma_rows() {
+    return TMA_TILE_BYTES / (TMA_CW * (int)sizeof(T));
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const void *tmap, int c0, int c1, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+
+struct alignas(64) TensorMap {  // same layout as CUtensorMap (128 opaque bytes)
+    unsigned long long opaque[16];
+};
+
+template <typename T, int NL, int NS, bool DIAG, unsigned KINDS>
+__global__ void __launch_bounds__(TMA_THREADS)
+    agf_k1_tma(const __grid_constant__ K1Params<T, NL, NS> p, const __grid_constant__ TensorMap tmap) {
+    constexpr int TT = tma_rows<T>();
+    constexpr int UNROLL = NL <= 4 ? 8 : (NL <= 16 ? 2 : 1);
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    T *tiles = reinterpret_cast<T *>(smem_raw);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + TMA_STAGES * TMA_TILE_BYTES);
+    uint64_t *empty = full + TMA_STAGES;
+
+    const Stripe st = p.stripes[p.stripe0 + blockIdx.y];
+    int g = st.g1_begin;
+    const int g_end = st.g1_end;
+    if (g >= g_end) return;  // uniform
+    const int k_begin = p.b1[g];
+    const int k_end = p.b1[g_end];
+    const int n_tiles = (k_end - k_begin + TT - 1) / TT;
+    const int cell0 = blockIdx.x * TMA_CW;
+
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < TMA_STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], TMA_CW / 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (threadIdx.x >= TMA_CW) {
+        // ===== producer warp: one elected lane issues every tile load =====
+        if (threadIdx.x == TMA_CW) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+            for (int i = 0; i < n_tiles; ++i) {
+                const int s = i % TMA_STAGES;
+                if (i >= TMA_STAGES) mbar_wait(&empty[s], ((i / TMA_STAGES) - 1) & 1);
+                mbar_expect_tx(&full[s], TMA_TILE_BYTES);
+                tma_load_2d(smem_raw + s * TMA_TILE_BYTES, &tmap, cell0, (int)(k_begin + i * TT - p.row0), &full[s]);
+            }
+        }
+        return;
+    }
+
+    // ===== consumers: thread t owns cell cell0 + t =====
+    const int cell = cell0 + threadIdx.x;
+    const bool active = cell < p.n_cells;
+    int g2 = st.g2_first;
+    int rec = st.rec0;
+    int next_b2 = (NS > 0) ? p.b2[g2 + 1] : 0;
+    CellState<T, NL, NS> s;
+    l1_init(p, s);
+    l2_init(p, s);
+    int k = k_begin;
+    int glo = k_begin;
+    int nb = p.b1[g + 1];
+
+    for (int i = 0; i < n_tiles; ++i) {
+        const int stg = i % TMA_STAGES;
+        mbar_wait(&full[stg], (i / TMA_STAGES) & 1);
+        const T *col = tiles + (size_t)stg * (TMA_TILE_BYTES / sizeof(T)) + threadIdx.x;
+        const int rows = min(TT, k_end - (k_begin + i * TT));
+        int r = 0;
+        while (r < rows || (k == nb && g < g_end)) {
+            const int run = min(rows - r, nb - k);
+            int j = 0;
+            for (; j + UNROLL <= run; j += UNROLL) {
+                T v[UNROLL];
+#pragma unroll
+                for (int u = 0; u < UNROLL; ++u) v[u] = col[(r + j + u) * TMA_CW];
+#pragma unroll
+                for (int u = 0; u < UNROLL; ++u) l1_acc<KINDS>(p, s, v[u]);
+            }
+            for (; j < run; ++j) l1_acc<KINDS>(p, s, col[(r + j) * TMA_CW]);
+            r += run;
+            k += run;
+            if (k == nb) {  // level-1 group g is complete
+                if (active) l1_flush<T, NL, NS, DIAG>(p, s, g, nb - glo, cell);
+                l1_init(p, s);
+                if (NS > 0) {
+                    if (g + 1 == next_b2 || g + 1 == g_end) {
+                        if (active) l2_write_rec(p, s, rec, cell);
+                        l2_init(p, s);
+                        ++rec;
+                        if (g + 1 < g_end && g + 1 == next_b2) {
+                            do {  // skip zero-width level-2 groups (no record -> NaN in finalize)
+                                ++g2;
+                                next_b2 = p.b2[g2 + 1];
+                            } while (next_b2 == g + 1);
+                        }
+                    }
+                }
+                glo = nb;
+                ++g;
+                nb = (g < g_end) ? p.b1[g + 1] : 0x7fffffff;
+            }
+        }
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) mbar_arrive(&empty[stg]);
     }
 }
 

@@ -141,7 +141,9 @@ typedef struct {
     int64_t out_bytes;      /* size of X */
     int64_t valid_bytes;    /* size of V */
     int32_t kernel_lanes, kernel_slots, kernel_mode; /* which instantiation will run */
-    int32_t uses_tma;
+    int32_t uses_tma;     /* 16-byte aligned rasters run the TMA / shared-memory-ring variant */
+    int32_t kernel_kinds; /* compile-time lane-kind set of the chosen instantiation */
+    int32_t pad_;
 } agf_program_info_t;
 
 typedef struct agf_program agf_program_t;

@@ -15,13 +15,21 @@ from oracle import oracle as orc
 from tests import refcases as rc
 
 
-@pytest.fixture(autouse=True)
-def _need_cuda():
+@pytest.fixture(autouse=True, params=["tma", "ldg"])
+def _variant(request):
+    """Every test runs against both temporal-kernel variants: the TMA/shared-memory ring (default
+    whenever the raster view is 16-byte aligned) and the direct-load kernel (any shape)."""
+    import os
     import torch
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     engine.OPTIONS["target_stripes"] = 0
+    if request.param == "ldg":
+        os.environ["AGF_DISABLE_TMA"] = "1"
+    else:
+        os.environ.pop("AGF_DISABLE_TMA", None)
     yield
+    os.environ.pop("AGF_DISABLE_TMA", None)
     engine.OPTIONS["target_stripes"] = 0
 
 
