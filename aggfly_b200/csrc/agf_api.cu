@@ -130,10 +130,12 @@ static int validate_desc(const agf_program_desc_t *d, int64_t n_cells) {
 }
 
 // lane kinds + 1:1 mapping flags of a descriptor
-static void analyse_desc(const agf_program_desc_t *d, unsigned *kinds, int *diag_ok) {
-    unsigned k = 0;
+static void analyse_desc(const agf_program_desc_t *d, unsigned *kinds, unsigned *slot_kinds, int *diag_ok) {
+    unsigned k = 0, sk = 0;
     for (int l = 0; l < d->n_lanes; ++l) k |= kind_of_calc(d->lanes[l].calc);
+    for (int j = 0; j < d->n_slots; ++j) sk |= slot_kind_of(d->slots[j].calc, d->slots[j].xform);
     *kinds = k;
+    *slot_kinds = sk;
     bool dg;
     if (d->n_slots == 0) {
         dg = d->n_cols <= d->n_lanes;
@@ -167,7 +169,7 @@ static int k1_select(const K1Launch &a, int mode, K1Choice *choice, int *rc) {
 }
 
 static int choose_kernel(agf_program *p) {
-    analyse_desc(&p->desc, &p->kinds, &p->diag_ok);
+    analyse_desc(&p->desc, &p->kinds, &p->slot_kinds, &p->diag_ok);
     K1Launch q{};
     q.p = p;
     q.use_tma = 1;
@@ -482,6 +484,7 @@ extern "C" int agf_temporal_finalize(const agf_program_t *p, const double *d_par
         S.flag = d.slots[j].flag;
         S.t0 = d.slots[j].t0;
         S.t1 = d.slots[j].t1;
+        S.ip = (S.xform == AGF_XF_POWI) ? (int)S.xparam : 1;
     }
     for (int c = 0; c < d.n_cols; ++c) {
         ColP &C = fp.cols[c];

@@ -16,7 +16,8 @@ struct agf_program {
     int device = -1;
     int kernel_lanes = 0, kernel_slots = 0, kernel_diag = 0;  // instantiation picked for the TMA variant
     unsigned kernel_kinds = 0;
-    unsigned kinds = 0;  // lane kinds the program uses
+    unsigned kinds = 0;       // lane kinds the program uses
+    unsigned slot_kinds = 0;  // slot kinds the program uses
     int diag_ok = 0;     // columns (single-level) / slots (two-level) map 1:1 onto lanes
     int need_nan = 0, need_cnt = 0, has_sine = 0;
     // device copies
@@ -55,7 +56,7 @@ struct K1Launch {
 
 struct K1Choice {
     int lanes, slots, diag;
-    unsigned kinds;
+    unsigned kinds, slot_kinds;
 };
 
 // One per translation unit (agf_k1_*.cu).  mode 0: launch the first instantiation of that unit

@@ -29,7 +29,7 @@ static inline void set_thresholds(LaneP<double> &L, double t0, double t1) {
     L.hi = t1;
 }
 
-template <typename T, int NL, int NS, bool DIAG, unsigned KINDS, bool TMA>
+template <typename T, int NL, int NS, bool DIAG, unsigned KINDS, unsigned SK, bool TMA>
 static int launch_k1(const K1Launch &a) {
     const agf_program *p = a.p;
     K1Params<T, NL, NS> kp;
@@ -78,6 +78,17 @@ static int launch_k1(const K1Launch &a) {
             S.t0 = d.slots[j].t0;
             S.t1 = d.slots[j].t1;
             S.base = (S.flag == 0) ? S.t0 : S.t1;
+            S.ip = (S.xform == AGF_XF_POWI) ? (int)S.xparam : 1;
+        }
+        // pad the unused slots of a fast kind set with reducers that cannot fault or branch
+        // (their accumulators are never written back: l2_write_rec stops at n_slots)
+        for (int j = d.n_slots; j < NS; ++j) {
+            SlotP &S = kp.slots[j];
+            S.ip = 1;
+            S.x_f64 = 1;
+            S.calc = (SK & SK_BINS) ? AGF_CALC_BINS : AGF_CALC_SUM;
+            S.t0 = INFINITY;
+            S.t1 = -INFINITY;
         }
     } else {
         for (int c = 0; c < d.n_cols; ++c) {
@@ -96,38 +107,39 @@ static int launch_k1(const K1Launch &a) {
         int rc = agf_make_tensor_map(&tm, a.d_x, (int)sizeof(T), (uint64_t)p->n_cells, (uint64_t)(row_end - a.row0),
                                      (uint64_t)a.ld, tma_rows<T>());
         if (rc) return rc;
-        constexpr int smem = TMA_STAGES * TMA_TILE_BYTES + 2 * TMA_STAGES * 8;
+        constexpr int smem = TMA_STAGES_DEFAULT * TMA_TILE_BYTES_DEFAULT + 2 * TMA_STAGES_DEFAULT * 8;
         static bool attr_set = false;  // per instantiation
         if (!attr_set) {
-            CU(cudaFuncSetAttribute(agf_k1_tma<T, NL, NS, DIAG, KINDS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            CU(cudaFuncSetAttribute(agf_k1_tma<T, NL, NS, DIAG, KINDS, SK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
             attr_set = true;
         }
         dim3 grid((unsigned)((p->n_cells + TMA_CW - 1) / TMA_CW), (unsigned)(a.s1 - a.s0));
-        agf_k1_tma<T, NL, NS, DIAG, KINDS><<<grid, TMA_THREADS, smem, a.stream>>>(kp, tm);
+        agf_k1_tma<T, NL, NS, DIAG, KINDS, SK><<<grid, TMA_THREADS, smem, a.stream>>>(kp, tm);
     } else {
         dim3 grid((unsigned)((p->n_cells + K1_THREADS - 1) / K1_THREADS), (unsigned)(a.s1 - a.s0));
-        agf_k1_ldg<T, NL, NS, DIAG, KINDS><<<grid, K1_THREADS, 0, a.stream>>>(kp);
+        agf_k1_ldg<T, NL, NS, DIAG, KINDS, SK><<<grid, K1_THREADS, 0, a.stream>>>(kp);
     }
     CU(cudaGetLastError());
     return 0;
 }
 
-static inline bool k1_fits(const agf_program *p, int NL, int NS, bool DG, unsigned KINDS) {
+static inline bool k1_fits(const agf_program *p, int NL, int NS, bool DG, unsigned KINDS, unsigned SK) {
     const agf_program_desc_t &d = p->desc;
     if (d.n_lanes > NL) return false;
     if ((NS == 0) != (d.n_slots == 0) || d.n_slots > NS) return false;
     if (DG && !p->diag_ok) return false;
     if (NS > 0 && NL > 4 && !DG) return false;  // select-chain form only for <= 4 lanes
+    if (NS > 0 && (p->slot_kinds & ~SK) != 0) return false;
     return (p->kinds & ~KINDS) == 0;
 }
 
 int AGF_FN(const K1Launch &a, int mode, K1Choice *choice, int *rc) {
     const agf_program *p = a.p;
-#define K1CASE(NL, NS, DG, KINDS)                                             \
-    if (k1_fits(p, NL, NS, DG, KINDS)) {                                      \
-        if (choice) *choice = K1Choice{NL, NS, DG ? 1 : 0, KINDS};            \
-        if (mode == 0) *rc = launch_k1<AGF_T, NL, NS, DG, KINDS, AGF_TMA>(a); \
-        return 0;                                                             \
+#define K1CASE(NL, NS, DG, KINDS, SK)                                             \
+    if (k1_fits(p, NL, NS, DG, KINDS, SK)) {                                      \
+        if (choice) *choice = K1Choice{NL, NS, DG ? 1 : 0, KINDS, SK};            \
+        if (mode == 0) *rc = launch_k1<AGF_T, NL, NS, DG, KINDS, SK, AGF_TMA>(a); \
+        return 0;                                                                 \
     }
     AGF_LIST
 #undef K1CASE

@@ -48,6 +48,23 @@ __host__ __device__ constexpr unsigned kind_of_calc(int calc) {
                                                              : KIND_SINE;
 }
 
+// Slot-kind sets (level-2 reducers), compile-time like the lane kinds: the per-group flush runs
+// once per level-1 group and thread, so a runtime switch per slot (with pow() inlined per
+// slot) made the flush ~30 instructions per raster value -- 5x the scan itself (ncu r1a).
+enum : unsigned {
+    SK_SUM = 1u,   // sum / mean of x or x^p (p a small non-negative integer)
+    SK_BINS = 2u,  // bin count of x
+    SK_GEN = 4u,   // min / max / dd, general pow / spline transforms
+    SK_ALL = 7u
+};
+
+__host__ __device__ constexpr unsigned slot_kind_of(int calc, int xform) {
+    return ((calc == AGF_CALC_MEAN || calc == AGF_CALC_SUM) && (xform == AGF_XF_NONE || xform == AGF_XF_POWI))
+               ? SK_SUM
+           : (calc == AGF_CALC_BINS && xform == AGF_XF_NONE) ? SK_BINS
+                                                             : SK_GEN;
+}
+
 // ------------------------------------------------------------------------------------------
 // kernel parameter blocks (passed by value, live in the constant bank)
 // ------------------------------------------------------------------------------------------
@@ -66,7 +83,7 @@ struct SlotP {
     int x_f64;
     int calc;
     int flag;
-    int pad_;
+    int ip;  // integer exponent of a POWI transform (1 for no transform)
     double t0, t1, base;
 };
 
@@ -224,26 +241,34 @@ struct CellState {
     bool nan;                   // NaN seen in the current level-1 group
 };
 
-template <typename T, int NL, int NS>
+template <unsigned KINDS, typename T, int NL, int NS>
 __device__ __forceinline__ void l1_init(const K1Params<T, NL, NS> &p, CellState<T, NL, NS> &s) {
 #pragma unroll
     for (int l = 0; l < NL; ++l) {
-        int c = (l < p.n_lanes) ? p.lanes[l].calc : AGF_CALC_SUM;
-        s.a[l] = (c == AGF_CALC_MIN || c == AGF_CALC_HIDDEN_MIN)   ? agf_inf()
-                 : (c == AGF_CALC_MAX || c == AGF_CALC_HIDDEN_MAX) ? -agf_inf()
-                                                                   : 0.0;
+        if constexpr ((KINDS & (KIND_MINMAX | KIND_SINE)) == 0) {
+            s.a[l] = 0.0;
+        } else {
+            int c = (l < p.n_lanes) ? p.lanes[l].calc : AGF_CALC_SUM;
+            s.a[l] = (c == AGF_CALC_MIN || c == AGF_CALC_HIDDEN_MIN)   ? agf_inf()
+                     : (c == AGF_CALC_MAX || c == AGF_CALC_HIDDEN_MAX) ? -agf_inf()
+                                                                       : 0.0;
+        }
     }
     s.nn = 0;
     s.nan = false;
 }
 
-template <typename T, int NL, int NS>
+template <unsigned SK, typename T, int NL, int NS>
 __device__ __forceinline__ void l2_init(const K1Params<T, NL, NS> &p, CellState<T, NL, NS> &s) {
     if (NS > 0) {
 #pragma unroll
         for (int j = 0; j < NS; ++j) {
-            int c = (j < p.n_slots) ? p.slots[j].calc : AGF_CALC_SUM;
-            s.b[j] = (c == AGF_CALC_MIN) ? agf_inf() : (c == AGF_CALC_MAX) ? -agf_inf() : 0.0;
+            if constexpr ((SK & SK_GEN) == 0) {
+                s.b[j] = 0.0;
+            } else {
+                int c = (j < p.n_slots) ? p.slots[j].calc : AGF_CALC_SUM;
+                s.b[j] = (c == AGF_CALC_MIN) ? agf_inf() : (c == AGF_CALC_MAX) ? -agf_inf() : 0.0;
+            }
         }
     }
 }
@@ -313,33 +338,44 @@ __device__ __forceinline__ void l1_acc(const K1Params<T, NL, NS> &p, CellState<T
 }
 
 // value of lane l for a finished group of n_grp rows, rounded to the raster dtype (:143-155, :260)
-template <typename T, int NL, int NS>
+template <unsigned KINDS, typename T, int NL, int NS>
 __device__ __forceinline__ double l1_value(const K1Params<T, NL, NS> &p,
                                            const CellState<T, NL, NS> &s, int l, int n_grp) {
     const LaneP<T> &L = p.lanes[l];
     double r;
-    switch (L.calc) {
-        case AGF_CALC_MEAN:
-            r = s.a[l] / (double)n_grp;
-            break;
-        case AGF_CALC_NANMEAN:
-            r = (s.nn > 0) ? s.a[l] / (double)s.nn : agf_nan();
-            break;
-        case AGF_CALC_MIN:
-        case AGF_CALC_MAX:
-        case AGF_CALC_DD:
-            r = s.nan ? agf_nan() : s.a[l];
-            break;
-        case AGF_CALC_SINE_DD:
-            // lanes 0..2 are the hidden sum / min / max helpers (host guarantees it)
-            r = (s.nan || s.nn == 0)
-                    ? agf_nan()
-                    : sine_dd_value(s.a[0] / (double)s.nn, s.a[NL > 1 ? 1 : 0], s.a[NL > 2 ? 2 : 0],
-                                    L.t0, L.t1, L.flag);
-            break;
-        default:  // SUM, BINS, hidden helpers
-            r = s.a[l];
-            break;
+    if constexpr (KINDS == KIND_SUM) {
+        r = (L.calc == AGF_CALC_MEAN) ? s.a[l] / (double)n_grp : s.a[l];
+    } else if constexpr (KINDS == KIND_BINS) {
+        r = s.a[l];
+    } else if constexpr (KINDS == KIND_DD) {
+        r = s.nan ? agf_nan() : s.a[l];
+    } else {
+        switch (L.calc) {
+            case AGF_CALC_MEAN:
+                r = s.a[l] / (double)n_grp;
+                break;
+            case AGF_CALC_NANMEAN:
+                r = (s.nn > 0) ? s.a[l] / (double)s.nn : agf_nan();
+                break;
+            case AGF_CALC_MIN:
+            case AGF_CALC_MAX:
+            case AGF_CALC_DD:
+                r = s.nan ? agf_nan() : s.a[l];
+                break;
+            case AGF_CALC_SINE_DD:
+                // lanes 0..2 are the hidden sum / min / max helpers (host guarantees it)
+                if constexpr ((KINDS & KIND_SINE) != 0)
+                    r = (s.nan || s.nn == 0)
+                            ? agf_nan()
+                            : sine_dd_value(s.a[0] / (double)s.nn, s.a[NL > 1 ? 1 : 0], s.a[NL > 2 ? 2 : 0],
+                                            L.t0, L.t1, L.flag);
+                else
+                    r = agf_nan();
+                break;
+            default:  // SUM, BINS, hidden helpers
+                r = s.a[l];
+                break;
+        }
     }
     if (n_grp == 0) r = agf_nan();  // empty resample bin -> NaN for every reducer
     return round_to<T>(r);
@@ -391,13 +427,27 @@ __device__ __forceinline__ void store_col(void *out, int out_f64, size_t idx, do
         reinterpret_cast<float *>(out)[idx] = (float)v;
 }
 
+// slot kinds SK_SUM / SK_BINS: straight-line code, no transform switch
+template <typename T>
+__device__ __forceinline__ void l2_acc_sum(const SlotP &S, double &b, double x) {
+    double r = x;
+    if (S.ip != 1) {  // uniform
+        r = (S.ip == 2) ? x * x : ipow(x, S.ip);
+        if (!S.x_f64) r = round_to<T>(r);
+    }
+    b += r;  // a NaN group value poisons the sum == "any NaN -> NaN"
+}
+__device__ __forceinline__ void l2_acc_bins(const SlotP &S, double &b, double x) {
+    if (x > S.t0 && x < S.t1) b += 1.0;
+}
+
 // end of level-1 group g (n_grp rows): emit columns (single-level) or feed the slots
-template <typename T, int NL, int NS, bool DIAG>
+template <typename T, int NL, int NS, bool DIAG, unsigned KINDS, unsigned SK>
 __device__ __forceinline__ void l1_flush(const K1Params<T, NL, NS> &p, CellState<T, NL, NS> &s,
                                          int g, int n_grp, int cell) {
     double val[NL];
 #pragma unroll
-    for (int l = 0; l < NL; ++l) val[l] = (l < p.n_lanes) ? l1_value(p, s, l, n_grp) : 0.0;
+    for (int l = 0; l < NL; ++l) val[l] = (NL == 1 || l < p.n_lanes) ? l1_value<KINDS>(p, s, l, n_grp) : 0.0;
 
     if (NS == 0) {
         bool ok = true;
@@ -421,13 +471,28 @@ __device__ __forceinline__ void l1_flush(const K1Params<T, NL, NS> &p, CellState
         unsigned char *vp = p.valid + (size_t)g * p.n_cells + cell;
         *vp = (p.valid_and ? (*vp != 0) && ok : ok) ? 1 : 0;
     } else {
+        // Slots beyond n_slots are padded by the launcher with harmless reducers of the
+        // instantiation's kind set (their registers are never written back), so the fast kinds
+        // need no per-slot bound check.
 #pragma unroll
         for (int j = 0; j < NS; ++j) {
-            if (j < p.n_slots) {
-                const SlotP &S = p.slots[j];
-                double x = DIAG ? val[j < NL ? j : 0] : select_reg<NL>(val, S.src);
-                double xt = apply_xform<T>(x, S.xform, S.xparam, S.x_f64);
-                l2_acc_one(S, s.b[j], xt);
+            const SlotP &S = p.slots[j];
+            if constexpr (SK == SK_SUM) {
+                l2_acc_sum<T>(S, s.b[j], DIAG ? val[j < NL ? j : 0] : select_reg<NL>(val, S.src));
+            } else if constexpr (SK == SK_BINS) {
+                l2_acc_bins(S, s.b[j], DIAG ? val[j < NL ? j : 0] : select_reg<NL>(val, S.src));
+            } else if constexpr (SK == (SK_SUM | SK_BINS)) {
+                const double x = DIAG ? val[j < NL ? j : 0] : select_reg<NL>(val, S.src);
+                if (S.calc == AGF_CALC_BINS)  // uniform
+                    l2_acc_bins(S, s.b[j], x);
+                else
+                    l2_acc_sum<T>(S, s.b[j], x);
+            } else {
+                if (j < p.n_slots) {
+                    double x = DIAG ? val[j < NL ? j : 0] : select_reg<NL>(val, S.src);
+                    double xt = apply_xform<T>(x, S.xform, S.xparam, S.x_f64);
+                    l2_acc_one(S, s.b[j], xt);
+                }
             }
         }
     }
@@ -449,7 +514,7 @@ __device__ __forceinline__ void l2_write_rec(const K1Params<T, NL, NS> &p,
 // rows that never cross a level-1 group boundary; next batch's loads are issued before the
 // current batch is reduced.
 // ------------------------------------------------------------------------------------------
-template <typename T, int NL, int NS, bool DIAG, unsigned KINDS>
+template <typename T, int NL, int NS, bool DIAG, unsigned KINDS, unsigned SK>
 __global__ void __launch_bounds__(K1_THREADS)
     agf_k1_ldg(const __grid_constant__ K1Params<T, NL, NS> p) {
     const int cell = blockIdx.x * K1_THREADS + threadIdx.x;
@@ -463,8 +528,8 @@ __global__ void __launch_bounds__(K1_THREADS)
     int next_b2 = (NS > 0) ? p.b2[g2 + 1] : 0;
 
     CellState<T, NL, NS> s;
-    l1_init(p, s);
-    l2_init(p, s);
+    l1_init<KINDS>(p, s);
+    l2_init<SK>(p, s);
 
     const T *xc = p.x + cell;
     int glo = p.b1[g];      // first row of the current group
@@ -496,13 +561,13 @@ __global__ void __launch_bounds__(K1_THREADS)
             if (i < clen) l1_acc<KINDS>(p, s, cur[i]);
 
         if (ends) {
-            l1_flush<T, NL, NS, DIAG>(p, s, g, nb - glo, cell);
-            l1_init(p, s);
+            l1_flush<T, NL, NS, DIAG, KINDS, SK>(p, s, g, nb - glo, cell);
+            l1_init<KINDS>(p, s);
             if (NS > 0) {
                 // close every level-2 group that ends with level-1 group g
                 if (g + 1 == next_b2 || g + 1 == g_end) {
                     l2_write_rec(p, s, rec, cell);
-                    l2_init(p, s);
+                    l2_init<SK>(p, s);
                     ++rec;
                     if (g + 1 < g_end && g + 1 == next_b2) {
                         do {  // skip zero-width level-2 groups (they get no record -> NaN)
@@ -534,13 +599,13 @@ __global__ void __launch_bounds__(K1_THREADS)
 // agf_k1_ldg.
 // ------------------------------------------------------------------------------------------
 constexpr int TMA_CW = 256;         // cells per tile row == consumer threads
-constexpr int TMA_TILE_BYTES = 24 * 1024;
-constexpr int TMA_STAGES = 4;
+constexpr int TMA_TILE_BYTES_DEFAULT = 24 * 1024;
+constexpr int TMA_STAGES_DEFAULT = 4;
 constexpr int TMA_THREADS = TMA_CW + 32;
 
 template <typename T>
 __host__ __device__ constexpr int tma_rows() {
-    return TMA_TILE_BYTES / (TMA_CW * (int)sizeof(T));
+    return TMA_TILE_BYTES_DEFAULT / (TMA_CW * (int)sizeof(T));
 }
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -579,10 +644,11 @@ struct alignas(64) TensorMap {  // same layout as CUtensorMap (128 opaque bytes)
     unsigned long long opaque[16];
 };
 
-template <typename T, int NL, int NS, bool DIAG, unsigned KINDS>
-__global__ void __launch_bounds__(TMA_THREADS)
+template <typename T, int NL, int NS, bool DIAG, unsigned KINDS, unsigned SK, int TT = tma_rows<T>(),
+          int TMA_STAGES = TMA_STAGES_DEFAULT, int MINB = 2>
+__global__ void __launch_bounds__(TMA_THREADS, MINB)
     agf_k1_tma(const __grid_constant__ K1Params<T, NL, NS> p, const __grid_constant__ TensorMap tmap) {
-    constexpr int TT = tma_rows<T>();
+    constexpr int TMA_TILE_BYTES = TT * TMA_CW * (int)sizeof(T);
     constexpr int UNROLL = NL <= 4 ? 8 : (NL <= 16 ? 2 : 1);
     extern __shared__ __align__(128) unsigned char smem_raw[];
     T *tiles = reinterpret_cast<T *>(smem_raw);
@@ -629,11 +695,13 @@ __global__ void __launch_bounds__(TMA_THREADS)
     int rec = st.rec0;
     int next_b2 = (NS > 0) ? p.b2[g2 + 1] : 0;
     CellState<T, NL, NS> s;
-    l1_init(p, s);
-    l2_init(p, s);
+    l1_init<KINDS>(p, s);
+    l2_init<SK>(p, s);
     int k = k_begin;
     int glo = k_begin;
     int nb = p.b1[g + 1];
+    // bound after next, fetched one group ahead so the group-end path never waits on the load
+    int nb_next = (g + 1 < g_end) ? p.b1[g + 2] : 0x7fffffff;
 
     for (int i = 0; i < n_tiles; ++i) {
         const int stg = i % TMA_STAGES;
@@ -643,24 +711,27 @@ __global__ void __launch_bounds__(TMA_THREADS)
         int r = 0;
         while (r < rows || (k == nb && g < g_end)) {
             const int run = min(rows - r, nb - k);
-            int j = 0;
-            for (; j + UNROLL <= run; j += UNROLL) {
+            const T *cp = col + r * TMA_CW;
+            int j = run;
+#pragma unroll 1
+            for (; j >= UNROLL; j -= UNROLL, cp += UNROLL * TMA_CW) {
                 T v[UNROLL];
 #pragma unroll
-                for (int u = 0; u < UNROLL; ++u) v[u] = col[(r + j + u) * TMA_CW];
+                for (int u = 0; u < UNROLL; ++u) v[u] = cp[u * TMA_CW];
 #pragma unroll
                 for (int u = 0; u < UNROLL; ++u) l1_acc<KINDS>(p, s, v[u]);
             }
-            for (; j < run; ++j) l1_acc<KINDS>(p, s, col[(r + j) * TMA_CW]);
+#pragma unroll 1
+            for (; j > 0; --j, cp += TMA_CW) l1_acc<KINDS>(p, s, *cp);
             r += run;
             k += run;
             if (k == nb) {  // level-1 group g is complete
-                if (active) l1_flush<T, NL, NS, DIAG>(p, s, g, nb - glo, cell);
-                l1_init(p, s);
+                if (active) l1_flush<T, NL, NS, DIAG, KINDS, SK>(p, s, g, nb - glo, cell);
+                l1_init<KINDS>(p, s);
                 if (NS > 0) {
                     if (g + 1 == next_b2 || g + 1 == g_end) {
                         if (active) l2_write_rec(p, s, rec, cell);
-                        l2_init(p, s);
+                        l2_init<SK>(p, s);
                         ++rec;
                         if (g + 1 < g_end && g + 1 == next_b2) {
                             do {  // skip zero-width level-2 groups (no record -> NaN in finalize)
@@ -672,7 +743,8 @@ __global__ void __launch_bounds__(TMA_THREADS)
                 }
                 glo = nb;
                 ++g;
-                nb = (g < g_end) ? p.b1[g + 1] : 0x7fffffff;
+                nb = nb_next;
+                nb_next = (g + 1 < g_end) ? p.b1[g + 2] : 0x7fffffff;
             }
         }
         __syncwarp();
