@@ -130,12 +130,19 @@ static int validate_desc(const agf_program_desc_t *d, int64_t n_cells) {
 }
 
 // lane kinds + 1:1 mapping flags of a descriptor
-static void analyse_desc(const agf_program_desc_t *d, unsigned *kinds, unsigned *slot_kinds, int *diag_ok) {
+static void analyse_desc(const agf_program_desc_t *d, unsigned *kinds, unsigned *slot_kinds, int *n_bin_slots,
+                         int *diag_ok) {
     unsigned k = 0, sk = 0;
+    int nbins = 0;
     for (int l = 0; l < d->n_lanes; ++l) k |= kind_of_calc(d->lanes[l].calc);
-    for (int j = 0; j < d->n_slots; ++j) sk |= slot_kind_of(d->slots[j].calc, d->slots[j].xform);
+    for (int j = 0; j < d->n_slots; ++j) {
+        const unsigned kind = slot_kind_of(d->slots[j].calc, d->slots[j].xform);
+        sk |= kind;
+        nbins += kind == SK_BINS;
+    }
     *kinds = k;
     *slot_kinds = sk;
+    *n_bin_slots = nbins;
     bool dg;
     if (d->n_slots == 0) {
         dg = d->n_cols <= d->n_lanes;
@@ -169,7 +176,7 @@ static int k1_select(const K1Launch &a, int mode, K1Choice *choice, int *rc) {
 }
 
 static int choose_kernel(agf_program *p) {
-    analyse_desc(&p->desc, &p->kinds, &p->slot_kinds, &p->diag_ok);
+    analyse_desc(&p->desc, &p->kinds, &p->slot_kinds, &p->n_bin_slots, &p->diag_ok);
     K1Launch q{};
     q.p = p;
     q.use_tma = 1;

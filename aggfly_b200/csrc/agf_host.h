@@ -18,6 +18,7 @@ struct agf_program {
     unsigned kernel_kinds = 0;
     unsigned kinds = 0;       // lane kinds the program uses
     unsigned slot_kinds = 0;  // slot kinds the program uses
+    int n_bin_slots = 0;      // slots of kind SK_BINS
     int diag_ok = 0;     // columns (single-level) / slots (two-level) map 1:1 onto lanes
     int need_nan = 0, need_cnt = 0, has_sine = 0;
     // device copies
@@ -56,7 +57,8 @@ struct K1Launch {
 
 struct K1Choice {
     int lanes, slots, diag;
-    unsigned kinds, slot_kinds;
+    unsigned kinds;
+    int typed_bins;  // NB of the instantiation (-1: general slots)
 };
 
 // One per translation unit (agf_k1_*.cu).  mode 0: launch the first instantiation of that unit

@@ -29,7 +29,7 @@ static inline void set_thresholds(LaneP<double> &L, double t0, double t1) {
     L.hi = t1;
 }
 
-template <typename T, int NL, int NS, bool DIAG, unsigned KINDS, unsigned SK, bool TMA>
+template <typename T, int NL, int NS, bool DIAG, unsigned KINDS, int NB, bool TMA>
 static int launch_k1(const K1Launch &a) {
     const agf_program *p = a.p;
     K1Params<T, NL, NS> kp;
@@ -67,8 +67,7 @@ static int launch_k1(const K1Launch &a) {
         set_thresholds(L, L.t0, L.t1);
     }
     if (NS > 0) {
-        for (int j = 0; j < d.n_slots; ++j) {
-            SlotP &S = kp.slots[j];
+        auto fill = [&](SlotP &S, int j) {
             S.src = d.slots[j].src;
             S.xform = d.slots[j].xform;
             S.xparam = d.slots[j].xparam;
@@ -79,16 +78,35 @@ static int launch_k1(const K1Launch &a) {
             S.t1 = d.slots[j].t1;
             S.base = (S.flag == 0) ? S.t0 : S.t1;
             S.ip = (S.xform == AGF_XF_POWI) ? (int)S.xparam : 1;
-        }
-        // pad the unused slots of a fast kind set with reducers that cannot fault or branch
-        // (their accumulators are never written back: l2_write_rec stops at n_slots)
-        for (int j = d.n_slots; j < NS; ++j) {
-            SlotP &S = kp.slots[j];
-            S.ip = 1;
-            S.x_f64 = 1;
-            S.calc = (SK & SK_BINS) ? AGF_CALC_BINS : AGF_CALC_SUM;
-            S.t0 = INFINITY;
-            S.t1 = -INFINITY;
+            S.flo = f32_round_down(S.t0);
+            S.fhi = f32_round_up(S.t1);
+            S.dst = j;
+        };
+        if (NB >= 0) {
+            // typed form: kernel slots [0, NB) = the program's bin slots, [NB, NS) = its power
+            // sums, both in program order; the rest are inert pads (dst = -1: never written back)
+            int nb = 0, ns = NB;
+            for (int j = 0; j < d.n_slots; ++j) {
+                const bool bins = slot_kind_of(d.slots[j].calc, d.slots[j].xform) == SK_BINS;
+                fill(kp.slots[bins ? nb++ : ns++], j);
+            }
+            for (; nb < NB; ++nb) {
+                SlotP &S = kp.slots[nb];
+                S.calc = AGF_CALC_BINS;
+                S.t0 = S.flo = INFINITY;
+                S.t1 = S.fhi = -INFINITY;
+                S.ip = 1;
+                S.dst = -1;
+            }
+            for (; ns < NS; ++ns) {
+                SlotP &S = kp.slots[ns];
+                S.calc = AGF_CALC_SUM;
+                S.ip = 1;
+                S.x_f64 = 1;
+                S.dst = -1;
+            }
+        } else {
+            for (int j = 0; j < d.n_slots; ++j) fill(kp.slots[j], j);
         }
     } else {
         for (int c = 0; c < d.n_cols; ++c) {
@@ -103,42 +121,55 @@ static int launch_k1(const K1Launch &a) {
     if constexpr (TMA) {
         // rows of the view the stripes of this launch can touch
         const int64_t row_end = p->b1[p->stripes[a.s1 - 1].g1_end];
+        // Ring shape by register budget of the instantiation (measured with tools/k1_sweep on the
+        // C3 program: 3 CTAs x 3 stages 6.87 TB/s, 2 x 4 6.01 TB/s, 4 x 2 6.68 TB/s; tiles of 8 or
+        // 12 rows lose 20-40% to per-tile synchronisation): three 9-warp CTAs per SM need <= 72
+        // registers per thread, two need <= 112.
+        constexpr int state_regs = 2 * NL + (NB >= 0 ? NB + 2 * (NS - NB) : 2 * NS);
+        constexpr int MINB = state_regs <= 30 ? 3 : (state_regs <= 48 ? 2 : 1);
+        constexpr int STAGES = MINB == 3 ? 3 : (MINB == 2 ? 4 : 8);
+        constexpr int TT = tma_rows<T>();
         TensorMap tm;
         int rc = agf_make_tensor_map(&tm, a.d_x, (int)sizeof(T), (uint64_t)p->n_cells, (uint64_t)(row_end - a.row0),
-                                     (uint64_t)a.ld, tma_rows<T>());
+                                     (uint64_t)a.ld, TT);
         if (rc) return rc;
-        constexpr int smem = TMA_STAGES_DEFAULT * TMA_TILE_BYTES_DEFAULT + 2 * TMA_STAGES_DEFAULT * 8;
+        constexpr int smem = STAGES * TMA_TILE_BYTES_DEFAULT + 2 * STAGES * 8;
+        auto kern = agf_k1_tma<T, NL, NS, DIAG, KINDS, NB, TT, STAGES, MINB>;
         static bool attr_set = false;  // per instantiation
         if (!attr_set) {
-            CU(cudaFuncSetAttribute(agf_k1_tma<T, NL, NS, DIAG, KINDS, SK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
             attr_set = true;
         }
         dim3 grid((unsigned)((p->n_cells + TMA_CW - 1) / TMA_CW), (unsigned)(a.s1 - a.s0));
-        agf_k1_tma<T, NL, NS, DIAG, KINDS, SK><<<grid, TMA_THREADS, smem, a.stream>>>(kp, tm);
+        kern<<<grid, TMA_THREADS, smem, a.stream>>>(kp, tm);
     } else {
         dim3 grid((unsigned)((p->n_cells + K1_THREADS - 1) / K1_THREADS), (unsigned)(a.s1 - a.s0));
-        agf_k1_ldg<T, NL, NS, DIAG, KINDS, SK><<<grid, K1_THREADS, 0, a.stream>>>(kp);
+        agf_k1_ldg<T, NL, NS, DIAG, KINDS, NB><<<grid, K1_THREADS, 0, a.stream>>>(kp);
     }
     CU(cudaGetLastError());
     return 0;
 }
 
-static inline bool k1_fits(const agf_program *p, int NL, int NS, bool DG, unsigned KINDS, unsigned SK) {
+static inline bool k1_fits(const agf_program *p, int NL, int NS, bool DG, unsigned KINDS, int NB) {
     const agf_program_desc_t &d = p->desc;
     if (d.n_lanes > NL) return false;
     if ((NS == 0) != (d.n_slots == 0) || d.n_slots > NS) return false;
     if (DG && !p->diag_ok) return false;
     if (NS > 0 && NL > 4 && !DG) return false;  // select-chain form only for <= 4 lanes
-    if (NS > 0 && (p->slot_kinds & ~SK) != 0) return false;
+    if (NS > 0 && NB >= 0) {                     // typed slots: bins -> [0, NB), power sums -> [NB, NS)
+        if (p->slot_kinds & SK_GEN) return false;
+        if (p->n_bin_slots > NB || d.n_slots - p->n_bin_slots > NS - NB) return false;
+        if (DG && p->n_bin_slots != 0 && p->n_bin_slots != d.n_slots) return false;  // keep slot j == lane j
+    }
     return (p->kinds & ~KINDS) == 0;
 }
 
 int AGF_FN(const K1Launch &a, int mode, K1Choice *choice, int *rc) {
     const agf_program *p = a.p;
-#define K1CASE(NL, NS, DG, KINDS, SK)                                             \
-    if (k1_fits(p, NL, NS, DG, KINDS, SK)) {                                      \
-        if (choice) *choice = K1Choice{NL, NS, DG ? 1 : 0, KINDS, SK};            \
-        if (mode == 0) *rc = launch_k1<AGF_T, NL, NS, DG, KINDS, SK, AGF_TMA>(a); \
+#define K1CASE(NL, NS, DG, KINDS, NB)                                             \
+    if (k1_fits(p, NL, NS, DG, KINDS, NB)) {                                      \
+        if (choice) *choice = K1Choice{NL, NS, DG ? 1 : 0, KINDS, NB};            \
+        if (mode == 0) *rc = launch_k1<AGF_T, NL, NS, DG, KINDS, NB, AGF_TMA>(a); \
         return 0;                                                                 \
     }
     AGF_LIST

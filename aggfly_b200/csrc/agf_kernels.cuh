@@ -51,12 +51,17 @@ __host__ __device__ constexpr unsigned kind_of_calc(int calc) {
 // Slot-kind sets (level-2 reducers), compile-time like the lane kinds: the per-group flush runs
 // once per level-1 group and thread, so a runtime switch per slot (with pow() inlined per
 // slot) made the flush ~30 instructions per raster value -- 5x the scan itself (ncu r1a).
+// The kernels take this as the template parameter NB: NB >= 0 means "typed" slots -- the launcher
+// sorts the program's slots so that kernel slots [0, NB) are bin counters (int registers) and
+// [NB, NS) are power sums (double registers), padding each group with inert reducers; NB == -1
+// is the general form (any calc / transform per slot, runtime switch).
 enum : unsigned {
     SK_SUM = 1u,   // sum / mean of x or x^p (p a small non-negative integer)
     SK_BINS = 2u,  // bin count of x
     SK_GEN = 4u,   // min / max / dd, general pow / spline transforms
     SK_ALL = 7u
 };
+constexpr int NB_GENERAL = -1;
 
 __host__ __device__ constexpr unsigned slot_kind_of(int calc, int xform) {
     return ((calc == AGF_CALC_MEAN || calc == AGF_CALC_SUM) && (xform == AGF_XF_NONE || xform == AGF_XF_POWI))
@@ -83,7 +88,9 @@ struct SlotP {
     int x_f64;
     int calc;
     int flag;
-    int ip;  // integer exponent of a POWI transform (1 for no transform)
+    int ip;   // integer exponent of a POWI transform (1 for no transform)
+    int dst;  // slot index in the partial records (kernel slot order may differ); -1 = padding
+    float flo, fhi;  // t0 / t1 rounded outward to float: exact strict compares of float values
     double t0, t1, base;
 };
 
@@ -233,16 +240,18 @@ __device__ __forceinline__ double sine_dd_value(double tavg, double tmin, double
 // ------------------------------------------------------------------------------------------
 // per-thread reducer state (everything statically indexed -> registers)
 // ------------------------------------------------------------------------------------------
-template <typename T, int NL, int NS>
+template <typename T, int NL, int NS, int NB = NB_GENERAL>
 struct CellState {
+    static constexpr int ND = (NB >= 0) ? (NS - NB) : NS;  // double-typed level-2 accumulators
     double a[NL];               // level-1 accumulators
-    double b[NS > 0 ? NS : 1];  // level-2 accumulators
+    double b[ND > 0 ? ND : 1];  // level-2 accumulators (typed form: the power sums)
+    int c[NB > 0 ? NB : 1];     // level-2 bin counters (typed form only)
     int nn;                     // non-NaN values in the current level-1 group
     bool nan;                   // NaN seen in the current level-1 group
 };
 
-template <unsigned KINDS, typename T, int NL, int NS>
-__device__ __forceinline__ void l1_init(const K1Params<T, NL, NS> &p, CellState<T, NL, NS> &s) {
+template <unsigned KINDS, typename T, int NL, int NS, typename ST>
+__device__ __forceinline__ void l1_init(const K1Params<T, NL, NS> &p, ST &s) {
 #pragma unroll
     for (int l = 0; l < NL; ++l) {
         if constexpr ((KINDS & (KIND_MINMAX | KIND_SINE)) == 0) {
@@ -258,14 +267,17 @@ __device__ __forceinline__ void l1_init(const K1Params<T, NL, NS> &p, CellState<
     s.nan = false;
 }
 
-template <unsigned SK, typename T, int NL, int NS>
-__device__ __forceinline__ void l2_init(const K1Params<T, NL, NS> &p, CellState<T, NL, NS> &s) {
-    if (NS > 0) {
+template <int NB, typename T, int NL, int NS, typename ST>
+__device__ __forceinline__ void l2_init(const K1Params<T, NL, NS> &p, ST &s) {
+    if constexpr (NS > 0) {
+        if constexpr (NB >= 0) {
 #pragma unroll
-        for (int j = 0; j < NS; ++j) {
-            if constexpr ((SK & SK_GEN) == 0) {
-                s.b[j] = 0.0;
-            } else {
+            for (int j = 0; j < NB; ++j) s.c[j] = 0;
+#pragma unroll
+            for (int j = 0; j < NS - NB; ++j) s.b[j] = 0.0;
+        } else {
+#pragma unroll
+            for (int j = 0; j < NS; ++j) {
                 int c = (j < p.n_slots) ? p.slots[j].calc : AGF_CALC_SUM;
                 s.b[j] = (c == AGF_CALC_MIN) ? agf_inf() : (c == AGF_CALC_MAX) ? -agf_inf() : 0.0;
             }
@@ -274,8 +286,8 @@ __device__ __forceinline__ void l2_init(const K1Params<T, NL, NS> &p, CellState<
 }
 
 // one raster value into every level-1 lane (nb_kernels.py:134-141, 170-177, 193-196, 213-220)
-template <unsigned KINDS, typename T, int NL, int NS>
-__device__ __forceinline__ void l1_acc(const K1Params<T, NL, NS> &p, CellState<T, NL, NS> &s, T v) {
+template <unsigned KINDS, typename T, int NL, int NS, typename ST>
+__device__ __forceinline__ void l1_acc(const K1Params<T, NL, NS> &p, ST &s, T v) {
     const double vd = (double)v;
     bool isn = false;
     if constexpr ((KINDS & (KIND_NANMEAN | KIND_MINMAX | KIND_DD | KIND_SINE)) != 0) isn = (v != v);
@@ -338,9 +350,8 @@ __device__ __forceinline__ void l1_acc(const K1Params<T, NL, NS> &p, CellState<T
 }
 
 // value of lane l for a finished group of n_grp rows, rounded to the raster dtype (:143-155, :260)
-template <unsigned KINDS, typename T, int NL, int NS>
-__device__ __forceinline__ double l1_value(const K1Params<T, NL, NS> &p,
-                                           const CellState<T, NL, NS> &s, int l, int n_grp) {
+template <unsigned KINDS, typename T, int NL, int NS, typename ST>
+__device__ __forceinline__ double l1_value(const K1Params<T, NL, NS> &p, const ST &s, int l, int n_grp) {
     const LaneP<T> &L = p.lanes[l];
     double r;
     if constexpr (KINDS == KIND_SUM) {
@@ -427,7 +438,7 @@ __device__ __forceinline__ void store_col(void *out, int out_f64, size_t idx, do
         reinterpret_cast<float *>(out)[idx] = (float)v;
 }
 
-// slot kinds SK_SUM / SK_BINS: straight-line code, no transform switch
+// typed slots: straight-line code, no transform switch
 template <typename T>
 __device__ __forceinline__ void l2_acc_sum(const SlotP &S, double &b, double x) {
     double r = x;
@@ -437,19 +448,26 @@ __device__ __forceinline__ void l2_acc_sum(const SlotP &S, double &b, double x) 
     }
     b += r;  // a NaN group value poisons the sum == "any NaN -> NaN"
 }
-__device__ __forceinline__ void l2_acc_bins(const SlotP &S, double &b, double x) {
-    if (x > S.t0 && x < S.t1) b += 1.0;
+// x is a value of the raster dtype: for float the compare runs in fp32 against thresholds rounded
+// outward (same truth value as the reference's fp64 compare, see set_thresholds in agf_k1_inst.cuh)
+template <typename T>
+__device__ __forceinline__ void l2_acc_bins(const SlotP &S, int &c, double x) {
+    if constexpr (sizeof(T) == 4) {
+        const float xf = (float)x;  // exact: x holds a float
+        if (xf > S.flo && xf < S.fhi) c += 1;
+    } else {
+        if (x > S.t0 && x < S.t1) c += 1;
+    }
 }
 
 // end of level-1 group g (n_grp rows): emit columns (single-level) or feed the slots
-template <typename T, int NL, int NS, bool DIAG, unsigned KINDS, unsigned SK>
-__device__ __forceinline__ void l1_flush(const K1Params<T, NL, NS> &p, CellState<T, NL, NS> &s,
-                                         int g, int n_grp, int cell) {
+template <typename T, int NL, int NS, bool DIAG, unsigned KINDS, int NB, typename ST>
+__device__ __forceinline__ void l1_flush(const K1Params<T, NL, NS> &p, ST &s, int g, int n_grp, int cell) {
     double val[NL];
 #pragma unroll
     for (int l = 0; l < NL; ++l) val[l] = (NL == 1 || l < p.n_lanes) ? l1_value<KINDS>(p, s, l, n_grp) : 0.0;
 
-    if (NS == 0) {
+    if constexpr (NS == 0) {
         bool ok = true;
         const size_t base = (size_t)g * p.out_ncols;
         if (DIAG) {  // column c == lane c, no transform
@@ -470,42 +488,46 @@ __device__ __forceinline__ void l1_flush(const K1Params<T, NL, NS> &p, CellState
         }
         unsigned char *vp = p.valid + (size_t)g * p.n_cells + cell;
         *vp = (p.valid_and ? (*vp != 0) && ok : ok) ? 1 : 0;
+    } else if constexpr (NB >= 0) {
+        // typed slots; unused ones are padded by the launcher with inert reducers whose registers
+        // are never written back, so there is no per-slot bound check or branch
+#pragma unroll
+        for (int j = 0; j < NB; ++j)
+            l2_acc_bins<T>(p.slots[j], s.c[j], DIAG ? val[j < NL ? j : 0] : select_reg<NL>(val, p.slots[j].src));
+#pragma unroll
+        for (int j = NB; j < NS; ++j)
+            l2_acc_sum<T>(p.slots[j], s.b[j - NB], DIAG ? val[j < NL ? j : 0] : select_reg<NL>(val, p.slots[j].src));
     } else {
-        // Slots beyond n_slots are padded by the launcher with harmless reducers of the
-        // instantiation's kind set (their registers are never written back), so the fast kinds
-        // need no per-slot bound check.
 #pragma unroll
         for (int j = 0; j < NS; ++j) {
-            const SlotP &S = p.slots[j];
-            if constexpr (SK == SK_SUM) {
-                l2_acc_sum<T>(S, s.b[j], DIAG ? val[j < NL ? j : 0] : select_reg<NL>(val, S.src));
-            } else if constexpr (SK == SK_BINS) {
-                l2_acc_bins(S, s.b[j], DIAG ? val[j < NL ? j : 0] : select_reg<NL>(val, S.src));
-            } else if constexpr (SK == (SK_SUM | SK_BINS)) {
-                const double x = DIAG ? val[j < NL ? j : 0] : select_reg<NL>(val, S.src);
-                if (S.calc == AGF_CALC_BINS)  // uniform
-                    l2_acc_bins(S, s.b[j], x);
-                else
-                    l2_acc_sum<T>(S, s.b[j], x);
-            } else {
-                if (j < p.n_slots) {
-                    double x = DIAG ? val[j < NL ? j : 0] : select_reg<NL>(val, S.src);
-                    double xt = apply_xform<T>(x, S.xform, S.xparam, S.x_f64);
-                    l2_acc_one(S, s.b[j], xt);
-                }
+            if (j < p.n_slots) {
+                const SlotP &S = p.slots[j];
+                double x = DIAG ? val[j < NL ? j : 0] : select_reg<NL>(val, S.src);
+                double xt = apply_xform<T>(x, S.xform, S.xparam, S.x_f64);
+                l2_acc_one(S, s.b[j], xt);
             }
         }
     }
 }
 
-template <typename T, int NL, int NS>
-__device__ __forceinline__ void l2_write_rec(const K1Params<T, NL, NS> &p,
-                                             const CellState<T, NL, NS> &s, int rec, int cell) {
-    if (NS > 0) {
+// one partial record: slot values of a finished (stripe, level-2 group) intersection
+template <int NB, typename T, int NL, int NS, typename ST>
+__device__ __forceinline__ void l2_write_rec(const K1Params<T, NL, NS> &p, const ST &s, int rec, int cell) {
+    if constexpr (NS > 0) {
+        if constexpr (NB >= 0) {
 #pragma unroll
-        for (int j = 0; j < NS; ++j)
-            if (j < p.n_slots)
-                p.partial[((size_t)rec * p.n_slots + j) * p.n_cells + cell] = s.b[j];
+            for (int j = 0; j < NS; ++j) {
+                const int dst = p.slots[j].dst;
+                if (dst >= 0)
+                    p.partial[((size_t)rec * p.n_slots + dst) * p.n_cells + cell] =
+                        (j < NB) ? (double)s.c[j < NB ? j : 0] : s.b[j >= NB ? j - NB : 0];
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < NS; ++j)
+                if (j < p.n_slots)
+                    p.partial[((size_t)rec * p.n_slots + j) * p.n_cells + cell] = s.b[j];
+        }
     }
 }
 
@@ -514,7 +536,7 @@ __device__ __forceinline__ void l2_write_rec(const K1Params<T, NL, NS> &p,
 // rows that never cross a level-1 group boundary; next batch's loads are issued before the
 // current batch is reduced.
 // ------------------------------------------------------------------------------------------
-template <typename T, int NL, int NS, bool DIAG, unsigned KINDS, unsigned SK>
+template <typename T, int NL, int NS, bool DIAG, unsigned KINDS, int NB>
 __global__ void __launch_bounds__(K1_THREADS)
     agf_k1_ldg(const __grid_constant__ K1Params<T, NL, NS> p) {
     const int cell = blockIdx.x * K1_THREADS + threadIdx.x;
@@ -527,9 +549,9 @@ __global__ void __launch_bounds__(K1_THREADS)
     int rec = st.rec0;
     int next_b2 = (NS > 0) ? p.b2[g2 + 1] : 0;
 
-    CellState<T, NL, NS> s;
+    CellState<T, NL, NS, NB> s;
     l1_init<KINDS>(p, s);
-    l2_init<SK>(p, s);
+    l2_init<NB>(p, s);
 
     const T *xc = p.x + cell;
     int glo = p.b1[g];      // first row of the current group
@@ -561,13 +583,13 @@ __global__ void __launch_bounds__(K1_THREADS)
             if (i < clen) l1_acc<KINDS>(p, s, cur[i]);
 
         if (ends) {
-            l1_flush<T, NL, NS, DIAG, KINDS, SK>(p, s, g, nb - glo, cell);
+            l1_flush<T, NL, NS, DIAG, KINDS, NB>(p, s, g, nb - glo, cell);
             l1_init<KINDS>(p, s);
             if (NS > 0) {
                 // close every level-2 group that ends with level-1 group g
                 if (g + 1 == next_b2 || g + 1 == g_end) {
-                    l2_write_rec(p, s, rec, cell);
-                    l2_init<SK>(p, s);
+                    l2_write_rec<NB>(p, s, rec, cell);
+                    l2_init<NB>(p, s);
                     ++rec;
                     if (g + 1 < g_end && g + 1 == next_b2) {
                         do {  // skip zero-width level-2 groups (they get no record -> NaN)
@@ -644,7 +666,7 @@ struct alignas(64) TensorMap {  // same layout as CUtensorMap (128 opaque bytes)
     unsigned long long opaque[16];
 };
 
-template <typename T, int NL, int NS, bool DIAG, unsigned KINDS, unsigned SK, int TT = tma_rows<T>(),
+template <typename T, int NL, int NS, bool DIAG, unsigned KINDS, int NB, int TT = tma_rows<T>(),
           int TMA_STAGES = TMA_STAGES_DEFAULT, int MINB = 2>
 __global__ void __launch_bounds__(TMA_THREADS, MINB)
     agf_k1_tma(const __grid_constant__ K1Params<T, NL, NS> p, const __grid_constant__ TensorMap tmap) {
@@ -694,9 +716,9 @@ __global__ void __launch_bounds__(TMA_THREADS, MINB)
     int g2 = st.g2_first;
     int rec = st.rec0;
     int next_b2 = (NS > 0) ? p.b2[g2 + 1] : 0;
-    CellState<T, NL, NS> s;
+    CellState<T, NL, NS, NB> s;
     l1_init<KINDS>(p, s);
-    l2_init<SK>(p, s);
+    l2_init<NB>(p, s);
     int k = k_begin;
     int glo = k_begin;
     int nb = p.b1[g + 1];
@@ -726,12 +748,12 @@ __global__ void __launch_bounds__(TMA_THREADS, MINB)
             r += run;
             k += run;
             if (k == nb) {  // level-1 group g is complete
-                if (active) l1_flush<T, NL, NS, DIAG, KINDS, SK>(p, s, g, nb - glo, cell);
+                if (active) l1_flush<T, NL, NS, DIAG, KINDS, NB>(p, s, g, nb - glo, cell);
                 l1_init<KINDS>(p, s);
                 if (NS > 0) {
                     if (g + 1 == next_b2 || g + 1 == g_end) {
-                        if (active) l2_write_rec(p, s, rec, cell);
-                        l2_init<SK>(p, s);
+                        if (active) l2_write_rec<NB>(p, s, rec, cell);
+                        l2_init<NB>(p, s);
                         ++rec;
                         if (g + 1 < g_end && g + 1 == next_b2) {
                             do {  // skip zero-width level-2 groups (no record -> NaN in finalize)

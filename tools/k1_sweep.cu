@@ -130,6 +130,7 @@ struct Ctx {
     double *partial;
     cudaEvent_t e0, e1;
     int reps;
+    const char *filter;
 };
 
 template <typename F>
@@ -152,8 +153,9 @@ static void report(const char *name, Ctx &c, float ms) {
     fflush(stdout);
 }
 
-template <int NS, unsigned SK, int TT, int STAGES, int MINB>
+template <int NS, int NB, int TT, int STAGES, int MINB>
 static void run_k1(Ctx &c, const char *name, int n_bins, int n_pow) {
+    if (c.filter && !strstr(name, c.filter)) return;
     K1Params<float, 1, NS> kp;
     memset(&kp, 0, sizeof(kp));
     kp.x = c.x;
@@ -169,32 +171,37 @@ static void run_k1(Ctx &c, const char *name, int n_bins, int n_pow) {
     kp.n_slots = n_bins + n_pow;
     kp.lanes[0].calc = AGF_CALC_MEAN;
     int j = 0;
-    for (int b = 0; b < n_bins; ++b, ++j) {
+    for (int b = 0; b < NB; ++b, ++j) {
         SlotP &S = kp.slots[j];
         S.calc = AGF_CALC_BINS;
-        S.t0 = -20.0 + 5.0 * b;
-        S.t1 = -15.0 + 5.0 * b;
         S.ip = 1;
+        if (b < n_bins) {
+            S.t0 = S.flo = -20.0 + 5.0 * b;
+            S.t1 = S.fhi = -15.0 + 5.0 * b;
+            S.dst = b;
+        } else {
+            S.t0 = S.flo = INFINITY;
+            S.t1 = S.fhi = -INFINITY;
+            S.dst = -1;
+        }
     }
-    for (int q = 0; q < n_pow; ++q, ++j) {
+    for (int q = 0; q < NS - NB; ++q, ++j) {
         SlotP &S = kp.slots[j];
         S.calc = AGF_CALC_SUM;
-        S.xform = q == 0 ? AGF_XF_NONE : AGF_XF_POWI;
-        S.ip = q + 1;
-        S.xparam = q + 1;
         S.x_f64 = 1;
-    }
-    for (; j < NS; ++j) {
-        SlotP &S = kp.slots[j];
-        S.ip = 1;
-        S.x_f64 = 1;
-        S.calc = (SK & SK_BINS) ? AGF_CALC_BINS : AGF_CALC_SUM;
-        S.t0 = INFINITY;
-        S.t1 = -INFINITY;
+        if (q < n_pow) {
+            S.xform = q == 0 ? AGF_XF_NONE : AGF_XF_POWI;
+            S.ip = q + 1;
+            S.xparam = q + 1;
+            S.dst = n_bins + q;
+        } else {
+            S.ip = 1;
+            S.dst = -1;
+        }
     }
     TensorMap tm = make_map(c.x, c.n_cells, c.T, TMA_CW, TT, 2);
     constexpr int smem = STAGES * TT * TMA_CW * 4 + 2 * STAGES * 8;
-    auto kern = agf_k1_tma<float, 1, NS, false, KIND_SUM, SK, TT, STAGES, MINB>;
+    auto kern = agf_k1_tma<float, 1, NS, false, KIND_SUM, NB, TT, STAGES, MINB>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     dim3 grid((c.n_cells + TMA_CW - 1) / TMA_CW, 1);
     float ms = time_it(c, [&] { kern<<<grid, TMA_THREADS, smem>>>(kp, tm); });
@@ -203,6 +210,7 @@ static void run_k1(Ctx &c, const char *name, int n_bins, int n_pow) {
 
 template <int TT, int STAGES, int MINB>
 static void run_ring(Ctx &c, const char *name, float *out) {
+    if (c.filter && !strstr(name, c.filter)) return;
     TensorMap tm = make_map(c.x, c.n_cells, c.T, TMA_CW, TT, 2);
     constexpr int smem = STAGES * TT * TMA_CW * 4 + 2 * STAGES * 8;
     auto kern = probe_ring<TT, STAGES, MINB>;
@@ -217,6 +225,7 @@ int main(int argc, char **argv) {
     c.T = argc > 1 ? atoi(argv[1]) : 8760;
     c.n_cells = argc > 2 ? atoi(argv[2]) : 721 * 1440;
     c.reps = argc > 3 ? atoi(argv[3]) : 5;
+    c.filter = argc > 4 ? argv[4] : nullptr;
     const size_t n = (size_t)c.T * c.n_cells;
     CK(cudaMalloc(&c.x, n * 4));
     fill_kernel<<<148 * 16, 512>>>(c.x, n, c.n_cells);
@@ -238,29 +247,27 @@ int main(int argc, char **argv) {
     CK(cudaMalloc(&out, 4));
     printf("raster %d x %d f32 = %.2f GB, reps %d\n", c.T, c.n_cells, n * 4 / 1e9, c.reps);
 
-    {
+    if (!c.filter) {
         float ms = time_it(c, [&] { probe_read<<<148 * 4, 512>>>((const float4 *)c.x, n / 4, out); });
         report("probe_read float4 (148x4 CTAs x 512)", c, ms);
-        ms = time_it(c, [&] { probe_read<<<148 * 8, 256>>>((const float4 *)c.x, n / 4, out); });
-        report("probe_read float4 (148x8 CTAs x 256)", c, ms);
     }
-    run_ring<24, 4, 2>(c, "probe_ring TT=24 ST=4 B=2", out);
     run_ring<24, 3, 3>(c, "probe_ring TT=24 ST=3 B=3", out);
-    run_ring<24, 2, 4>(c, "probe_ring TT=24 ST=2 B=4", out);
-    run_ring<48, 2, 2>(c, "probe_ring TT=48 ST=2 B=2", out);
-    run_ring<12, 8, 2>(c, "probe_ring TT=12 ST=8 B=2", out);
-    run_ring<24, 8, 1>(c, "probe_ring TT=24 ST=8 B=1", out);
+    run_ring<8, 9, 3>(c, "probe_ring TT=8 ST=9 B=3", out);
 
-    constexpr unsigned SB = SK_SUM | SK_BINS;
-    run_k1<16, SB, 24, 4, 2>(c, "k1 C3 (13 bins + 2 pow) TT=24 ST=4 B=2", 13, 2);
-    run_k1<16, SB, 24, 3, 3>(c, "k1 C3 TT=24 ST=3 B=3", 13, 2);
-    run_k1<16, SB, 24, 2, 4>(c, "k1 C3 TT=24 ST=2 B=4", 13, 2);
-    run_k1<16, SB, 48, 2, 2>(c, "k1 C3 TT=48 ST=2 B=2", 13, 2);
-    run_k1<16, SB, 12, 8, 2>(c, "k1 C3 TT=12 ST=8 B=2", 13, 2);
-    run_k1<16, SK_BINS, 24, 4, 2>(c, "k1 13 bins only TT=24 ST=4 B=2", 13, 0);
-    run_k1<4, SK_SUM, 24, 4, 2>(c, "k1 2 pow only TT=24 ST=4 B=2", 0, 2);
-    run_k1<1, SK_SUM, 24, 4, 2>(c, "k1 mean->sum TT=24 ST=4 B=2", 0, 1);
-    run_k1<1, SK_SUM, 24, 3, 3>(c, "k1 mean->sum TT=24 ST=3 B=3", 0, 1);
-    run_k1<1, SK_SUM, 24, 2, 4>(c, "k1 mean->sum TT=24 ST=2 B=4", 0, 1);
+#define C3(TT, ST, B) run_k1<18, 16, TT, ST, B>(c, "k1 C3 (13 bins + 2 pow) NS=18 NB=16 TT=" #TT " ST=" #ST " B=" #B, 13, 2)
+    C3(24, 4, 2);
+    C3(24, 3, 3);
+    C3(24, 2, 4);
+    C3(12, 6, 3);
+    C3(12, 4, 4);
+    C3(8, 12, 2);
+    C3(8, 9, 3);
+    C3(8, 6, 4);
+    C3(8, 5, 5);
+    C3(4, 12, 4);
+    run_k1<16, 16, 24, 3, 3>(c, "k1 13 bins only NS=16 NB=16 TT=24 ST=3 B=3", 13, 0);
+    run_k1<4, 0, 24, 3, 3>(c, "k1 2 pow only NS=4 NB=0 TT=24 ST=3 B=3", 0, 2);
+    run_k1<1, 0, 24, 3, 3>(c, "k1 mean->sum NS=1 TT=24 ST=3 B=3", 0, 1);
+    run_k1<1, 0, 8, 9, 3>(c, "k1 mean->sum NS=1 TT=8 ST=9 B=3", 0, 1);
     return 0;
 }
