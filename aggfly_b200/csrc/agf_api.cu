@@ -160,6 +160,7 @@ static int k1_select(const K1Launch &a, int mode, K1Choice *choice, int *rc) {
     int miss;
     if (a.use_tma) {
         if (f32) {
+            if (a.p->uniform_gl > 0 && !agf_k1_f32_tma_uni(a, mode, choice, rc)) return 0;
             miss = a.p->desc.n_slots > 0 ? agf_k1_f32_tma_two(a, mode, choice, rc) : agf_k1_f32_tma_single(a, mode, choice, rc);
         } else {
             miss = agf_k1_f64_tma(a, mode, choice, rc);
@@ -175,7 +176,16 @@ static int k1_select(const K1Launch &a, int mode, K1Choice *choice, int *rc) {
     return 0;
 }
 
+static int uniform_group_rows(const agf_program *p) {
+    const size_t G = p->b1.size() - 1;
+    const int gl = p->b1[1] - p->b1[0];
+    for (size_t g = 1; g < G; ++g)
+        if (p->b1[g + 1] - p->b1[g] != gl) return 0;
+    return gl > 0 ? gl : 0;
+}
+
 static int choose_kernel(agf_program *p) {
+    p->uniform_gl = p->b1.size() >= 2 ? uniform_group_rows(p) : 0;
     analyse_desc(&p->desc, &p->kinds, &p->slot_kinds, &p->n_bin_slots, &p->diag_ok);
     K1Launch q{};
     q.p = p;
@@ -269,6 +279,7 @@ extern "C" int agf_program_plan(const agf_program_desc_t *desc, int64_t n_cells,
     if (rc) return rc;
     agf_program tmp;
     tmp.desc = *desc;
+    tmp.b1.assign(desc->bounds1, desc->bounds1 + desc->n_groups1 + 1);
     rc = choose_kernel(&tmp);
     if (rc) return rc;
     const int kl = tmp.kernel_lanes, ks = tmp.kernel_slots, dg = tmp.kernel_diag;

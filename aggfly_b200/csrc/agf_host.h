@@ -19,6 +19,7 @@ struct agf_program {
     unsigned kinds = 0;       // lane kinds the program uses
     unsigned slot_kinds = 0;  // slot kinds the program uses
     int n_bin_slots = 0;      // slots of kind SK_BINS
+    int uniform_gl = 0;       // rows per level-1 group when every group has the same size, else 0
     int diag_ok = 0;     // columns (single-level) / slots (two-level) map 1:1 onto lanes
     int need_nan = 0, need_cnt = 0, has_sine = 0;
     // device copies
@@ -59,12 +60,14 @@ struct K1Choice {
     int lanes, slots, diag;
     unsigned kinds;
     int typed_bins;  // NB of the instantiation (-1: general slots)
+    int uniform_gl;  // GL of the instantiation (0: general group bounds)
 };
 
 // One per translation unit (agf_k1_*.cu).  mode 0: launch the first instantiation of that unit
 // that fits the program; mode 1: only report it in *choice.  Returns 1 if nothing in the unit fits.
 int agf_k1_f32_tma_single(const K1Launch &a, int mode, K1Choice *choice, int *rc);
 int agf_k1_f32_tma_two(const K1Launch &a, int mode, K1Choice *choice, int *rc);
+int agf_k1_f32_tma_uni(const K1Launch &a, int mode, K1Choice *choice, int *rc);
 int agf_k1_f32_ldg(const K1Launch &a, int mode, K1Choice *choice, int *rc);
 int agf_k1_f64_tma(const K1Launch &a, int mode, K1Choice *choice, int *rc);
 int agf_k1_f64_ldg(const K1Launch &a, int mode, K1Choice *choice, int *rc);

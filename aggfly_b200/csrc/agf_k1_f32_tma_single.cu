@@ -4,15 +4,15 @@
 #define AGF_TMA 1
 #define AGF_FN agf_k1_f32_tma_single
 #define AGF_LIST \
-    K1CASE(1, 0, false, KIND_SUM, NB_GENERAL)                 \
-    K1CASE(1, 0, false, KIND_DD, NB_GENERAL)                  \
-    K1CASE(16, 0, true, KIND_BINS, NB_GENERAL)                \
-    K1CASE(16, 0, true, KIND_SUM | KIND_BINS, NB_GENERAL)     \
-    K1CASE(32, 0, true, KIND_SUM | KIND_BINS, NB_GENERAL)     \
-    K1CASE(1, 0, false, KIND_ALL, NB_GENERAL)   \
-    K1CASE(4, 0, false, KIND_ALL, NB_GENERAL)   \
-    K1CASE(16, 0, true, KIND_ALL, NB_GENERAL)   \
-    K1CASE(16, 0, false, KIND_ALL, NB_GENERAL)  \
-    K1CASE(32, 0, true, KIND_ALL, NB_GENERAL)   \
-    K1CASE(32, 0, false, KIND_ALL, NB_GENERAL)
+    K1CASE(1, 0, false, KIND_SUM, NB_GENERAL, 0)                 \
+    K1CASE(1, 0, false, KIND_DD, NB_GENERAL, 0)                  \
+    K1CASE(16, 0, true, KIND_BINS, NB_GENERAL, 0)                \
+    K1CASE(16, 0, true, KIND_SUM | KIND_BINS, NB_GENERAL, 0)     \
+    K1CASE(32, 0, true, KIND_SUM | KIND_BINS, NB_GENERAL, 0)     \
+    K1CASE(1, 0, false, KIND_ALL, NB_GENERAL, 0)   \
+    K1CASE(4, 0, false, KIND_ALL, NB_GENERAL, 0)   \
+    K1CASE(16, 0, true, KIND_ALL, NB_GENERAL, 0)   \
+    K1CASE(16, 0, false, KIND_ALL, NB_GENERAL, 0)  \
+    K1CASE(32, 0, true, KIND_ALL, NB_GENERAL, 0)   \
+    K1CASE(32, 0, false, KIND_ALL, NB_GENERAL, 0)
 #include "agf_k1_inst.cuh"

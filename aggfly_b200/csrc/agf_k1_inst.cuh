@@ -29,7 +29,7 @@ static inline void set_thresholds(LaneP<double> &L, double t0, double t1) {
     L.hi = t1;
 }
 
-template <typename T, int NL, int NS, bool DIAG, unsigned KINDS, int NB, bool TMA>
+template <typename T, int NL, int NS, bool DIAG, unsigned KINDS, int NB, int GL, bool TMA>
 static int launch_k1(const K1Launch &a) {
     const agf_program *p = a.p;
     K1Params<T, NL, NS> kp;
@@ -134,7 +134,11 @@ static int launch_k1(const K1Launch &a) {
                                      (uint64_t)a.ld, TT);
         if (rc) return rc;
         constexpr int smem = STAGES * TMA_TILE_BYTES_DEFAULT + 2 * STAGES * 8;
-        auto kern = agf_k1_tma<T, NL, NS, DIAG, KINDS, NB, TT, STAGES, MINB>;
+        void (*kern)(const K1Params<T, NL, NS>, const TensorMap);
+        if constexpr (GL > 0)
+            kern = agf_k1_tma_uni<T, NL, NS, DIAG, KINDS, NB, GL, TT, STAGES, MINB>;
+        else
+            kern = agf_k1_tma<T, NL, NS, DIAG, KINDS, NB, TT, STAGES, MINB>;
         static bool attr_set = false;  // per instantiation
         if (!attr_set) {
             CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -150,8 +154,9 @@ static int launch_k1(const K1Launch &a) {
     return 0;
 }
 
-static inline bool k1_fits(const agf_program *p, int NL, int NS, bool DG, unsigned KINDS, int NB) {
+static inline bool k1_fits(const agf_program *p, int NL, int NS, bool DG, unsigned KINDS, int NB, int GL) {
     const agf_program_desc_t &d = p->desc;
+    if (GL > 0 && p->uniform_gl != GL) return false;  // uniform-group kernel: every level-1 group has GL rows
     if (d.n_lanes > NL) return false;
     if ((NS == 0) != (d.n_slots == 0) || d.n_slots > NS) return false;
     if (DG && !p->diag_ok) return false;
@@ -166,11 +171,11 @@ static inline bool k1_fits(const agf_program *p, int NL, int NS, bool DG, unsign
 
 int AGF_FN(const K1Launch &a, int mode, K1Choice *choice, int *rc) {
     const agf_program *p = a.p;
-#define K1CASE(NL, NS, DG, KINDS, NB)                                             \
-    if (k1_fits(p, NL, NS, DG, KINDS, NB)) {                                      \
-        if (choice) *choice = K1Choice{NL, NS, DG ? 1 : 0, KINDS, NB};            \
-        if (mode == 0) *rc = launch_k1<AGF_T, NL, NS, DG, KINDS, NB, AGF_TMA>(a); \
-        return 0;                                                                 \
+#define K1CASE(NL, NS, DG, KINDS, NB, GL)                                             \
+    if (k1_fits(p, NL, NS, DG, KINDS, NB, GL)) {                                      \
+        if (choice) *choice = K1Choice{NL, NS, DG ? 1 : 0, KINDS, NB, GL};            \
+        if (mode == 0) *rc = launch_k1<AGF_T, NL, NS, DG, KINDS, NB, GL, AGF_TMA>(a); \
+        return 0;                                                                     \
     }
     AGF_LIST
 #undef K1CASE

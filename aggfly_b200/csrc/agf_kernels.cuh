@@ -349,13 +349,37 @@ __device__ __forceinline__ void l1_acc(const K1Params<T, NL, NS> &p, ST &s, T v)
     }
 }
 
+// s / n for a group of n rows.  With a compile-time row count GLC and a float raster this is the
+// IEEE quotient without the division subroutine (whose special-case path ncu showed running for
+// every NaN / zero sum, ~75 instructions): rcp = RN(1/n) is exact to half an ulp, q0 = RN(s*rcp)
+// is within 1.5 ulp of s/n, the FMA residual r = s - n*q0 is exact, and RN(q0 + r*rcp) is the
+// correctly rounded quotient (Markstein's correction step: the perturbation |r/n|*2^-53 cannot
+// cross a rounding boundary because s/n with n < 2^31 is never closer than 2^-32 ulp to one, and
+// an odd n > 1 cannot produce an exact midpoint).  A sum of floats is 0, NaN, +-inf or
+// >= 2^-149 in magnitude, so there is no underflow; +-inf and NaN pass through.
+template <typename T, int GLC>
+__device__ __forceinline__ double mean_of(double s, int n) {
+    if constexpr (GLC == 1) {
+        return s;
+    } else if constexpr (GLC > 1 && sizeof(T) == 4) {
+        constexpr double dn = (double)GLC;
+        constexpr double rcp = 1.0 / dn;
+        const double q0 = s * rcp;
+        const double r = fma(-dn, q0, s);
+        const double q = fma(r, rcp, q0);
+        return (fabs(q0) <= 1.7976931348623157e308) ? q : q0;
+    } else {
+        return s / (double)n;
+    }
+}
+
 // value of lane l for a finished group of n_grp rows, rounded to the raster dtype (:143-155, :260)
-template <unsigned KINDS, typename T, int NL, int NS, typename ST>
+template <unsigned KINDS, int GLC, typename T, int NL, int NS, typename ST>
 __device__ __forceinline__ double l1_value(const K1Params<T, NL, NS> &p, const ST &s, int l, int n_grp) {
     const LaneP<T> &L = p.lanes[l];
     double r;
     if constexpr (KINDS == KIND_SUM) {
-        r = (L.calc == AGF_CALC_MEAN) ? s.a[l] / (double)n_grp : s.a[l];
+        r = (L.calc == AGF_CALC_MEAN) ? mean_of<T, GLC>(s.a[l], n_grp) : s.a[l];
     } else if constexpr (KINDS == KIND_BINS) {
         r = s.a[l];
     } else if constexpr (KINDS == KIND_DD) {
@@ -363,7 +387,7 @@ __device__ __forceinline__ double l1_value(const K1Params<T, NL, NS> &p, const S
     } else {
         switch (L.calc) {
             case AGF_CALC_MEAN:
-                r = s.a[l] / (double)n_grp;
+                r = mean_of<T, GLC>(s.a[l], n_grp);
                 break;
             case AGF_CALC_NANMEAN:
                 r = (s.nn > 0) ? s.a[l] / (double)s.nn : agf_nan();
@@ -388,7 +412,8 @@ __device__ __forceinline__ double l1_value(const K1Params<T, NL, NS> &p, const S
                 break;
         }
     }
-    if (n_grp == 0) r = agf_nan();  // empty resample bin -> NaN for every reducer
+    if constexpr (GLC == 0)
+        if (n_grp == 0) r = agf_nan();  // empty resample bin -> NaN for every reducer
     return round_to<T>(r);
 }
 
@@ -454,18 +479,26 @@ template <typename T>
 __device__ __forceinline__ void l2_acc_bins(const SlotP &S, int &c, double x) {
     if constexpr (sizeof(T) == 4) {
         const float xf = (float)x;  // exact: x holds a float
-        if (xf > S.flo && xf < S.fhi) c += 1;
+        // two compares + one predicated add (the C form compiles to add / select / move chains)
+        asm("{\n\t"
+            ".reg .pred p;\n\t"
+            "setp.gt.f32 p, %1, %2;\n\t"
+            "setp.lt.and.f32 p, %1, %3, p;\n\t"
+            "@p add.s32 %0, %0, 1;\n\t"
+            "}"
+            : "+r"(c)
+            : "f"(xf), "f"(S.flo), "f"(S.fhi));
     } else {
         if (x > S.t0 && x < S.t1) c += 1;
     }
 }
 
 // end of level-1 group g (n_grp rows): emit columns (single-level) or feed the slots
-template <typename T, int NL, int NS, bool DIAG, unsigned KINDS, int NB, typename ST>
+template <typename T, int NL, int NS, bool DIAG, unsigned KINDS, int NB, int GLC = 0, typename ST>
 __device__ __forceinline__ void l1_flush(const K1Params<T, NL, NS> &p, ST &s, int g, int n_grp, int cell) {
     double val[NL];
 #pragma unroll
-    for (int l = 0; l < NL; ++l) val[l] = (NL == 1 || l < p.n_lanes) ? l1_value<KINDS>(p, s, l, n_grp) : 0.0;
+    for (int l = 0; l < NL; ++l) val[l] = (NL == 1 || l < p.n_lanes) ? l1_value<KINDS, GLC>(p, s, l, n_grp) : 0.0;
 
     if constexpr (NS == 0) {
         bool ok = true;
@@ -771,6 +804,125 @@ __global__ void __launch_bounds__(TMA_THREADS, MINB)
         }
         __syncwarp();
         if ((threadIdx.x & 31) == 0) mbar_arrive(&empty[stg]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K1, TMA variant for uniform level-1 groups: every group of the launched stripes has exactly
+// GL rows and GL divides the tile height TT (hourly -> date: GL = TT = 24; daily data grouped by
+// date: GL = 1).  Same ring as agf_k1_tma; what goes away is the per-group bookkeeping of the
+// general kernel (run lengths, bound loads, min/compare chains: ~110 of its ~440 instructions per
+// warp-day in ncu r1c), the loop around the scan (fully unrolled: GL loads, GL converts, GL adds)
+// and the division subroutine (mean_of with a compile-time count).
+// ------------------------------------------------------------------------------------------
+template <typename T, int NL, int NS, bool DIAG, unsigned KINDS, int NB, int GL, int TT, int TMA_STAGES, int MINB>
+__global__ void __launch_bounds__(TMA_THREADS, MINB)
+    agf_k1_tma_uni(const __grid_constant__ K1Params<T, NL, NS> p, const __grid_constant__ TensorMap tmap) {
+    static_assert(TT % GL == 0, "group length must divide the tile height");
+    constexpr int TMA_TILE_BYTES = TT * TMA_CW * (int)sizeof(T);
+    constexpr int GPT = TT / GL;  // groups per tile
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    T *tiles = reinterpret_cast<T *>(smem_raw);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + TMA_STAGES * TMA_TILE_BYTES);
+    uint64_t *empty = full + TMA_STAGES;
+
+    const Stripe st = p.stripes[p.stripe0 + blockIdx.y];
+    int g = st.g1_begin;
+    const int g_end = st.g1_end;
+    if (g >= g_end) return;  // uniform
+    const int k_begin = p.b1[g];
+    const int n_groups = g_end - g;
+    const int n_tiles = (n_groups + GPT - 1) / GPT;
+    const int cell0 = blockIdx.x * TMA_CW;
+
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < TMA_STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], TMA_CW / 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (threadIdx.x >= TMA_CW) {
+        // ===== producer warp: one elected lane issues every tile load =====
+        if (threadIdx.x == TMA_CW) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+            int s = 0, ph = 0;
+            for (int i = 0; i < n_tiles; ++i) {
+                if (i >= TMA_STAGES) mbar_wait(&empty[s], ph ^ 1);
+                mbar_expect_tx(&full[s], TMA_TILE_BYTES);
+                tma_load_2d(smem_raw + s * TMA_TILE_BYTES, &tmap, cell0, (int)(k_begin + i * TT - p.row0), &full[s]);
+                if (++s == TMA_STAGES) {
+                    s = 0;
+                    ph ^= 1;
+                }
+            }
+        }
+        return;
+    }
+
+    // ===== consumers: thread t owns cell cell0 + t =====
+    const int cell = cell0 + threadIdx.x;
+    const bool active = cell < p.n_cells;
+    int g2 = st.g2_first;
+    int rec = st.rec0;
+    int next_b2 = (NS > 0) ? p.b2[g2 + 1] : 0;
+    CellState<T, NL, NS, NB> s;
+    l1_init<KINDS>(p, s);
+    l2_init<NB>(p, s);
+
+    // end of level-1 group g: flush, close level-2 groups that end with it
+    auto group_end = [&]() {
+        if (active) l1_flush<T, NL, NS, DIAG, KINDS, NB, GL>(p, s, g, GL, cell);
+        l1_init<KINDS>(p, s);
+        if constexpr (NS > 0) {
+            if (g + 1 == next_b2 || g + 1 == g_end) {
+                if (active) l2_write_rec<NB>(p, s, rec, cell);
+                l2_init<NB>(p, s);
+                ++rec;
+                if (g + 1 < g_end && g + 1 == next_b2) {
+                    do {  // skip zero-width level-2 groups (no record -> NaN in finalize)
+                        ++g2;
+                        next_b2 = p.b2[g2 + 1];
+                    } while (next_b2 == g + 1);
+                }
+            }
+        }
+        ++g;
+    };
+
+    int stg = 0, ph = 0;
+#pragma unroll 1
+    for (int i = 0; i < n_tiles; ++i) {
+        mbar_wait(&full[stg], ph);
+        const T *col = tiles + (size_t)stg * (TMA_TILE_BYTES / sizeof(T)) + threadIdx.x;
+        if constexpr (GPT == 1) {
+            // one group per tile: pull the column into registers, hand the stage back, then reduce
+            T v[TT];
+#pragma unroll
+            for (int r = 0; r < TT; ++r) v[r] = col[r * TMA_CW];
+            __syncwarp();
+            if ((threadIdx.x & 31) == 0) mbar_arrive(&empty[stg]);
+#pragma unroll
+            for (int r = 0; r < TT; ++r) l1_acc<KINDS>(p, s, v[r]);
+            group_end();
+        } else {
+            const int ng = min(GPT, g_end - g);
+#pragma unroll 1
+            for (int gi = 0; gi < ng; ++gi) {
+#pragma unroll
+                for (int r = 0; r < GL; ++r) l1_acc<KINDS>(p, s, col[(gi * GL + r) * TMA_CW]);
+                group_end();
+            }
+            __syncwarp();
+            if ((threadIdx.x & 31) == 0) mbar_arrive(&empty[stg]);
+        }
+        if (++stg == TMA_STAGES) {
+            stg = 0;
+            ph ^= 1;
+        }
     }
 }
 

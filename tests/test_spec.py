@@ -59,7 +59,7 @@ def test_shared_prefix_is_one_lane_and_one_program():
     n_str, n_rec, kl, ks, kd = (C.c_int32() for _ in range(5))
     _lib.check(_lib.lib().agf_program_plan(C.byref(desc), 1038240, 0, 148, None, 0, C.byref(n_str), C.byref(n_rec),
                                            C.byref(kl), C.byref(ks), C.byref(kd)))
-    assert (kl.value, ks.value, kd.value) == (1, 16, 0)
+    assert (kl.value, ks.value, kd.value) == (1, 20, 0)       # 16 bin counters + 4 power sums (typed slots)
 
 
 def test_hourly_bins_plus_mean_is_single_level_diag():

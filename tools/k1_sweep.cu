@@ -153,7 +153,7 @@ static void report(const char *name, Ctx &c, float ms) {
     fflush(stdout);
 }
 
-template <int NS, int NB, int TT, int STAGES, int MINB>
+template <int NS, int NB, int TT, int STAGES, int MINB, int GL = 0>
 static void run_k1(Ctx &c, const char *name, int n_bins, int n_pow) {
     if (c.filter && !strstr(name, c.filter)) return;
     K1Params<float, 1, NS> kp;
@@ -201,7 +201,11 @@ static void run_k1(Ctx &c, const char *name, int n_bins, int n_pow) {
     }
     TensorMap tm = make_map(c.x, c.n_cells, c.T, TMA_CW, TT, 2);
     constexpr int smem = STAGES * TT * TMA_CW * 4 + 2 * STAGES * 8;
-    auto kern = agf_k1_tma<float, 1, NS, false, KIND_SUM, NB, TT, STAGES, MINB>;
+    void (*kern)(const K1Params<float, 1, NS>, const TensorMap);
+    if constexpr (GL > 0)
+        kern = agf_k1_tma_uni<float, 1, NS, false, KIND_SUM, NB, GL, TT, STAGES, MINB>;
+    else
+        kern = agf_k1_tma<float, 1, NS, false, KIND_SUM, NB, TT, STAGES, MINB>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     dim3 grid((c.n_cells + TMA_CW - 1) / TMA_CW, 1);
     float ms = time_it(c, [&] { kern<<<grid, TMA_THREADS, smem>>>(kp, tm); });
@@ -254,20 +258,18 @@ int main(int argc, char **argv) {
     run_ring<24, 3, 3>(c, "probe_ring TT=24 ST=3 B=3", out);
     run_ring<8, 9, 3>(c, "probe_ring TT=8 ST=9 B=3", out);
 
-#define C3(TT, ST, B) run_k1<18, 16, TT, ST, B>(c, "k1 C3 (13 bins + 2 pow) NS=18 NB=16 TT=" #TT " ST=" #ST " B=" #B, 13, 2)
-    C3(24, 4, 2);
+#define C3(TT, ST, B) run_k1<18, 16, TT, ST, B>(c, "k1 general C3 (13 bins + 2 pow) NS=18 NB=16 TT=" #TT " ST=" #ST " B=" #B, 13, 2)
+#define U3(ST, B) run_k1<18, 16, 24, ST, B, 24>(c, "k1 uni24 C3 (13 bins + 2 pow) NS=18 NB=16 ST=" #ST " B=" #B, 13, 2)
     C3(24, 3, 3);
-    C3(24, 2, 4);
-    C3(12, 6, 3);
-    C3(12, 4, 4);
-    C3(8, 12, 2);
-    C3(8, 9, 3);
-    C3(8, 6, 4);
-    C3(8, 5, 5);
-    C3(4, 12, 4);
-    run_k1<16, 16, 24, 3, 3>(c, "k1 13 bins only NS=16 NB=16 TT=24 ST=3 B=3", 13, 0);
-    run_k1<4, 0, 24, 3, 3>(c, "k1 2 pow only NS=4 NB=0 TT=24 ST=3 B=3", 0, 2);
-    run_k1<1, 0, 24, 3, 3>(c, "k1 mean->sum NS=1 TT=24 ST=3 B=3", 0, 1);
-    run_k1<1, 0, 8, 9, 3>(c, "k1 mean->sum NS=1 TT=8 ST=9 B=3", 0, 1);
+    U3(4, 2);
+    U3(3, 3);
+    U3(2, 4);
+    U3(8, 1);
+    run_k1<32, 24, 24, 4, 2, 24>(c, "k1 uni24 24 bins + 4 pow NS=32 NB=24 ST=4 B=2", 24, 4);
+    run_k1<32, 24, 24, 3, 3, 24>(c, "k1 uni24 24 bins + 4 pow NS=32 NB=24 ST=3 B=3", 24, 4);
+    run_k1<16, 16, 24, 3, 3, 24>(c, "k1 uni24 13 bins only NS=16 NB=16 ST=3 B=3", 13, 0);
+    run_k1<4, 0, 24, 3, 3, 24>(c, "k1 uni24 2 pow only NS=4 NB=0 ST=3 B=3", 0, 2);
+    run_k1<1, 0, 24, 3, 3, 24>(c, "k1 uni24 mean->sum NS=1 ST=3 B=3", 0, 1);
+    run_k1<1, 0, 24, 3, 3>(c, "k1 general mean->sum NS=1 TT=24 ST=3 B=3", 0, 1);
     return 0;
 }
