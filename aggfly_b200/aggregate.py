@@ -16,6 +16,7 @@ import numpy as np
 import pandas as pd
 
 from . import engine as _engine
+from . import stream as _stream
 from .dataset import Dataset
 from .spec import Graph, Planner, TemporalAggregator, compile_spec
 from .timeaxis import CalendarIndex, label_values, labels_equal
@@ -70,10 +71,30 @@ def _plan(dataset: Dataset, aggregator_dict: Optional[Dict[str, list]]):
     return names, Planner(graph).plan(nodes)
 
 
+def _is_device_tensor(values) -> bool:
+    return type(values).__module__.startswith("torch") and values.is_cuda
+
+
 def _temporal_device(dataset: Dataset, aggregator_dict, target_stripes: int = 0):
+    """Temporal chains of one call -> X / V on the device.  A raster already on the device is
+    scanned in place; a host raster is streamed (chunked copies overlapped with the kernels)."""
     names, stage = _plan(dataset, aggregator_dict)
-    raster = _DeviceRaster(dataset)
-    res = _engine.run_stage(stage, raster.flat, raster.n_cells, target_stripes=target_stripes)
+    if _is_device_tensor(dataset.values):
+        raster = _DeviceRaster(dataset)
+        res = _engine.run_stage(stage, raster.flat, raster.n_cells, target_stripes=target_stripes)
+        return names, res, raster
+    import torch
+    n_cells = len(dataset.latitude) * len(dataset.longitude)
+    if not (target_stripes or _engine.OPTIONS["target_stripes"]):
+        # stripes of about four copy chunks: the kernels of a stripe start when its rows have landed
+        nbytes = int(np.prod(dataset.shape)) * dataset.dtype.itemsize
+        target_stripes = -int(min(64, nbytes // (4 * _stream.OPTIONS["chunk_bytes"])))
+    runner = _engine.StageRunner(stage, n_cells, target_stripes=target_stripes)
+    try:
+        res, raster = _stream.feed_and_run(runner, dataset.values, n_cells)
+    finally:
+        torch.cuda.current_stream().synchronize()
+        runner.close()
     return names, res, raster
 
 

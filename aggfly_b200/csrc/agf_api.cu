@@ -218,6 +218,9 @@ static void make_plan(const agf_program_desc_t *d, int64_t n_cells, int target_s
         const int64_t want_ctas = 16LL * (sm_count > 0 ? sm_count : 148);
         S = (want_ctas + cell_blocks - 1) / cell_blocks;
         S = std::min<int64_t>(S, std::max<int64_t>(1, rows / 96));  // keep stripes >= ~96 rows
+        // target_stripes < 0: "the heuristic, but at least -target_stripes" (streamed rasters want
+        // stripes no longer than a few host->device chunks so kernels start before the copy ends)
+        S = std::max<int64_t>(S, -(int64_t)target_stripes);
     }
     S = std::max<int64_t>(1, std::min<int64_t>(S, std::min<int64_t>(G1, 65535)));
 

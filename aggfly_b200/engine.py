@@ -135,7 +135,9 @@ class StageRunner:
         self.programs: List[Program] = []
         self.partials = []
         for spec in stage.programs:
-            prog = Program(spec, stage.dtype, n_cells, target_stripes)
+            # a negative target ("at least") is meant for the programs that scan the streamed raster
+            ts = target_stripes if getattr(spec, "_source", None) is None else max(target_stripes, 0)
+            prog = Program(spec, stage.dtype, n_cells, ts)
             self.programs.append(prog)
             self.partials.append(torch.empty(prog.info.partial_bytes // 8, dtype=torch.float64, device=self.device)
                                  if prog.info.partial_bytes else None)
@@ -198,6 +200,84 @@ class StageRunner:
                                                    n_cols, 0 if first else 1, sptr))
                 first = False
         self._ran_token = token
+        return self.result
+
+    # ---- streamed execution (host-resident raster, see stream.py) -------------------------------
+    def _walk(self, seen=None) -> List["StageRunner"]:
+        """This runner and the sub-stage runners it reads from, dependencies first, each once."""
+        seen = [] if seen is None else seen
+        for sub in self.inputs:
+            sub._walk(seen)
+        if self not in seen:
+            seen.append(self)
+        return seen
+
+    def begin_streamed(self, stream) -> None:
+        """Reset the per-program stripe cursors.  The programs of a stage launch in chunk order, not
+        program order, so the shared validity mask starts at 1 and every program ANDs into it."""
+        torch = _torch()
+        for r in self._walk():
+            r._cursor = [0] * len(r.programs)
+            if not hasattr(r, "_stripe_ends"):
+                r._stripe_ends = [np.array([p.stripe_rows(s)[1] for s in range(p.info.n_stripes)], dtype=np.int64)
+                                  for p in r.programs]
+            with torch.cuda.stream(stream):
+                r.V.fill_(1)
+            r._ran_token = None
+
+    def feed(self, raster, rows_ready: int, stream, k1_events=None) -> int:
+        """Rows [0, rows_ready) of ``raster`` are (stream-ordered) resident: launch every stripe of
+        every raster-reading program that is now complete.  Returns the number of launches."""
+        torch = _torch()
+        L = _lib.lib()
+        n = 0
+        for r in self._walk():
+            n_cols = len(r.stage.nodes)
+            for i, (prog, partial) in enumerate(zip(r.programs, r.partials)):
+                if getattr(prog.spec, "_source", None) is not None:
+                    continue
+                if raster.dtype != _tdtype(prog.spec.in_dtype):
+                    raise TypeError(f"raster dtype {raster.dtype} does not match the planned {prog.spec.in_dtype}")
+                s0 = r._cursor[i]
+                # stripes are ordered in time; a stripe is complete when its last row is resident
+                s1 = int(np.searchsorted(r._stripe_ends[i], rows_ready, side="right"))
+                if s1 <= s0:
+                    continue
+                pptr = partial.data_ptr() if partial is not None else None
+                ev = None
+                if k1_events is not None:
+                    ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                    ev[0].record(stream)
+                _lib.check(L.agf_temporal_run(prog.handle, raster.data_ptr(), r.n_cells, 0, s0, s1, pptr,
+                                              r.X.data_ptr(), r.V.data_ptr(), n_cols, 1, stream.cuda_stream))
+                if ev is not None:
+                    ev[1].record(stream)
+                    k1_events.append(ev)
+                r._cursor[i] = s1
+                n += 1
+        return n
+
+    def finish_streamed(self, raster, stream) -> StageResult:
+        """After the last ``feed``: merge partial records, then run the programs that read
+        materialised sub-stage results (never the raster)."""
+        L = _lib.lib()
+        sptr = stream.cuda_stream
+        for r in self._walk():
+            n_cols = len(r.stage.nodes)
+            for i, (prog, partial) in enumerate(zip(r.programs, r.partials)):
+                pptr = partial.data_ptr() if partial is not None else None
+                src = getattr(prog.spec, "_source", None)
+                if src is None:
+                    if r._cursor[i] != prog.info.n_stripes:
+                        raise RuntimeError(f"streamed run ended with {prog.info.n_stripes - r._cursor[i]} stripes "
+                                           "of a program not launched (raster shorter than the time axis?)")
+                else:
+                    sub_res = r._by_stage[id(src[0])].result
+                    ld = sub_res.n_cols * r.n_cells
+                    x_ptr = sub_res.X.data_ptr() + src[1] * r.n_cells * sub_res.X.element_size()
+                    _lib.check(L.agf_temporal_run(prog.handle, x_ptr, ld, 0, 0, prog.info.n_stripes, pptr,
+                                                  r.X.data_ptr(), r.V.data_ptr(), n_cols, 1, sptr))
+                _lib.check(L.agf_temporal_finalize(prog.handle, pptr, r.X.data_ptr(), r.V.data_ptr(), n_cols, 1, sptr))
         return self.result
 
     def close(self):

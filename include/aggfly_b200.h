@@ -155,7 +155,9 @@ const char *agf_last_error(void);
 /* ---- programs (replace numba_resample + Dataset.power/spline chains) ------------------- */
 
 /* Lower a descriptor for a raster of n_cells cells on the current device.  `target_stripes`
- * <= 0 lets the library choose how many time stripes to cut (enough CTAs to fill 148 SMs). */
+ * == 0 lets the library choose how many time stripes to cut (enough CTAs to fill 148 SMs);
+ * < 0 means "the library's choice, but at least -target_stripes" (a raster that is streamed from
+ * the host wants stripes of a few copy chunks, so that stripes can start before the copy ends). */
 int agf_program_create(agf_program_t **out, const agf_program_desc_t *desc, int64_t n_cells,
                        int32_t target_stripes);
 int agf_program_destroy(agf_program_t *prog);

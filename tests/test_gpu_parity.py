@@ -305,3 +305,44 @@ def test_no_spec_aggregates_the_raw_series():
     got = af.aggregate_dataset(weights=w, dataset=ds)
     assert list(got.columns) == ["geoid", "time", "variable"] and len(got) == len(want)
     _close(got["variable"].values, want["variable"].values, 1e-12)
+
+
+# ---- host-resident rasters: chunked feed overlapped with the kernels (stream.py) ---------------------
+@pytest.mark.parametrize("feed", ["pinned", "pageable", "pageable_f64"])
+@pytest.mark.parametrize("name", ["c3_bins_and_poly", "c3b_daily", "monthly_mix", "three_levels"])
+def test_streamed_feed_is_bitwise_the_device_resident_result(name, feed):
+    import torch
+    from aggfly_b200 import stream
+    dtype = "float64" if feed.endswith("f64") else "float32"
+    arr, t, lat, lon = _raster(dtype, True, T=24 * 40 + 5, seed=13)
+    rng = np.random.default_rng(3)
+    wdf, shp = _weights_case(lat, lon, rng)
+    want = orc.aggregate_dataset(orc.OWeights(wdf, np.arange(arr.shape[1] * arr.shape[2]), shp, "geoid", "nan"),
+                                 orc.ODataset(arr, t, lat, lon, True), aggregator_dict=SPECS[name])
+
+    def run(values):
+        ds = af.Dataset.from_arrays(values, t, lat, lon, True)
+        w = af.weights_from_objects(ds, af.GeoRegions(shp, "geoid"), zero_weight="nan")
+        w.weights = wdf
+        return af.aggregate_dataset(weights=w, dataset=ds, aggregator_dict=SPECS[name])
+
+    engine.OPTIONS["target_stripes"] = 11
+    old = dict(stream.OPTIONS)
+    try:
+        stream.OPTIONS.update(chunk_bytes=13 * arr[0].nbytes, staging_slots=3, staging_threads=2)   # 13-row chunks
+        resident = run(torch.from_numpy(arr).cuda())
+        if feed == "pinned":
+            host = torch.from_numpy(arr).pin_memory()
+            assert host.is_pinned()
+        else:
+            host = arr
+        stats_before = dict(stream.LAST_STATS)
+        streamed = run(host)
+        assert stream.LAST_STATS is not stats_before and stream.LAST_STATS["chunks"] == -(-arr.shape[0] // 13)
+        assert stream.LAST_STATS["pinned"] == (feed == "pinned")
+    finally:
+        stream.OPTIONS.update(old)
+    vals = [c for c in want.columns if c not in ("geoid", "time")]
+    assert list(streamed.columns) == list(want.columns) and len(streamed) == len(want)
+    _exact(streamed[vals].values, resident[vals].values)          # same stripes, same merge order
+    _close(streamed[vals].values, want[vals].values, 1e-11)
