@@ -16,7 +16,7 @@ MAX_LANES, MAX_SLOTS, MAX_COLS = 32, 32, 64
 E_INVALID, E_UNSUPPORTED, E_NOMEM, E_STATE = -1, -2, -3, -4
 
 CALC = {"mean": 0, "sum": 1, "min": 2, "max": 3, "nanmean": 4, "dd": 5, "bins": 6, "sine_dd": 7,
-        "_hidden_sum": 8, "_hidden_min": 9, "_hidden_max": 10}
+        "_hidden_sum": 8, "_hidden_min": 9, "_hidden_max": 10, "dd_r": 11}
 XF_NONE, XF_POWI, XF_POW, XF_SPLINE2 = 0, 1, 2, 3
 F32, F64 = 0, 1
 

@@ -69,7 +69,7 @@ struct agf_csr {
 // ------------------------------------------------------------------------------------------
 // descriptor validation + planning (host only)
 // ------------------------------------------------------------------------------------------
-static bool is_l1_calc(int c) { return c >= AGF_CALC_MEAN && c <= AGF_CALC_HIDDEN_MAX; }
+static bool is_l1_calc(int c) { return c >= AGF_CALC_MEAN && c <= AGF_CALC_DD_R; }
 static bool is_l2_calc(int c) {
     return c == AGF_CALC_MEAN || c == AGF_CALC_SUM || c == AGF_CALC_MIN || c == AGF_CALC_MAX ||
            c == AGF_CALC_DD || c == AGF_CALC_BINS;
@@ -120,7 +120,7 @@ static int validate_desc(const agf_program_desc_t *d, int64_t n_cells) {
         const agf_col_t &k = d->cols[c];
         if (k.src < 0 || k.src >= nsrc) return fail(AGF_E_INVALID, "col %d: bad src", c);
         if (!is_xform(k.xform)) return fail(AGF_E_INVALID, "col %d: bad xform", c);
-        if (d->n_slots == 0 && d->lanes[k.src].calc >= AGF_CALC_HIDDEN_SUM)
+        if (d->n_slots == 0 && d->lanes[k.src].calc >= AGF_CALC_HIDDEN_SUM && d->lanes[k.src].calc <= AGF_CALC_HIDDEN_MAX)
             return fail(AGF_E_INVALID, "col %d reads a hidden lane", c);
         if (k.dst < 0) return fail(AGF_E_INVALID, "col %d: negative dst", c);
         if (k.x_f64 && d->out_dtype != AGF_F64)
@@ -349,7 +349,7 @@ extern "C" int agf_program_create(agf_program_t **out, const agf_program_desc_t 
     }
     for (int l = 0; l < desc->n_lanes; ++l) {
         const int c = desc->lanes[l].calc;
-        if (c == AGF_CALC_MIN || c == AGF_CALC_MAX || c == AGF_CALC_DD || c == AGF_CALC_SINE_DD)
+        if (c == AGF_CALC_MIN || c == AGF_CALC_MAX || c == AGF_CALC_DD || c == AGF_CALC_DD_R || c == AGF_CALC_SINE_DD)
             p->need_nan = 1;
         if (c == AGF_CALC_NANMEAN || c == AGF_CALC_SINE_DD) p->need_cnt = 1;
         if (c == AGF_CALC_SINE_DD) p->has_sine = 1;
@@ -556,18 +556,27 @@ extern "C" int agf_spmm_run(const agf_csr_t *c, const void *d_x, int32_t x_dtype
     if (n_groups <= 0 || n_cols <= 0) return fail(AGF_E_INVALID, "bad sizes");
     int rc = check_device(c->device);
     if (rc) return rc;
-    const long long warps = (long long)c->n_regions * n_groups;
-    const long long blocks = (warps * 32 + 255) / 256;
+    // lanes per (period, region) pair: the smallest of 8 / 16 / 32 that covers the mean row length
+    const double mean_row = (double)c->nnz / (double)c->n_regions;
+    const int gs = mean_row <= 8.0 ? 8 : (mean_row <= 16.0 ? 16 : 32);
+    const long long pairs = (long long)c->n_regions * n_groups;
+    const long long blocks = (pairs * gs + 255) / 256;
     if (blocks > 0x7fffffffLL) return fail(AGF_E_UNSUPPORTED, "panel too large for one launch");
     cudaStream_t st = (cudaStream_t)stream;
-    if (x_dtype == AGF_F64)
-        agf_spmm<double><<<(unsigned)blocks, 256, 0, st>>>(c->d_row_ptr, c->d_cell_idx, c->d_w, (const double *)d_x,
-                                                           d_valid, c->n_cells, n_groups, n_cols, c->n_regions,
-                                                           d_panel, d_den);
-    else
-        agf_spmm<float><<<(unsigned)blocks, 256, 0, st>>>(c->d_row_ptr, c->d_cell_idx, c->d_w, (const float *)d_x,
-                                                          d_valid, c->n_cells, n_groups, n_cols, c->n_regions,
-                                                          d_panel, d_den);
+#define AGF_SPMM(TX, GS)                                                                                      \
+    agf_spmm<TX, GS><<<(unsigned)blocks, 256, 0, st>>>(c->d_row_ptr, c->d_cell_idx, c->d_w, (const TX *)d_x, \
+                                                       d_valid, c->n_cells, n_groups, n_cols, c->n_regions,  \
+                                                       d_panel, d_den)
+    if (x_dtype == AGF_F64) {
+        if (gs == 8) AGF_SPMM(double, 8);
+        else if (gs == 16) AGF_SPMM(double, 16);
+        else AGF_SPMM(double, 32);
+    } else {
+        if (gs == 8) AGF_SPMM(float, 8);
+        else if (gs == 16) AGF_SPMM(float, 16);
+        else AGF_SPMM(float, 32);
+    }
+#undef AGF_SPMM
     CU(cudaGetLastError());
     return 0;
 }

@@ -15,7 +15,9 @@
     K1CASE(1, 0, false, KIND_DD, NB_GENERAL, 24)        \
     K1CASE(1, 1, false, KIND_DD, 0, 24)                 \
     K1CASE(4, 4, true, KIND_DD, 0, 24)                  \
-    K1CASE(16, 0, true, KIND_BINS, NB_GENERAL, 24)      \
+    K1CASE(8, 0, true, KIND_SUM | KIND_BINS, 6, 24)     \
+    K1CASE(16, 0, true, KIND_SUM | KIND_BINS, 14, 24)   \
+    K1CASE(32, 0, true, KIND_SUM | KIND_BINS, 28, 24)   \
     K1CASE(16, 16, true, KIND_BINS, 0, 24)              \
     K1CASE(1, 1, false, KIND_SUM, 0, 1)                 \
     K1CASE(1, 4, false, KIND_SUM, 0, 1)                 \

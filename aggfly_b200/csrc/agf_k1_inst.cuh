@@ -57,8 +57,27 @@ static int launch_k1(const K1Launch &a) {
     kp.need_cnt = p->need_cnt;
     kp.has_sine = p->has_sine;
     kp.diag = DIAG;
+    // kernel lane of each program lane: identity, except for typed lanes (single-level, NB >= 0),
+    // where the bin lanes go to [0, NB) and the mean / sum lanes to [NB, NL), both in program order
+    int lane_of[AGF_MAX_LANES];
+    constexpr bool TL = typed_lanes<NS, NB>();
+    if constexpr (TL) {
+        int nb = 0, ns = NB;
+        for (int l = 0; l < d.n_lanes; ++l) lane_of[l] = (d.lanes[l].calc == AGF_CALC_BINS) ? nb++ : ns++;
+        for (int l = 0; l < NL; ++l) {  // inert pads: a bin no value falls in / a sum nobody stores
+            LaneP<T> &L = kp.lanes[l];
+            L.calc = l < NB ? AGF_CALC_BINS : AGF_CALC_SUM;
+            L.lo = (T)INFINITY;
+            L.hi = (T)-INFINITY;
+            L.t0 = INFINITY;
+            L.t1 = -INFINITY;
+            kp.cols[l].dst = -1;
+        }
+    } else {
+        for (int l = 0; l < d.n_lanes; ++l) lane_of[l] = l;
+    }
     for (int l = 0; l < d.n_lanes; ++l) {
-        LaneP<T> &L = kp.lanes[l];
+        LaneP<T> &L = kp.lanes[lane_of[l]];
         L.calc = d.lanes[l].calc;
         L.flag = d.lanes[l].flag;
         L.t0 = d.lanes[l].t0;
@@ -110,8 +129,9 @@ static int launch_k1(const K1Launch &a) {
         }
     } else {
         for (int c = 0; c < d.n_cols; ++c) {
-            ColP &C = kp.cols[c];
-            C.src = d.cols[c].src;
+            // typed lanes are diagonal (column c reads lane c): the column moves with its lane
+            ColP &C = kp.cols[TL ? lane_of[d.cols[c].src] : c];
+            C.src = TL ? lane_of[d.cols[c].src] : d.cols[c].src;
             C.xform = d.cols[c].xform;
             C.xparam = d.cols[c].xparam;
             C.x_f64 = d.cols[c].x_f64;
@@ -125,7 +145,7 @@ static int launch_k1(const K1Launch &a) {
         // C3 program: 3 CTAs x 3 stages 6.87 TB/s, 2 x 4 6.01 TB/s, 4 x 2 6.68 TB/s; tiles of 8 or
         // 12 rows lose 20-40% to per-tile synchronisation): three 9-warp CTAs per SM need <= 72
         // registers per thread, two need <= 112.
-        constexpr int state_regs = 2 * NL + (NB >= 0 ? NB + 2 * (NS - NB) : 2 * NS);
+        constexpr int state_regs = TL ? NB + 2 * (NL - NB) : 2 * NL + (NB >= 0 ? NB + 2 * (NS - NB) : 2 * NS);
         constexpr int MINB = state_regs <= 30 ? 3 : (state_regs <= 48 ? 2 : 1);
         constexpr int STAGES = MINB == 3 ? 3 : (MINB == 2 ? 4 : 8);
         constexpr int TT = tma_rows<T>();
@@ -161,6 +181,12 @@ static inline bool k1_fits(const agf_program *p, int NL, int NS, bool DG, unsign
     if ((NS == 0) != (d.n_slots == 0) || d.n_slots > NS) return false;
     if (DG && !p->diag_ok) return false;
     if (NS > 0 && NL > 4 && !DG) return false;  // select-chain form only for <= 4 lanes
+    if (NS == 0 && NB >= 0) {  // typed lanes: bins -> [0, NB), mean / sum -> [NB, NL); diagonal columns
+        if (!DG || !p->diag_ok || (p->kinds & ~(KIND_SUM | KIND_BINS))) return false;
+        int nbins = 0;
+        for (int l = 0; l < d.n_lanes; ++l) nbins += d.lanes[l].calc == AGF_CALC_BINS;
+        if (nbins > NB || d.n_lanes - nbins > NL - NB) return false;
+    }
     if (NS > 0 && NB >= 0) {                     // typed slots: bins -> [0, NB), power sums -> [NB, NS)
         if (p->slot_kinds & SK_GEN) return false;
         if (p->n_bin_slots > NB || d.n_slots - p->n_bin_slots > NS - NB) return false;

@@ -36,7 +36,8 @@ enum : unsigned {
     KIND_DD = 8u,       // degree days
     KIND_BINS = 16u,    // bin counts
     KIND_SINE = 32u,    // sine_dd + its hidden sum/min/max helper lanes
-    KIND_ALL = 63u
+    KIND_DDR = 64u,     // degree days with every term rounded to the raster dtype (AGF_CALC_DD_R)
+    KIND_ALL = 127u
 };
 
 __host__ __device__ constexpr unsigned kind_of_calc(int calc) {
@@ -44,6 +45,7 @@ __host__ __device__ constexpr unsigned kind_of_calc(int calc) {
            : (calc == AGF_CALC_NANMEAN)                      ? KIND_NANMEAN
            : (calc == AGF_CALC_MIN || calc == AGF_CALC_MAX)  ? KIND_MINMAX
            : (calc == AGF_CALC_DD)                           ? KIND_DD
+           : (calc == AGF_CALC_DD_R)                         ? KIND_DDR
            : (calc == AGF_CALC_BINS)                         ? KIND_BINS
                                                              : KIND_SINE;
 }
@@ -240,18 +242,37 @@ __device__ __forceinline__ double sine_dd_value(double tavg, double tmin, double
 // ------------------------------------------------------------------------------------------
 // per-thread reducer state (everything statically indexed -> registers)
 // ------------------------------------------------------------------------------------------
+// Typed lanes (single-level programs, NS == 0 and NB >= 0): the launcher orders the lanes so that
+// kernel lanes [0, NB) are bin counters (int registers, predicated adds) and [NB, NL) are mean / sum
+// lanes (double registers) -- the level-1 mirror of the typed slots.
+template <int NS, int NB>
+__host__ __device__ constexpr bool typed_lanes() {
+    return NS == 0 && NB >= 0;
+}
+
 template <typename T, int NL, int NS, int NB = NB_GENERAL>
 struct CellState {
+    static constexpr bool TL = typed_lanes<NS, NB>();
     static constexpr int ND = (NB >= 0) ? (NS - NB) : NS;  // double-typed level-2 accumulators
-    double a[NL];               // level-1 accumulators
-    double b[ND > 0 ? ND : 1];  // level-2 accumulators (typed form: the power sums)
-    int c[NB > 0 ? NB : 1];     // level-2 bin counters (typed form only)
+    static constexpr int NA = TL ? (NL - NB) : NL;         // double-typed level-1 accumulators
+    double a[NA > 0 ? NA : 1];  // level-1 accumulators (typed lanes: the mean / sum lanes)
+    double b[ND > 0 ? ND : 1];  // level-2 accumulators (typed slots: the power sums)
+    int c[NB > 0 ? NB : 1];     // bin counters: level-2 (typed slots) or level-1 (typed lanes)
     int nn;                     // non-NaN values in the current level-1 group
     bool nan;                   // NaN seen in the current level-1 group
 };
 
 template <unsigned KINDS, typename T, int NL, int NS, typename ST>
 __device__ __forceinline__ void l1_init(const K1Params<T, NL, NS> &p, ST &s) {
+    if constexpr (ST::TL) {
+#pragma unroll
+        for (int j = 0; j < NL - ST::NA; ++j) s.c[j] = 0;
+#pragma unroll
+        for (int l = 0; l < ST::NA; ++l) s.a[l] = 0.0;
+        s.nn = 0;
+        s.nan = false;
+        return;
+    }
 #pragma unroll
     for (int l = 0; l < NL; ++l) {
         if constexpr ((KINDS & (KIND_MINMAX | KIND_SINE)) == 0) {
@@ -285,13 +306,37 @@ __device__ __forceinline__ void l2_init(const K1Params<T, NL, NS> &p, ST &s) {
     }
 }
 
+// c += (v > lo && v < hi): two compares + one predicated add (the C form compiles to add / select /
+// move chains).  lo / hi are the thresholds rounded outward to the raster dtype (set_thresholds).
+__device__ __forceinline__ void count_in_range(int &c, float v, float lo, float hi) {
+    asm("{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.gt.f32 p, %1, %2;\n\t"
+        "setp.lt.and.f32 p, %1, %3, p;\n\t"
+        "@p add.s32 %0, %0, 1;\n\t"
+        "}"
+        : "+r"(c)
+        : "f"(v), "f"(lo), "f"(hi));
+}
+__device__ __forceinline__ void count_in_range(int &c, double v, double lo, double hi) {
+    if (v > lo && v < hi) c += 1;
+}
+
 // one raster value into every level-1 lane (nb_kernels.py:134-141, 170-177, 193-196, 213-220)
 template <unsigned KINDS, typename T, int NL, int NS, typename ST>
 __device__ __forceinline__ void l1_acc(const K1Params<T, NL, NS> &p, ST &s, T v) {
     const double vd = (double)v;
+    if constexpr (ST::TL) {  // typed lanes: straight-line, no per-lane dispatch
+        constexpr int NBL = NL - ST::NA;
+#pragma unroll
+        for (int j = 0; j < NBL; ++j) count_in_range(s.c[j], v, p.lanes[j].lo, p.lanes[j].hi);
+#pragma unroll
+        for (int l = 0; l < ST::NA; ++l) s.a[l] += vd;  // a NaN value poisons the sum
+        return;
+    }
     bool isn = false;
-    if constexpr ((KINDS & (KIND_NANMEAN | KIND_MINMAX | KIND_DD | KIND_SINE)) != 0) isn = (v != v);
-    if constexpr ((KINDS & (KIND_MINMAX | KIND_DD | KIND_SINE)) != 0) s.nan |= isn;
+    if constexpr ((KINDS & (KIND_NANMEAN | KIND_MINMAX | KIND_DD | KIND_DDR | KIND_SINE)) != 0) isn = (v != v);
+    if constexpr ((KINDS & (KIND_MINMAX | KIND_DD | KIND_DDR | KIND_SINE)) != 0) s.nan |= isn;
     if constexpr ((KINDS & (KIND_NANMEAN | KIND_SINE)) != 0) s.nn += isn ? 0 : 1;
 #pragma unroll
     for (int l = 0; l < NL; ++l) {
@@ -303,6 +348,8 @@ __device__ __forceinline__ void l1_acc(const K1Params<T, NL, NS> &p, ST &s, T v)
                 if (v > L.lo && v < L.hi) s.a[l] += 1.0;
             } else if constexpr (KINDS == KIND_DD) {
                 if (v > L.lo && v < L.hi) s.a[l] += fabs(vd - L.base);
+            } else if constexpr (KINDS == KIND_DDR) {
+                if (v > L.lo && v < L.hi) s.a[l] += round_to<T>(fabs(vd - L.base));
             } else {
                 switch (L.calc) {
                     case AGF_CALC_MEAN:
@@ -336,6 +383,10 @@ __device__ __forceinline__ void l1_acc(const K1Params<T, NL, NS> &p, ST &s, T v)
                     case AGF_CALC_DD:
                         if constexpr ((KINDS & KIND_DD) != 0)
                             if (v > L.lo && v < L.hi) s.a[l] += fabs(vd - L.base);
+                        break;
+                    case AGF_CALC_DD_R:
+                        if constexpr ((KINDS & KIND_DDR) != 0)
+                            if (v > L.lo && v < L.hi) s.a[l] += round_to<T>(fabs(vd - L.base));
                         break;
                     case AGF_CALC_BINS:
                         if constexpr ((KINDS & KIND_BINS) != 0)
@@ -382,7 +433,7 @@ __device__ __forceinline__ double l1_value(const K1Params<T, NL, NS> &p, const S
         r = (L.calc == AGF_CALC_MEAN) ? mean_of<T, GLC>(s.a[l], n_grp) : s.a[l];
     } else if constexpr (KINDS == KIND_BINS) {
         r = s.a[l];
-    } else if constexpr (KINDS == KIND_DD) {
+    } else if constexpr (KINDS == KIND_DD || KINDS == KIND_DDR) {
         r = s.nan ? agf_nan() : s.a[l];
     } else {
         switch (L.calc) {
@@ -395,6 +446,7 @@ __device__ __forceinline__ double l1_value(const K1Params<T, NL, NS> &p, const S
             case AGF_CALC_MIN:
             case AGF_CALC_MAX:
             case AGF_CALC_DD:
+            case AGF_CALC_DD_R:
                 r = s.nan ? agf_nan() : s.a[l];
                 break;
             case AGF_CALC_SINE_DD:
@@ -478,24 +530,40 @@ __device__ __forceinline__ void l2_acc_sum(const SlotP &S, double &b, double x) 
 template <typename T>
 __device__ __forceinline__ void l2_acc_bins(const SlotP &S, int &c, double x) {
     if constexpr (sizeof(T) == 4) {
-        const float xf = (float)x;  // exact: x holds a float
-        // two compares + one predicated add (the C form compiles to add / select / move chains)
-        asm("{\n\t"
-            ".reg .pred p;\n\t"
-            "setp.gt.f32 p, %1, %2;\n\t"
-            "setp.lt.and.f32 p, %1, %3, p;\n\t"
-            "@p add.s32 %0, %0, 1;\n\t"
-            "}"
-            : "+r"(c)
-            : "f"(xf), "f"(S.flo), "f"(S.fhi));
+        count_in_range(c, (float)x, S.flo, S.fhi);  // exact: x holds a float
     } else {
-        if (x > S.t0 && x < S.t1) c += 1;
+        count_in_range(c, x, S.t0, S.t1);
     }
 }
 
 // end of level-1 group g (n_grp rows): emit columns (single-level) or feed the slots
 template <typename T, int NL, int NS, bool DIAG, unsigned KINDS, int NB, int GLC = 0, typename ST>
 __device__ __forceinline__ void l1_flush(const K1Params<T, NL, NS> &p, ST &s, int g, int n_grp, int cell) {
+    if constexpr (ST::TL) {
+        // typed lanes: column of kernel lane l is cols[l].dst (-1: inert pad, nothing stored)
+        constexpr int NBL = NL - ST::NA;
+        const bool empty = (GLC == 0) && n_grp == 0;  // empty resample bin -> NaN for every reducer
+        bool ok = !empty;
+        const size_t base = (size_t)g * p.out_ncols;
+#pragma unroll
+        for (int j = 0; j < NBL; ++j) {
+            const int dst = p.cols[j].dst;
+            if (dst >= 0) store_col<T>(p.out, p.out_f64, (base + dst) * p.n_cells + cell, empty ? agf_nan() : (double)s.c[j]);
+        }
+#pragma unroll
+        for (int l = 0; l < ST::NA; ++l) {
+            const int dst = p.cols[NBL + l].dst;
+            if (dst >= 0) {
+                double r = (p.lanes[NBL + l].calc == AGF_CALC_MEAN) ? mean_of<T, GLC>(s.a[l], n_grp) : s.a[l];
+                r = empty ? agf_nan() : round_to<T>(r);
+                ok &= (r == r);
+                store_col<T>(p.out, p.out_f64, (base + dst) * p.n_cells + cell, r);
+            }
+        }
+        unsigned char *vp = p.valid + (size_t)g * p.n_cells + cell;
+        *vp = (p.valid_and ? (*vp != 0) && ok : ok) ? 1 : 0;
+        return;
+    }
     double val[NL];
 #pragma unroll
     for (int l = 0; l < NL; ++l) val[l] = (NL == 1 || l < p.n_lanes) ? l1_value<KINDS, GLC>(p, s, l, n_grp) : 0.0;

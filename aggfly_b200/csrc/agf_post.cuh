@@ -62,30 +62,37 @@ __global__ void __launch_bounds__(256) agf_finalize(const __grid_constant__ FinP
 }
 
 // ------------------------------------------------------------------------------------------
-// K2: CSR weighted regional average, one warp per (region, period)
+// K2: CSR weighted regional average.  A group of GS lanes (8, 16 or 32, picked from the mean row
+// length) owns one (period g, region r) pair; pairs are numbered g-major / r-fastest so that the
+// warps in flight at any moment gather from the same X[g, c, :] planes at neighbouring cells
+// (regions are spatially coherent in shapefile order): DRAM pages and 32-byte sectors touched by
+// one region are still open / in L2 when its neighbours read them.  (r-major numbering made every
+// warp of a CTA read a different 58 MB-apart plane: 40 ms for the C3b daily panel.)
 // ------------------------------------------------------------------------------------------
 constexpr int SPMM_NCB = 8;  // columns accumulated per pass over a region's entries
 
-template <typename TX>
+template <typename TX, int GS>
 __global__ void __launch_bounds__(256)
     agf_spmm(const int *__restrict__ row_ptr, const int *__restrict__ cell_idx,
              const double *__restrict__ w, const TX *__restrict__ X,
              const unsigned char *__restrict__ V, long long n_cells, long long G, int n_cols,
              int n_regions, double *__restrict__ panel, double *__restrict__ den_out) {
-    const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (wid >= (long long)n_regions * G) return;
-    const int r = (int)(wid / G);
-    const long long g = wid % G;
+    const long long gid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / GS;
+    const int lane = threadIdx.x % GS;
+    if (gid >= (long long)n_regions * G) return;  // whole groups leave together (256 % GS == 0)
+    const long long g = gid / n_regions;
+    const int r = (int)(gid % n_regions);
     const int e0 = row_ptr[r], e1 = row_ptr[r + 1];
     const unsigned char *Vg = V + (size_t)g * n_cells;
+    // lanes of this group inside the warp (shuffles must name exactly the participating lanes)
+    const unsigned gmask = (GS == 32) ? 0xffffffffu : (((1u << GS) - 1u) << ((threadIdx.x & 31) / GS * GS));
 
     for (int c0 = 0; c0 < n_cols; c0 += SPMM_NCB) {
         double acc[SPMM_NCB];
 #pragma unroll
         for (int c = 0; c < SPMM_NCB; ++c) acc[c] = 0.0;
         double den = 0.0;
-        for (int e = e0 + lane; e < e1; e += 32) {
+        for (int e = e0 + lane; e < e1; e += GS) {
             const int cell = cell_idx[e];
             const double we = w[e];
             if (Vg[cell]) {
@@ -97,10 +104,10 @@ __global__ void __launch_bounds__(256)
             }
         }
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            den += __shfl_xor_sync(0xffffffffu, den, off);
+        for (int off = GS / 2; off > 0; off >>= 1) {
+            den += __shfl_xor_sync(gmask, den, off);
 #pragma unroll
-            for (int c = 0; c < SPMM_NCB; ++c) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], off);
+            for (int c = 0; c < SPMM_NCB; ++c) acc[c] += __shfl_xor_sync(gmask, acc[c], off);
         }
         if (lane == 0) {
 #pragma unroll

@@ -305,9 +305,32 @@ class Planner:
             return ("l1", a.freq)
         # s1 is an aggregate: can agg2(mid?(agg1(raw))) be fused?
         s2, pre = _peel(s1.src)
+        if s2.kind == "raw" and not pre and not mid and self._collapsed_lane(s1, a) is not None:
+            return ("l1c", s1.freq, a.freq)
         if (s2.kind == "raw" and not pre and len(mid) <= 1 and a.calc in FUSABLE_L2):
             return ("l2", s1.freq, a.freq)
         return ("outer", a.src.key, a.freq)     # single-level program over the materialised a.src
+
+    def _collapsed_lane(self, s1: Node, a: Node):
+        """``a(s1(raw))`` where every group of ``s1`` is exactly ONE row (daily data grouped by date):
+        the inner step is the identity (mean / sum / min / max / nanmean of one value), a 0/1 bin
+        indicator, or one degree-day term, so the pair is a single-level reduction of the raster
+        over the composed bounds.  Returns the (calc, ddargs) of that lane, or None.
+
+        Same bits as the two-step chain: a one-value mean is the value itself, counts are exact,
+        and ``dd_r`` rounds every degree-day term to the raster dtype before adding it (the inner
+        step stores its result in the input dtype, nb_kernels.py:260)."""
+        b1, _ = self.g.axis(s1)
+        n_rows = len(self.g.labels(self.g.raw))
+        if len(b1) - 1 != n_rows or (n_rows and not np.all(np.diff(b1) == 1)):
+            return None
+        if s1.calc in ("mean", "sum", "min", "max", "nanmean"):
+            return (a.calc, a.dd)
+        if s1.calc == "dd" and a.calc == "sum":
+            return ("dd_r", s1.dd)
+        if s1.calc == "bins" and a.calc == "sum":
+            return ("bins", s1.dd)
+        return None
 
     # ---- lowering ------------------------------------------------------------------------------
     def _lower_group(self, stage: Stage, pat: tuple, members: List[Tuple[int, Node]]):
@@ -325,6 +348,13 @@ class Planner:
             a0, _ = _peel(members[0][1])
             b1, _ = self.g.axis(a0)
             self._emit_single_level(stage, self.g.raw, b1, pat[1], members)
+        elif kind == "l1c":
+            a0, _ = _peel(members[0][1])
+            b1, _ = self.g.axis(a0.src)                       # one row per inner group
+            b2, _ = self.g.axis(a0)
+            composed = np.asarray(b1)[np.asarray(b2)]
+            self._emit_single_level(stage, self.g.raw, composed, pat[2], members,
+                                    lane_of=lambda a: self._collapsed_lane(_peel(a.src)[0], a))
         elif kind == "outer":
             a0, _ = _peel(members[0][1])
             inner = a0.src
@@ -344,13 +374,13 @@ class Planner:
             self._materialised[node.key] = hit
         return hit
 
-    def _emit_single_level(self, stage, input_node, b1, freq, members, identity=False, source=None):
+    def _emit_single_level(self, stage, input_node, b1, freq, members, identity=False, source=None, lane_of=None):
         n_time = int(len(self.g.labels(input_node)))
         prog = None
         for col, node in members:
             a, tail = _peel(node)
             xf, xparam, xnode = _xf_fields(tail)
-            calc, dd = ("mean", None) if identity else (a.calc, a.dd)
+            calc, dd = ("mean", None) if identity else (lane_of(a) if lane_of is not None else (a.calc, a.dd))
             need = (1 if calc != "sine_dd" else 4)
             if prog is None or len(prog.lanes) + need > _lib.MAX_LANES or len(prog.cols) + 1 > _lib.MAX_COLS:
                 prog = ProgramSpec(input=input_node, in_dtype=input_node.dtype, bounds1=b1, bounds2=None,

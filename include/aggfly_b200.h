@@ -69,7 +69,10 @@ enum {
     AGF_CALC_SINE_DD = 7,  /* single-sine degree days,                 nb_kernels.py:202-251 */
     AGF_CALC_HIDDEN_SUM = 8, /* helper lanes the host inserts in front of SINE_DD lanes */
     AGF_CALC_HIDDEN_MIN = 9,
-    AGF_CALC_HIDDEN_MAX = 10
+    AGF_CALC_HIDDEN_MAX = 10,
+    AGF_CALC_DD_R = 11     /* dd whose every term |v - base| is rounded to the raster dtype before it is
+                              added: the one-pass form of `dd` over single-row groups followed by `sum`
+                              (daily data: dd/date -> sum/month), same bits as the two-step chain */
 };
 
 /* transforms between / after aggregate steps: aggfly/dataset/dataset.py:442-481, 527-543 */

@@ -346,3 +346,69 @@ def test_streamed_feed_is_bitwise_the_device_resident_result(name, feed):
     assert list(streamed.columns) == list(want.columns) and len(streamed) == len(want)
     _exact(streamed[vals].values, resident[vals].values)          # same stripes, same merge order
     _close(streamed[vals].values, want[vals].values, 1e-11)
+
+
+# ---- daily rasters: single-row inner groups collapse to one pass (spec.Planner._collapsed_lane) ----------
+DAILY_SPECS = {
+    "gdd_month": dict(gdd=[("aggregate", {"calc": "dd", "groupby": "date", "ddargs": [10, 30, 0]}),
+                           ("aggregate", {"calc": "sum", "groupby": "month"})]),
+    "gdd_year_two": dict(x=[("aggregate", {"calc": "dd", "groupby": "date", "ddargs": [[10, 30, 0], [0.1, 17.3, 1]]}),
+                            ("aggregate", {"calc": "sum", "groupby": "year"})]),
+    "mixed_month": dict(
+        gdd=[("aggregate", {"calc": "dd", "groupby": "date", "ddargs": [10, 30, 0]}), ("aggregate", {"calc": "sum", "groupby": "month"})],
+        tavg=[("aggregate", {"calc": "mean", "groupby": "date"}), ("aggregate", {"calc": "mean", "groupby": "month"})],
+        hot=[("aggregate", {"calc": "bins", "groupby": "date", "ddargs": [[25, 99, 0], [-99, 0, 0]]}),
+             ("aggregate", {"calc": "sum", "groupby": "month"})],
+        tx=[("aggregate", {"calc": "max", "groupby": "date"}), ("aggregate", {"calc": "max", "groupby": "month"})],
+        nm=[("aggregate", {"calc": "nanmean", "groupby": "date"}), ("aggregate", {"calc": "nanmean", "groupby": "month"})]),
+    "poly_month": dict(p=[("aggregate", {"calc": "mean", "groupby": "date"}),
+                          ("transform", {"transform": "power", "exp": np.arange(1, 4)}),
+                          ("aggregate", {"calc": "sum", "groupby": "month"})]),
+    "daily_bins_of_daily": dict(b=[("aggregate", {"calc": "mean", "groupby": "date"}),
+                                   ("aggregate", {"calc": "bins", "groupby": "month", "ddargs": BINS13})],
+                                m=[("aggregate", {"calc": "mean", "groupby": "month"})]),
+}
+
+
+@pytest.mark.parametrize("name", list(DAILY_SPECS))
+@pytest.mark.parametrize("calendar", ["standard", "noleap"])
+@pytest.mark.parametrize("stripes", [1, 7])
+def test_daily_raster_chains_match_oracle(name, calendar, stripes):
+    engine.OPTIONS["target_stripes"] = stripes
+    n = 365 * 2 + 40
+    rng = np.random.default_rng(21)
+    arr = (14 + 12 * np.sin(2 * np.pi * np.arange(n) / 365.0)[:, None, None] + rng.normal(0, 6, (n, 4, 7))).astype(np.float32)
+    arr[rng.random(arr.shape) < 0.002] = np.nan
+    arr[:, 0, 0] = np.nan
+    lat, lon = np.linspace(40, 37, 4), np.linspace(250, 256, 7)
+    if calendar == "standard":
+        t = pd.date_range("1999-03-05", periods=n, freq="D")
+        got, want = _both_time(arr, t, lat, lon, DAILY_SPECS[name])
+    else:
+        want = orc.aggregate_time(orc.ODataset(arr, orc.cal_range("noleap", 1999, n), lat, lon, True), DAILY_SPECS[name])
+        got = af.aggregate_time(dataset=af.Dataset.from_arrays(arr, af.CalendarIndex.range("noleap", 1999, n), lat, lon, True),
+                                weights=None, aggregator_dict=DAILY_SPECS[name])
+        assert list(got) == list(want)
+    for k in want:
+        assert got[k].values.dtype == want[k][0].dtype, k
+        if stripes == 1 or "hot" in k or k in ("tx",) or k.startswith("b_"):
+            _exact(got[k].values, want[k][0])
+        else:
+            _close(got[k].values, want[k][0], 1e-12)
+
+
+def test_hourly_bins_and_mean_by_date_typed_lanes_many_shapes():
+    """bins + mean per date on hourly data: the typed-lane kernels (int bin counters) with 3, 13 and
+    27 bins, ragged first/last day, NaNs."""
+    for nb in (3, 13, 27):
+        bins = [[-30 + 3.0 * i, -27 + 3.0 * i + (0.5 if i % 2 else 0.0), 0] for i in range(nb)]
+        spec = dict(hb=[("aggregate", {"calc": "bins", "groupby": "date", "ddargs": bins})],
+                    tavg=[("aggregate", {"calc": "mean", "groupby": "date"})],
+                    tsum=[("aggregate", {"calc": "sum", "groupby": "date"})])
+        for T in (24 * 12, 24 * 12 + 7):
+            arr, t, lat, lon = _raster("float32", True, T=T, Y=3, X=70, seed=nb)
+            if T % 24 == 0:
+                t = pd.date_range("2001-11-20 00:00", periods=T, freq="h")       # uniform 24-row groups
+            got, want = _both_time(arr, t, lat, lon, spec)
+            for k in want:
+                _exact(got[k].values, want[k][0])

@@ -122,3 +122,32 @@ def test_temporal_aggregator_attributes():
     a = TemporalAggregator("dd", "date", ddargs=[10, 30, 0])
     assert (a.calc, a.groupby, a.multi_dd, a.kwargs) == ("dd", "1D", False, {"ddargs": [10, 30, 0]})
     assert TemporalAggregator("bins", "month", ddargs=[[0, 1, 0], [1, 2, 0]]).multi_dd
+
+
+def test_single_row_inner_groups_collapse_to_one_level():
+    """Daily data grouped by date: the inner step is per-value, so dd/date -> sum/month is ONE
+    single-level program over the composed (month) bounds -- no partial records, no finalize."""
+    from aggfly_b200.timeaxis import CalendarIndex
+    t = CalendarIndex.range("noleap", 1950, 365 * 3)
+    spec = dict(gdd=[("aggregate", {"calc": "dd", "groupby": "date", "ddargs": [10, 30, 0]}),
+                     ("aggregate", {"calc": "sum", "groupby": "month"})],
+                tavg=[("aggregate", {"calc": "mean", "groupby": "date"}), ("aggregate", {"calc": "mean", "groupby": "month"})],
+                hot=[("aggregate", {"calc": "bins", "groupby": "date", "ddargs": [30, 99, 0]}),
+                     ("aggregate", {"calc": "sum", "groupby": "month"})])
+    g, outs, stage = _plan(spec, t=t)
+    assert len(stage.programs) == 1 and not stage.programs[0].two_level and not stage.inputs
+    p = stage.programs[0]
+    assert [(l.calc, l.dd) for l in p.lanes] == [("dd_r", (10.0, 30.0, 0.0)), ("mean", None), ("bins", (30.0, 99.0, 0.0))]
+    assert len(p.bounds1) == 37 and list(p.bounds1[:4]) == [0, 31, 59, 90] and p.bounds1[-1] == 365 * 3
+    # hourly data: groups of 24 rows do not collapse
+    _, _, stage = _plan(spec)
+    assert all(q.two_level for q in stage.programs)
+    # a transform between the steps keeps the two-level form (the power applies to the daily value)
+    _, _, stage = _plan(dict(a=[("aggregate", {"calc": "mean", "groupby": "date"}),
+                                ("transform", {"transform": "power", "exp": np.arange(1, 3)}),
+                                ("aggregate", {"calc": "sum", "groupby": "month"})]), t=t)
+    assert all(q.two_level for q in stage.programs)
+    # dd -> mean is not a plain sum of rounded terms: stays two-level
+    _, _, stage = _plan(dict(a=[("aggregate", {"calc": "dd", "groupby": "date", "ddargs": [10, 30, 0]}),
+                                ("aggregate", {"calc": "mean", "groupby": "month"})]), t=t)
+    assert all(q.two_level for q in stage.programs)
