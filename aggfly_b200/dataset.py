@@ -148,6 +148,14 @@ class Dataset:
         new.history = list(self.history)
         return new
 
+    def isel_time(self, row0: int, row1: int) -> "Dataset":
+        """Rows [row0, row1) of the time axis (a view of the raster, no copy)."""
+        new = copy(self)
+        new.values = self.values[row0:row1]
+        new.time = self.time[row0:row1]
+        new.history = list(self.history)
+        return new
+
     def lon_sort_order(self) -> np.ndarray:
         """Column order the reference's ``rescale_longitude`` puts a 0-360 raster in
         (relabel to -180..180, then ``sortby('longitude')``; dataset.py:419-440,

@@ -412,3 +412,32 @@ def test_hourly_bins_and_mean_by_date_typed_lanes_many_shapes():
             got, want = _both_time(arr, t, lat, lon, spec)
             for k in want:
                 _exact(got[k].values, want[k][0])
+
+
+def test_sharded_call_world1_nccl_equals_plain_call():
+    """aggregate_dataset_sharded through NCCL (world_size 1 on this box's GPU) == aggregate_dataset."""
+    import socket
+    import torch
+    import torch.distributed as dist
+    from aggfly_b200 import shard
+    arr, t, lat, lon = _raster("float32", True, T=24 * 500, Y=4, X=6, seed=17)          # spans two year ends
+    rng = np.random.default_rng(4)
+    wdf, shp = _weights_case(lat, lon, rng)
+    spec = SPECS["monthly_mix"]
+    ds = af.Dataset.from_arrays(arr, t, lat, lon, True)
+    w = af.weights_from_objects(ds, af.GeoRegions(shp, "geoid"), zero_weight="nan")
+    w.weights = wdf
+    plain = af.aggregate_dataset(weights=w, dataset=ds, aggregator_dict=spec)
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=0, world_size=1,
+                            device_id=torch.device("cuda", 0))
+    try:
+        sharded = shard.aggregate_dataset_sharded(w, ds, spec, shard_by="year")
+    finally:
+        dist.destroy_process_group()
+    assert list(sharded.columns) == list(plain.columns) and len(sharded) == len(plain)
+    vals = [c for c in plain.columns if c not in ("geoid", "time")]
+    assert (sharded["time"].values == plain["time"].values).all()
+    _exact(sharded[vals].values, plain[vals].values)
