@@ -12,6 +12,7 @@ from typing import Optional
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libaggfly_b200.so")
 
+ABI_VERSION = 2                      # AGF_ABI_VERSION of include/aggfly_b200.h
 MAX_LANES, MAX_SLOTS, MAX_COLS = 32, 32, 64
 E_INVALID, E_UNSUPPORTED, E_NOMEM, E_STATE = -1, -2, -3, -4
 
@@ -36,12 +37,20 @@ class Col(C.Structure):
                 ("x_f64", C.c_int32), ("dst", C.c_int32)]
 
 
+MAX_PRE = 4
+
+
+class Pre(C.Structure):
+    _fields_ = [("op", C.c_int32), ("pad_", C.c_int32), ("c", C.c_double)]
+
+
 class ProgramDesc(C.Structure):
     _fields_ = [("in_dtype", C.c_int32), ("out_dtype", C.c_int32), ("n_lanes", C.c_int32),
                 ("n_slots", C.c_int32), ("n_cols", C.c_int32), ("pad_", C.c_int32),
                 ("n_time", C.c_int64), ("n_groups1", C.c_int64), ("n_groups2", C.c_int64),
                 ("bounds1", C.POINTER(C.c_int32)), ("bounds2", C.POINTER(C.c_int32)),
-                ("lanes", Lane * MAX_LANES), ("slots", Slot * MAX_SLOTS), ("cols", Col * MAX_COLS)]
+                ("lanes", Lane * MAX_LANES), ("slots", Slot * MAX_SLOTS), ("cols", Col * MAX_COLS),
+                ("n_pre", C.c_int32), ("pad2_", C.c_int32), ("pre", Pre * MAX_PRE)]
 
 
 class ProgramInfo(C.Structure):
@@ -100,8 +109,8 @@ def lib() -> C.CDLL:
         fn = getattr(L, name)
         if name not in ("agf_version", "agf_last_error"):
             fn.restype = C.c_int
-    if L.agf_version() != 1:
-        raise ImportError(f"{LIB_PATH}: ABI version {L.agf_version()} != 1")
+    if L.agf_version() != ABI_VERSION:
+        raise ImportError(f"{LIB_PATH}: ABI version {L.agf_version()} != {ABI_VERSION}")
     _lib = L
     return L
 

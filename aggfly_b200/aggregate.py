@@ -49,7 +49,7 @@ class _DeviceRaster:
 
 
 def _compile(dataset: Dataset, aggregator_dict: Optional[Dict[str, list]]):
-    graph = Graph(dataset.dtype, dataset.time)
+    graph = Graph(dataset.dtype, dataset.time, getattr(dataset, "pre_ops", None))
     if aggregator_dict is None:
         outputs = {"variable": graph.raw}                               # aggregate.py:269-270
     else:

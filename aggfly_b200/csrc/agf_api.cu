@@ -92,6 +92,9 @@ static int validate_desc(const agf_program_desc_t *d, int64_t n_cells) {
         if (d->bounds1[g] > d->bounds1[g + 1]) return fail(AGF_E_INVALID, "bounds1 not monotonic");
     if (d->bounds1[0] < 0 || d->bounds1[d->n_groups1] > d->n_time)
         return fail(AGF_E_INVALID, "bounds1 outside the time axis");
+    if (d->n_pre < 0 || d->n_pre > AGF_MAX_PRE) return fail(AGF_E_INVALID, "n_pre out of range");
+    for (int i = 0; i < d->n_pre; ++i)
+        if (d->pre[i].op < AGF_PRE_ADD || d->pre[i].op > AGF_PRE_NEG) return fail(AGF_E_INVALID, "pre %d: bad op", i);
     bool sine = false;
     for (int l = 0; l < d->n_lanes; ++l) {
         if (!is_l1_calc(d->lanes[l].calc)) return fail(AGF_E_INVALID, "lane %d: bad calc", l);
@@ -558,8 +561,15 @@ extern "C" int agf_spmm_run(const agf_csr_t *c, const void *d_x, int32_t x_dtype
     if (rc) return rc;
     // lanes per (period, region) pair: the smallest of 8 / 16 / 32 that covers the mean row length
     const double mean_row = (double)c->nnz / (double)c->n_regions;
-    const int gs = mean_row <= 8.0 ? 8 : (mean_row <= 16.0 ? 16 : 32);
     const long long pairs = (long long)c->n_regions * n_groups;
+    int sms = 148;
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
+    // enough pairs for >= 2048 threads on every SM: one thread per pair (no cross-lane reduction)
+    int gs = pairs >= 2048LL * sms ? 1 : (mean_row <= 8.0 ? 8 : (mean_row <= 16.0 ? 16 : 32));
+    if (const char *force = getenv("AGF_SPMM_GS")) {  // test hook: pin the variant (1, 8, 16 or 32)
+        const int f = atoi(force);
+        if (f == 1 || f == 8 || f == 16 || f == 32) gs = f;
+    }
     const long long blocks = (pairs * gs + 255) / 256;
     if (blocks > 0x7fffffffLL) return fail(AGF_E_UNSUPPORTED, "panel too large for one launch");
     cudaStream_t st = (cudaStream_t)stream;
@@ -568,11 +578,13 @@ extern "C" int agf_spmm_run(const agf_csr_t *c, const void *d_x, int32_t x_dtype
                                                        d_valid, c->n_cells, n_groups, n_cols, c->n_regions,  \
                                                        d_panel, d_den)
     if (x_dtype == AGF_F64) {
-        if (gs == 8) AGF_SPMM(double, 8);
+        if (gs == 1) AGF_SPMM(double, 1);
+        else if (gs == 8) AGF_SPMM(double, 8);
         else if (gs == 16) AGF_SPMM(double, 16);
         else AGF_SPMM(double, 32);
     } else {
-        if (gs == 8) AGF_SPMM(float, 8);
+        if (gs == 1) AGF_SPMM(float, 1);
+        else if (gs == 8) AGF_SPMM(float, 8);
         else if (gs == 16) AGF_SPMM(float, 16);
         else AGF_SPMM(float, 32);
     }

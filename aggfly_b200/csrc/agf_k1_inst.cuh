@@ -57,6 +57,11 @@ static int launch_k1(const K1Launch &a) {
     kp.need_cnt = p->need_cnt;
     kp.has_sine = p->has_sine;
     kp.diag = DIAG;
+    kp.n_pre = d.n_pre;
+    for (int i = 0; i < d.n_pre; ++i) {
+        kp.pre[i].op = d.pre[i].op;
+        kp.pre[i].c = (T)d.pre[i].c;
+    }
     // kernel lane of each program lane: identity, except for typed lanes (single-level, NB >= 0),
     // where the bin lanes go to [0, NB) and the mean / sum lanes to [NB, NL), both in program order
     int lane_of[AGF_MAX_LANES];

@@ -110,6 +110,12 @@ struct Stripe {  // one time stripe, cut at level-1 group boundaries
     int rec0;      // first partial record of this stripe
 };
 
+template <typename T>
+struct PreP {  // one preprocess operation (AGF_PRE_*), constant already in the raster dtype
+    int op;
+    T c;
+};
+
 template <typename T, int NL, int NS>
 struct K1Params {
     const T *x;
@@ -127,6 +133,8 @@ struct K1Params {
     int out_ncols, valid_and;  // column count of the (possibly shared) X; AND into V or overwrite
     int in_f64, out_f64;
     int need_nan, need_cnt, has_sine, diag;
+    int n_pre;
+    PreP<T> pre[AGF_MAX_PRE];
     LaneP<T> lanes[NL];
     SlotP slots[NS > 0 ? NS : 1];
     ColP cols[NS > 0 ? 1 : AGF_MAX_COLS];
@@ -320,6 +328,35 @@ __device__ __forceinline__ void count_in_range(int &c, float v, float lo, float 
 }
 __device__ __forceinline__ void count_in_range(int &c, double v, double lo, double hi) {
     if (v > lo && v < hi) c += 1;
+}
+
+// the program's preprocess chain on one raster value, in the raster dtype (one rounding per op)
+template <typename T, int NL, int NS>
+__device__ __forceinline__ T pre_apply(const K1Params<T, NL, NS> &p, T v) {
+#pragma unroll
+    for (int i = 0; i < AGF_MAX_PRE; ++i) {
+        if (i < p.n_pre) {
+            const T c = p.pre[i].c;
+            switch (p.pre[i].op) {
+                case AGF_PRE_ADD: v = v + c; break;
+                case AGF_PRE_SUB: v = v - c; break;
+                case AGF_PRE_RSUB: v = c - v; break;
+                case AGF_PRE_MUL: v = v * c; break;
+                case AGF_PRE_DIV: v = v / c; break;
+                case AGF_PRE_RDIV: v = c / v; break;
+                default: v = -v; break;
+            }
+        }
+    }
+    return v;
+}
+// a register batch of raster values: one uniform branch per batch, nothing when there is no chain
+template <int N, typename T, int NL, int NS>
+__device__ __forceinline__ void pre_apply_batch(const K1Params<T, NL, NS> &p, T (&v)[N]) {
+    if (p.n_pre != 0) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) v[i] = pre_apply(p, v[i]);
+    }
 }
 
 // one raster value into every level-1 lane (nb_kernels.py:134-141, 170-177, 193-196, 213-220)
@@ -679,6 +716,7 @@ __global__ void __launch_bounds__(K1_THREADS)
             nxt[i] = (i < nlen) ? __ldg(xc + (size_t)(nk + i - p.row0) * p.ld) : T(0);
 
         // reduce the current batch in time order
+        pre_apply_batch(p, cur);
 #pragma unroll
         for (int i = 0; i < K1_U; ++i)
             if (i < clen) l1_acc<KINDS>(p, s, cur[i]);
@@ -841,11 +879,12 @@ __global__ void __launch_bounds__(TMA_THREADS, MINB)
                 T v[UNROLL];
 #pragma unroll
                 for (int u = 0; u < UNROLL; ++u) v[u] = cp[u * TMA_CW];
+                pre_apply_batch(p, v);
 #pragma unroll
                 for (int u = 0; u < UNROLL; ++u) l1_acc<KINDS>(p, s, v[u]);
             }
 #pragma unroll 1
-            for (; j > 0; --j, cp += TMA_CW) l1_acc<KINDS>(p, s, *cp);
+            for (; j > 0; --j, cp += TMA_CW) l1_acc<KINDS>(p, s, p.n_pre ? pre_apply(p, *cp) : *cp);
             r += run;
             k += run;
             if (k == nb) {  // level-1 group g is complete
@@ -973,6 +1012,7 @@ __global__ void __launch_bounds__(TMA_THREADS, MINB)
             for (int r = 0; r < TT; ++r) v[r] = col[r * TMA_CW];
             __syncwarp();
             if ((threadIdx.x & 31) == 0) mbar_arrive(&empty[stg]);
+            pre_apply_batch(p, v);
 #pragma unroll
             for (int r = 0; r < TT; ++r) l1_acc<KINDS>(p, s, v[r]);
             group_end();
@@ -980,8 +1020,12 @@ __global__ void __launch_bounds__(TMA_THREADS, MINB)
             const int ng = min(GPT, g_end - g);
 #pragma unroll 1
             for (int gi = 0; gi < ng; ++gi) {
+                T v[GL];
 #pragma unroll
-                for (int r = 0; r < GL; ++r) l1_acc<KINDS>(p, s, col[(gi * GL + r) * TMA_CW]);
+                for (int r = 0; r < GL; ++r) v[r] = col[(gi * GL + r) * TMA_CW];
+                pre_apply_batch(p, v);
+#pragma unroll
+                for (int r = 0; r < GL; ++r) l1_acc<KINDS>(p, s, v[r]);
                 group_end();
             }
             __syncwarp();

@@ -69,7 +69,16 @@ __global__ void __launch_bounds__(256) agf_finalize(const __grid_constant__ FinP
 // one region are still open / in L2 when its neighbours read them.  (r-major numbering made every
 // warp of a CTA read a different 58 MB-apart plane: 40 ms for the C3b daily panel.)
 // ------------------------------------------------------------------------------------------
-constexpr int SPMM_NCB = 8;  // columns accumulated per pass over a region's entries
+// GS == 1 (one thread per pair, entries walked sequentially in weights-frame order like the
+// reference's np.add.at) is used when there are enough pairs to fill the GPU (daily / monthly
+// panels): no shuffles, 16 columns per pass, and the lanes of a warp are 32 neighbouring regions of
+// the same period, so their gathers fall into a few shared sectors that stay in L1 while the
+// threads walk their rows.  Measured on the C3b daily panel (45 000 x 365 pairs x 14 columns): the
+// warp-per-pair form was instruction-bound (25e9 warp instructions, 43.7 ms, 5 % of DRAM peak).
+template <int GS>
+__host__ __device__ constexpr int spmm_ncb() {  // columns accumulated per pass over a region's entries
+    return GS == 1 ? 16 : 8;
+}
 
 template <typename TX, int GS>
 __global__ void __launch_bounds__(256)
@@ -86,6 +95,8 @@ __global__ void __launch_bounds__(256)
     const unsigned char *Vg = V + (size_t)g * n_cells;
     // lanes of this group inside the warp (shuffles must name exactly the participating lanes)
     const unsigned gmask = (GS == 32) ? 0xffffffffu : (((1u << GS) - 1u) << ((threadIdx.x & 31) / GS * GS));
+    constexpr int SPMM_NCB = spmm_ncb<GS>();
+    const TX *Xg = X + (size_t)g * n_cols * n_cells;
 
     for (int c0 = 0; c0 < n_cols; c0 += SPMM_NCB) {
         double acc[SPMM_NCB];
@@ -100,7 +111,7 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
                 for (int c = 0; c < SPMM_NCB; ++c)
                     if (c0 + c < n_cols)
-                        acc[c] += we * (double)X[((size_t)g * n_cols + c0 + c) * n_cells + cell];
+                        acc[c] += we * (double)Xg[(size_t)(c0 + c) * n_cells + cell];
             }
         }
 #pragma unroll

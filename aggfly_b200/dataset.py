@@ -15,6 +15,7 @@ from typing import Any, Optional, Sequence
 import numpy as np
 import pandas as pd
 
+from .preprocess import FusedPreprocess, constants_for, resolve
 from .timeaxis import CalendarIndex
 
 
@@ -64,6 +65,13 @@ class RasterArray:
         self.data, self.dims, self.coords = data, tuple(dims), dict(coords)
 
 
+def _fusable(preprocess):
+    """FusedPreprocess for names / expressions / FusedPreprocess objects, None for other callables."""
+    if isinstance(preprocess, (str, FusedPreprocess)):
+        return resolve(preprocess) or FusedPreprocess([])
+    return None
+
+
 def _is_torch(x) -> bool:
     return type(x).__module__.startswith("torch")
 
@@ -86,10 +94,15 @@ class Dataset:
         order = [dims.index(timecoord), dims.index(ydim), dims.index(xdim)]
         if order != [0, 1, 2]:
             values = values.permute(*order).contiguous() if _is_torch(values) else np.transpose(values, order)
+        fused = None
         if preprocess is not None:
-            values = preprocess(values)
+            fused = _fusable(preprocess)
+            if fused is None:
+                values = preprocess(values)              # arbitrary callable: applied to the array now
         self._init(values, da.coords[timecoord], da.coords[ydim], da.coords[xdim], lon_is_360, name)
         self.georegions = georegions
+        if fused is not None:
+            self.pre_ops = constants_for(fused.ops, self.dtype)
 
     def _init(self, values, time, latitude, longitude, lon_is_360, name):
         if not isinstance(time, CalendarIndex):
@@ -113,16 +126,25 @@ class Dataset:
         self.name = name
         self.history = []
         self.georegions = None
+        self.pre_ops = []             # fused preprocess chain (preprocess.py), applied by the kernels
         if tuple(self.values.shape) != (len(self.time), len(self.latitude), len(self.longitude)):
             raise ValueError(f"values shape {tuple(self.values.shape)} does not match axes "
                              f"({len(self.time)}, {len(self.latitude)}, {len(self.longitude)})")
         self.grid = Grid(self.longitude, self.latitude, name, self.lon_is_360)
 
     @classmethod
-    def from_arrays(cls, values, time, latitude, longitude, lon_is_360=True, name=None) -> "Dataset":
-        """values[time, lat, lon] (numpy or torch, float32/float64), time = DatetimeIndex | CalendarIndex."""
+    def from_arrays(cls, values, time, latitude, longitude, lon_is_360=True, name=None, preprocess=None) -> "Dataset":
+        """values[time, lat, lon] (numpy or torch, float32/float64), time = DatetimeIndex | CalendarIndex.
+        ``preprocess``: builtin name (``"kelvin_to_celsius"``), arithmetic expression in ``x`` or a
+        ``FusedPreprocess`` -- fused into the temporal kernel, the stored raster stays untouched."""
         self = cls.__new__(cls)
         self._init(values, time, latitude, longitude, lon_is_360, name)
+        fused = None if preprocess is None else _fusable(preprocess)
+        if preprocess is not None and fused is None:
+            raise TypeError("from_arrays(preprocess=...) takes a builtin name, an expression in x or a "
+                            "FusedPreprocess; apply other callables to the array yourself")
+        if fused is not None:
+            self.pre_ops = constants_for(fused.ops, self.dtype)
         return self
 
     # -- reference API surface used on the hot path ----------------------------------------------

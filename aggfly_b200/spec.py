@@ -55,8 +55,9 @@ class Node:
 class Graph:
     """Hash-consing factory for nodes over one raster (dtype + time axis)."""
 
-    def __init__(self, raster_dtype, time_index):
+    def __init__(self, raster_dtype, time_index, pre_ops=None):
         self.nodes: Dict[tuple, Node] = {}
+        self.pre_ops = list(pre_ops or [])          # fused preprocess of the raster (preprocess.py)
         self.raw = Node("raw", dtype=raster_dtype, key=("raw",))
         self.raw._axis = (None, time_index)
         self.nodes[self.raw.key] = self.raw
@@ -224,6 +225,7 @@ class ProgramSpec:
     freq1: str = ""
     freq2: Optional[str] = None
     n_time: int = 0
+    pre: list = field(default_factory=list)   # (op, constant) chain applied to raster values
 
     @property
     def two_level(self) -> bool:
@@ -384,7 +386,7 @@ class Planner:
             need = (1 if calc != "sine_dd" else 4)
             if prog is None or len(prog.lanes) + need > _lib.MAX_LANES or len(prog.cols) + 1 > _lib.MAX_COLS:
                 prog = ProgramSpec(input=input_node, in_dtype=input_node.dtype, bounds1=b1, bounds2=None,
-                                   freq1=freq, n_time=n_time)
+                                   freq1=freq, n_time=n_time, pre=self.g.pre_ops if source is None else [])
                 prog._source = source
                 stage.programs.append(prog)
                 if source is not None and source[0] not in stage.inputs:
@@ -411,7 +413,7 @@ class Planner:
                     b1, _ = self.g.axis(s1)
                     b2, _ = self.g.axis(a)
                     prog = ProgramSpec(input=self.g.raw, in_dtype=self.g.raw.dtype, bounds1=b1, bounds2=b2,
-                                       freq1=freq1, freq2=freq2, n_time=n_time)
+                                       freq1=freq1, freq2=freq2, n_time=n_time, pre=self.g.pre_ops)
                     prog._source = None
                     stage.programs.append(prog)
                 lanes = [LaneSpec(l.calc, l.dd) for l in prog.lanes]
@@ -481,6 +483,9 @@ def build_desc(prog: ProgramSpec, out_dtype) -> Tuple[_lib.ProgramDesc, list]:
         S.calc = _lib.CALC[s.calc]
         if s.dd is not None:
             S.t0, S.t1, S.flag = s.dd[0], s.dd[1], int(s.dd[2] != 0)
+    d.n_pre = len(prog.pre)
+    for i, (op, c) in enumerate(prog.pre):
+        d.pre[i].op, d.pre[i].c = int(op), float(c)
     for c, k in enumerate(prog.cols):
         Cc = d.cols[c]
         Cc.src, Cc.xform, Cc.xparam, Cc.x_f64 = k.src, _xf_code(k.xf, k.xparam), k.xparam, int(k.x_f64)

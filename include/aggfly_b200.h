@@ -45,7 +45,7 @@
 extern "C" {
 #endif
 
-#define AGF_ABI_VERSION 1
+#define AGF_ABI_VERSION 2
 
 #define AGF_MAX_LANES 32  /* level-1 reducers per program */
 #define AGF_MAX_SLOTS 32  /* level-2 reducers per program */
@@ -84,6 +84,27 @@ enum {
 };
 
 enum { AGF_F32 = 0, AGF_F64 = 1 };
+
+/* Elementwise preprocess of every raster value, applied in the raster dtype before any reducer
+ * sees it (the reference's Dataset(preprocess=...): aggfly/cli/preprocess.py:24-30 named
+ * conversions such as kelvin_to_celsius = x - 273.15, :33-113 arithmetic in x).  One IEEE
+ * operation per entry, constants rounded to the raster dtype, no FMA contraction -- the same
+ * bits NumPy produces -- fused into the scan instead of a separate pass over the raster. */
+enum {
+    AGF_PRE_ADD = 0,  /* x + c */
+    AGF_PRE_SUB = 1,  /* x - c */
+    AGF_PRE_RSUB = 2, /* c - x */
+    AGF_PRE_MUL = 3,  /* x * c */
+    AGF_PRE_DIV = 4,  /* x / c */
+    AGF_PRE_RDIV = 5, /* c / x */
+    AGF_PRE_NEG = 6   /* -x    */
+};
+#define AGF_MAX_PRE 4
+typedef struct {
+    int32_t op;
+    int32_t pad_;
+    double c;
+} agf_pre_t;
 
 /* One level-1 reducer over the raw time axis (one `('aggregate', {...})` step applied to the
  * raster; one lane per ddargs row for multi-ddargs). */
@@ -132,6 +153,9 @@ typedef struct {
     agf_lane_t lanes[AGF_MAX_LANES];
     agf_slot_t slots[AGF_MAX_SLOTS];
     agf_col_t cols[AGF_MAX_COLS];
+    int32_t n_pre; /* 0..AGF_MAX_PRE preprocess operations, applied in order */
+    int32_t pad2_;
+    agf_pre_t pre[AGF_MAX_PRE];
 } agf_program_desc_t;
 
 typedef struct {

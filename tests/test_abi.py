@@ -19,12 +19,38 @@ def test_library_exports_every_declared_symbol():
     L = _lib.lib()
     for name in declared:
         assert hasattr(L, name), name
-    assert L.agf_version() == 1
+    assert L.agf_version() == 2          # AGF_ABI_VERSION
 
 
-def test_struct_sizes_match_the_header():
-    assert C.sizeof(_lib.Lane) == 24 and C.sizeof(_lib.Slot) == 48 and C.sizeof(_lib.Col) == 24
-    assert C.sizeof(_lib.ProgramDesc) == 64 + 32 * 24 + 32 * 48 + 64 * 24
+def test_struct_layouts_match_the_header_as_gcc_sees_it(tmp_path):
+    """sizeof / offsetof of every struct of the header, from a C program compiled here, against the
+    ctypes mirror in _lib.py (a silent mismatch would shift every field after it)."""
+    import subprocess
+    fields = {"agf_lane_t": (_lib.Lane, ["calc", "flag", "t0", "t1"]),
+              "agf_slot_t": (_lib.Slot, ["src", "xform", "xparam", "x_f64", "calc", "flag", "t0", "t1"]),
+              "agf_col_t": (_lib.Col, ["src", "xform", "xparam", "x_f64", "dst"]),
+              "agf_pre_t": (_lib.Pre, ["op", "c"]),
+              "agf_program_desc_t": (_lib.ProgramDesc, ["in_dtype", "out_dtype", "n_lanes", "n_slots", "n_cols", "n_time",
+                                                        "n_groups1", "n_groups2", "bounds1", "bounds2", "lanes", "slots",
+                                                        "cols", "n_pre", "pre"]),
+              "agf_program_info_t": (_lib.ProgramInfo, ["n_stripes", "n_recs", "n_cols", "out_dtype", "n_out_groups",
+                                                        "partial_bytes", "out_bytes", "valid_bytes", "kernel_lanes",
+                                                        "kernel_slots", "kernel_mode", "uses_tma", "kernel_kinds"])}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "aggfly_b200.h"', "int main(void) {"]
+    for st, (_, names) in fields.items():
+        lines.append(f'printf("{st} %zu\\n", sizeof({st}));')
+        lines += [f'printf("{st}.{n} %zu\\n", offsetof({st}, {n}));' for n in names]
+    lines += ['printf("abi %d\\n", AGF_ABI_VERSION);', "return 0; }"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["/usr/bin/gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = dict(l.split() for l in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for st, (cls, names) in fields.items():
+        assert int(got[st]) == C.sizeof(cls), st
+        for n in names:
+            assert int(got[f"{st}.{n}"]) == getattr(cls, n).offset, (st, n)
+    assert int(got["abi"]) == _lib.ABI_VERSION
 
 
 def _desc(b1, b2=None, n_lanes=1, n_slots=0, n_cols=1):
