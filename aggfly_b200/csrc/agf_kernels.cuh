@@ -437,6 +437,46 @@ __device__ __forceinline__ void l1_acc(const K1Params<T, NL, NS> &p, ST &s, T v)
     }
 }
 
+// A whole level-1 group held in registers (uniform-group kernel).  Typed lanes with many bins: the
+// bins a warp can possibly hit are bounded by the min / max of its 32 x N values, and neighbouring
+// cells at the same hours are close in value, so each bin's N x (2 compares + add) block is guarded
+// by one warp-uniform test -- the cost follows the bins that are populated, not the bins that
+// exist (the scan is ALU-bound: ncu r1f, 13 bins x 24 h = 1008 ALU-pipe instructions per warp-day).
+// Must be called by all 32 lanes of a warp.
+template <unsigned KINDS, int N, typename T, int NL, int NS, typename ST>
+__device__ __forceinline__ void l1_acc_group(const K1Params<T, NL, NS> &p, ST &s, const T (&v)[N]) {
+    if constexpr (ST::TL && (NL - ST::NA) > 4 && N >= 8) {
+        constexpr int NBL = NL - ST::NA;
+        T mn = v[0], mx = v[0];  // fmin / fmax skip NaNs; an all-NaN group compares false everywhere
+#pragma unroll
+        for (int r = 1; r < N; ++r) {
+            mn = fmin(mn, v[r]);
+            mx = fmax(mx, v[r]);
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, off));
+            mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+        }
+#pragma unroll
+        for (int j = 0; j < NBL; ++j) {
+            if (mx > p.lanes[j].lo && mn < p.lanes[j].hi) {  // warp-uniform
+#pragma unroll
+                for (int r = 0; r < N; ++r) count_in_range(s.c[j], v[r], p.lanes[j].lo, p.lanes[j].hi);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < N; ++r) {
+            const double vd = (double)v[r];
+#pragma unroll
+            for (int l = 0; l < ST::NA; ++l) s.a[l] += vd;
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < N; ++r) l1_acc<KINDS>(p, s, v[r]);
+    }
+}
+
 // s / n for a group of n rows.  With a compile-time row count GLC and a float raster this is the
 // IEEE quotient without the division subroutine (whose special-case path ncu showed running for
 // every NaN / zero sum, ~75 instructions): rcp = RN(1/n) is exact to half an ulp, q0 = RN(s*rcp)
@@ -1013,8 +1053,7 @@ __global__ void __launch_bounds__(TMA_THREADS, MINB)
             __syncwarp();
             if ((threadIdx.x & 31) == 0) mbar_arrive(&empty[stg]);
             pre_apply_batch(p, v);
-#pragma unroll
-            for (int r = 0; r < TT; ++r) l1_acc<KINDS>(p, s, v[r]);
+            l1_acc_group<KINDS>(p, s, v);
             group_end();
         } else {
             const int ng = min(GPT, g_end - g);
@@ -1024,8 +1063,7 @@ __global__ void __launch_bounds__(TMA_THREADS, MINB)
 #pragma unroll
                 for (int r = 0; r < GL; ++r) v[r] = col[(gi * GL + r) * TMA_CW];
                 pre_apply_batch(p, v);
-#pragma unroll
-                for (int r = 0; r < GL; ++r) l1_acc<KINDS>(p, s, v[r]);
+                l1_acc_group<KINDS>(p, s, v);
                 group_end();
             }
             __syncwarp();

@@ -94,6 +94,8 @@ def feed_and_run(runner, values, n_cells: int, stream=None, k1_events: Optional[
         staging = _Staging(torch, host.dtype, slot_elems, OPTIONS["staging_slots"], OPTIONS["staging_threads"])
 
     copy.wait_stream(comp)                    # the raster buffer may be a recycled block still in use
+    ev_first, ev_last = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev_first.record(copy)
     runner.begin_streamed(comp)
     launches = 0
     try:
@@ -122,13 +124,15 @@ def feed_and_run(runner, values, n_cells: int, stream=None, k1_events: Optional[
                     submit(i + ahead)
             comp.wait_event(ev)
             launches += runner.feed(raster, r1, comp, k1_events)
+        ev_last.record(copy)
         res = runner.finish_streamed(raster, comp)
     finally:
         if staging:
             staging.close()
     raster.record_stream(comp)
     global LAST_STATS
-    LAST_STATS = dict(chunks=len(chunks), pinned=bool(pinned), h2d_bytes=T * row_bytes, k1_launches=launches)
+    LAST_STATS = dict(chunks=len(chunks), pinned=bool(pinned), h2d_bytes=T * row_bytes, k1_launches=launches,
+                      copy_events=(ev_first, ev_last))      # elapsed_time() once the caller has synchronised
     if stats is not None:
         stats.update(LAST_STATS)
     return res, raster

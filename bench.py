@@ -319,7 +319,13 @@ def main_ours(args, rank, world, local_rank):
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dt = float(tt[0])
+        from aggfly_b200 import stream as _stream
+        st = dict(_stream.LAST_STATS)
+        h2d_ms = st["copy_events"][0].elapsed_time(st["copy_events"][1]) if "copy_events" in st else None
         e2e = {"value": world * wl.cell_steps / dt, "unit": UNIT,
+               "feed": {"chunks": st.get("chunks"), "pinned": st.get("pinned"), "k1_launches": st.get("k1_launches"),
+                        "h2d_ms": h2d_ms,
+                        "h2d_gbs": (st.get("h2d_bytes", 0) / (h2d_ms * 1e-3) / 1e9) if h2d_ms else None},
                "h2d_bytes_per_step": int(host.numel() * host.element_size()),
                "d2h_bytes_per_step": int(R * G * NC * 8), "ms_per_step": dt * 1e3, "steps": e2e_steps,
                "api": "aggfly_b200.aggregate_dataset(weights, Dataset(pinned host tensor), aggregator_dict)",
