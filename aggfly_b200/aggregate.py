@@ -20,7 +20,7 @@ from . import stream as _stream
 from .dataset import Dataset
 from .spec import Graph, Planner, TemporalAggregator, compile_spec
 from .timeaxis import CalendarIndex, label_values, labels_equal
-from .weights import GridWeights, lower_to_csr
+from .weights import GridWeights, lower_to_csr, lower_to_csr_cached
 
 ALLOWED_ENGINE = ("auto", "cuda", "dask", "numba")          # reference: cli/config.py:27 + "cuda"
 
@@ -122,9 +122,9 @@ def aggregate_time(dataset: Dataset, weights: GridWeights = None,
     done: Dict[str, Dataset] = {}
     for grp in groups:
         res = _engine.run_stage(planner.plan([outputs[n] for n in grp]), raster.flat, raster.n_cells)
-        X = res.X.cpu().numpy()                                         # [G, n_cols, cells]
+        X = res.X.cpu().numpy()                                         # [G, cells, n_cols]
         for c, name in enumerate(grp):
-            vals = X[:, c, :].astype(res.nodes[c].dtype, copy=False)
+            vals = X[:, :, c].astype(res.nodes[c].dtype, copy=False)
             vals = np.ascontiguousarray(vals).reshape(len(res.labels), raster.n_lat, raster.n_lon)
             done[name] = Dataset.from_arrays(vals, res.labels, dataset.latitude, dataset.longitude,
                                              lon_is_360=dataset.lon_is_360, name=name)
@@ -154,8 +154,8 @@ def _device_csr(weights: GridWeights, dataset: Dataset) -> _engine.DeviceCSR:
         except Exception:
             pass
     if key not in cache:
-        host = lower_to_csr(weights.weights, weights.grid.cell_id, len(dataset.latitude),
-                            len(dataset.longitude), lon_order)
+        host = lower_to_csr_cached(weights.weights, weights.grid.cell_id, len(dataset.latitude),
+                                   len(dataset.longitude), lon_order, getattr(weights, "project_dir", None))
         cache[key] = _engine.DeviceCSR(host)
     return cache[key]
 
@@ -201,7 +201,7 @@ class SpatialAggregator:
         G = len(d0.time)
         dt = np.result_type(*[d.dtype for d in self.dataset])
         X = torch.stack([_engine.to_device(d.values).reshape(G, n_cells).to(_engine._tdtype(dt))
-                         for d in self.dataset], dim=1).contiguous()
+                         for d in self.dataset], dim=2).contiguous()         # [G, cells, names]
         # validity mask = AND over names of ~isnan  (spatial.py:114-119), by the library's kernel
         V = torch.empty((G, n_cells), dtype=torch.uint8, device=X.device)
         _engine.valid_mask(X, dt, V)
@@ -242,10 +242,43 @@ def aggregate_dataset(weights: GridWeights, dataset: Dataset = None,
     if aggregator_dict is None and dataset_dict is not None:
         df = aggregate_space(dataset_dict, weights)
     else:
+        tr = _Trace()
+        csr = _device_csr(weights, dataset)               # cached on the weights object after the first call
+        tr.mark("csr")
         names, res, raster = _temporal_device(dataset, aggregator_dict)
-        csr = _device_csr(weights, dataset)
+        tr.mark("temporal (+ host feed)")
         panel = _engine.run_spmm(csr, res).cpu().numpy()
+        tr.mark("spmm + d2h")
         df = _assemble_panel(panel, names, res.labels, csr.host.region_ids, weights)
+        tr.mark("assemble")
     rid = weights.georegions.regionid
     df = weights.georegions.shp[[rid]].merge(df, left_index=True, right_on="region_id").drop(columns="region_id")
+    if aggregator_dict is not None or dataset_dict is None:
+        tr.mark("merge")
+        tr.done()
     return df
+
+
+class _Trace:
+    """Wall-clock phases of one call; printed when AGF_TRACE is set, always kept in LAST_TRACE."""
+
+    def __init__(self):
+        import time
+        self._t = time.perf_counter
+        self.t0 = self.last = self._t()
+        self.phases = []
+
+    def mark(self, name):
+        now = self._t()
+        self.phases.append((name, (now - self.last) * 1e3))
+        self.last = now
+
+    def done(self):
+        import os
+        global LAST_TRACE
+        LAST_TRACE = {"total_ms": (self.last - self.t0) * 1e3, "phases_ms": dict(self.phases)}
+        if os.environ.get("AGF_TRACE"):
+            print("[aggfly_b200] " + ", ".join(f"{k} {v:.1f} ms" for k, v in self.phases), flush=True)
+
+
+LAST_TRACE: dict = {}

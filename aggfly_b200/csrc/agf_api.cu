@@ -573,21 +573,36 @@ extern "C" int agf_spmm_run(const agf_csr_t *c, const void *d_x, int32_t x_dtype
     const long long blocks = (pairs * gs + 255) / 256;
     if (blocks > 0x7fffffffLL) return fail(AGF_E_UNSUPPORTED, "panel too large for one launch");
     cudaStream_t st = (cudaStream_t)stream;
-#define AGF_SPMM(TX, GS)                                                                                      \
-    agf_spmm<TX, GS><<<(unsigned)blocks, 256, 0, st>>>(c->d_row_ptr, c->d_cell_idx, c->d_w, (const TX *)d_x, \
-                                                       d_valid, c->n_cells, n_groups, n_cols, c->n_regions,  \
-                                                       d_panel, d_den)
+    // columns per load: the widest of 16 / 8 / sizeof(X) bytes that divides the row pitch (d_x itself
+    // must then be aligned to it; torch allocations are 256-byte aligned)
+    const int esz = x_dtype == AGF_F64 ? 8 : 4;
+    int vb = esz;
+    for (int cand = 16; cand > esz; cand >>= 1)
+        if (((long long)n_cols * esz) % cand == 0 && ((uintptr_t)d_x % cand) == 0) {
+            vb = cand;
+            break;
+        }
+    const int ev = vb / esz;
+#define AGF_SPMM(TX, GS, EV)                                                                                      \
+    agf_spmm<TX, GS, EV><<<(unsigned)blocks, 256, 0, st>>>(c->d_row_ptr, c->d_cell_idx, c->d_w, (const TX *)d_x, \
+                                                           d_valid, c->n_cells, n_groups, n_cols, c->n_regions,  \
+                                                           d_panel, d_den)
+#define AGF_SPMM_GS(TX, EV)                    \
+    do {                                       \
+        if (gs == 1) AGF_SPMM(TX, 1, EV);      \
+        else if (gs == 8) AGF_SPMM(TX, 8, EV); \
+        else if (gs == 16) AGF_SPMM(TX, 16, EV); \
+        else AGF_SPMM(TX, 32, EV);             \
+    } while (0)
     if (x_dtype == AGF_F64) {
-        if (gs == 1) AGF_SPMM(double, 1);
-        else if (gs == 8) AGF_SPMM(double, 8);
-        else if (gs == 16) AGF_SPMM(double, 16);
-        else AGF_SPMM(double, 32);
+        if (ev == 2) AGF_SPMM_GS(double, 2);
+        else AGF_SPMM_GS(double, 1);
     } else {
-        if (gs == 1) AGF_SPMM(float, 1);
-        else if (gs == 8) AGF_SPMM(float, 8);
-        else if (gs == 16) AGF_SPMM(float, 16);
-        else AGF_SPMM(float, 32);
+        if (ev == 4) AGF_SPMM_GS(float, 4);
+        else if (ev == 2) AGF_SPMM_GS(float, 2);
+        else AGF_SPMM_GS(float, 1);
     }
+#undef AGF_SPMM_GS
 #undef AGF_SPMM
     CU(cudaGetLastError());
     return 0;

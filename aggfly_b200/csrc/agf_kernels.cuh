@@ -9,7 +9,7 @@
 //                   in time order, result rounded to the raster dtype, NaN rules :15-25) and
 //                   aggfly/dataset/dataset.py:442-481,527-543 (power / spline).
 // K1f agf_finalize  merges the per-stripe partial records, mean division, dtype rounding,
-//                   trailing transforms, writes X[G, n_cols, cells] and the shared validity mask.
+//                   trailing transforms, writes X[G, cells, n_cols] and the shared validity mask.
 // K2  agf_spmm      CSR weighted regional average, one warp per (region, period):
 //                   aggfly/aggregate/spatial.py:114-133, 181-186.
 #pragma once
@@ -127,7 +127,7 @@ struct K1Params {
     const int *b2;
     const Stripe *stripes;
     double *partial;  // [n_recs, n_slots, n_cells]      (NS > 0)
-    void *out;        // X[G1, n_cols, n_cells]           (NS == 0)
+    void *out;        // X[G1, n_cells, n_cols]           (NS == 0)
     unsigned char *valid;
     int n_lanes, n_slots, n_cols;
     int out_ncols, valid_and;  // column count of the (possibly shared) X; AND into V or overwrite
@@ -621,11 +621,11 @@ __device__ __forceinline__ void l1_flush(const K1Params<T, NL, NS> &p, ST &s, in
         constexpr int NBL = NL - ST::NA;
         const bool empty = (GLC == 0) && n_grp == 0;  // empty resample bin -> NaN for every reducer
         bool ok = !empty;
-        const size_t base = (size_t)g * p.out_ncols;
+        const size_t base = ((size_t)g * p.n_cells + cell) * p.out_ncols;  // X[g, cell, :]
 #pragma unroll
         for (int j = 0; j < NBL; ++j) {
             const int dst = p.cols[j].dst;
-            if (dst >= 0) store_col<T>(p.out, p.out_f64, (base + dst) * p.n_cells + cell, empty ? agf_nan() : (double)s.c[j]);
+            if (dst >= 0) store_col<T>(p.out, p.out_f64, base + dst, empty ? agf_nan() : (double)s.c[j]);
         }
 #pragma unroll
         for (int l = 0; l < ST::NA; ++l) {
@@ -634,7 +634,7 @@ __device__ __forceinline__ void l1_flush(const K1Params<T, NL, NS> &p, ST &s, in
                 double r = (p.lanes[NBL + l].calc == AGF_CALC_MEAN) ? mean_of<T, GLC>(s.a[l], n_grp) : s.a[l];
                 r = empty ? agf_nan() : round_to<T>(r);
                 ok &= (r == r);
-                store_col<T>(p.out, p.out_f64, (base + dst) * p.n_cells + cell, r);
+                store_col<T>(p.out, p.out_f64, base + dst, r);
             }
         }
         unsigned char *vp = p.valid + (size_t)g * p.n_cells + cell;
@@ -647,13 +647,13 @@ __device__ __forceinline__ void l1_flush(const K1Params<T, NL, NS> &p, ST &s, in
 
     if constexpr (NS == 0) {
         bool ok = true;
-        const size_t base = (size_t)g * p.out_ncols;
+        const size_t base = ((size_t)g * p.n_cells + cell) * p.out_ncols;  // X[g, cell, :]
         if (DIAG) {  // column c == lane c, no transform
 #pragma unroll
             for (int l = 0; l < NL; ++l) {
                 if (l < p.n_cols) {
                     ok &= (val[l] == val[l]);
-                    store_col<T>(p.out, p.out_f64, (base + p.cols[l].dst) * p.n_cells + cell, val[l]);
+                    store_col<T>(p.out, p.out_f64, base + p.cols[l].dst, val[l]);
                 }
             }
         } else {
@@ -661,7 +661,7 @@ __device__ __forceinline__ void l1_flush(const K1Params<T, NL, NS> &p, ST &s, in
                 const ColP &C = p.cols[c];
                 double x = apply_xform<T>(select_reg<NL>(val, C.src), C.xform, C.xparam, C.x_f64);
                 ok &= (x == x);
-                store_col<T>(p.out, p.out_f64, (base + C.dst) * p.n_cells + cell, x);
+                store_col<T>(p.out, p.out_f64, base + C.dst, x);
             }
         }
         unsigned char *vp = p.valid + (size_t)g * p.n_cells + cell;

@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(256) agf_finalize(const __grid_constant__ FinP
             }
         }
         ok &= (v == v);
-        const size_t idx = ((size_t)g2 * p.out_ncols + C.dst) * p.n_cells + cell;
+        const size_t idx = ((size_t)g2 * p.n_cells + cell) * p.out_ncols + C.dst;  // X[g, cell, :]
         if (p.out_f64)
             reinterpret_cast<double *>(p.out)[idx] = v;
         else
@@ -80,7 +80,30 @@ __host__ __device__ constexpr int spmm_ncb() {  // columns accumulated per pass 
     return GS == 1 ? 16 : 8;
 }
 
-template <typename TX, int GS>
+// EV consecutive columns of one cell with a single load (EV * sizeof(TX) = 4, 8 or 16 bytes; the
+// launcher picks the widest width the row pitch n_cols * sizeof(TX) is a multiple of)
+template <typename TX, int EV>
+__device__ __forceinline__ void load_cols(const TX *p, double (&x)[EV]) {
+    if constexpr (EV == 1) {
+        x[0] = (double)__ldg(p);
+    } else if constexpr (sizeof(TX) * EV == 8) {  // float2
+        const float2 v = __ldg(reinterpret_cast<const float2 *>(p));
+        x[0] = (double)v.x;
+        x[1] = (double)v.y;
+    } else if constexpr (sizeof(TX) == 4) {  // float4
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(p));
+        x[0] = (double)v.x;
+        x[1] = (double)v.y;
+        x[2] = (double)v.z;
+        x[3] = (double)v.w;
+    } else {  // double2
+        const double2 v = __ldg(reinterpret_cast<const double2 *>(p));
+        x[0] = v.x;
+        x[1] = v.y;
+    }
+}
+
+template <typename TX, int GS, int EV>
 __global__ void __launch_bounds__(256)
     agf_spmm(const int *__restrict__ row_ptr, const int *__restrict__ cell_idx,
              const double *__restrict__ w, const TX *__restrict__ X,
@@ -96,7 +119,7 @@ __global__ void __launch_bounds__(256)
     // lanes of this group inside the warp (shuffles must name exactly the participating lanes)
     const unsigned gmask = (GS == 32) ? 0xffffffffu : (((1u << GS) - 1u) << ((threadIdx.x & 31) / GS * GS));
     constexpr int SPMM_NCB = spmm_ncb<GS>();
-    const TX *Xg = X + (size_t)g * n_cols * n_cells;
+    const TX *Xg = X + (size_t)g * n_cols * n_cells;  // X[g, cell, c]: a cell's columns are contiguous
 
     for (int c0 = 0; c0 < n_cols; c0 += SPMM_NCB) {
         double acc[SPMM_NCB];
@@ -107,11 +130,17 @@ __global__ void __launch_bounds__(256)
             const int cell = cell_idx[e];
             const double we = w[e];
             if (Vg[cell]) {
+                const TX *Xc = Xg + (size_t)cell * n_cols;
                 den += we;
 #pragma unroll
-                for (int c = 0; c < SPMM_NCB; ++c)
-                    if (c0 + c < n_cols)
-                        acc[c] += we * (double)Xg[(size_t)(c0 + c) * n_cells + cell];
+                for (int c = 0; c < SPMM_NCB; c += EV) {
+                    if (c0 + c < n_cols) {  // n_cols is a multiple of EV
+                        double x[EV];
+                        load_cols<TX, EV>(Xc + c0 + c, x);
+#pragma unroll
+                        for (int k = 0; k < EV; ++k) acc[c + k] += we * x[k];
+                    }
+                }
             }
         }
 #pragma unroll
@@ -139,7 +168,7 @@ __global__ void __launch_bounds__(256)
     const size_t g = blockIdx.y;
     bool ok = true;
     for (int c = 0; c < n_cols; ++c) {
-        const TX v = X[(g * n_cols + c) * n_cells + cell];
+        const TX v = X[(g * n_cells + cell) * n_cols + c];
         ok &= (v == v);
     }
     V[g * n_cells + cell] = ok ? 1 : 0;

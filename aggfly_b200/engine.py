@@ -99,7 +99,7 @@ class DeviceCSR:
 
 
 class StageResult:
-    """X[G, n_cols, cells] + V[G, cells] on the device."""
+    """X[G, cells, n_cols] + V[G, cells] on the device."""
 
     def __init__(self, X, V, dtype, labels, nodes):
         self.X, self.V, self.dtype, self.labels, self.nodes = X, V, np.dtype(dtype), labels, nodes
@@ -110,7 +110,7 @@ class StageResult:
 
     @property
     def n_cols(self) -> int:
-        return int(self.X.shape[1])
+        return int(self.X.shape[2])
 
 
 class StageRunner:
@@ -130,7 +130,7 @@ class StageRunner:
             self.inputs.append(shared[id(sub)])
         self._by_stage = {id(r.stage): r for r in self.inputs}
         G, n_cols = len(stage.labels), len(stage.nodes)
-        self.X = torch.empty((G, n_cols, n_cells), dtype=_tdtype(stage.dtype), device=self.device)
+        self.X = torch.empty((G, n_cells, n_cols), dtype=_tdtype(stage.dtype), device=self.device)
         self.V = torch.empty((G, n_cells), dtype=torch.uint8, device=self.device)
         self.programs: List[Program] = []
         self.partials = []
@@ -183,8 +183,8 @@ class StageRunner:
                         raise TypeError(f"raster dtype {raster.dtype} does not match the planned {spec.in_dtype}")
                 else:
                     sub_res = self._by_stage[id(src[0])].result
-                    ld = sub_res.n_cols * self.n_cells
-                    x_ptr = sub_res.X.data_ptr() + src[1] * self.n_cells * sub_res.X.element_size()
+                    assert sub_res.n_cols == 1 and src[1] == 0     # a materialised series is its own raster
+                    ld, x_ptr = self.n_cells, sub_res.X.data_ptr()
                     assert sub_res.dtype == np.dtype(spec.in_dtype)
                 pptr = partial.data_ptr() if partial is not None else None
                 ev = None
@@ -273,8 +273,8 @@ class StageRunner:
                                            "of a program not launched (raster shorter than the time axis?)")
                 else:
                     sub_res = r._by_stage[id(src[0])].result
-                    ld = sub_res.n_cols * r.n_cells
-                    x_ptr = sub_res.X.data_ptr() + src[1] * r.n_cells * sub_res.X.element_size()
+                    assert sub_res.n_cols == 1 and src[1] == 0
+                    ld, x_ptr = r.n_cells, sub_res.X.data_ptr()
                     _lib.check(L.agf_temporal_run(prog.handle, x_ptr, ld, 0, 0, prog.info.n_stripes, pptr,
                                                   r.X.data_ptr(), r.V.data_ptr(), n_cols, 1, sptr))
                 _lib.check(L.agf_temporal_finalize(prog.handle, pptr, r.X.data_ptr(), r.V.data_ptr(), n_cols, 1, sptr))
@@ -320,7 +320,7 @@ def valid_mask(X, dtype, V, stream=None) -> None:
     """V[g, cell] = AND over columns of ~isnan(X[g, c, cell]) (library kernel, no torch math)."""
     torch = _torch()
     st = torch.cuda.current_stream() if stream is None else stream
-    G, NC, n_cells = X.shape
+    G, n_cells, NC = X.shape
     with torch.cuda.stream(st):
         _lib.check(_lib.lib().agf_valid_mask_run(X.data_ptr(), _lib.F64 if np.dtype(dtype) == np.float64 else _lib.F32,
                                                  G, NC, n_cells, V.data_ptr(), st.cuda_stream))

@@ -234,7 +234,7 @@ class ProgramSpec:
 
 @dataclass
 class Stage:
-    """Programs that together fill one X[G, n_cols, cells] (+ shared validity mask)."""
+    """Programs that together fill one X[G, cells, n_cols] (+ shared validity mask)."""
     programs: List[ProgramSpec]
     nodes: List[Node]            # node of each X column
     dtype: np.dtype              # dtype of X

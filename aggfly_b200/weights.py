@@ -122,13 +122,21 @@ class GridWeights:
         if self.raster_weights is None:
             w["weight"] = w["area_weight"]
         else:
-            rw = np.asarray(self.raster_weights, dtype=float).reshape(-1)
-            w["raster_weight"] = np.nan_to_num(rw[w["cell_id"].to_numpy()], nan=0.0)
-            prod = w["area_weight"] * w["raster_weight"]
-            tot = prod.groupby(w["index_right"]).transform("sum")
+            # aggfly/weights/grid_weights.py:447-489: missing / non-finite raster values count as zero;
+            # weight = area_weight * raster_weight / (the region's summed raster_weight)
+            rw = np.asarray(self.raster_weights, dtype=float).reshape(-1)[w["cell_id"].to_numpy()]
+            n_missing = int((~np.isfinite(rw)).sum())
+            if n_missing:
+                warnings.warn(f"{n_missing} of {len(w)} cell-region pairs had no secondary raster value (outside its "
+                              "extent, or entirely nodata) and were given zero weight. A region with no valid cells "
+                              "at all falls back to whatever the zero_weight policy specifies.", stacklevel=2)
+            w["raster_weight"] = np.where(np.isfinite(rw), rw, 0.0)
+            tot = w["raster_weight"].groupby(w["index_right"]).transform("sum")
+            w["total_weight"] = tot
             with np.errstate(invalid="ignore", divide="ignore"):
-                w["weight"] = np.where(tot > 0, prod / tot, 0.0)          # per-region normalisation
+                w["weight"] = np.where(tot > 0, w["area_weight"] * (w["raster_weight"] / tot), 0.0)
             empty = ~(tot > 0)
+            w["zero_weight"] = empty
             if empty.any():
                 if self.zero_weight == "area":
                     warnings.warn("regions with no secondary weight fall back to AREA weights", UserWarning)
@@ -209,3 +217,46 @@ def lower_to_csr(wdf: pd.DataFrame, grid_cell_id: np.ndarray, n_lat: int, n_lon:
     np.cumsum(np.bincount(rows, minlength=len(region_ids)), out=row_ptr[1:])
     return HostCSR(row_ptr.astype(np.int32), pos.astype(np.int32), np.ascontiguousarray(w),
                    region_ids, n_cells)
+
+
+# ---------------------------------------------------------------------------------------------
+# on-disk cache of the lowered CSR (next to the reference's feather cache, same keying idea)
+# ---------------------------------------------------------------------------------------------
+def csr_cache_key(wdf: pd.DataFrame, grid_cell_id: np.ndarray, n_lat: int, n_lon: int,
+                  lon_order: Optional[np.ndarray]) -> str:
+    """sha256 over everything the lowering depends on, truncated like the reference's cache ids
+    (aggfly/cache/project_cache.py:207-226 keeps 15 hex digits)."""
+    import hashlib
+    h = hashlib.sha256()
+    for col in ("cell_id", "index_right", "weight"):
+        h.update(np.ascontiguousarray(wdf[col].to_numpy()).tobytes())
+    h.update(np.ascontiguousarray(np.asarray(grid_cell_id)).tobytes())
+    h.update(np.asarray([n_lat, n_lon], dtype=np.int64).tobytes())
+    h.update(b"none" if lon_order is None else np.ascontiguousarray(np.asarray(lon_order, dtype=np.int64)).tobytes())
+    return h.hexdigest()[:15]
+
+
+def lower_to_csr_cached(wdf: pd.DataFrame, grid_cell_id: np.ndarray, n_lat: int, n_lon: int,
+                        lon_order: Optional[np.ndarray] = None, project_dir: Optional[str] = None) -> HostCSR:
+    """``lower_to_csr`` memoised under ``{project_dir}/tmp/DeviceCSR/mod-{sha}/{sha}.npz`` (the layout of
+    the reference's ProjectCache, aggfly/cache/project_cache.py:26-57): the yearly loop of a pipeline and
+    the ranks of a sharded run lower the weights once."""
+    import os
+    if not project_dir:
+        return lower_to_csr(wdf, grid_cell_id, n_lat, n_lon, lon_order)
+    sha = csr_cache_key(wdf, grid_cell_id, n_lat, n_lon, lon_order)
+    d = os.path.join(project_dir, "tmp", "DeviceCSR", f"mod-{sha}")
+    path = os.path.join(d, f"{sha}.npz")
+    if os.path.exists(path):
+        try:
+            with np.load(path) as z:
+                return HostCSR(z["row_ptr"], z["cell_idx"], z["w"], z["region_ids"], int(z["n_cells"]))
+        except Exception:
+            pass                                                   # unreadable cache entry: rebuild it
+    csr = lower_to_csr(wdf, grid_cell_id, n_lat, n_lon, lon_order)
+    os.makedirs(d, exist_ok=True)
+    tmp = f"{path}.{os.getpid()}.tmp.npz"
+    np.savez(tmp, row_ptr=csr.row_ptr, cell_idx=csr.cell_idx, w=csr.w, region_ids=csr.region_ids,
+             n_cells=np.int64(csr.n_cells))
+    os.replace(tmp, path)                                          # atomic: ranks may race
+    return csr

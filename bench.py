@@ -319,10 +319,11 @@ def main_ours(args, rank, world, local_rank):
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dt = float(tt[0])
-        from aggfly_b200 import stream as _stream
+        from aggfly_b200 import aggregate as _agg_mod, stream as _stream
         st = dict(_stream.LAST_STATS)
         h2d_ms = st["copy_events"][0].elapsed_time(st["copy_events"][1]) if "copy_events" in st else None
         e2e = {"value": world * wl.cell_steps / dt, "unit": UNIT,
+               "phases_ms": {k: round(v, 2) for k, v in _agg_mod.LAST_TRACE.get("phases_ms", {}).items()},
                "feed": {"chunks": st.get("chunks"), "pinned": st.get("pinned"), "k1_launches": st.get("k1_launches"),
                         "h2d_ms": h2d_ms,
                         "h2d_gbs": (st.get("h2d_bytes", 0) / (h2d_ms * 1e-3) / 1e9) if h2d_ms else None},

@@ -30,7 +30,9 @@
  * Data layout
  *   raster   x[T, n_cells]      time-major, cell = lat_index * n_lon + lon_index fastest
  *                               (row stride `ld` elements), float32 or float64
- *   columns  X[G, n_cols, n_cells]  per-cell temporal results, G = output periods
+ *   columns  X[G, n_cells, n_cols]  per-cell temporal results, G = output periods; the columns of
+ *                                   a cell are contiguous (the regional average gathers whole
+ *                                   cells: one or two sectors per entry instead of n_cols)
  *   valid    V[G, n_cells] uint8    1 iff every column of the call is non-NaN there
  *                                   (shared validity mask, aggfly/aggregate/spatial.py:114-119)
  *   panel    P[n_regions, G, n_cols] float64
@@ -205,7 +207,7 @@ int agf_program_stripe_rows(const agf_program_t *prog, int32_t stripe, int64_t *
  * elements.  Single-level programs write X / V directly; two-level programs write partial
  * records that agf_temporal_finalize merges.
  * Several programs of one call may share X / V: column c of this program goes to
- * X[:, cols[c].dst, :] of an X with `out_ncols` columns, and with valid_and != 0 its validity
+ * X[:, :, cols[c].dst] of an X with `out_ncols` columns, and with valid_and != 0 its validity
  * is AND-ed into V instead of overwriting it. */
 int agf_temporal_run(const agf_program_t *prog, const void *d_x, int64_t ld, int64_t row0,
                      int32_t stripe_begin, int32_t stripe_end, double *d_partial, void *d_out,

@@ -62,7 +62,7 @@ def _run_lanes(cube, bounds, lanes):
     stage = Stage(programs=[prog], nodes=[None] * len(lanes), dtype=cube.dtype, labels=np.arange(len(bounds) - 1))
     res = engine.run_stage(stage, engine.to_device(cube).reshape(T, Y * X), Y * X)
     torch.cuda.synchronize()
-    return res.X.cpu().numpy().reshape(len(bounds) - 1, len(lanes), Y, X), res.V.cpu().numpy()
+    return np.moveaxis(res.X.cpu().numpy().reshape(len(bounds) - 1, Y, X, len(lanes)), -1, 1), res.V.cpu().numpy()
 
 
 @pytest.mark.parametrize("dt", ["float32", "float64"])
@@ -454,7 +454,7 @@ def test_every_spmm_variant_matches_oracle(gs, monkeypatch):
     wdf, shp = _weights_case(lat, lon, rng, n_regions=9)
     big = pd.DataFrame({"cell_id": rng.permutation(66)[:50], "index_right": 10 + 3 * 8, "weight": rng.random(50)})
     wdf = pd.concat([wdf, big], ignore_index=True)                  # one region with more entries than a warp
-    for name in ("c3b_daily", "c3_bins_and_poly"):
+    for name in ("c3b_daily", "c3_bins_and_poly", "monthly_mix", "c1_tavg_poly"):     # float2, double, float4, double2 loads
         want = orc.aggregate_dataset(orc.OWeights(wdf, np.arange(66), shp, "geoid", "nan"),
                                      orc.ODataset(arr, t, lat, lon, True), aggregator_dict=SPECS[name])
         ds = af.Dataset.from_arrays(arr, t, lat, lon, True)

@@ -78,7 +78,7 @@ def _worker(rank, world, port, out_dir):
         def fake_temporal(sub, spec_):
             out = orc.aggregate_time(orc.ODataset(np.asarray(sub.values), sub.time, sub.latitude, sub.longitude, True), spec_)
             res = _Res()
-            res.X = np.stack([out[k][0].reshape(out[k][0].shape[0], -1) for k in out], axis=1)      # [G, NC, cells]
+            res.X = np.stack([out[k][0].reshape(out[k][0].shape[0], -1) for k in out], axis=2)      # [G, cells, NC]
             res.labels = list(out.values())[0][1]
             return list(out), res, None
 
@@ -87,8 +87,8 @@ def _worker(rank, world, port, out_dir):
 
         def fake_spmm(csr, res):
             h = csr.host
-            G, NC, _ = res.X.shape
-            valid = ~np.isnan(res.X).any(axis=1)                                                    # [G, cells]
+            G, _, NC = res.X.shape
+            valid = ~np.isnan(res.X).any(axis=2)                                                    # [G, cells]
             panel = np.full((h.n_regions, G, NC), np.nan)
             for r in range(h.n_regions):
                 e = slice(h.row_ptr[r], h.row_ptr[r + 1])
@@ -97,7 +97,7 @@ def _worker(rank, world, port, out_dir):
                     m = valid[g, cells]
                     den = (ww * m).sum()
                     if den != 0:
-                        panel[r, g] = (np.where(m, res.X[g][:, cells], 0.0) * ww).sum(axis=1) / den
+                        panel[r, g] = (np.where(m[:, None], res.X[g][cells, :], 0.0) * ww[:, None]).sum(axis=0) / den
             return torch.from_numpy(panel)
 
         agg._temporal_device = fake_temporal

@@ -151,3 +151,22 @@ def test_single_row_inner_groups_collapse_to_one_level():
     _, _, stage = _plan(dict(a=[("aggregate", {"calc": "dd", "groupby": "date", "ddargs": [10, 30, 0]}),
                                 ("aggregate", {"calc": "mean", "groupby": "month"})]), t=t)
     assert all(q.two_level for q in stage.programs)
+
+
+def test_csr_lowering_is_cached_on_disk_by_content(tmp_path):
+    from aggfly_b200 import weights as W
+    wdf = pd.DataFrame({"cell_id": [3, 1, 0, 2, 9], "index_right": [7, 7, 2, 2, 2], "weight": [0.5, 0.25, 1.0, 2.0, 3.0]})
+    lon_order = np.array([1, 0])
+    a = W.lower_to_csr_cached(wdf, np.arange(4), 2, 2, lon_order, str(tmp_path))
+    files = list(tmp_path.rglob("*.npz"))
+    assert len(files) == 1 and files[0].parent.name.startswith("mod-") and files[0].parent.parent.name == "DeviceCSR"
+    b = W.lower_to_csr_cached(wdf, np.arange(4), 2, 2, lon_order, str(tmp_path))       # served from disk
+    ref = W.lower_to_csr(wdf, np.arange(4), 2, 2, lon_order)
+    for x in (a, b):
+        assert np.array_equal(x.row_ptr, ref.row_ptr) and np.array_equal(x.cell_idx, ref.cell_idx)
+        assert np.array_equal(x.w, ref.w) and np.array_equal(x.region_ids, ref.region_ids) and x.n_cells == 4
+    assert list(ref.region_ids) == [2, 7] and list(ref.row_ptr) == [0, 2, 4]           # cell 9 is off-grid: dropped
+    assert list(ref.cell_idx) == [1, 3, 2, 0]                                          # columns swapped by lon_order
+    wdf2 = wdf.assign(weight=wdf["weight"] * 2)
+    W.lower_to_csr_cached(wdf2, np.arange(4), 2, 2, lon_order, str(tmp_path))
+    assert len(list(tmp_path.rglob("*.npz"))) == 2                                     # different content, new key
