@@ -152,13 +152,18 @@ static int launch_k1(const K1Launch &a) {
         // registers per thread, two need <= 112.
         constexpr int state_regs = TL ? NB + 2 * (NL - NB) : 2 * NL + (NB >= 0 ? NB + 2 * (NS - NB) : 2 * NS);
         constexpr int MINB = state_regs <= 30 ? 3 : (state_regs <= 48 ? 2 : 1);
-        constexpr int STAGES = MINB == 3 ? 3 : (MINB == 2 ? 4 : 8);
+        // kernels that stage their output block (single-level, several columns) give one ring stage
+        // back to the staging area so that MINB CTAs still fit in the SM's 227 KB
+        constexpr int SW = stage_bytes_per_warp<NL, NS>();
+        constexpr int STAGES = (MINB == 3 ? 3 : (MINB == 2 ? 4 : 8)) - (SW > 0 ? 1 : 0);
         constexpr int TT = tma_rows<T>();
+        const int out_esz = d.out_dtype == AGF_F64 ? 8 : 4;
+        kp.stage_out = (SW > 0 && d.n_cols == a.ncols && a.ncols > 1 && 32 * a.ncols * out_esz <= SW) ? 1 : 0;
         TensorMap tm;
         int rc = agf_make_tensor_map(&tm, a.d_x, (int)sizeof(T), (uint64_t)p->n_cells, (uint64_t)(row_end - a.row0),
                                      (uint64_t)a.ld, TT);
         if (rc) return rc;
-        constexpr int smem = STAGES * TMA_TILE_BYTES_DEFAULT + 2 * STAGES * 8;
+        constexpr int smem = STAGES * TMA_TILE_BYTES_DEFAULT + 2 * STAGES * 8 + (TMA_CW / 32) * SW;
         void (*kern)(const K1Params<T, NL, NS>, const TensorMap);
         if constexpr (GL > 0)
             kern = agf_k1_tma_uni<T, NL, NS, DIAG, KINDS, NB, GL, TT, STAGES, MINB>;

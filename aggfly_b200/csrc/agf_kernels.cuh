@@ -134,6 +134,7 @@ struct K1Params {
     int in_f64, out_f64;
     int need_nan, need_cnt, has_sine, diag;
     int n_pre;
+    int stage_out;  // single-level: stage a warp's X[g, 32 cells, :] block in shared memory, store it coalesced
     PreP<T> pre[AGF_MAX_PRE];
     LaneP<T> lanes[NL];
     SlotP slots[NS > 0 ? NS : 1];
@@ -613,9 +614,58 @@ __device__ __forceinline__ void l2_acc_bins(const SlotP &S, int &c, double x) {
     }
 }
 
+// Where a single-level program's columns go.  X is cell-major (X[g, cell, :]), so the 32 cells of a warp
+// own one contiguous block of 32 * out_ncols elements; written straight from registers that is
+// out_ncols stores per thread with a stride of out_ncols elements between lanes (every store
+// instruction touches 32 sectors: +8.5 ms on the C3b daily panel, ncu r1i).  With a per-warp staging
+// area in shared memory the block is assembled there and copied out with fully coalesced stores.
+// All 32 lanes of the warp must reach l1_flush when `stage` is set (cells past the grid are `!active`).
+struct OutSink {
+    void *stage;  // this warp's staging area (nullptr: direct stores)
+    bool active;  // this thread's cell exists
+};
+
+// bytes of staging per consumer warp an instantiation reserves (0: never stages)
+template <int NL, int NS>
+__host__ __device__ constexpr int stage_bytes_per_warp() {
+    return (NS == 0 && NL > 1) ? 32 * NL * 4 : 0;
+}
+
+template <typename T, int NL, int NS>
+__device__ __forceinline__ void sink_put(const K1Params<T, NL, NS> &p, const OutSink &o, size_t base, int dst, double v) {
+    if (o.stage != nullptr) {
+        const int i = (threadIdx.x & 31) * p.out_ncols + dst;
+        if (p.out_f64)
+            reinterpret_cast<double *>(o.stage)[i] = v;
+        else
+            reinterpret_cast<float *>(o.stage)[i] = (float)v;
+    } else if (o.active) {
+        store_col<T>(p.out, p.out_f64, base + dst, v);
+    }
+}
+
+// copy the staged block of this warp to X (32-bit words, 128 contiguous bytes per store instruction)
+template <typename T, int NL, int NS>
+__device__ __forceinline__ void sink_commit(const K1Params<T, NL, NS> &p, const OutSink &o, int g, int cell) {
+    if (o.stage == nullptr) return;
+    __syncwarp();
+    const int lane = threadIdx.x & 31;
+    const int cell0 = cell - lane;
+    const int n_valid = min(32, p.n_cells - cell0);
+    if (n_valid > 0) {
+        const int wpe = p.out_f64 ? 2 : 1;  // 32-bit words per element
+        const int words = n_valid * p.out_ncols * wpe;
+        uint32_t *dst = reinterpret_cast<uint32_t *>(p.out) + ((size_t)g * p.n_cells + cell0) * p.out_ncols * wpe;
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(o.stage);
+        for (int i = lane; i < words; i += 32) dst[i] = src[i];
+    }
+    __syncwarp();
+}
+
 // end of level-1 group g (n_grp rows): emit columns (single-level) or feed the slots
 template <typename T, int NL, int NS, bool DIAG, unsigned KINDS, int NB, int GLC = 0, typename ST>
-__device__ __forceinline__ void l1_flush(const K1Params<T, NL, NS> &p, ST &s, int g, int n_grp, int cell) {
+__device__ __forceinline__ void l1_flush(const K1Params<T, NL, NS> &p, ST &s, int g, int n_grp, int cell,
+                                         const OutSink &o) {
     if constexpr (ST::TL) {
         // typed lanes: column of kernel lane l is cols[l].dst (-1: inert pad, nothing stored)
         constexpr int NBL = NL - ST::NA;
@@ -625,7 +675,7 @@ __device__ __forceinline__ void l1_flush(const K1Params<T, NL, NS> &p, ST &s, in
 #pragma unroll
         for (int j = 0; j < NBL; ++j) {
             const int dst = p.cols[j].dst;
-            if (dst >= 0) store_col<T>(p.out, p.out_f64, base + dst, empty ? agf_nan() : (double)s.c[j]);
+            if (dst >= 0) sink_put(p, o, base, dst, empty ? agf_nan() : (double)s.c[j]);
         }
 #pragma unroll
         for (int l = 0; l < ST::NA; ++l) {
@@ -634,11 +684,14 @@ __device__ __forceinline__ void l1_flush(const K1Params<T, NL, NS> &p, ST &s, in
                 double r = (p.lanes[NBL + l].calc == AGF_CALC_MEAN) ? mean_of<T, GLC>(s.a[l], n_grp) : s.a[l];
                 r = empty ? agf_nan() : round_to<T>(r);
                 ok &= (r == r);
-                store_col<T>(p.out, p.out_f64, base + dst, r);
+                sink_put(p, o, base, dst, r);
             }
         }
-        unsigned char *vp = p.valid + (size_t)g * p.n_cells + cell;
-        *vp = (p.valid_and ? (*vp != 0) && ok : ok) ? 1 : 0;
+        if (o.active) {
+            unsigned char *vp = p.valid + (size_t)g * p.n_cells + cell;
+            *vp = (p.valid_and ? (*vp != 0) && ok : ok) ? 1 : 0;
+        }
+        sink_commit(p, o, g, cell);
         return;
     }
     double val[NL];
@@ -653,7 +706,7 @@ __device__ __forceinline__ void l1_flush(const K1Params<T, NL, NS> &p, ST &s, in
             for (int l = 0; l < NL; ++l) {
                 if (l < p.n_cols) {
                     ok &= (val[l] == val[l]);
-                    store_col<T>(p.out, p.out_f64, base + p.cols[l].dst, val[l]);
+                    sink_put(p, o, base, p.cols[l].dst, val[l]);
                 }
             }
         } else {
@@ -661,11 +714,14 @@ __device__ __forceinline__ void l1_flush(const K1Params<T, NL, NS> &p, ST &s, in
                 const ColP &C = p.cols[c];
                 double x = apply_xform<T>(select_reg<NL>(val, C.src), C.xform, C.xparam, C.x_f64);
                 ok &= (x == x);
-                store_col<T>(p.out, p.out_f64, base + C.dst, x);
+                sink_put(p, o, base, C.dst, x);
             }
         }
-        unsigned char *vp = p.valid + (size_t)g * p.n_cells + cell;
-        *vp = (p.valid_and ? (*vp != 0) && ok : ok) ? 1 : 0;
+        if (o.active) {
+            unsigned char *vp = p.valid + (size_t)g * p.n_cells + cell;
+            *vp = (p.valid_and ? (*vp != 0) && ok : ok) ? 1 : 0;
+        }
+        sink_commit(p, o, g, cell);
     } else if constexpr (NB >= 0) {
         // typed slots; unused ones are padded by the launcher with inert reducers whose registers
         // are never written back, so there is no per-slot bound check or branch
@@ -762,7 +818,7 @@ __global__ void __launch_bounds__(K1_THREADS)
             if (i < clen) l1_acc<KINDS>(p, s, cur[i]);
 
         if (ends) {
-            l1_flush<T, NL, NS, DIAG, KINDS, NB>(p, s, g, nb - glo, cell);
+            l1_flush<T, NL, NS, DIAG, KINDS, NB>(p, s, g, nb - glo, cell, OutSink{nullptr, true});
             l1_init<KINDS>(p, s);
             if (NS > 0) {
                 // close every level-2 group that ends with level-1 group g
@@ -892,6 +948,12 @@ __global__ void __launch_bounds__(TMA_THREADS, MINB)
     // ===== consumers: thread t owns cell cell0 + t =====
     const int cell = cell0 + threadIdx.x;
     const bool active = cell < p.n_cells;
+    // per-warp output staging lives behind the ring and its barriers (see OutSink)
+    void *stage = nullptr;
+    if constexpr (stage_bytes_per_warp<NL, NS>() > 0)
+        if (p.stage_out)
+            stage = smem_raw + TMA_STAGES * TMA_TILE_BYTES + 2 * TMA_STAGES * 8 +
+                    (threadIdx.x >> 5) * stage_bytes_per_warp<NL, NS>();
     int g2 = st.g2_first;
     int rec = st.rec0;
     int next_b2 = (NS > 0) ? p.b2[g2 + 1] : 0;
@@ -928,7 +990,7 @@ __global__ void __launch_bounds__(TMA_THREADS, MINB)
             r += run;
             k += run;
             if (k == nb) {  // level-1 group g is complete
-                if (active) l1_flush<T, NL, NS, DIAG, KINDS, NB>(p, s, g, nb - glo, cell);
+                if (NS == 0 || active) l1_flush<T, NL, NS, DIAG, KINDS, NB>(p, s, g, nb - glo, cell, OutSink{stage, active});
                 l1_init<KINDS>(p, s);
                 if (NS > 0) {
                     if (g + 1 == next_b2 || g + 1 == g_end) {
@@ -1013,6 +1075,12 @@ __global__ void __launch_bounds__(TMA_THREADS, MINB)
     // ===== consumers: thread t owns cell cell0 + t =====
     const int cell = cell0 + threadIdx.x;
     const bool active = cell < p.n_cells;
+    // per-warp output staging lives behind the ring and its barriers (see OutSink)
+    void *stage = nullptr;
+    if constexpr (stage_bytes_per_warp<NL, NS>() > 0)
+        if (p.stage_out)
+            stage = smem_raw + TMA_STAGES * TMA_TILE_BYTES + 2 * TMA_STAGES * 8 +
+                    (threadIdx.x >> 5) * stage_bytes_per_warp<NL, NS>();
     int g2 = st.g2_first;
     int rec = st.rec0;
     int next_b2 = (NS > 0) ? p.b2[g2 + 1] : 0;
@@ -1022,7 +1090,7 @@ __global__ void __launch_bounds__(TMA_THREADS, MINB)
 
     // end of level-1 group g: flush, close level-2 groups that end with it
     auto group_end = [&]() {
-        if (active) l1_flush<T, NL, NS, DIAG, KINDS, NB, GL>(p, s, g, GL, cell);
+        if (NS == 0 || active) l1_flush<T, NL, NS, DIAG, KINDS, NB, GL>(p, s, g, GL, cell, OutSink{stage, active});
         l1_init<KINDS>(p, s);
         if constexpr (NS > 0) {
             if (g + 1 == next_b2 || g + 1 == g_end) {

@@ -237,6 +237,24 @@ int agf_spmm_run(const agf_csr_t *csr, const void *d_x, int32_t x_dtype, const u
 int agf_valid_mask_run(const void *d_x, int32_t x_dtype, int64_t n_groups, int32_t n_cols,
                        int64_t n_cells, uint8_t *d_valid, uintptr_t stream);
 
+/* ---- weights builder geometry (host only; replaces the GEOS work of calculate_weights) ---------- */
+
+/* For every region the fraction of each grid cell's rectangle that it covers -- what
+ * aggfly/weights/grid_weights.py:238-421 obtains from two buffered centroid joins plus shapely
+ * intersections of the border cells (interior cells: exactly 1; cells with no overlap: absent).
+ *   regions   region r owns rings [region_ring_ptr[r], region_ring_ptr[r+1]); ring k owns vertices
+ *             [ring_ptr[k], ring_ptr[k+1]) of xy (x0, y0, x1, y1, ...; closing vertex optional).
+ *             Holes must be oriented opposite to their shell (shapefile / OGC convention).
+ *   grid      cell (i, j) is the rectangle lon[j] +- dlon/2, lat[i] +- dlat/2 (centres in any
+ *             monotonic order); cell_id = i * n_lon + j (aggfly/dataset/grid.py:74-80).
+ * Pairs come out grouped by region, cell_id ascending.  Pure host code, no device needed. */
+typedef struct agf_overlap agf_overlap_t;
+int agf_overlap_create(agf_overlap_t **out, int32_t n_regions, const int64_t *region_ring_ptr,
+                       const int64_t *ring_ptr, const double *xy, int32_t n_lon, const double *lon,
+                       double dlon, int32_t n_lat, const double *lat, double dlat, int64_t *n_pairs);
+int agf_overlap_fetch(const agf_overlap_t *h, int32_t *region, int64_t *cell_id, double *fraction);
+int agf_overlap_destroy(agf_overlap_t *h);
+
 #ifdef __cplusplus
 }
 #endif
