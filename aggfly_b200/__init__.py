@@ -10,13 +10,13 @@ from .aggregate import (ALLOWED_ENGINE, SpatialAggregator, aggregate_dataset, ag
 from .dataset import Dataset, Grid, RasterArray, lon_to_180, lon_to_360
 from .spec import TemporalAggregator
 from .timeaxis import CalendarIndex, CFDate, group_bounds, translate_groupby
-from .weights import GeoRegions, GridWeights, lower_to_csr, weights_from_objects
+from .weights import GeoRegions, GridWeights, SecondaryWeights, lower_to_csr, weights_from_objects
 
 __version__ = "0.1.0"
 
 __all__ = [
     "aggregate_dataset", "aggregate_time", "aggregate_space", "TemporalAggregator", "SpatialAggregator",
     "resolve_engine", "ALLOWED_ENGINE", "Dataset", "Grid", "RasterArray", "GridWeights", "GeoRegions",
-    "weights_from_objects", "lower_to_csr", "CalendarIndex", "CFDate", "group_bounds", "translate_groupby",
+    "weights_from_objects", "SecondaryWeights", "lower_to_csr", "CalendarIndex", "CFDate", "group_bounds", "translate_groupby",
     "lon_to_180", "lon_to_360",
 ]

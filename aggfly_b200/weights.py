@@ -11,10 +11,10 @@ module keeps exactly that contract:
   reads (``weights.weights``, ``weights.grid.cell_id``, ``weights.zero_weight``,
   ``weights.georegions.shp[[regionid]]``);
 * :func:`weights_from_objects` -- same name/signature as the reference; ``calculate_weights()``
-  supports axis-aligned rectangular regions exactly (rectangle / cell overlap x cos(lat) x
-  optional secondary raster, i.e. what ``get_area_weights`` / ``get_weighted_area_weights`` return
-  for such regions) -- enough for synthetic benchmarks; arbitrary polygons need the geometry
-  stack and are the "next" row f-2;
+  returns what ``get_area_weights`` / ``get_weighted_area_weights`` return: exact cell / region
+  overlap fractions (x cos(lat), x a secondary raster normalised per region) for polygon regions
+  (rings clipped against every candidate cell by the library, csrc/agf_geom.cu -- no GEOS) and,
+  through a closed form, for axis-aligned rectangles (synthetic tessellations);
 * :func:`lower_to_csr` -- ``_weight_triplets`` (aggfly/aggregate/spatial.py:157-178) + the cell
   re-ordering of ``rescale_longitude`` folded into ``cell_idx`` (raster memory order), so the
   raster itself is never permuted on the device.
@@ -49,6 +49,39 @@ class GeoRegions:
     @property
     def regions(self):
         return self.shp[self.regionid]
+
+    @classmethod
+    def from_polygons(cls, ids, polygons, regionid="geoid", attrs: Optional[pd.DataFrame] = None) -> "GeoRegions":
+        """Regions given as rings in lon/lat degrees (-180..180).  ``polygons[i]`` is one ``(n, 2)``
+        array (a simple polygon), or a list of rings ``[shell, hole, ...]`` / several parts; holes must be
+        oriented opposite to their shell (``geometry.orient_polygon`` does that)."""
+        rings = []
+        for poly in polygons:
+            if isinstance(poly, np.ndarray) and poly.ndim == 2:
+                poly = [poly]
+            rings.append([np.asarray(r, dtype=float) for r in poly])
+        shp = pd.DataFrame({regionid: list(ids)}) if attrs is None else attrs.reset_index(drop=True).copy()
+        if regionid not in shp.columns:
+            shp[regionid] = list(ids)
+        shp["rings"] = rings
+        return cls(shp, regionid)
+
+    @classmethod
+    def from_shapefile(cls, path: str, regionid: Optional[str] = None, region_list=None) -> "GeoRegions":
+        """``georegions_from_path`` (aggfly/regions/georegions.py:220-323) for an ESRI shapefile, without
+        geopandas: polygons from the ``.shp``, attributes from the ``.dbf`` next to it (if any)."""
+        import os
+        from .geometry import read_dbf, read_shp_polygons
+        rings = read_shp_polygons(path)
+        dbf = os.path.splitext(path)[0] + ".dbf"
+        attrs = read_dbf(dbf) if os.path.exists(dbf) else pd.DataFrame(index=range(len(rings)))
+        if len(attrs) != len(rings):
+            raise ValueError(f"{path}: {len(rings)} shapes but {len(attrs)} attribute records")
+        if regionid is None:
+            regionid = "region_id" if "region_id" not in attrs.columns else "region_id_"
+            attrs[regionid] = np.arange(len(rings))
+        attrs["rings"] = rings
+        return cls(attrs, regionid, region_list)
 
     @classmethod
     def from_rectangles(cls, ids, lon_min, lon_max, lat_min, lat_max, regionid="geoid") -> "GeoRegions":
@@ -98,13 +131,16 @@ class GridWeights:
         """Exact area (x cos(lat), x secondary raster) weights for rectangular regions."""
         shp = self.georegions.shp
         need = {"lon_min", "lon_max", "lat_min", "lat_max"}
-        if not need.issubset(shp.columns):
-            raise NotImplementedError(
-                "calculate_weights() here only handles axis-aligned rectangular regions "
-                "(GeoRegions.from_rectangles); for polygon regions compute the frame with the "
-                "reference and wrap it with GridWeights.from_frame (SURVEY.md section 8 f-2)")
         lon, lat = self.grid.longitude, self.grid.latitude
         dlon, dlat = self.grid.resolution_lon, self.grid.resolution_lat
+        if "rings" in shp.columns:
+            self.weights = self._finish(self._polygon_area_weights(shp, lon, lat, dlon, dlat))
+            return
+        if not need.issubset(shp.columns):
+            raise NotImplementedError(
+                "calculate_weights() needs polygon rings (GeoRegions.from_polygons / from_shapefile) or "
+                "rectangles (GeoRegions.from_rectangles); a frame computed elsewhere can be wrapped with "
+                "GridWeights.from_frame")
         rows = []
         for ridx, r in zip(shp.index, shp.itertuples(index=False)):
             ox = np.clip(np.minimum(lon + dlon / 2, r.lon_max) - np.maximum(lon - dlon / 2, r.lon_min), 0, None)
@@ -118,13 +154,33 @@ class GridWeights:
             rows.append(pd.DataFrame({"cell_id": (yy * len(lon) + xx).ravel(), "index_right": ridx,
                                       "area_weight": aw.ravel(), "longitude": lon[xx].ravel(),
                                       "latitude": lat[yy].ravel()}))
-        w = pd.concat(rows, ignore_index=True)
+        self.weights = self._finish(pd.concat(rows, ignore_index=True))
+
+    def _polygon_area_weights(self, shp, lon, lat, dlon, dlat) -> pd.DataFrame:
+        """get_area_weights (aggfly/weights/grid_weights.py:379-421) for polygon regions: interior
+        cells 1, border cells their covered fraction, x cos(latitude) when ``cosine_area``."""
+        from .geometry import cell_overlaps
+        region, cell, frac = cell_overlaps(list(shp["rings"]), lon, lat, dlon, dlat)
+        yy, xx = cell // len(lon), cell % len(lon)
+        aw = frac * (np.cos(np.radians(lat[yy])) if self.cosine_area else 1.0)
+        return pd.DataFrame({"cell_id": np.asarray(self.grid.cell_id)[cell], "index_right": np.asarray(shp.index)[region],
+                             "area_weight": aw, "longitude": lon[xx], "latitude": lat[yy]})
+
+    def _finish(self, w: pd.DataFrame) -> pd.DataFrame:
+        """Secondary-raster weighting, zero-weight policy, region ids (grid_weights.py:423-521, 194-196)."""
+        shp = self.georegions.shp
         if self.raster_weights is None:
             w["weight"] = w["area_weight"]
         else:
             # aggfly/weights/grid_weights.py:447-489: missing / non-finite raster values count as zero;
             # weight = area_weight * raster_weight / (the region's summed raster_weight)
-            rw = np.asarray(self.raster_weights, dtype=float).reshape(-1)[w["cell_id"].to_numpy()]
+            raster = self.raster_weights
+            if isinstance(raster, SecondaryWeights):
+                raster = raster.on_grid(self.grid)
+            # raster is laid out like the weights grid: position = lat_index * n_lon + lon_index
+            pos = np.searchsorted(np.asarray(self.grid.cell_id), w["cell_id"].to_numpy()) \
+                if not np.array_equal(self.grid.cell_id, np.arange(len(self.grid.cell_id))) else w["cell_id"].to_numpy()
+            rw = np.asarray(raster, dtype=float).reshape(-1)[pos]
             n_missing = int((~np.isfinite(rw)).sum())
             if n_missing:
                 warnings.warn(f"{n_missing} of {len(w)} cell-region pairs had no secondary raster value (outside its "
@@ -144,8 +200,27 @@ class GridWeights:
                 elif self.zero_weight == "drop":
                     warnings.warn("regions with no secondary weight are DROPPED", UserWarning)
                     w = w.loc[~empty].reset_index(drop=True)
-        self.weights = shp[[self.georegions.regionid]].merge(w, right_on="index_right", left_index=True)
         self._csr_cache.clear()
+        return shp[[self.georegions.regionid]].merge(w, right_on="index_right", left_index=True)
+
+
+class SecondaryWeights:
+    """A secondary raster (population, cropland ...) on its own regular lat/lon grid
+    (aggfly/weights/secondary_weights.py:13-109 without rioxarray): ``on_grid`` averages it onto the
+    climate grid like ``rescale_raster_to_grid`` (``Resampling.average``, nodata excluded)."""
+
+    def __init__(self, values, latitude, longitude, nodata: Optional[float] = None, name: Optional[str] = None):
+        self.values = np.asarray(values, dtype=float)
+        if self.values.ndim == 3 and self.values.shape[0] == 1:
+            self.values = self.values[0]                        # a single band
+        self.latitude = np.asarray(latitude, dtype=float)
+        self.longitude = np.asarray(longitude, dtype=float)
+        self.nodata, self.name = nodata, name
+
+    def on_grid(self, grid: Grid) -> np.ndarray:
+        from .geometry import rescale_raster_to_grid
+        return rescale_raster_to_grid(self.values, self.latitude, self.longitude, grid.latitude, grid.longitude,
+                                      grid.resolution_lat, grid.resolution_lon, self.nodata)
 
 
 def weights_from_objects(clim: Dataset, georegions: GeoRegions, secondary_weights=None,
