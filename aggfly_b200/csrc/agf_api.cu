@@ -621,3 +621,35 @@ extern "C" int agf_valid_mask_run(const void *d_x, int32_t x_dtype, int64_t n_gr
     CU(cudaGetLastError());
     return 0;
 }
+
+extern "C" int agf_elementwise_run(const void *d_in, int32_t in_dtype, void *d_out, int32_t out_dtype, int64_t n,
+                                   int32_t xform, double xparam, const void *d_other, int32_t other_dtype,
+                                   uint8_t *d_valid, uintptr_t stream) {
+    if (!d_in || !d_out) return fail(AGF_E_INVALID, "null argument");
+    if (n <= 0) return fail(AGF_E_INVALID, "bad size");
+    if (!d_other && !(xform >= AGF_XF_POWI && xform <= AGF_XF_SPLINE2)) return fail(AGF_E_INVALID, "bad xform");
+    if (in_dtype == AGF_F64 && out_dtype != AGF_F64) return fail(AGF_E_INVALID, "float64 input needs float64 output");
+    if (d_other && other_dtype == AGF_F64 && out_dtype != AGF_F64)
+        return fail(AGF_E_INVALID, "float64 interaction needs float64 output");
+    int dev = 0, sms = 148;
+    CU(cudaGetDevice(&dev));
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const unsigned blocks = (unsigned)std::min<int64_t>((n + 255) / 256, (int64_t)sms * 16);
+    cudaStream_t st = (cudaStream_t)stream;
+#define AGF_EW(TI, TO, TB)                                                                                  \
+    agf_elementwise<TI, TO, TB><<<blocks, 256, 0, st>>>((const TI *)d_in, (TO *)d_out, (const TB *)d_other, \
+                                                        (long long)n, xform, xparam, d_valid)
+    const bool of64 = d_other && other_dtype == AGF_F64;
+    if (in_dtype == AGF_F64) {
+        if (of64) AGF_EW(double, double, double);
+        else AGF_EW(double, double, float);
+    } else if (out_dtype == AGF_F64) {
+        if (of64) AGF_EW(float, double, double);
+        else AGF_EW(float, double, float);
+    } else {
+        AGF_EW(float, float, float);
+    }
+#undef AGF_EW
+    CU(cudaGetLastError());
+    return 0;
+}

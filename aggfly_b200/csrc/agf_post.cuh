@@ -174,4 +174,34 @@ __global__ void __launch_bounds__(256)
     V[g * n_cells + cell] = ok ? 1 : 0;
 }
 
+// ------------------------------------------------------------------------------------------
+// elementwise transform of a whole series (materialised transforms: a power / spline / interaction
+// that cannot ride inside a fused program, e.g. applied to the raster before the first aggregate
+// step, or two transforms in a row): out[i] = f(in[i]) (* other[i]), V[i] = !isnan(out[i]).
+// Dtype rules are those of apply_xform (NumPy promotion decided by the host).
+// ------------------------------------------------------------------------------------------
+template <typename TI, typename TO, typename TB>
+__global__ void __launch_bounds__(256)
+    agf_elementwise(const TI *__restrict__ in, TO *__restrict__ out, const TB *__restrict__ other, long long n,
+                    int xform, double xparam, unsigned char *__restrict__ valid) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double x = (double)in[i];
+        double r;
+        if (other != nullptr) {
+            // np.multiply(array, inter) in the promoted dtype (dataset.py:547-563)
+            if (sizeof(TO) == 4)
+                r = (double)((float)x * (float)other[i]);
+            else
+                r = x * (double)other[i];
+        } else if (sizeof(TI) == 4) {
+            r = apply_xform<float>(x, xform, xparam, sizeof(TO) == 8);
+        } else {
+            r = apply_xform64(x, xform, xparam);
+        }
+        out[i] = (TO)r;
+        if (valid != nullptr) valid[i] = (r == r) ? 1 : 0;
+    }
+}
+
 }  // namespace agf

@@ -35,6 +35,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+RESULT_LINE = []                 # the JSON line, printed by main() once stdout is restored
 METRIC = "cell-hours aggregated/sec"
 UNIT = "cell-hours/s"
 
@@ -149,6 +150,15 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi -lms 100"}
 
 
+def host_threads() -> int:
+    """Host cores this process may use.  torchrun exports OMP_NUM_THREADS=1, which would make the CPU
+    arm single-threaded; the CPU baseline is defined as "all the host threads it can use"."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
 def host_mem_available_gb() -> float:
     """Host memory this process tree may still take: min(MemAvailable, cgroup limit - usage)."""
     avail = float("inf")
@@ -215,7 +225,7 @@ def main_reference(args, rank, world):
     from aggfly_b200 import synthetic as syn
     from oracle import oracle as orc
     wl = syn.make_workload(args.workload)
-    threads = orc.lib().orc_max_threads()
+    threads = host_threads()
     rows = args.cpu_rows
     dev = torch.device("cuda", 0) if torch.cuda.is_available() else torch.device("cpu")
     # generate only the sampled band (same generator, same seed; the band is what gets timed)
@@ -233,7 +243,7 @@ def main_reference(args, rank, world):
     value = arr.shape[0] * cells / sec
     sample = (f"{rows} latitude rows x {arr.shape[2]} lon x {arr.shape[0]} steps "
               f"({arr.shape[0] * cells / 1e6:.0f} M cell-hours per step) of {wl.name}")
-    print(json.dumps({
+    RESULT_LINE.append(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32 values, f64 accumulation", "data": "synthetic",
@@ -367,8 +377,7 @@ def main_ours(args, rank, world, local_rank):
     # ---- CPU baseline (rank 0, N = 1 only) ------------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        from oracle import oracle as orc
-        threads = orc.lib().orc_max_threads()
+        threads = host_threads()
         arr, sds, sw = cpu_sample(wl, raster_for_cpu, args.cpu_rows)
         sec, cdf = run_cpu_port(wl, arr, sds, sw, threads, 1, 0)
         cells = arr.shape[1] * arr.shape[2]
@@ -378,7 +387,7 @@ def main_ours(args, rank, world, local_rank):
                          f"({arr.shape[0] * cells / 1e6:.0f} M cell-hours), full chain + spatial step"}
 
     if rank == 0:
-        print(json.dumps({
+        RESULT_LINE.append(json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32 values, f64 accumulation", "data": "synthetic",
@@ -414,10 +423,22 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.impl == "reference":
-        main_reference(args, rank, world)
-    else:
-        main_ours(args, rank, world, local_rank)
+    # stdout carries exactly ONE JSON line: libraries that print to fd 1 (NCCL's version banner, ...)
+    # are sent to stderr for the duration of the run
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        if args.impl == "reference":
+            main_reference(args, rank, world)
+        else:
+            main_ours(args, rank, world, local_rank)
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
+    if RESULT_LINE:
+        print(RESULT_LINE[0], flush=True)
 
 
 if __name__ == "__main__":

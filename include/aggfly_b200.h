@@ -237,6 +237,15 @@ int agf_spmm_run(const agf_csr_t *csr, const void *d_x, int32_t x_dtype, const u
 int agf_valid_mask_run(const void *d_x, int32_t x_dtype, int64_t n_groups, int32_t n_cols,
                        int64_t n_cells, uint8_t *d_valid, uintptr_t stream);
 
+/* out[i] = f(in[i]) for a whole series of n values: AGF_XF_POWI / AGF_XF_POW / AGF_XF_SPLINE2, or, when
+ * d_other != NULL, in[i] * other[i] (the reference's `inter` transform, aggfly/dataset/dataset.py:483-563).
+ * For transforms that cannot be fused into a program (applied to the raster before the first aggregate
+ * step, two in a row, interactions).  out_dtype follows NumPy's promotion, decided by the caller; d_valid
+ * (may be NULL) receives !isnan(out[i]). */
+int agf_elementwise_run(const void *d_in, int32_t in_dtype, void *d_out, int32_t out_dtype, int64_t n,
+                        int32_t xform, double xparam, const void *d_other, int32_t other_dtype,
+                        uint8_t *d_valid, uintptr_t stream);
+
 /* ---- weights builder geometry (host only; replaces the GEOS work of calculate_weights) ---------- */
 
 /* For every region the fraction of each grid cell's rectangle that it covers -- what
