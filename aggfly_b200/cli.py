@@ -1,0 +1,230 @@
+"""``aggfly run config.yaml`` on the CUDA engine (``python -m aggfly_b200 run ...``).
+
+Same commands and flags as the reference's click group for the parts that touch the hot path
+(aggfly/cli/main.py:16-255: ``validate``, ``weights``, ``run``) and the same orchestration order as
+``run_pipeline`` (aggfly/cli/pipeline.py:124-172): regions -> sample layer -> weights (cached) ->
+``aggregate_dataset`` for every ``{year}`` path -> concat -> write.  What changes underneath:
+
+* the yearly loop is time-sharded over the ranks of a ``torch.distributed`` job when there is one
+  (``torchrun --nproc-per-node 8 -m aggfly_b200 run ...``): rank r aggregates years r, r+W, ... and
+  rank 0 concatenates the gathered frames -- the reference runs the years serially;
+* ``dataset.preprocess`` names / expressions are fused into the temporal kernel;
+* ``execution.backend`` / ``n_workers`` are accepted and ignored (there is no dask here).
+"""
+from __future__ import annotations
+
+import importlib.util
+import os
+import sys
+from typing import Callable, List, Optional
+
+import click
+import pandas as pd
+
+from . import io as _io
+from . import preprocess as _pp
+from . import runconfig as _cfg
+
+
+def _log_fn(verbose: bool) -> Callable[[str], None]:
+    return (lambda m: click.echo(m, err=True)) if verbose else (lambda m: None)
+
+
+def resolve_preprocess(config: _cfg.RunConfig):
+    """Builtin name / expression -> fused chain; ``preprocess_from: file.py:func`` -> that callable
+    (trusted user code, applied to the array on the host, as in aggfly/cli/preprocess.py:116-175)."""
+    if config.preprocess_from:
+        path, _, func = str(config.preprocess_from).rpartition(":")
+        if not os.path.exists(path):
+            raise _pp.PreprocessError(f"preprocess_from: file not found: {path}")
+        spec = importlib.util.spec_from_file_location("_aggfly_user_preprocess", path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        if not hasattr(mod, func):
+            raise _pp.PreprocessError(f"preprocess_from: {path} has no function {func!r}")
+        return getattr(mod, func)
+    if config.preprocess is None:
+        return None
+    _pp.resolve(str(config.preprocess))                      # validate now, fail before any data is read
+    return str(config.preprocess)
+
+
+def load_dataset(config: _cfg.RunConfig, path: str, georegions=None):
+    ds = _io.dataset_from_path(path, var=config.var, xycoords=config.xycoords, timecoord=config.timecoord,
+                               time_sel=config.time_sel, lon_is_360=config.lon_is_360,
+                               preprocess=resolve_preprocess(config), name=config.var)
+    if georegions is not None and config.clip_to_regions:
+        box = region_extent(georegions)
+        if box is not None:
+            ds = _io.clip_to_extent(ds, *box)
+    return ds
+
+
+def region_extent(georegions):
+    import numpy as np
+    shp = georegions.shp
+    if "rings" in shp.columns:
+        pts = [r for rings in shp["rings"] for r in rings if len(r)]
+        if not pts:
+            return None
+        allp = np.concatenate(pts)
+        return float(allp[:, 0].min()), float(allp[:, 0].max()), float(allp[:, 1].min()), float(allp[:, 1].max())
+    if {"lon_min", "lon_max", "lat_min", "lat_max"}.issubset(shp.columns):
+        return float(shp.lon_min.min()), float(shp.lon_max.max()), float(shp.lat_min.min()), float(shp.lat_max.max())
+    return None
+
+
+def compute_weights(config: _cfg.RunConfig, log=lambda m: None):
+    from .weights import weights_from_objects
+    log(f"Loading regions: {config.regions_path}")
+    georegions = _io.georegions_from_path(config.regions_path, config.regionid, config.region_list)
+    path0 = config.resolved_paths()[0]
+    log(f"Building weights from sample layer: {path0}")
+    sample = load_dataset(config, path0, georegions)
+    secondary = None if config.secondary is None else _io.secondary_weights_from_path(config.secondary.path)
+    w = weights_from_objects(sample, georegions, secondary_weights=secondary, project_dir=config.project_dir,
+                             zero_weight=config.zero_weight)
+    w.calculate_weights()
+    return w, georegions, sample
+
+
+def run_pipeline(config: _cfg.RunConfig, log=lambda m: None) -> Optional[pd.DataFrame]:
+    """The panel (on rank 0; None on the other ranks of a distributed job)."""
+    from .aggregate import aggregate_dataset
+    rank, world = _dist_info()
+    weights, georegions, sample = compute_weights(config, log)
+    paths = config.resolved_paths()
+    spec = config.to_aggregator_dict()
+    frames: List[pd.DataFrame] = []
+    for i, path in enumerate(paths):
+        if i % world != rank:
+            continue
+        log(f"[rank {rank}] Aggregating [{i + 1}/{len(paths)}]: {path}")
+        ds = sample if i == 0 else load_dataset(config, path, georegions)
+        frames.append((i, aggregate_dataset(dataset=ds, weights=weights, aggregator_dict=spec, engine=config.engine)))
+    if world > 1:
+        import torch.distributed as dist
+        gathered = [None] * world
+        dist.all_gather_object(gathered, frames)               # small frames; the rasters never leave their rank
+        frames = [f for part in gathered for f in part]
+        if rank != 0:
+            return None
+    frames = [f for _, f in sorted(frames, key=lambda t: t[0])]
+    return pd.concat(frames, ignore_index=True) if len(frames) > 1 else frames[0]
+
+
+def _dist_info():
+    try:
+        import torch
+        import torch.distributed as dist
+    except Exception:
+        return 0, 1
+    if "RANK" in os.environ and "WORLD_SIZE" in os.environ and int(os.environ["WORLD_SIZE"]) > 1:
+        if not dist.is_initialized():
+            local = int(os.environ.get("LOCAL_RANK", "0"))
+            torch.cuda.set_device(local)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+# ---------------------------------------------------------------------------------------------
+# click group
+# ---------------------------------------------------------------------------------------------
+@click.group()
+def cli():
+    """aggfly on the B200 CUDA engine."""
+
+
+def _load(config_path: str) -> _cfg.RunConfig:
+    try:
+        return _cfg.load_config(config_path)
+    except _cfg.ConfigError as e:
+        click.echo("Config is invalid:", err=True)
+        for msg in e.errors:
+            click.echo(f"  - {msg}", err=True)
+        raise SystemExit(1)
+
+
+@cli.command()
+@click.argument("config", type=click.Path())
+def validate(config):
+    """Check a config file (schema, step lists, preprocess) without reading any data."""
+    cfg = _load(config)
+    try:
+        resolve_preprocess(cfg)
+    except _pp.PreprocessError as e:
+        raise click.ClickException(f"preprocess: {e}")
+    n = len(cfg.resolved_paths())
+    click.echo(f"Config OK: {len(cfg.variables)} variable(s), {n} dataset path(s), engine={cfg.engine}, "
+               f"output={cfg.output_path} ({cfg.output_format}).")
+
+
+@cli.command()
+@click.argument("config", type=click.Path())
+@click.option("--project-dir", default=None, help="Override weights.project_dir (weight cache).")
+@click.option("-v", "--verbose", is_flag=True)
+def weights(config, project_dir, verbose):
+    """Build the weights (and the lowered CSR cache) for a config."""
+    cfg = _load(config)
+    if project_dir is not None:
+        cfg.project_dir = project_dir
+    w, _, sample = compute_weights(cfg, _log_fn(verbose))
+    from .weights import lower_to_csr_cached
+    csr = lower_to_csr_cached(w.weights, w.grid.cell_id, len(sample.latitude), len(sample.longitude),
+                              sample.lon_sort_order() if sample.lon_is_360 else None, cfg.project_dir)
+    click.echo(f"Weights: {len(w.weights)} cell-region pairs, {csr.n_regions} regions, {csr.nnz} CSR entries.")
+    click.echo(f"Cached under: {cfg.project_dir}" if cfg.project_dir else
+               "No weights.project_dir set — the lowered CSR was computed but not cached.")
+
+
+@cli.command()
+@click.argument("config", type=click.Path())
+@click.option("-o", "--output", default=None, help="Override output.path from the config.")
+@click.option("--engine", type=click.Choice(sorted(_cfg.ALLOWED_ENGINE)), default=None,
+              help="Override the temporal engine (every value runs the CUDA engine here).")
+@click.option("--years", default=None, help="Override years for a {year}-templated dataset path (e.g. 1980:1990).")
+@click.option("--project-dir", default=None, help="Override weights.project_dir (weight cache).")
+@click.option("--backend", type=click.Choice(sorted(_cfg.ALLOWED_BACKEND)), default=None,
+              help="Accepted for compatibility; there is no dask backend on this engine.")
+@click.option("--n-workers", type=int, default=None, help="Accepted for compatibility; ignored.")
+@click.option("-v", "--verbose", is_flag=True, help="Print per-step progress.")
+def run(config, output, engine, years, project_dir, backend, n_workers, verbose):
+    """Run the full aggregation pipeline from a config file."""
+    cfg = _load(config)
+    if output is not None:
+        cfg.output_path = output
+        ext = output.rsplit(".", 1)[-1].lower() if "." in output else ""
+        cfg.output_format = {"pq": "parquet"}.get(ext, ext) or cfg.output_format
+    if engine is not None:
+        cfg.engine = engine
+    if project_dir is not None:
+        cfg.project_dir = project_dir
+    if backend is not None:
+        cfg.backend = backend
+    if years is not None:
+        errs: List[str] = []
+        cfg.years = _cfg.parse_years(years, errs)
+        if errs:
+            raise click.ClickException("; ".join(errs))
+    try:
+        resolve_preprocess(cfg)
+    except _pp.PreprocessError as e:
+        raise click.ClickException(f"preprocess: {e}")
+    try:
+        df = run_pipeline(cfg, log=_log_fn(verbose))
+    except Exception as e:
+        if verbose:
+            raise
+        raise click.ClickException(f"{type(e).__name__}: {e}")
+    if df is not None:
+        _io.write_output(df, cfg.output_path, cfg.output_format)
+        click.echo(f"Wrote {len(df)} rows to {cfg.output_path} ({cfg.output_format}).")
+
+
+def main(argv=None):
+    cli.main(args=argv, prog_name="aggfly")
+
+
+if __name__ == "__main__":
+    main(sys.argv[1:])

@@ -141,13 +141,36 @@ class StageRunner:
             self.programs.append(prog)
             self.partials.append(torch.empty(prog.info.partial_bytes // 8, dtype=torch.float64, device=self.device)
                                  if prog.info.partial_bytes else None)
+        self.other = None
+        if stage.elementwise is not None and stage.elementwise.other is not None:
+            o = stage.elementwise.other
+            if int(np.prod(o.shape)) != G * n_cells:
+                raise AssertionError(f"interaction array of shape {o.shape} does not match the series "
+                                     f"({G} steps x {n_cells} cells)")                     # dataset.py:500
+            self.other = to_device(np.ascontiguousarray(o).reshape(G, n_cells), self.device)
         self.result = StageResult(self.X, self.V, stage.dtype, stage.labels, stage.nodes)
         self._ran_token = None
+
+    def _run_elementwise(self, raster, stream) -> None:
+        """X = f(source series) for a materialised-transform stage (one launch)."""
+        ew = self.stage.elementwise
+        src = raster if ew.source is None else self._by_stage[id(ew.source)].result.X
+        G = len(self.stage.labels)
+        if ew.source is None and (raster.dtype != _tdtype(ew.in_dtype) or raster.shape[0] != G):
+            raise TypeError("raster does not match the planned transform (dtype / length)")
+        code = {"pow": _lib.XF_POWI if (float(ew.xparam).is_integer() and 0 <= ew.xparam <= 64) else _lib.XF_POW,
+                "spline2": _lib.XF_SPLINE2, "inter": _lib.XF_NONE}[ew.xf]
+        f = lambda dt: _lib.F64 if np.dtype(dt) == np.float64 else _lib.F32          # noqa: E731
+        _lib.check(_lib.lib().agf_elementwise_run(
+            src.data_ptr(), f(ew.in_dtype), self.X.data_ptr(), f(self.stage.dtype), G * self.n_cells, code,
+            float(ew.xparam), self.other.data_ptr() if self.other is not None else None,
+            f(np.float64 if (self.other is not None and self.other.dtype == _torch().float64) else np.float32),
+            self.V.data_ptr(), stream.cuda_stream))
 
     @property
     def launches_per_run(self) -> int:
         n = sum(r.launches_per_run for r in self.inputs)
-        return n + sum(2 if p.spec.two_level else 1 for p in self.programs)
+        return n + sum(2 if p.spec.two_level else 1 for p in self.programs) + (1 if self.stage.elementwise else 0)
 
     def algorithmic_input_bytes(self) -> int:
         """Bytes of raster the temporal kernels of this stage must read (each program reads its
@@ -174,6 +197,8 @@ class StageRunner:
         n_cols = len(self.stage.nodes)
         first = True
         with torch.cuda.stream(st):
+            if self.stage.elementwise is not None:
+                self._run_elementwise(raster, st)
             for prog, partial in zip(self.programs, self.partials):
                 spec = prog.spec
                 src = getattr(spec, "_source", None)
@@ -264,6 +289,9 @@ class StageRunner:
         sptr = stream.cuda_stream
         for r in self._walk():
             n_cols = len(r.stage.nodes)
+            if r.stage.elementwise is not None:
+                with _torch().cuda.stream(stream):
+                    r._run_elementwise(raster, stream)          # overwrites the V = 1 of begin_streamed
             for i, (prog, partial) in enumerate(zip(r.programs, r.partials)):
                 pptr = partial.data_ptr() if partial is not None else None
                 src = getattr(prog.spec, "_source", None)

@@ -1,0 +1,213 @@
+"""Readers / writers around the hot path: rasters, region files, secondary rasters, panels.
+
+The reference opens everything through xarray / geopandas / rioxarray (aggfly/dataset/dataset.py:636-740,
+aggfly/regions/georegions.py:220-323, aggfly/weights/secondary_weights.py:201-245).  None of those
+exist in this image, so the formats that can be read with numpy / scipy / the standard library are
+read natively, and xarray is used only if it happens to be importable:
+
+=====================  =========================================================================
+``.npz``               arrays ``values`` (or the ``var`` name) ``[time, lat, lon]``, ``time``
+                       (datetime64 or ISO strings), ``latitude``, ``longitude``  -- also the format of
+                       secondary rasters (``values[lat, lon]``, ``latitude``, ``longitude``)
+``.npy``               the raster alone, memory-mapped; axes from ``<path>.axes.npz``
+``.nc`` (NetCDF-3)     ``scipy.io.netcdf_file`` (memory-mapped); CF ``units = "<unit> since <date>"``
+                       time axes, ``scale_factor`` / ``add_offset`` unpacked like xarray (float64)
+anything else          ``xarray.open_dataset`` / ``open_zarr`` when xarray is installed
+``.shp``               polygons (+ ``.dbf`` attributes), aggfly_b200.geometry
+``.geojson`` / ``.json``  FeatureCollection of Polygon / MultiPolygon features
+=====================  =========================================================================
+"""
+from __future__ import annotations
+
+import json
+import os
+from typing import Optional, Sequence
+
+import numpy as np
+import pandas as pd
+
+from .dataset import Dataset
+from .geometry import orient_polygon
+from .weights import GeoRegions, SecondaryWeights
+
+
+# ---------------------------------------------------------------------------------------------
+# rasters
+# ---------------------------------------------------------------------------------------------
+def _cf_time(values: np.ndarray, units: str, calendar: str = "standard"):
+    unit, _, origin = units.partition(" since ")
+    unit = unit.strip().lower().rstrip("s")
+    step = {"second": "s", "minute": "m", "hour": "h", "day": "D"}.get(unit)
+    if step is None:
+        raise ValueError(f"unsupported CF time unit {units!r}")
+    if calendar not in ("standard", "gregorian", "proleptic_gregorian"):
+        raise NotImplementedError(f"calendar {calendar!r} in a NetCDF-3 file: build a CalendarIndex yourself "
+                                  "(Dataset.from_arrays)")
+    vals = np.asarray(values, dtype=np.float64)
+    origin = pd.Timestamp(origin.strip())
+    if origin.tzinfo is not None:
+        origin = origin.tz_convert(None)
+    ns = {"s": 1e9, "m": 60e9, "h": 3600e9, "D": 86400e9}[step]
+    return pd.DatetimeIndex(origin.value + np.round(vals * ns).astype(np.int64))
+
+
+def dataset_from_path(path: str, var: Optional[str] = None, xycoords: Sequence[str] = ("longitude", "latitude"),
+                      timecoord: str = "time", lon_is_360: bool = True, preprocess=None, time_sel=None,
+                      name: Optional[str] = None, **kwargs) -> Dataset:
+    """``af.dataset_from_path`` (aggfly/dataset/dataset.py:636-740) for the formats listed in the module
+    docstring.  ``preprocess``: builtin name / expression in ``x`` (fused on the device) or a callable."""
+    xdim, ydim = xycoords
+    ext = os.path.splitext(path.rstrip("/"))[1].lower()
+    keepalive = None
+    if ext == ".npz":
+        z = np.load(path, allow_pickle=False)
+        key = var if (var and var in z.files) else "values"
+        values, time, lat, lon = z[key], z[timecoord], z[ydim], z[xdim]
+        time = pd.DatetimeIndex(time.astype("datetime64[ns]") if time.dtype.kind == "M" else pd.to_datetime(time.astype(str)))
+    elif ext == ".npy":
+        values = np.load(path, mmap_mode="r")
+        z = np.load(path + ".axes.npz", allow_pickle=False)
+        time, lat, lon = pd.DatetimeIndex(z[timecoord].astype("datetime64[ns]")), z[ydim], z[xdim]
+    elif ext in (".nc", ".nc3", ".cdf") and _is_netcdf3(path):
+        from scipy.io import netcdf_file
+        f = netcdf_file(path, "r", mmap=True, maskandscale=False)
+        if var not in f.variables:
+            raise KeyError(f"{path}: variable {var!r} not found (have {sorted(f.variables)})")
+        v = f.variables[var]
+        dims = list(v.dimensions)
+        order = [dims.index(timecoord), dims.index(ydim), dims.index(xdim)]
+        values = np.transpose(v.data, order) if order != [0, 1, 2] else v.data
+        scale, offset = getattr(v, "scale_factor", None), getattr(v, "add_offset", None)
+        if scale is not None or offset is not None:                 # CF packing -> float64, like xarray
+            values = np.asarray(values, dtype=np.float64) * (1.0 if scale is None else float(scale)) \
+                + (0.0 if offset is None else float(offset))
+        elif values.dtype.byteorder == ">":
+            values = values.astype(values.dtype.newbyteorder("="))   # NetCDF-3 is big-endian on disk
+        tv = f.variables[timecoord]
+        units = tv.units.decode() if isinstance(tv.units, bytes) else tv.units
+        cal = getattr(tv, "calendar", b"standard")
+        time = _cf_time(tv.data, units, cal.decode() if isinstance(cal, bytes) else cal)
+        lat, lon = np.array(f.variables[ydim].data, dtype=float), np.array(f.variables[xdim].data, dtype=float)
+        keepalive = f                                                # the raster is a view of the mapped file
+    else:
+        try:
+            import xarray as xr                                      # optional dependency
+        except Exception as exc:
+            raise ImportError(f"{path}: reading this format needs xarray (not installed); natively supported: "
+                              ".npz, .npy (+ .axes.npz), NetCDF-3 .nc") from exc
+        dsx = xr.open_zarr(path, **kwargs) if ext == ".zarr" else xr.open_dataset(path, **kwargs)
+        return Dataset(dsx[var], xycoords=xycoords, timecoord=timecoord, time_sel=time_sel, lon_is_360=lon_is_360,
+                       preprocess=preprocess, name=name)
+    ds = Dataset.from_arrays(values, time, lat, lon, lon_is_360=lon_is_360, name=name or var,
+                             preprocess=preprocess if isinstance(preprocess, str) else None)
+    ds._keepalive = keepalive
+    if preprocess is not None and not isinstance(preprocess, str):
+        ds.values = preprocess(np.asarray(ds.values))
+    if time_sel is not None:
+        ds = select_time(ds, time_sel)
+    return ds
+
+
+def _is_netcdf3(path: str) -> bool:
+    with open(path, "rb") as f:
+        return f.read(3) == b"CDF"
+
+
+def select_time(ds: Dataset, time_sel) -> Dataset:
+    """``da.sel(time=time_sel)`` for a year / ``"YYYY"`` / ``slice(start, end)`` on a datetime axis."""
+    t = pd.DatetimeIndex(ds.time)
+    if isinstance(time_sel, slice):
+        a = 0 if time_sel.start is None else int(t.searchsorted(pd.Timestamp(time_sel.start), "left"))
+        b = len(t) if time_sel.stop is None else int(t.searchsorted(pd.Timestamp(time_sel.stop), "right"))
+    else:
+        year = int(str(time_sel)[:4])
+        idx = np.nonzero(t.year == year)[0]
+        a, b = (int(idx[0]), int(idx[-1]) + 1) if len(idx) else (0, 0)
+    return ds.isel_time(a, b)
+
+
+def clip_to_extent(ds: Dataset, lon_min: float, lon_max: float, lat_min: float, lat_max: float) -> Dataset:
+    """Keep the block of cells that can touch the box (one cell of margin), like the reference's
+    ``clip_to_regions`` (aggfly/dataset/dataset.py:225-312): fewer cells to move and scan.  The box is
+    in -180..180 longitudes; a 0-360 dataset whose kept columns would wrap is left unclipped in
+    longitude."""
+    from copy import copy
+    from .dataset import Grid, lon_to_180
+    lat, lon = ds.latitude, ds.longitude
+    lon180 = lon_to_180(lon) if ds.lon_is_360 else lon
+    dlat, dlon = ds.grid.resolution_lat, ds.grid.resolution_lon
+    iy = np.nonzero((lat >= lat_min - 1.5 * dlat) & (lat <= lat_max + 1.5 * dlat))[0]
+    ix = np.nonzero((lon180 >= lon_min - 1.5 * dlon) & (lon180 <= lon_max + 1.5 * dlon))[0]
+    if len(iy) == 0 or len(ix) == 0:
+        raise ValueError("the regions do not overlap the dataset's grid")
+    y0, y1 = int(iy[0]), int(iy[-1]) + 1
+    x0, x1 = (int(ix[0]), int(ix[-1]) + 1) if len(ix) == ix[-1] - ix[0] + 1 else (0, len(lon))
+    new = copy(ds)
+    new.values = ds.values[:, y0:y1, x0:x1]
+    new.latitude, new.longitude = lat[y0:y1], lon[x0:x1]
+    new.grid = Grid(new.longitude, new.latitude, ds.name, ds.lon_is_360)
+    new.history = list(ds.history) + ["clipped"]
+    return new
+
+
+# ---------------------------------------------------------------------------------------------
+# regions / secondary rasters
+# ---------------------------------------------------------------------------------------------
+def georegions_from_path(path: str, regionid: Optional[str] = None, region_list=None) -> GeoRegions:
+    ext = os.path.splitext(path)[1].lower()
+    if ext == ".shp":
+        return GeoRegions.from_shapefile(path, regionid, region_list)
+    if ext in (".geojson", ".json"):
+        fc = json.load(open(path))
+        feats = fc["features"] if fc.get("type") == "FeatureCollection" else [fc]
+        polys, props = [], []
+        for ft in feats:
+            g = ft["geometry"]
+            parts = [g["coordinates"]] if g["type"] == "Polygon" else g["coordinates"] if g["type"] == "MultiPolygon" else None
+            if parts is None:
+                raise ValueError(f"{path}: geometry type {g['type']!r} is not a polygon")
+            rings = []
+            for part in parts:
+                rings += orient_polygon(np.asarray(part[0], float)[:, :2], [np.asarray(h, float)[:, :2] for h in part[1:]])
+            polys.append(rings)
+            props.append(ft.get("properties") or {})
+        attrs = pd.DataFrame(props)
+        if regionid is None:
+            regionid = "region_id"
+            attrs[regionid] = np.arange(len(polys))
+        gr = GeoRegions.from_polygons(attrs[regionid], polys, regionid, attrs)
+        if region_list is not None:
+            gr = GeoRegions(gr.shp[gr.shp[regionid].isin(region_list)], regionid)
+        return gr
+    raise ImportError(f"{path}: only .shp and .geojson region files are read natively (no geopandas here)")
+
+
+def secondary_weights_from_path(path: str, nodata: Optional[float] = None) -> SecondaryWeights:
+    ext = os.path.splitext(path)[1].lower()
+    if ext != ".npz":
+        raise ImportError(f"{path}: secondary rasters are read from .npz (values, latitude, longitude); "
+                          "GeoTIFF needs rasterio, which is not installed")
+    z = np.load(path, allow_pickle=False)
+    return SecondaryWeights(z["values"], z["latitude"], z["longitude"], nodata=nodata, name=os.path.basename(path))
+
+
+# ---------------------------------------------------------------------------------------------
+# panels
+# ---------------------------------------------------------------------------------------------
+def write_output(df: pd.DataFrame, path: str, fmt: Optional[str] = None) -> str:
+    """aggfly/cli/pipeline.py:159-172: parquet / feather / csv by ``fmt`` or the extension."""
+    fmt = fmt or {"pq": "parquet"}.get(os.path.splitext(path)[1].lstrip(".").lower(),
+                                       os.path.splitext(path)[1].lstrip(".").lower())
+    os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+    out = df.copy()
+    if len(out) and not isinstance(out["time"].iloc[0], (pd.Timestamp, np.datetime64)):
+        out["time"] = out["time"].map(lambda t: t.isoformat() if hasattr(t, "isoformat") else str(t))   # cftime-like labels
+    if fmt == "parquet":
+        out.to_parquet(path, index=False)
+    elif fmt == "feather":
+        out.reset_index(drop=True).to_feather(path)
+    elif fmt == "csv":
+        out.to_csv(path, index=False)
+    else:
+        raise ValueError(f"output format {fmt!r} not in ['csv', 'feather', 'parquet']")
+    return path

@@ -86,6 +86,23 @@ class Graph:
         key = ("pow", src.key, float(exp), str(dtype))
         return self._intern(Node("xf", src, xf="pow", xparam=float(exp), dtype=dtype, key=key))
 
+    def inter(self, src: Node, other) -> Node:
+        """``Dataset.interact`` (aggfly/dataset/dataset.py:483-563): the series times another array of the
+        same shape.  ``other``: a Dataset-like (``.values``) or an array [G, lat, lon]."""
+        arr = getattr(other, "values", other)
+        if type(arr).__module__.startswith("torch"):
+            arr = arr.detach().cpu().numpy()
+        arr = np.asarray(arr)
+        if arr.dtype not in (np.float32, np.float64):
+            arr = arr.astype(np.float64)
+        n = len(self.labels(src))
+        if arr.shape[0] != n:
+            raise AssertionError(f"interaction array has {arr.shape[0]} time steps, the series has {n}")   # dataset.py:500
+        dtype = np.result_type(src.dtype, arr.dtype)
+        key = ("inter", src.key, id(arr))
+        node = self._intern(Node("xf", src, xf="inter", dtype=dtype, key=key, other=arr))
+        return node
+
     def spline2(self, src: Node) -> Node:
         key = ("spline2", src.key)
         return self._intern(Node("xf", src, xf="spline2", dtype=src.dtype, key=key))
@@ -171,7 +188,8 @@ def compile_spec(graph: Graph, aggregator_dict: Dict[str, Sequence]) -> Dict[str
                         nd.extend(graph.power(d, e) for e in exps)
                         nk.extend(f"{k}_{e}" for e in exps)
                     elif "inter" in params:
-                        raise NotImplementedError("transform 'inter' is not lowered to the CUDA engine yet")
+                        nd.append(graph.inter(d, params["inter"]))                     # aggregate.py:65-69
+                        nk.append(k)
                     elif "spline" in params.get("transform", ""):
                         nd.extend([d, graph.spline2(d)])
                         nk.extend([f"{k}_spline1", f"{k}_spline2"])
@@ -241,6 +259,17 @@ class Stage:
     labels: Any
     inputs: List["Stage"] = field(default_factory=list)   # stages that must run first
     column_of: Dict[tuple, int] = field(default_factory=dict)
+    elementwise: Optional["ElemSpec"] = None              # a materialised transform: X = f(source series)
+
+
+@dataclass
+class ElemSpec:
+    """X[G, cells, 1] = xf(source): source is the raster (``source is None``) or column 0 of a stage."""
+    source: Optional["Stage"]
+    in_dtype: np.dtype
+    xf: str
+    xparam: float
+    other: Optional[np.ndarray] = None
 
 
 def _peel(node: Node):
@@ -296,20 +325,20 @@ class Planner:
     def _pattern(self, node: Node) -> tuple:
         a, tail = _peel(node)
         if a.kind == "raw":
-            return ("identity",) if not tail else ("deep_raw",)
-        if len(tail) > 1:
-            return ("deep", id(node))
+            return ("identity",) if not tail else ("mat", node.key)   # transforms of the raster itself
+        if len(tail) > 1 or any(x.xf == "inter" for x in tail):
+            return ("mat", node.key)            # transforms the programs cannot carry: materialise, copy out
         s1, mid = _peel(a.src)
         if s1.kind == "raw":
-            if mid:
-                raise NotImplementedError("a transform applied to the raster before the first aggregate "
-                                          "step is not lowered to the CUDA engine yet")
+            if mid:                             # aggregate of a transformed raster
+                return ("outer", a.src.key, a.freq)
             return ("l1", a.freq)
         # s1 is an aggregate: can agg2(mid?(agg1(raw))) be fused?
         s2, pre = _peel(s1.src)
+        fusable_mid = len(mid) == 0 or (len(mid) == 1 and mid[0].xf != "inter")
         if s2.kind == "raw" and not pre and not mid and self._collapsed_lane(s1, a) is not None:
             return ("l1c", s1.freq, a.freq)
-        if (s2.kind == "raw" and not pre and len(mid) <= 1 and a.calc in FUSABLE_L2):
+        if (s2.kind == "raw" and not pre and fusable_mid and a.calc in FUSABLE_L2):
             return ("l2", s1.freq, a.freq)
         return ("outer", a.src.key, a.freq)     # single-level program over the materialised a.src
 
@@ -341,11 +370,14 @@ class Planner:
             T = len(self.g.labels(self.g.raw))
             b1 = np.arange(T + 1, dtype=np.int64)
             self._emit_single_level(stage, self.g.raw, b1, "id", members, identity=True)
-        elif kind == "deep_raw":
-            raise NotImplementedError("a transform with no aggregate step is not lowered to the CUDA engine yet")
-        elif kind == "deep":
-            raise NotImplementedError("more than one transform after the last aggregate step is not "
-                                      "lowered to the CUDA engine yet")
+        elif kind == "mat":
+            # the whole node is materialised by elementwise passes in its own stage, then copied into
+            # this stage's column by an identity program (one row per group)
+            for col, node in members:
+                sub, _ = self._materialise(node)
+                n = len(self.g.labels(node))
+                self._emit_single_level(stage, node, np.arange(n + 1, dtype=np.int64), "id", [(col, node)],
+                                        identity=True, source=(sub, 0))
         elif kind == "l1":
             a0, _ = _peel(members[0][1])
             b1, _ = self.g.axis(a0)
@@ -371,7 +403,15 @@ class Planner:
     def _materialise(self, node: Node) -> Tuple[Stage, int]:
         hit = self._materialised.get(node.key)
         if hit is None:
-            sub = self.plan([node], dtype=node.dtype)          # X dtype == node dtype: no extra rounding
+            if node.kind == "xf":
+                # X = xf(source series): one elementwise pass over the materialised source (or the raster)
+                src_stage = None if node.src.kind == "raw" else self._materialise(node.src)[0]
+                xf, xparam = ("inter", 0.0) if node.xf == "inter" else (node.xf, node.xparam if node.xf == "pow" else 0.0)
+                sub = Stage(programs=[], nodes=[node], dtype=np.dtype(node.dtype), labels=self.g.labels(node),
+                            inputs=[] if src_stage is None else [src_stage],
+                            elementwise=ElemSpec(src_stage, np.dtype(node.src.dtype), xf, float(xparam), node.other))
+            else:
+                sub = self.plan([node], dtype=node.dtype)      # X dtype == node dtype: no extra rounding
             hit = (sub, 0)
             self._materialised[node.key] = hit
         return hit
@@ -381,7 +421,7 @@ class Planner:
         prog = None
         for col, node in members:
             a, tail = _peel(node)
-            xf, xparam, xnode = _xf_fields(tail)
+            xf, xparam, xnode = (None, 0.0, None) if identity else _xf_fields(tail)
             calc, dd = ("mean", None) if identity else (lane_of(a) if lane_of is not None else (a.calc, a.dd))
             need = (1 if calc != "sine_dd" else 4)
             if prog is None or len(prog.lanes) + need > _lib.MAX_LANES or len(prog.cols) + 1 > _lib.MAX_COLS:

@@ -31,17 +31,22 @@ OPTIONS = {
 }
 
 
-def _as_cpu_tensor(values):
+def _host_source(values):
+    """(pinned torch tensor | None, numpy view | None): a pinned contiguous tensor is copied from in place;
+    everything else -- numpy arrays (any strides: memory maps, clipped views), pageable tensors -- goes
+    through the pinned staging ring chunk by chunk, so no whole-raster host copy is ever made."""
     import torch
-    if isinstance(values, np.ndarray):
-        if values.dtype not in (np.float32, np.float64):
-            values = values.astype(np.float64)
-        if not values.flags.c_contiguous:
-            values = np.ascontiguousarray(values)
-        return torch.from_numpy(values)
-    if values.dtype not in (torch.float32, torch.float64):
-        values = values.to(torch.float64)
-    return values.contiguous()
+    if isinstance(values, np.ndarray) or not type(values).__module__.startswith("torch"):
+        arr = np.asarray(values)
+        if arr.dtype not in (np.float32, np.float64) or not arr.dtype.isnative:
+            arr = arr.astype(np.float64 if arr.dtype.itemsize > 4 or arr.dtype.kind != "f" else np.float32)
+        return None, arr
+    t = values
+    if t.dtype not in (torch.float32, torch.float64):
+        t = t.to(torch.float64)
+    if t.is_pinned() and t.is_contiguous():
+        return t, None
+    return None, t.detach().numpy()
 
 
 def chunk_rows(n_rows: int, row_bytes: int, chunk_bytes: int):
@@ -59,12 +64,12 @@ class _Staging:
         self.events = [None] * n_slots                 # copy-done event of the slot's last use
         self.pool = ThreadPoolExecutor(max_workers=max(1, n_threads))
 
-    def fill(self, slot: int, src_flat):
+    def fill(self, slot: int, chunk: np.ndarray):
         ev = self.events[slot]
         if ev is not None:
             ev.synchronize()                           # the previous async copy out of this slot
-        dst = self.slots[slot][: src_flat.numel()]
-        dst.numpy()[...] = src_flat.numpy()            # plain memcpy, GIL released
+        dst = self.slots[slot][: chunk.size]
+        np.copyto(dst.numpy().reshape(chunk.shape), chunk)   # (strided) memcpy, GIL released
         return dst
 
     def close(self):
@@ -78,20 +83,26 @@ def feed_and_run(runner, values, n_cells: int, stream=None, k1_events: Optional[
     Returns (StageResult, device raster [T, n_cells]).  Everything is asynchronous with respect to
     the host except the staging memcpys of a pageable source."""
     import torch
-    host = _as_cpu_tensor(values)
-    T = int(host.shape[0])
-    host = host.reshape(T, n_cells)
+    host, host_np = _host_source(values)
+    pinned = host is not None
+    T = int(host.shape[0] if pinned else host_np.shape[0])
+    if pinned:
+        host = host.reshape(T, n_cells)
+        tdtype = host.dtype
+    else:
+        if int(np.prod(host_np.shape[1:])) != n_cells:
+            raise ValueError(f"raster of shape {host_np.shape} does not have {n_cells} cells per step")
+        tdtype = torch.float64 if host_np.dtype == np.float64 else torch.float32
     dev = runner.device
     comp = torch.cuda.current_stream(dev) if stream is None else stream
     copy = _copy_stream(dev)
-    raster = torch.empty((T, n_cells), dtype=host.dtype, device=dev)
-    row_bytes = n_cells * host.element_size()
+    raster = torch.empty((T, n_cells), dtype=tdtype, device=dev)
+    row_bytes = n_cells * raster.element_size()
     chunks = chunk_rows(T, row_bytes, chunk_bytes or OPTIONS["chunk_bytes"])
-    pinned = host.is_pinned()
     staging = None
     if not pinned:
         slot_elems = max(r1 - r0 for r0, r1 in chunks) * n_cells
-        staging = _Staging(torch, host.dtype, slot_elems, OPTIONS["staging_slots"], OPTIONS["staging_threads"])
+        staging = _Staging(torch, tdtype, slot_elems, OPTIONS["staging_slots"], OPTIONS["staging_threads"])
 
     copy.wait_stream(comp)                    # the raster buffer may be a recycled block still in use
     ev_first, ev_last = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -104,7 +115,7 @@ def feed_and_run(runner, values, n_cells: int, stream=None, k1_events: Optional[
 
         def submit(i):
             r0, r1 = chunks[i]
-            futs[i] = staging.pool.submit(staging.fill, i % ahead, host[r0:r1].reshape(-1))
+            futs[i] = staging.pool.submit(staging.fill, i % ahead, host_np[r0:r1])
 
         if staging:
             for i in range(min(ahead, len(chunks))):

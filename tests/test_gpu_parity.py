@@ -484,3 +484,51 @@ def test_fused_preprocess_equals_numpy_then_aggregate(name, dtype, expr):
     assert list(got) == list(want)
     for k in want:
         _exact(got[k].values, want[k][0])
+
+
+# ---- transforms the fused programs cannot carry: materialised by elementwise passes (never the CPU) ------
+def test_materialised_transforms_and_interactions_match_oracle():
+    arr, t, lat, lon = _raster("float32", True, T=24 * 45 + 3, Y=3, X=5, seed=31)
+    rng = np.random.default_rng(12)
+    n_days = len(pd.DatetimeIndex(t).normalize().unique())
+    precip = rng.gamma(2.0, 1.5, (n_days, 3, 5)).astype(np.float32)              # a second daily variable
+    precip64 = precip.astype(np.float64)
+    hourly_w = rng.random((len(t), 3, 5)).astype(np.float32)
+    spec = dict(
+        poly=[("transform", {"transform": "power", "exp": np.arange(1, 3)}),      # powers of the HOURLY values
+              ("aggregate", {"calc": "mean", "groupby": "month"})],
+        txp=[("aggregate", {"calc": "mean", "groupby": "date"}), ("transform", {"inter": precip}),
+             ("aggregate", {"calc": "sum", "groupby": "month"})],
+        txp64=[("aggregate", {"calc": "mean", "groupby": "date"}), ("transform", {"inter": precip64}),
+               ("aggregate", {"calc": "sum", "groupby": "month"})],
+        hw=[("transform", {"inter": hourly_w}), ("aggregate", {"calc": "max", "groupby": "date"}),
+            ("aggregate", {"calc": "mean", "groupby": "month"})],
+        two=[("aggregate", {"calc": "mean", "groupby": "month"}), ("transform", {"transform": "power", "exp": [[2]]}),
+             ("transform", {"transform": "spline"})])
+    for stripes in (1, 4):
+        engine.OPTIONS["target_stripes"] = stripes
+        got, want = _both_time(arr, t, lat, lon, spec)
+        for k in want:
+            assert got[k].values.dtype == want[k][0].dtype, (k, got[k].values.dtype, want[k][0].dtype)
+            _close(got[k].values, want[k][0], 1e-6 if got[k].values.dtype == np.float32 else 1e-12)
+    # and end to end (the streamed host path runs the elementwise stages after the last chunk)
+    wdf, shp = _weights_case(lat, lon, np.random.default_rng(1))
+    want = orc.aggregate_dataset(orc.OWeights(wdf, np.arange(15), shp, "geoid", "nan"), orc.ODataset(arr, t, lat, lon, True),
+                                 aggregator_dict=spec)
+    ds = af.Dataset.from_arrays(arr, t, lat, lon, True)
+    w = af.weights_from_objects(ds, af.GeoRegions(shp, "geoid"), zero_weight="nan")
+    w.weights = wdf
+    got = af.aggregate_dataset(weights=w, dataset=ds, aggregator_dict=spec)
+    vals = [c for c in want.columns if c not in ("geoid", "time")]
+    assert list(got.columns) == list(want.columns) and len(got) == len(want)
+    _close(got[vals].values, want[vals].values, 1e-6)
+
+
+def test_transform_of_the_raster_alone_and_shape_mismatch():
+    arr, t, lat, lon = _raster("float32", True, T=30, Y=2, X=3, seed=33)
+    got, want = _both_time(arr, t, lat, lon, dict(sq=[("transform", {"transform": "power", "exp": np.arange(2, 3)})]))
+    assert got["sq_2"].values.dtype == np.float64
+    _exact(got["sq_2"].values, want["sq_2"][0])
+    with pytest.raises(AssertionError):
+        af.aggregate_time(dataset=af.Dataset.from_arrays(arr, t, lat, lon, True), weights=None,
+                          bad=[("transform", {"inter": np.ones((7, 2, 3), np.float32)})])
