@@ -160,6 +160,21 @@ def _device_csr(weights: GridWeights, dataset: Dataset) -> _engine.DeviceCSR:
     return cache[key]
 
 
+def _zero_weight_regions(weights) -> np.ndarray:
+    """Regions whose weights sum to <= 0 (spatial.py:144-151), computed once per weights frame: the
+    groupby over ~1 M rows would otherwise be the largest host cost of a yearly call."""
+    frame = weights.weights
+    hit = getattr(weights, "_zero_regions", None)
+    if hit is None or hit[0] is not frame:
+        wsum = frame.groupby("index_right")["weight"].sum()
+        hit = (frame, np.asarray(wsum.index[~(wsum > 0)]))
+        try:
+            weights._zero_regions = hit
+        except Exception:
+            pass
+    return hit[1]
+
+
 def _assemble_panel(panel: np.ndarray, names: List[str], labels, region_ids: np.ndarray,
                     weights: GridWeights) -> pd.DataFrame:
     """spatial.py:136-153: long frame, then the row-drop rules."""
@@ -171,9 +186,7 @@ def _assemble_panel(panel: np.ndarray, names: List[str], labels, region_ids: np.
         out[nm] = flat[:, c]
     ok = ~np.isnan(flat).any(axis=1)
     if getattr(weights, "zero_weight", "area") == "nan":
-        wsum = weights.weights.groupby("index_right")["weight"].sum()
-        zero_regions = np.asarray(wsum.index[~(wsum > 0)])
-        keep = np.isin(out["region_id"].to_numpy(), zero_regions) | ok
+        keep = np.isin(out["region_id"].to_numpy(), _zero_weight_regions(weights)) | ok
     else:
         keep = ok
     return out.loc[keep].reset_index(drop=True)

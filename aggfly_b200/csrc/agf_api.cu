@@ -583,10 +583,16 @@ extern "C" int agf_spmm_run(const agf_csr_t *c, const void *d_x, int32_t x_dtype
             break;
         }
     const int ev = vb / esz;
-#define AGF_SPMM(TX, GS, EV)                                                                                      \
-    agf_spmm<TX, GS, EV><<<(unsigned)blocks, 256, 0, st>>>(c->d_row_ptr, c->d_cell_idx, c->d_w, (const TX *)d_x, \
-                                                           d_valid, c->n_cells, n_groups, n_cols, c->n_regions,  \
-                                                           d_panel, d_den)
+    const bool wide = n_cols > 4;
+#define AGF_SPMM_W(TX, GS, EV, W)                                                                                    \
+    agf_spmm<TX, GS, EV, W><<<(unsigned)blocks, 256, 0, st>>>(c->d_row_ptr, c->d_cell_idx, c->d_w, (const TX *)d_x, \
+                                                              d_valid, c->n_cells, n_groups, n_cols, c->n_regions,  \
+                                                              d_panel, d_den)
+#define AGF_SPMM(TX, GS, EV)                \
+    do {                                    \
+        if (wide) AGF_SPMM_W(TX, GS, EV, true); \
+        else AGF_SPMM_W(TX, GS, EV, false); \
+    } while (0)
 #define AGF_SPMM_GS(TX, EV)                    \
     do {                                       \
         if (gs == 1) AGF_SPMM(TX, 1, EV);      \
@@ -603,6 +609,7 @@ extern "C" int agf_spmm_run(const agf_csr_t *c, const void *d_x, int32_t x_dtype
         else AGF_SPMM_GS(float, 1);
     }
 #undef AGF_SPMM_GS
+#undef AGF_SPMM_W
 #undef AGF_SPMM
     CU(cudaGetLastError());
     return 0;

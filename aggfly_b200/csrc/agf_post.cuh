@@ -75,9 +75,12 @@ __global__ void __launch_bounds__(256) agf_finalize(const __grid_constant__ FinP
 // the same period, so their gathers fall into a few shared sectors that stay in L1 while the
 // threads walk their rows.  Measured on the C3b daily panel (45 000 x 365 pairs x 14 columns): the
 // warp-per-pair form was instruction-bound (25e9 warp instructions, 43.7 ms, 5 % of DRAM peak).
-template <int GS>
-__host__ __device__ constexpr int spmm_ncb() {  // columns accumulated per pass over a region's entries
-    return GS == 1 ? 16 : 8;
+// columns accumulated per pass over a region's entries: WIDE = false for panels of <= 4 columns (a
+// 16-wide unrolled, guarded accumulator block cost 1900 instructions per warp on the one-column C5
+// panel), else 16 for the thread-per-pair form and 8 for the group forms
+template <int GS, bool WIDE>
+__host__ __device__ constexpr int spmm_ncb() {
+    return !WIDE ? 4 : (GS == 1 ? 16 : 8);
 }
 
 // EV consecutive columns of one cell with a single load (EV * sizeof(TX) = 4, 8 or 16 bytes; the
@@ -103,7 +106,7 @@ __device__ __forceinline__ void load_cols(const TX *p, double (&x)[EV]) {
     }
 }
 
-template <typename TX, int GS, int EV>
+template <typename TX, int GS, int EV, bool WIDE>
 __global__ void __launch_bounds__(256)
     agf_spmm(const int *__restrict__ row_ptr, const int *__restrict__ cell_idx,
              const double *__restrict__ w, const TX *__restrict__ X,
@@ -118,7 +121,7 @@ __global__ void __launch_bounds__(256)
     const unsigned char *Vg = V + (size_t)g * n_cells;
     // lanes of this group inside the warp (shuffles must name exactly the participating lanes)
     const unsigned gmask = (GS == 32) ? 0xffffffffu : (((1u << GS) - 1u) << ((threadIdx.x & 31) / GS * GS));
-    constexpr int SPMM_NCB = spmm_ncb<GS>();
+    constexpr int SPMM_NCB = spmm_ncb<GS, WIDE>();
     const TX *Xg = X + (size_t)g * n_cols * n_cells;  // X[g, cell, c]: a cell's columns are contiguous
 
     for (int c0 = 0; c0 < n_cols; c0 += SPMM_NCB) {

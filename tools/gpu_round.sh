@@ -23,7 +23,10 @@ if [ "$NCU" = "1" ]; then
       --log-file $O/${TAG}_launches.csv $CMD > $O/${TAG}_ncu_launch.log 2>&1
   echo "launch list rc=$?"
   $CMD > $O/${TAG}_plain2.log 2>&1 &&
-  ncu --set full --clock-control none --import-source on -k regex:agf_ -s 9 -c 3 \
-      -o $O/${TAG}_prof -f $CMD > $O/${TAG}_ncu_full.log 2>&1
-  echo "full capture rc=$?"
+  ncu --set full --clock-control none --import-source on -k regex:agf_k1 -s 3 -c 1 \
+      -o $O/${TAG}_prof_k1 -f $CMD > $O/${TAG}_ncu_full.log 2>&1
+  echo "full capture (k1) rc=$?"
+  ncu --set full --clock-control none --import-source on -k regex:agf_spmm -s 3 -c 1 \
+      -o $O/${TAG}_prof_k2 -f $CMD > $O/${TAG}_ncu_full_k2.log 2>&1
+  echo "full capture (k2) rc=$?"
 fi
