@@ -88,6 +88,8 @@ static int launch_k1(const K1Launch &a) {
         L.t0 = d.lanes[l].t0;
         L.t1 = d.lanes[l].t1;
         L.base = (d.lanes[l].flag == 0) ? L.t0 : L.t1;  // nb_kernels.py:168
+        L.base_f = (float)L.base;
+        L.base_is_f32 = (sizeof(T) == 4 && (double)L.base_f == L.base) ? 1 : 0;
         set_thresholds(L, L.t0, L.t1);
     }
     if (NS > 0) {

@@ -81,7 +81,24 @@ struct LaneP {
     int flag;
     T lo, hi;  // v > t0  <=>  v > lo ;  v < t1  <=>  v < hi   (thresholds pre-rounded for float)
     double t0, t1, base;
+    // float raster and a dd base that IS a float: float(|double(v) - base|) == |v - base_f| computed in
+    // float (rounding a float difference to double first never changes the float result: 53 >= 2*24+2),
+    // which replaces three float<->double conversions per value by one.  Conversions run on the XU
+    // pipe at a quarter of the fp64 rate and were the bound of the daily dd kernel (ncu r1n: XU 79 %).
+    float base_f;
+    int base_is_f32;
 };
+
+// one degree-day term rounded to the raster dtype (AGF_CALC_DD_R)
+template <typename T>
+__device__ __forceinline__ double dd_term_rounded(const LaneP<T> &L, T v, double vd) {
+    if constexpr (sizeof(T) == 4) {
+        if (L.base_is_f32) return (double)fabsf(v - L.base_f);
+        return (double)(float)fabs(vd - L.base);
+    } else {
+        return fabs(vd - L.base);
+    }
+}
 
 struct SlotP {
     int src;
@@ -387,7 +404,7 @@ __device__ __forceinline__ void l1_acc(const K1Params<T, NL, NS> &p, ST &s, T v)
             } else if constexpr (KINDS == KIND_DD) {
                 if (v > L.lo && v < L.hi) s.a[l] += fabs(vd - L.base);
             } else if constexpr (KINDS == KIND_DDR) {
-                if (v > L.lo && v < L.hi) s.a[l] += round_to<T>(fabs(vd - L.base));
+                if (v > L.lo && v < L.hi) s.a[l] += dd_term_rounded(L, v, vd);
             } else {
                 switch (L.calc) {
                     case AGF_CALC_MEAN:
@@ -424,7 +441,7 @@ __device__ __forceinline__ void l1_acc(const K1Params<T, NL, NS> &p, ST &s, T v)
                         break;
                     case AGF_CALC_DD_R:
                         if constexpr ((KINDS & KIND_DDR) != 0)
-                            if (v > L.lo && v < L.hi) s.a[l] += round_to<T>(fabs(vd - L.base));
+                            if (v > L.lo && v < L.hi) s.a[l] += dd_term_rounded(L, v, vd);
                         break;
                     case AGF_CALC_BINS:
                         if constexpr ((KINDS & KIND_BINS) != 0)
