@@ -13,6 +13,8 @@
     K1CASE(1, 32, false, KIND_SUM, 24, 0)                \
     K1CASE(1, 1, false, KIND_DD, 0, 0)                   \
     K1CASE(4, 4, true, KIND_DD, 0, 0)                    \
+    K1CASE(4, 4, false, KIND_MIX_SD, 0, 0)               \
+    K1CASE(4, 20, false, KIND_MIX_SD, 16, 0)             \
     K1CASE(16, 16, true, KIND_BINS, 0, 0)                \
     K1CASE(16, 16, true, KIND_DD | KIND_BINS, 0, 0)      \
     K1CASE(1, 4, false, KIND_ALL, NB_GENERAL, 0)         \

@@ -66,7 +66,23 @@ static int launch_k1(const K1Launch &a) {
     // where the bin lanes go to [0, NB) and the mean / sum lanes to [NB, NL), both in program order
     int lane_of[AGF_MAX_LANES];
     constexpr bool TL = typed_lanes<NS, NB>();
-    if constexpr (TL) {
+    constexpr bool MIX = !TL && KINDS == KIND_MIX_SD;  // lane 0 = the mean / sum lane, 1.. = the dd lanes
+    if constexpr (MIX) {
+        int nd = 1;
+        for (int l = 0; l < d.n_lanes; ++l)
+            lane_of[l] = (kind_of_calc(d.lanes[l].calc) == KIND_SUM) ? 0 : nd++;
+        for (int l = 0; l < NL; ++l) {  // inert pads: a sum nobody reads / a dd range no value falls in
+            LaneP<T> &L = kp.lanes[l];
+            L.calc = l == 0 ? AGF_CALC_SUM : AGF_CALC_DD;
+            L.lo = (T)INFINITY;
+            L.hi = (T)-INFINITY;
+            L.t0 = INFINITY;
+            L.t1 = -INFINITY;
+            if (NS == 0) kp.cols[l].dst = -1;
+        }
+        kp.n_lanes = NL;
+        if (NS == 0) kp.n_cols = NL;  // diagonal columns travel with their lanes; pads have dst = -1
+    } else if constexpr (TL) {
         int nb = 0, ns = NB;
         for (int l = 0; l < d.n_lanes; ++l) lane_of[l] = (d.lanes[l].calc == AGF_CALC_BINS) ? nb++ : ns++;
         for (int l = 0; l < NL; ++l) {  // inert pads: a bin no value falls in / a sum nobody stores
@@ -94,7 +110,7 @@ static int launch_k1(const K1Launch &a) {
     }
     if (NS > 0) {
         auto fill = [&](SlotP &S, int j) {
-            S.src = d.slots[j].src;
+            S.src = lane_of[d.slots[j].src];
             S.xform = d.slots[j].xform;
             S.xparam = d.slots[j].xparam;
             S.x_f64 = d.slots[j].x_f64;
@@ -137,8 +153,8 @@ static int launch_k1(const K1Launch &a) {
     } else {
         for (int c = 0; c < d.n_cols; ++c) {
             // typed lanes are diagonal (column c reads lane c): the column moves with its lane
-            ColP &C = kp.cols[TL ? lane_of[d.cols[c].src] : c];
-            C.src = TL ? lane_of[d.cols[c].src] : d.cols[c].src;
+            ColP &C = kp.cols[(TL || MIX) ? lane_of[d.cols[c].src] : c];
+            C.src = (TL || MIX) ? lane_of[d.cols[c].src] : d.cols[c].src;
             C.xform = d.cols[c].xform;
             C.xparam = d.cols[c].xparam;
             C.x_f64 = d.cols[c].x_f64;
@@ -193,6 +209,13 @@ static inline bool k1_fits(const agf_program *p, int NL, int NS, bool DG, unsign
     if ((NS == 0) != (d.n_slots == 0) || d.n_slots > NS) return false;
     if (DG && !p->diag_ok) return false;
     if (NS > 0 && NL > 4 && !DG) return false;  // select-chain form only for <= 4 lanes
+    if (KINDS == KIND_MIX_SD && !(NS == 0 && NB >= 0)) {  // mixed layout: at most one mean / sum lane + dd lanes
+        int nsum = 0;
+        for (int l = 0; l < d.n_lanes; ++l) nsum += kind_of_calc(d.lanes[l].calc) == KIND_SUM;
+        if ((p->kinds & ~KIND_MIX_SD) || nsum > 1 || d.n_lanes - nsum > NL - 1) return false;
+        if (NS == 0 && (!DG || !p->diag_ok)) return false;
+        if (NS > 0 && DG) return false;  // slots pick their lane through the select chain
+    }
     if (NS == 0 && NB >= 0) {  // typed lanes: bins -> [0, NB), mean / sum -> [NB, NL); diagonal columns
         if (!DG || !p->diag_ok || (p->kinds & ~(KIND_SUM | KIND_BINS))) return false;
         int nbins = 0;

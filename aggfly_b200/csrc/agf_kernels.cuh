@@ -39,6 +39,12 @@ enum : unsigned {
     KIND_DDR = 64u,     // degree days with every term rounded to the raster dtype (AGF_CALC_DD_R)
     KIND_ALL = 127u
 };
+// KIND_SUM | KIND_DD as a compile-time set means the MIXED layout: the launcher puts the program's one
+// mean / sum lane in kernel lane 0 and its degree-day lanes in lanes 1.. (inert pads elsewhere), so the
+// per-value code is straight-line -- the reference's own example config (daily mean -> annual mean
+// plus degree days -> annual sum, examples/era5_counties_area.yaml) would otherwise run the generic
+// switch-per-value kernel.
+constexpr unsigned KIND_MIX_SD = KIND_SUM | KIND_DD;
 
 __host__ __device__ constexpr unsigned kind_of_calc(int calc) {
     return (calc == AGF_CALC_MEAN || calc == AGF_CALC_SUM)  ? KIND_SUM
@@ -381,6 +387,14 @@ __device__ __forceinline__ void pre_apply_batch(const K1Params<T, NL, NS> &p, T 
 template <unsigned KINDS, typename T, int NL, int NS, typename ST>
 __device__ __forceinline__ void l1_acc(const K1Params<T, NL, NS> &p, ST &s, T v) {
     const double vd = (double)v;
+    if constexpr (KINDS == KIND_MIX_SD && !ST::TL) {  // lane 0: mean / sum, lanes 1..: degree days
+        s.nan |= (v != v);
+        s.a[0] += vd;
+#pragma unroll
+        for (int l = 1; l < NL; ++l)
+            if (v > p.lanes[l].lo && v < p.lanes[l].hi) s.a[l] += fabs(vd - p.lanes[l].base);
+        return;
+    }
     if constexpr (ST::TL) {  // typed lanes: straight-line, no per-lane dispatch
         constexpr int NBL = NL - ST::NA;
 #pragma unroll
@@ -530,6 +544,9 @@ __device__ __forceinline__ double l1_value(const K1Params<T, NL, NS> &p, const S
         r = s.a[l];
     } else if constexpr (KINDS == KIND_DD || KINDS == KIND_DDR) {
         r = s.nan ? agf_nan() : s.a[l];
+    } else if constexpr (KINDS == KIND_MIX_SD) {
+        r = (l == 0) ? ((L.calc == AGF_CALC_MEAN) ? mean_of<T, GLC>(s.a[0], n_grp) : s.a[0])
+                     : (s.nan ? agf_nan() : s.a[l]);
     } else {
         switch (L.calc) {
             case AGF_CALC_MEAN:
@@ -721,7 +738,7 @@ __device__ __forceinline__ void l1_flush(const K1Params<T, NL, NS> &p, ST &s, in
         if (DIAG) {  // column c == lane c, no transform
 #pragma unroll
             for (int l = 0; l < NL; ++l) {
-                if (l < p.n_cols) {
+                if (l < p.n_cols && p.cols[l].dst >= 0) {  // dst < 0: an inert pad lane of the mixed layout
                     ok &= (val[l] == val[l]);
                     sink_put(p, o, base, p.cols[l].dst, val[l]);
                 }
@@ -1006,43 +1023,9 @@ __global__ void __launch_bounds__(TMA_THREADS, MINB)
         nb_next = (g + 1 < g_end) ? p.b1[g + 2] : 0x7fffffff;
     };
 
-    if constexpr (NL == 1 && NS <= 4 && KINDS != KIND_ALL) {
-        // Register-tile mode (one specialised lane, few slots: the tile fits in registers next to the
-        // reducers and the flush is small enough to inline per row).  The tile column
-        // is pulled into registers and the stage handed back BEFORE it is reduced, as in the uniform
-        // kernel, so the ring keeps all its stages in flight while the consumers compute; holding the
-        // stage through the reduction left the ragged (month-bounded) daily kernel waiting on loads
-        // (ncu r1n: 4.4 TB/s, 4 % of issued instructions were barrier polls).  Every branch below is
-        // uniform across the CTA (group bounds do not depend on the cell).
-        int stg = 0, ph = 0;
-#pragma unroll 1
-        for (int i = 0; i < n_tiles; ++i) {
-            mbar_wait(&full[stg], ph);
-            const T *col = tiles + (size_t)stg * (TMA_TILE_BYTES / sizeof(T)) + threadIdx.x;
-            T v[TT];
-#pragma unroll
-            for (int r = 0; r < TT; ++r) v[r] = col[r * TMA_CW];  // rows past the view are zero-filled, never used
-            __syncwarp();
-            if ((threadIdx.x & 31) == 0) mbar_arrive(&empty[stg]);
-            pre_apply_batch(p, v);
-            const int rows = min(TT, k_end - (k_begin + i * TT));
-#pragma unroll
-            for (int r = 0; r < TT; ++r) {
-                if (r < rows) {
-                    while (k == nb) close_group();  // also walks zero-width groups
-                    l1_acc<KINDS>(p, s, v[r]);
-                    ++k;
-                }
-            }
-            if (++stg == TMA_STAGES) {
-                stg = 0;
-                ph ^= 1;
-            }
-        }
-        while (k == nb) close_group();  // the last group, and zero-width groups after it
-        return;
-    }
-
+    // (A register-tile variant of this loop -- pull the whole column, release the stage early, then walk
+    // the rows with a group-end test per row -- was tried for the month-bounded daily kernel and was
+    // 2x SLOWER: 24 inlined group-end sites doubled the instruction count, ncu r1p.)
     for (int i = 0; i < n_tiles; ++i) {
         const int stg = i % TMA_STAGES;
         mbar_wait(&full[stg], (i / TMA_STAGES) & 1);
@@ -1061,6 +1044,30 @@ __global__ void __launch_bounds__(TMA_THREADS, MINB)
                 pre_apply_batch(p, v);
 #pragma unroll
                 for (int u = 0; u < UNROLL; ++u) l1_acc<KINDS>(p, s, v[u]);
+            }
+            // tail of the run: one optional batch of 4, of 2, of 1 (a per-value loop cost ~12 instructions
+            // of overhead per value, and month-bounded runs cut by 24-row tiles are mostly tail)
+            if constexpr (UNROLL >= 8) {
+                if (j >= 4) {
+                    T v[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) v[u] = cp[u * TMA_CW];
+                    pre_apply_batch(p, v);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) l1_acc<KINDS>(p, s, v[u]);
+                    j -= 4;
+                    cp += 4 * TMA_CW;
+                }
+                if (j >= 2) {
+                    T v[2];
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) v[u] = cp[u * TMA_CW];
+                    pre_apply_batch(p, v);
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) l1_acc<KINDS>(p, s, v[u]);
+                    j -= 2;
+                    cp += 2 * TMA_CW;
+                }
             }
 #pragma unroll 1
             for (; j > 0; --j, cp += TMA_CW) l1_acc<KINDS>(p, s, p.n_pre ? pre_apply(p, *cp) : *cp);

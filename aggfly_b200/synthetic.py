@@ -28,6 +28,11 @@ SPECS: Dict[str, dict] = {
     "tavg_poly": dict(tavg=[("aggregate", {"calc": "mean", "groupby": "date"}),
                             ("transform", {"transform": "power", "exp": np.arange(1, 3)}),
                             ("aggregate", {"calc": "sum", "groupby": "year"})]),
+    # examples/era5_counties_area.yaml: daily mean -> annual mean, plus growing degree days -> annual sum
+    "area_example": dict(tavg=[("aggregate", {"calc": "mean", "groupby": "date"}),
+                               ("aggregate", {"calc": "mean", "groupby": "year"})],
+                         gdd_10_30=[("aggregate", {"calc": "dd", "groupby": "date", "ddargs": [10, 30, 0]}),
+                                    ("aggregate", {"calc": "sum", "groupby": "year"})]),
     # configs[1]: growing degree-days [10, 30, 0] date -> year sum
     "gdd": dict(gdd=[("aggregate", {"calc": "dd", "groupby": "date", "ddargs": [10, 30, 0]}),
                      ("aggregate", {"calc": "sum", "groupby": "year"})]),
@@ -182,6 +187,10 @@ def make_workload(name: str) -> Workload:
     if name == "c2_conus_gdd":
         return Workload(name, conus_grid(), "gdd", 8760, _hourly_year(), secondary=True, ocean_frac=0.0,
                         description="CONUS grid, population-weighted, dd[10,30,0] date -> year sum")
+    if name == "c3c_global_area_example":
+        return Workload(name, global_grid(), "area_example", 8760, _hourly_year(),
+                        description="global 0.25deg hourly year, the reference's example spec: daily mean -> annual mean "
+                                    "+ dd[10,30,0] -> annual sum (mixed mean / degree-day lanes, one pass)")
     if name == "c3_global_bins":
         return Workload(name, global_grid(), "bins_poly", 8760, _hourly_year(),
                         description="global 0.25deg hourly 721x1440x8760 (36.4 GB f32), 45000 pseudo admin-2 "

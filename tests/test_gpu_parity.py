@@ -153,11 +153,31 @@ SPECS = {
                             ("aggregate", {"calc": "max", "groupby": "year"})]),
     "nanmean_multipass": dict(a=[("aggregate", {"calc": "nanmean", "groupby": "date"}),
                                  ("aggregate", {"calc": "nanmean", "groupby": "month"})]),
+    # the reference's example config (examples/era5_counties_area.yaml) + a heating degree-day lane
+    "area_example": dict(
+        tavg=[("aggregate", {"calc": "mean", "groupby": "date"}), ("aggregate", {"calc": "mean", "groupby": "year"})],
+        gdd_10_30=[("aggregate", {"calc": "dd", "groupby": "date", "ddargs": [10, 30, 0]}),
+                   ("aggregate", {"calc": "sum", "groupby": "year"})],
+        hdd=[("aggregate", {"calc": "dd", "groupby": "date", "ddargs": [-99, 18.3, 1]}),
+             ("aggregate", {"calc": "sum", "groupby": "year"})]),
+    # one mean lane + degree days feeding typed slots (bins of the daily mean, polynomial, dd sums)
+    "mix_bins_poly_dd": dict(
+        tb=[("aggregate", {"calc": "mean", "groupby": "date"}),
+            ("aggregate", {"calc": "bins", "groupby": "month", "ddargs": BINS13})],
+        tavg=[("aggregate", {"calc": "mean", "groupby": "date"}),
+              ("transform", {"transform": "power", "exp": np.arange(1, 4)}),
+              ("aggregate", {"calc": "sum", "groupby": "month"})],
+        dd=[("aggregate", {"calc": "dd", "groupby": "date", "ddargs": [[10, 30, 0], [0.1, 17.3, 1]]}),
+            ("aggregate", {"calc": "sum", "groupby": "month"})]),
+    # daily panel: mean + degree days per date (single-level mixed layout)
+    "daily_mean_dd": dict(tavg=[("aggregate", {"calc": "mean", "groupby": "date"})],
+                          gdd=[("aggregate", {"calc": "dd", "groupby": "date", "ddargs": [10, 30, 0]})],
+                          tsum=[("aggregate", {"calc": "dd", "groupby": "date", "ddargs": [-99, 18.3, 1]})]),
     "sine": dict(s=[("aggregate", {"calc": "sine_dd", "groupby": "date", "ddargs": [10, 30, 0]}),
                     ("aggregate", {"calc": "sum", "groupby": "month"})],
                  h=[("aggregate", {"calc": "sine_dd", "groupby": "date", "ddargs": [[5, 18, 1], [12, 99, 0]]})]),
 }
-INEXACT = {"spline_and_pow": 1e-6, "sine": 1e-5}     # powf / libm transcendental differences only
+INEXACT = {"spline_and_pow": 1e-6, "sine": 1e-5, "mix_bins_poly_dd": 1e-14}   # pow: libm vs exact products     # powf / libm transcendental differences only
 
 
 def _raster(dtype, nan, T=24 * 75 + 7, Y=5, X=9, seed=0):
@@ -199,14 +219,15 @@ def test_chains_match_oracle_single_stripe(name, dtype, nan):
             _exact(got[k].values, w_arr)
 
 
-@pytest.mark.parametrize("name", ["c1_tavg_poly", "c3_bins_and_poly", "monthly_mix", "weekly", "c3b_daily"])
+@pytest.mark.parametrize("name", ["c1_tavg_poly", "c3_bins_and_poly", "monthly_mix", "weekly", "c3b_daily", "area_example",
+                                  "mix_bins_poly_dd", "daily_mean_dd"])
 @pytest.mark.parametrize("stripes", [0, 3, 17, 1000])
 def test_chains_match_oracle_many_stripes(name, stripes):
     engine.OPTIONS["target_stripes"] = stripes
     arr, t, lat, lon = _raster("float32", True, seed=3)
     got, want = _both_time(arr, t, lat, lon, SPECS[name])
     for k in want:
-        if "bins" in k or "tmin" in k or "tmax" in k or k == "w":
+        if "bins" in k or "tmin" in k or "tmax" in k or k == "w" or k.startswith("tb_"):
             _exact(got[k].values, want[k][0])              # counts / min / max do not depend on the split
         else:
             _close(got[k].values, want[k][0], 1e-12)
