@@ -8,6 +8,7 @@
     K1CASE(1, 0, false, KIND_DD, NB_GENERAL, 0)                  \
     K1CASE(1, 0, false, KIND_DDR, NB_GENERAL, 0)                 \
     K1CASE(4, 0, true, KIND_DD | KIND_DDR, NB_GENERAL, 0)        \
+    K1CASE(2, 0, true, KIND_MIX_SD, NB_GENERAL, 0)               \
     K1CASE(4, 0, true, KIND_MIX_SD, NB_GENERAL, 0)               \
     K1CASE(8, 0, true, KIND_SUM | KIND_BINS, 6, 0)               \
     K1CASE(16, 0, true, KIND_SUM | KIND_BINS, 14, 0)             \

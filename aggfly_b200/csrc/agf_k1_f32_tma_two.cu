@@ -13,6 +13,7 @@
     K1CASE(1, 32, false, KIND_SUM, 24, 0)                \
     K1CASE(1, 1, false, KIND_DD, 0, 0)                   \
     K1CASE(4, 4, true, KIND_DD, 0, 0)                    \
+    K1CASE(2, 4, false, KIND_MIX_SD, 0, 0)               \
     K1CASE(4, 4, false, KIND_MIX_SD, 0, 0)               \
     K1CASE(4, 20, false, KIND_MIX_SD, 16, 0)             \
     K1CASE(16, 16, true, KIND_BINS, 0, 0)                \

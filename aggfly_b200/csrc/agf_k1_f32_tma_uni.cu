@@ -15,6 +15,9 @@
     K1CASE(1, 0, false, KIND_DD, NB_GENERAL, 24)        \
     K1CASE(1, 1, false, KIND_DD, 0, 24)                 \
     K1CASE(4, 4, true, KIND_DD, 0, 24)                  \
+    K1CASE(2, 0, true, KIND_MIX_SD, NB_GENERAL, 24)     \
+    K1CASE(2, 4, false, KIND_MIX_SD, 0, 24)             \
+    K1CASE(2, 20, false, KIND_MIX_SD, 16, 24)           \
     K1CASE(4, 0, true, KIND_MIX_SD, NB_GENERAL, 24)     \
     K1CASE(4, 4, false, KIND_MIX_SD, 0, 24)             \
     K1CASE(4, 20, false, KIND_MIX_SD, 16, 24)           \

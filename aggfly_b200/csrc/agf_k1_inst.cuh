@@ -62,6 +62,43 @@ static int launch_k1(const K1Launch &a) {
         kp.pre[i].op = d.pre[i].op;
         kp.pre[i].c = (T)d.pre[i].c;
     }
+    {
+        // does the chain fit (v + b0) * a + b1, stage by stage?  stage 0: add, 1: multiply, 2: add
+        T b0 = (T)-0.0, a = (T)1.0, b1 = (T)-0.0;
+        int stage = 0;
+        bool ok = d.n_pre > 0;
+        for (int i = 0; i < d.n_pre && ok; ++i) {
+            const T c = (T)d.pre[i].c;
+            switch (d.pre[i].op) {
+                case AGF_PRE_ADD:
+                case AGF_PRE_SUB: {
+                    const T add = d.pre[i].op == AGF_PRE_ADD ? c : -c;
+                    if (stage == 0) { b0 = add; stage = 1; }
+                    else if (stage <= 2) { b1 = add; stage = 3; }
+                    else ok = false;
+                    break;
+                }
+                case AGF_PRE_MUL:
+                    if (stage <= 1) { a = c; stage = 2; }
+                    else ok = false;
+                    break;
+                case AGF_PRE_NEG:
+                    if (stage <= 1) { a = (T)-1.0; stage = 2; }
+                    else ok = false;
+                    break;
+                case AGF_PRE_RSUB:  // c - x == x * (-1) + c
+                    if (stage <= 1) { a = (T)-1.0; b1 = c; stage = 3; }
+                    else ok = false;
+                    break;
+                default:
+                    ok = false;  // divisions keep the exact out-of-line path
+            }
+        }
+        kp.pre_linear = ok ? 1 : 0;
+        kp.pre_b0 = b0;
+        kp.pre_a = a;
+        kp.pre_b1 = b1;
+    }
     // kernel lane of each program lane: identity, except for typed lanes (single-level, NB >= 0),
     // where the bin lanes go to [0, NB) and the mean / sum lanes to [NB, NL), both in program order
     int lane_of[AGF_MAX_LANES];

@@ -157,6 +157,8 @@ struct K1Params {
     int in_f64, out_f64;
     int need_nan, need_cnt, has_sine, diag;
     int n_pre;
+    int pre_linear;  // the chain has the form (v + b0) * a + b1 (identity fillers: -0.0, 1): inlined as 3 ops
+    T pre_b0, pre_a, pre_b1;
     int stage_out;  // single-level: stage a warp's X[g, 32 cells, :] block in shared memory, store it coalesced
     PreP<T> pre[AGF_MAX_PRE];
     LaneP<T> lanes[NL];
@@ -354,14 +356,16 @@ __device__ __forceinline__ void count_in_range(int &c, double v, double lo, doub
     if (v > lo && v < hi) c += 1;
 }
 
-// the program's preprocess chain on one raster value, in the raster dtype (one rounding per op)
-template <typename T, int NL, int NS>
-__device__ __forceinline__ T pre_apply(const K1Params<T, NL, NS> &p, T v) {
-#pragma unroll
-    for (int i = 0; i < AGF_MAX_PRE; ++i) {
-        if (i < p.n_pre) {
-            const T c = p.pre[i].c;
-            switch (p.pre[i].op) {
+// the program's preprocess chain on one raster value, in the raster dtype (one rounding per op).
+// General form: out of line -- the IEEE division routine inlined at every load site (24 per tile in
+// the uniform kernel) made the kernels 3x larger for a path most programs never take.
+template <typename T>
+__device__ __noinline__ T pre_apply_general(const PreP<T> *pre, int n_pre, T v) {
+#pragma unroll 1
+    for (int i = 0; i < n_pre; ++i) {
+        {
+            const T c = pre[i].c;
+            switch (pre[i].op) {
                 case AGF_PRE_ADD: v = v + c; break;
                 case AGF_PRE_SUB: v = v - c; break;
                 case AGF_PRE_RSUB: v = c - v; break;
@@ -374,12 +378,34 @@ __device__ __forceinline__ T pre_apply(const K1Params<T, NL, NS> &p, T v) {
     }
     return v;
 }
+// Linear chains (x - 273.15, x * 1000, 1.8 * x + 32, c - x ...) are three inline operations with
+// identity fillers: adding -0.0 and multiplying by 1 return their operand bit for bit, x - c == x + (-c)
+// and c - x == x * (-1) + c in IEEE arithmetic, and the library is built without FMA contraction.
+template <typename T, int NL, int NS>
+__device__ __forceinline__ T pre_apply(const K1Params<T, NL, NS> &p, T v) {
+    if (p.pre_linear) {
+        v = v + p.pre_b0;
+        v = v * p.pre_a;
+        v = v + p.pre_b1;
+        return v;
+    }
+    return pre_apply_general<T>(p.pre, p.n_pre, v);
+}
 // a register batch of raster values: one uniform branch per batch, nothing when there is no chain
 template <int N, typename T, int NL, int NS>
 __device__ __forceinline__ void pre_apply_batch(const K1Params<T, NL, NS> &p, T (&v)[N]) {
     if (p.n_pre != 0) {
+        if (p.pre_linear) {
 #pragma unroll
-        for (int i = 0; i < N; ++i) v[i] = pre_apply(p, v[i]);
+            for (int i = 0; i < N; ++i) {
+                v[i] = v[i] + p.pre_b0;
+                v[i] = v[i] * p.pre_a;
+                v[i] = v[i] + p.pre_b1;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < N; ++i) v[i] = pre_apply_general<T>(p.pre, p.n_pre, v[i]);  // N call sites: v stays in registers
+        }
     }
 }
 
