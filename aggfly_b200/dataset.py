@@ -178,6 +178,35 @@ class Dataset:
         new.history = list(self.history)
         return new
 
+    # -- elementwise transforms (aggfly/dataset/dataset.py:442-518), run by the library's kernel ---------
+    def _transformed(self, params: dict):
+        from .aggregate import aggregate_time
+        out = aggregate_time(self, None, {self.name or "x": [("transform", params)]})
+        return list(out.values())
+
+    def power(self, exp, update: bool = False) -> Optional["Dataset"]:
+        """``np.power(values, exp)`` with NumPy's promotion (a numpy-integer exponent makes float32 data
+        float64, a Python int does not)."""
+        new = self._transformed({"transform": "power", "exp": [[exp]]})[0]
+        new.history = list(self.history) + [f"power{exp}"]
+        return self._maybe_update(new, update)
+
+    def interact(self, inter, update: bool = False) -> Optional["Dataset"]:
+        """Multiply by another Dataset / array of the same shape."""
+        new = self._transformed({"inter": inter})[0]
+        new.history = list(self.history) + ["interacted"]
+        return self._maybe_update(new, update)
+
+    def spline(self):
+        """[x, (x > 20) * (x - 20)]  (aggfly/dataset/dataset.py:475-481)."""
+        return self._transformed({"transform": "spline"})
+
+    def _maybe_update(self, new: "Dataset", update: bool):
+        if update:
+            self.values, self.history = new.values, new.history
+            return None
+        return new
+
     def lon_sort_order(self) -> np.ndarray:
         """Column order the reference's ``rescale_longitude`` puts a 0-360 raster in
         (relabel to -180..180, then ``sortby('longitude')``; dataset.py:419-440,

@@ -553,3 +553,19 @@ def test_transform_of_the_raster_alone_and_shape_mismatch():
     with pytest.raises(AssertionError):
         af.aggregate_time(dataset=af.Dataset.from_arrays(arr, t, lat, lon, True), weights=None,
                           bad=[("transform", {"inter": np.ones((7, 2, 3), np.float32)})])
+
+
+def test_dataset_transform_methods_match_numpy():
+    arr, t, lat, lon = _raster("float32", True, T=50, Y=3, X=4, seed=41)
+    ds = af.Dataset.from_arrays(arr, t, lat, lon, True, name="t2m")
+    p2 = ds.power(np.int64(2))
+    assert p2.values.dtype == np.float64 and p2.history == ["power2"]
+    _exact(p2.values, np.power(arr, np.int64(2)))
+    assert ds.power(2).values.dtype == np.float32                       # python int: stays float32
+    other = np.random.default_rng(2).random(arr.shape).astype(np.float32)
+    _exact(ds.interact(other).values, np.multiply(arr, other))
+    s1, s2 = ds.spline()
+    _exact(s1.values, arr)
+    _exact(s2.values, (arr > 20) * (arr - 20))
+    ds2 = ds.deepcopy()
+    assert ds2.power(np.int64(2), update=True) is None and ds2.values.dtype == np.float64
