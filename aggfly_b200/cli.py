@@ -123,6 +123,8 @@ def _dist_info():
         if not dist.is_initialized():
             local = int(os.environ.get("LOCAL_RANK", "0"))
             torch.cuda.set_device(local)
+            from .stream import bind_host_to_device
+            bind_host_to_device(local)                          # staging buffers on the GPU's NUMA node
             dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         return dist.get_rank(), dist.get_world_size()
     return 0, 1

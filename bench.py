@@ -268,6 +268,8 @@ def main_ours(args, rank, world, local_rank):
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    from aggfly_b200 import stream as _stream_mod
+    numa = _stream_mod.bind_host_to_device(local_rank) if world > 1 else {"bound": False}   # pinned rasters on the GPU's node
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     wl = syn.make_workload(args.workload)
@@ -366,6 +368,7 @@ def main_ours(args, rank, world, local_rank):
                "feed": {"chunks": st.get("chunks"), "pinned": st.get("pinned"), "k1_launches": st.get("k1_launches"),
                         "h2d_ms": h2d_ms,
                         "h2d_gbs": (st.get("h2d_bytes", 0) / (h2d_ms * 1e-3) / 1e9) if h2d_ms else None},
+               "numa_binding": numa,
                "h2d_bytes_per_step": int(host.numel() * host.element_size()),
                "d2h_bytes_per_step": int(R * G * NC * 8), "ms_per_step": dt * 1e3, "steps": e2e_steps,
                "api": "aggfly_b200.aggregate_dataset(weights, Dataset(pinned host tensor), aggregator_dict)",
