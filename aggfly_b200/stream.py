@@ -24,10 +24,14 @@ from typing import Optional
 
 import numpy as np
 
+# Measured on a B200 box (16 cores, tools/feed_sweep.py, global year = 36.4 GB of pageable NumPy data):
+# 4 threads x 4 slots x 256 MB 949 ms; 8 x 8 x 128 MB 715 ms; 8 x 8 x 64 MB 710 ms; 16 x 16 x 64 MB 694 ms
+# -- the last three are PCIe-bound like the pinned path (655-700 ms).
 OPTIONS = {
-    "chunk_bytes": 256 << 20,     # bytes per host->device copy
-    "staging_slots": 4,           # pinned ring depth for pageable sources
-    "staging_threads": 4,         # host threads filling the ring
+    "chunk_bytes": 256 << 20,          # bytes per host->device copy, pinned sources
+    "staging_chunk_bytes": 64 << 20,   # ... pageable sources (also the size of a staging slot)
+    "staging_slots": 8,                # pinned ring depth for pageable sources
+    "staging_threads": 8,              # host threads filling the ring
 }
 
 
@@ -55,12 +59,19 @@ def chunk_rows(n_rows: int, row_bytes: int, chunk_bytes: int):
     return [(r, min(n_rows, r + step)) for r in range(0, n_rows, step)]
 
 
+_RINGS = {}          # (dtype, slot_elems, n_slots) -> pinned slots, kept across calls: pinning 512 MB costs ~100 ms
+
+
 class _Staging:
     """Ring of pinned buffers filled by worker threads (pageable sources only)."""
 
     def __init__(self, torch, dtype, slot_elems: int, n_slots: int, n_threads: int):
         self.torch = torch
-        self.slots = [torch.empty(slot_elems, dtype=dtype, pin_memory=True) for _ in range(n_slots)]
+        key = (str(dtype), int(slot_elems), int(n_slots))
+        if key not in _RINGS:
+            _RINGS.clear()                             # one ring at a time: it is pinned memory
+            _RINGS[key] = [torch.empty(slot_elems, dtype=dtype, pin_memory=True) for _ in range(n_slots)]
+        self.slots = _RINGS[key]
         self.events = [None] * n_slots                 # copy-done event of the slot's last use
         self.pool = ThreadPoolExecutor(max_workers=max(1, n_threads))
 
@@ -98,7 +109,7 @@ def feed_and_run(runner, values, n_cells: int, stream=None, k1_events: Optional[
     copy = _copy_stream(dev)
     raster = torch.empty((T, n_cells), dtype=tdtype, device=dev)
     row_bytes = n_cells * raster.element_size()
-    chunks = chunk_rows(T, row_bytes, chunk_bytes or OPTIONS["chunk_bytes"])
+    chunks = chunk_rows(T, row_bytes, chunk_bytes or OPTIONS["chunk_bytes" if pinned else "staging_chunk_bytes"])
     staging = None
     if not pinned:
         slot_elems = max(r1 - r0 for r0, r1 in chunks) * n_cells

@@ -350,7 +350,8 @@ def test_streamed_feed_is_bitwise_the_device_resident_result(name, feed):
     engine.OPTIONS["target_stripes"] = 11
     old = dict(stream.OPTIONS)
     try:
-        stream.OPTIONS.update(chunk_bytes=13 * arr[0].nbytes, staging_slots=3, staging_threads=2)   # 13-row chunks
+        stream.OPTIONS.update(chunk_bytes=13 * arr[0].nbytes, staging_chunk_bytes=13 * arr[0].nbytes, staging_slots=3,
+                              staging_threads=2)                                           # 13-row chunks
         resident = run(torch.from_numpy(arr).cuda())
         if feed == "pinned":
             host = torch.from_numpy(arr).pin_memory()
