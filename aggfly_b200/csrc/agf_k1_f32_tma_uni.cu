@@ -1,5 +1,5 @@
 // K1 instantiations of this unit: float raster, TMA ring, UNIFORM level-1 groups (agf_k1_tma_uni:
-// every group has GL rows; GL = 24 hourly -> date, GL = 1 daily data by date).  Rows are
+// every group has GL rows; GL = 24 hourly -> date, 8 / 4 three- / six-hourly -> date, 1 daily data by date).  Rows are
 // K1CASE(lanes, slots, diag, lane kinds, NB, GL); tried in order, cheapest first.
 #define AGF_T float
 #define AGF_TMA 1
@@ -25,6 +25,16 @@
     K1CASE(16, 0, true, KIND_SUM | KIND_BINS, 14, 24)   \
     K1CASE(32, 0, true, KIND_SUM | KIND_BINS, 28, 24)   \
     K1CASE(16, 16, true, KIND_BINS, 0, 24)              \
+    K1CASE(1, 0, false, KIND_SUM, NB_GENERAL, 8)        \
+    K1CASE(1, 4, false, KIND_SUM, 0, 8)                 \
+    K1CASE(1, 20, false, KIND_SUM, 16, 8)               \
+    K1CASE(1, 1, false, KIND_DD, 0, 8)                  \
+    K1CASE(2, 4, false, KIND_MIX_SD, 0, 8)              \
+    K1CASE(1, 0, false, KIND_SUM, NB_GENERAL, 4)        \
+    K1CASE(1, 4, false, KIND_SUM, 0, 4)                 \
+    K1CASE(1, 20, false, KIND_SUM, 16, 4)               \
+    K1CASE(1, 1, false, KIND_DD, 0, 4)                  \
+    K1CASE(2, 4, false, KIND_MIX_SD, 0, 4)              \
     K1CASE(1, 1, false, KIND_SUM, 0, 1)                 \
     K1CASE(1, 4, false, KIND_SUM, 0, 1)                 \
     K1CASE(1, 20, false, KIND_SUM, 16, 1)               \

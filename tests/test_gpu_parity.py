@@ -570,3 +570,22 @@ def test_dataset_transform_methods_match_numpy():
     _exact(s2.values, (arr > 20) * (arr - 20))
     ds2 = ds.deepcopy()
     assert ds2.power(np.int64(2), update=True) is None and ds2.values.dtype == np.float64
+
+
+@pytest.mark.parametrize("step_h", [3, 6])
+@pytest.mark.parametrize("name", ["c1_tavg_poly", "c3_bins_and_poly", "c2_gdd", "area_example", "c3b_daily"])
+def test_three_and_six_hourly_rasters_uniform_groups_of_8_and_4(name, step_h):
+    n = (24 // step_h) * 70
+    rng = np.random.default_rng(step_h)
+    t = pd.date_range("2001-02-10", periods=n, freq=f"{step_h}h")
+    arr = (11 + 9 * np.sin(np.arange(n) / 17.0)[:, None, None] + rng.normal(0, 6, (n, 4, 9))).astype(np.float32)
+    arr[rng.random(arr.shape) < 0.002] = np.nan
+    lat, lon = np.linspace(45, 42, 4), np.linspace(250, 258, 9)
+    for stripes in (1, 5):
+        engine.OPTIONS["target_stripes"] = stripes
+        got, want = _both_time(arr, t, lat, lon, SPECS[name])
+        for k in want:
+            if stripes == 1 or "bins" in k:
+                _exact(got[k].values, want[k][0])
+            else:
+                _close(got[k].values, want[k][0], 1e-12)
