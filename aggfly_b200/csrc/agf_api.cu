@@ -189,6 +189,8 @@ static int uniform_group_rows(const agf_program *p) {
 
 static int choose_kernel(agf_program *p) {
     p->uniform_gl = p->b1.size() >= 2 ? uniform_group_rows(p) : 0;
+    p->max_group_rows = 0;
+    for (size_t g = 0; g + 1 < p->b1.size(); ++g) p->max_group_rows = std::max(p->max_group_rows, p->b1[g + 1] - p->b1[g]);
     analyse_desc(&p->desc, &p->kinds, &p->slot_kinds, &p->n_bin_slots, &p->diag_ok);
     K1Launch q{};
     q.p = p;

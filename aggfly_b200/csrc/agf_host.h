@@ -20,6 +20,7 @@ struct agf_program {
     unsigned slot_kinds = 0;  // slot kinds the program uses
     int n_bin_slots = 0;      // slots of kind SK_BINS
     int uniform_gl = 0;       // rows per level-1 group when every group has the same size, else 0
+    int max_group_rows = 0;   // longest level-1 group
     int diag_ok = 0;     // columns (single-level) / slots (two-level) map 1:1 onto lanes
     int need_nan = 0, need_cnt = 0, has_sine = 0;
     // device copies

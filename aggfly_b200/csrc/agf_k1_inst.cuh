@@ -255,6 +255,7 @@ static inline bool k1_fits(const agf_program *p, int NL, int NS, bool DG, unsign
     }
     if (NS == 0 && NB >= 0) {  // typed lanes: bins -> [0, NB), mean / sum -> [NB, NL); diagonal columns
         if (!DG || !p->diag_ok || (p->kinds & ~(KIND_SUM | KIND_BINS))) return false;
+        if (p->max_group_rows >= (1 << 24)) return false;  // float bin counters stay exact below 2^24
         int nbins = 0;
         for (int l = 0; l < d.n_lanes; ++l) nbins += d.lanes[l].calc == AGF_CALC_BINS;
         if (nbins > NB || d.n_lanes - nbins > NL - NB) return false;

@@ -291,7 +291,12 @@ struct CellState {
     static constexpr int NA = TL ? (NL - NB) : NL;         // double-typed level-1 accumulators
     double a[NA > 0 ? NA : 1];  // level-1 accumulators (typed lanes: the mean / sum lanes)
     double b[ND > 0 ? ND : 1];  // level-2 accumulators (typed slots: the power sums)
-    int c[NB > 0 ? NB : 1];     // bin counters: level-2 (typed slots) or level-1 (typed lanes)
+    int c[NB > 0 ? NB : 1];     // bin counters: level-2 (typed slots)
+    // level-1 bin counters (typed lanes) are FLOAT registers: the predicated "+ 1.0f" then issues on the
+    // FMA pipe while the two compares of every (value, bin) pair keep the ALU pipe busy -- the hourly-bins
+    // scan is ALU-bound (ncu r1h) and an integer add would be a third ALU instruction.  Exact while a
+    // group has fewer than 2^24 rows (checked by the launcher).
+    float cf[TL && NB > 0 ? NB : 1];
     int nn;                     // non-NaN values in the current level-1 group
     bool nan;                   // NaN seen in the current level-1 group
 };
@@ -300,7 +305,7 @@ template <unsigned KINDS, typename T, int NL, int NS, typename ST>
 __device__ __forceinline__ void l1_init(const K1Params<T, NL, NS> &p, ST &s) {
     if constexpr (ST::TL) {
 #pragma unroll
-        for (int j = 0; j < NL - ST::NA; ++j) s.c[j] = 0;
+        for (int j = 0; j < NL - ST::NA; ++j) s.cf[j] = 0.0f;
 #pragma unroll
         for (int l = 0; l < ST::NA; ++l) s.a[l] = 0.0;
         s.nn = 0;
@@ -354,6 +359,20 @@ __device__ __forceinline__ void count_in_range(int &c, float v, float lo, float 
 }
 __device__ __forceinline__ void count_in_range(int &c, double v, double lo, double hi) {
     if (v > lo && v < hi) c += 1;
+}
+// float counters (typed lanes)
+__device__ __forceinline__ void count_in_range(float &c, float v, float lo, float hi) {
+    asm("{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.gt.f32 p, %1, %2;\n\t"
+        "setp.lt.and.f32 p, %1, %3, p;\n\t"
+        "@p add.f32 %0, %0, 0f3F800000;\n\t"
+        "}"
+        : "+f"(c)
+        : "f"(v), "f"(lo), "f"(hi));
+}
+__device__ __forceinline__ void count_in_range(float &c, double v, double lo, double hi) {
+    if (v > lo && v < hi) c += 1.0f;
 }
 
 // the program's preprocess chain on one raster value, in the raster dtype (one rounding per op).
@@ -424,7 +443,7 @@ __device__ __forceinline__ void l1_acc(const K1Params<T, NL, NS> &p, ST &s, T v)
     if constexpr (ST::TL) {  // typed lanes: straight-line, no per-lane dispatch
         constexpr int NBL = NL - ST::NA;
 #pragma unroll
-        for (int j = 0; j < NBL; ++j) count_in_range(s.c[j], v, p.lanes[j].lo, p.lanes[j].hi);
+        for (int j = 0; j < NBL; ++j) count_in_range(s.cf[j], v, p.lanes[j].lo, p.lanes[j].hi);
 #pragma unroll
         for (int l = 0; l < ST::NA; ++l) s.a[l] += vd;  // a NaN value poisons the sum
         return;
@@ -520,7 +539,7 @@ __device__ __forceinline__ void l1_acc_group(const K1Params<T, NL, NS> &p, ST &s
         for (int j = 0; j < NBL; ++j) {
             if (mx > p.lanes[j].lo && mn < p.lanes[j].hi) {  // warp-uniform
 #pragma unroll
-                for (int r = 0; r < N; ++r) count_in_range(s.c[j], v[r], p.lanes[j].lo, p.lanes[j].hi);
+                for (int r = 0; r < N; ++r) count_in_range(s.cf[j], v[r], p.lanes[j].lo, p.lanes[j].hi);
             }
         }
 #pragma unroll
@@ -735,7 +754,7 @@ __device__ __forceinline__ void l1_flush(const K1Params<T, NL, NS> &p, ST &s, in
 #pragma unroll
         for (int j = 0; j < NBL; ++j) {
             const int dst = p.cols[j].dst;
-            if (dst >= 0) sink_put(p, o, base, dst, empty ? agf_nan() : (double)s.c[j]);
+            if (dst >= 0) sink_put(p, o, base, dst, empty ? agf_nan() : (double)s.cf[j]);
         }
 #pragma unroll
         for (int l = 0; l < ST::NA; ++l) {
