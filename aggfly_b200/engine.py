@@ -181,6 +181,19 @@ class StageRunner:
                 n += int(p.spec.bounds1[-1] - p.spec.bounds1[0]) * self.n_cells * np.dtype(p.spec.in_dtype).itemsize
         return n
 
+    def algorithmic_output_bytes(self) -> int:
+        """Bytes the raster-reading temporal kernels must write: the columns + validity mask of single-level
+        programs, the partial records of two-level ones (their merge is the finalize kernel's traffic)."""
+        n = 0
+        for p in self.programs:
+            if getattr(p.spec, "_source", None) is None:
+                if p.spec.two_level:
+                    n += int(p.info.partial_bytes)
+                else:
+                    G = len(self.stage.labels)
+                    n += G * self.n_cells * (len(p.spec.cols) * self.X.element_size() + 1)
+        return n
+
     def run(self, raster, stream=None, token=None, k1_events=None) -> StageResult:
         """Launch everything on ``stream`` (asynchronous).  ``raster``: device tensor [T, n_cells].
         ``k1_events``: optional list that receives (start, end) CUDA event pairs bracketing each
