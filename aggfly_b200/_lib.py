@@ -105,7 +105,7 @@ def lib() -> C.CDLL:
     L.agf_csr_destroy.argtypes = [vp]
     L.agf_spmm_run.argtypes = [vp, vp, i32, vp, i64, i32, vp, vp, u64]
     L.agf_valid_mask_run.argtypes = [vp, i32, i64, i32, i64, vp, u64]
-    L.agf_elementwise_run.argtypes = [vp, i32, vp, i32, i64, i32, C.c_double, vp, i32, vp, u64]
+    L.agf_elementwise_run.argtypes = [vp, i32, vp, i32, i64, i32, C.c_double, vp, i32, vp, i32, C.POINTER(Pre), u64]
     dp, i64p, i32p = C.POINTER(C.c_double), C.POINTER(i64), C.POINTER(i32)
     L.agf_overlap_create.argtypes = [C.POINTER(vp), i32, i64p, i64p, dp, i32, dp, C.c_double, i32, dp, C.c_double, i64p]
     L.agf_overlap_fetch.argtypes = [vp, i32p, i64p, dp]

@@ -633,8 +633,17 @@ extern "C" int agf_valid_mask_run(const void *d_x, int32_t x_dtype, int64_t n_gr
 
 extern "C" int agf_elementwise_run(const void *d_in, int32_t in_dtype, void *d_out, int32_t out_dtype, int64_t n,
                                    int32_t xform, double xparam, const void *d_other, int32_t other_dtype,
-                                   uint8_t *d_valid, uintptr_t stream) {
+                                   uint8_t *d_valid, int32_t n_pre, const agf_pre_t *pre, uintptr_t stream) {
     if (!d_in || !d_out) return fail(AGF_E_INVALID, "null argument");
+    if (n_pre < 0 || n_pre > AGF_MAX_PRE || (n_pre > 0 && !pre)) return fail(AGF_E_INVALID, "bad preprocess chain");
+    EwPre ep;
+    memset(&ep, 0, sizeof(ep));
+    ep.n = n_pre;
+    for (int i = 0; i < n_pre; ++i) {
+        if (pre[i].op < AGF_PRE_ADD || pre[i].op > AGF_PRE_NEG) return fail(AGF_E_INVALID, "pre %d: bad op", i);
+        ep.op[i].op = pre[i].op;
+        ep.op[i].c = in_dtype == AGF_F64 ? pre[i].c : (double)(float)pre[i].c;
+    }
     if (n <= 0) return fail(AGF_E_INVALID, "bad size");
     if (!d_other && !(xform >= AGF_XF_POWI && xform <= AGF_XF_SPLINE2)) return fail(AGF_E_INVALID, "bad xform");
     if (in_dtype == AGF_F64 && out_dtype != AGF_F64) return fail(AGF_E_INVALID, "float64 input needs float64 output");
@@ -647,7 +656,7 @@ extern "C" int agf_elementwise_run(const void *d_in, int32_t in_dtype, void *d_o
     cudaStream_t st = (cudaStream_t)stream;
 #define AGF_EW(TI, TO, TB)                                                                                  \
     agf_elementwise<TI, TO, TB><<<blocks, 256, 0, st>>>((const TI *)d_in, (TO *)d_out, (const TB *)d_other, \
-                                                        (long long)n, xform, xparam, d_valid)
+                                                        (long long)n, xform, xparam, d_valid, ep)
     const bool of64 = d_other && other_dtype == AGF_F64;
     if (in_dtype == AGF_F64) {
         if (of64) AGF_EW(double, double, double);

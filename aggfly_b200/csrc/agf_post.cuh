@@ -183,13 +183,31 @@ __global__ void __launch_bounds__(256)
 // step, or two transforms in a row): out[i] = f(in[i]) (* other[i]), V[i] = !isnan(out[i]).
 // Dtype rules are those of apply_xform (NumPy promotion decided by the host).
 // ------------------------------------------------------------------------------------------
+struct EwPre {  // preprocess chain of the raster (by value in the parameter bank)
+    int n;
+    PreP<double> op[AGF_MAX_PRE];  // constants already rounded to the input dtype
+};
+
 template <typename TI, typename TO, typename TB>
 __global__ void __launch_bounds__(256)
     agf_elementwise(const TI *__restrict__ in, TO *__restrict__ out, const TB *__restrict__ other, long long n,
-                    int xform, double xparam, unsigned char *__restrict__ valid) {
+                    int xform, double xparam, unsigned char *__restrict__ valid, const __grid_constant__ EwPre pre) {
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const double x = (double)in[i];
+        TI xin = in[i];
+        for (int k = 0; k < pre.n; ++k) {  // one rounding per operation, in the input dtype
+            const TI c = (TI)pre.op[k].c;
+            switch (pre.op[k].op) {
+                case AGF_PRE_ADD: xin = xin + c; break;
+                case AGF_PRE_SUB: xin = xin - c; break;
+                case AGF_PRE_RSUB: xin = c - xin; break;
+                case AGF_PRE_MUL: xin = xin * c; break;
+                case AGF_PRE_DIV: xin = xin / c; break;
+                case AGF_PRE_RDIV: xin = c / xin; break;
+                default: xin = -xin; break;
+            }
+        }
+        const double x = (double)xin;
         double r;
         if (other != nullptr) {
             // np.multiply(array, inter) in the promoted dtype (dataset.py:547-563)

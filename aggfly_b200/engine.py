@@ -161,11 +161,14 @@ class StageRunner:
         code = {"pow": _lib.XF_POWI if (float(ew.xparam).is_integer() and 0 <= ew.xparam <= 64) else _lib.XF_POW,
                 "spline2": _lib.XF_SPLINE2, "inter": _lib.XF_NONE}[ew.xf]
         f = lambda dt: _lib.F64 if np.dtype(dt) == np.float64 else _lib.F32          # noqa: E731
+        pre = (_lib.Pre * max(1, len(ew.pre)))()
+        for i, (op, c) in enumerate(ew.pre):
+            pre[i].op, pre[i].c = int(op), float(c)
         _lib.check(_lib.lib().agf_elementwise_run(
             src.data_ptr(), f(ew.in_dtype), self.X.data_ptr(), f(self.stage.dtype), G * self.n_cells, code,
             float(ew.xparam), self.other.data_ptr() if self.other is not None else None,
             f(np.float64 if (self.other is not None and self.other.dtype == _torch().float64) else np.float32),
-            self.V.data_ptr(), stream.cuda_stream))
+            self.V.data_ptr(), len(ew.pre), pre, stream.cuda_stream))
 
     @property
     def launches_per_run(self) -> int:

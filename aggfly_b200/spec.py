@@ -270,6 +270,7 @@ class ElemSpec:
     xf: str
     xparam: float
     other: Optional[np.ndarray] = None
+    pre: list = field(default_factory=list)   # preprocess chain when the source is the raster
 
 
 def _peel(node: Node):
@@ -409,7 +410,8 @@ class Planner:
                 xf, xparam = ("inter", 0.0) if node.xf == "inter" else (node.xf, node.xparam if node.xf == "pow" else 0.0)
                 sub = Stage(programs=[], nodes=[node], dtype=np.dtype(node.dtype), labels=self.g.labels(node),
                             inputs=[] if src_stage is None else [src_stage],
-                            elementwise=ElemSpec(src_stage, np.dtype(node.src.dtype), xf, float(xparam), node.other))
+                            elementwise=ElemSpec(src_stage, np.dtype(node.src.dtype), xf, float(xparam), node.other,
+                                                 pre=self.g.pre_ops if src_stage is None else []))
             else:
                 sub = self.plan([node], dtype=node.dtype)      # X dtype == node dtype: no extra rounding
             hit = (sub, 0)

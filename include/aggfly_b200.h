@@ -241,10 +241,11 @@ int agf_valid_mask_run(const void *d_x, int32_t x_dtype, int64_t n_groups, int32
  * d_other != NULL, in[i] * other[i] (the reference's `inter` transform, aggfly/dataset/dataset.py:483-563).
  * For transforms that cannot be fused into a program (applied to the raster before the first aggregate
  * step, two in a row, interactions).  out_dtype follows NumPy's promotion, decided by the caller; d_valid
- * (may be NULL) receives !isnan(out[i]). */
+ * (may be NULL) receives !isnan(out[i]).  pre[0..n_pre) (host array, may be NULL) is the preprocess chain
+ * applied to in[i] first, in in_dtype -- for transforms that read the raster of a Dataset(preprocess=...). */
 int agf_elementwise_run(const void *d_in, int32_t in_dtype, void *d_out, int32_t out_dtype, int64_t n,
                         int32_t xform, double xparam, const void *d_other, int32_t other_dtype,
-                        uint8_t *d_valid, uintptr_t stream);
+                        uint8_t *d_valid, int32_t n_pre, const agf_pre_t *pre, uintptr_t stream);
 
 /* ---- weights builder geometry (host only; replaces the GEOS work of calculate_weights) ---------- */
 

@@ -589,3 +589,19 @@ def test_three_and_six_hourly_rasters_uniform_groups_of_8_and_4(name, step_h):
                 _exact(got[k].values, want[k][0])
             else:
                 _close(got[k].values, want[k][0], 1e-12)
+
+
+def test_preprocess_reaches_transforms_that_read_the_raster_directly():
+    from aggfly_b200 import preprocess as pp
+    arr, t, lat, lon = _raster("float32", True, T=24 * 20, Y=3, X=5, seed=43)
+    raw = arr + np.float32(273.15)
+    spec = dict(poly=[("transform", {"transform": "power", "exp": np.arange(1, 3)}),
+                      ("aggregate", {"calc": "mean", "groupby": "date"})],
+                plain=[("aggregate", {"calc": "mean", "groupby": "date"})])
+    want = orc.aggregate_time(orc.ODataset(pp.resolve("kelvin_to_celsius")(raw), t, lat, lon, True), spec)
+    got = af.aggregate_time(dataset=af.Dataset.from_arrays(raw, t, lat, lon, True, preprocess="kelvin_to_celsius"),
+                            weights=None, aggregator_dict=spec)
+    for k in want:
+        _exact(got[k].values, want[k][0])
+    none = af.aggregate_dataset(weights=_ref_weights(_ref_dataset()), dataset=_ref_dataset())     # no spec: raw series
+    assert list(none.columns) == ["geoid", "time", "variable"] and len(none) == 4
