@@ -292,6 +292,7 @@ def aggregate_dataset(weights: GridWeights, dataset: Dataset = None,
             DeprecationWarning, stacklevel=2)
     if aggregator_dict is None and kwargs:
         aggregator_dict = kwargs
+    tr = None
     if aggregator_dict is None and dataset_dict is not None:
         df = aggregate_space(dataset_dict, weights)
     else:
@@ -306,7 +307,7 @@ def aggregate_dataset(weights: GridWeights, dataset: Dataset = None,
         tr.mark("assemble")
     rid = weights.georegions.regionid
     df = weights.georegions.shp[[rid]].merge(df, left_index=True, right_on="region_id").drop(columns="region_id")
-    if aggregator_dict is not None or dataset_dict is None:
+    if tr is not None:
         tr.mark("merge")
         tr.done()
     return df
