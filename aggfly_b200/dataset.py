@@ -65,6 +65,27 @@ class RasterArray:
         self.data, self.dims, self.coords = data, tuple(dims), dict(coords)
 
 
+def time_selection(time, time_sel):
+    """Row range [a, b) of ``.sel(time=time_sel)`` on a sorted axis: a partial date string ("2001",
+    "2001-06", "2001-06-15"), a timestamp, or a slice of those (both ends inclusive, like pandas/xarray)."""
+    if isinstance(time, CalendarIndex):
+        key = str(time_sel.start if isinstance(time_sel, slice) else time_sel)
+        if isinstance(time_sel, slice) or len(key) != 4:
+            raise NotImplementedError("time_sel on a non-standard calendar supports a single year ('YYYY')")
+        idx = np.nonzero(np.asarray(time.year) == int(key))[0]
+        return (int(idx[0]), int(idx[-1]) + 1) if len(idx) else (0, 0)
+    t = pd.DatetimeIndex(time)
+    if isinstance(time_sel, slice):
+        sl = t.slice_indexer(time_sel.start, time_sel.stop)
+    else:
+        loc = t.get_loc(time_sel if not isinstance(time_sel, (int, np.integer)) else str(time_sel))
+        sl = loc if isinstance(loc, slice) else slice(int(loc), int(loc) + 1) if np.ndim(loc) == 0 else None
+        if sl is None:                                            # boolean mask (non-unique axis)
+            idx = np.nonzero(loc)[0]
+            sl = slice(int(idx[0]), int(idx[-1]) + 1)
+    return int(sl.start or 0), int(len(t) if sl.stop is None else sl.stop)
+
+
 def _fusable(preprocess):
     """FusedPreprocess for names / expressions / FusedPreprocess objects, None for other callables."""
     if isinstance(preprocess, (str, FusedPreprocess)):
@@ -100,6 +121,9 @@ class Dataset:
             if fused is None:
                 values = preprocess(values)              # arbitrary callable: applied to the array now
         self._init(values, da.coords[timecoord], da.coords[ydim], da.coords[xdim], lon_is_360, name)
+        if time_sel is not None:                                  # da.sortby("time").sel(time=time_sel), dataset.py:90-91
+            a, b = time_selection(self.time, time_sel)
+            self.values, self.time = self.values[a:b], self.time[a:b]
         self.georegions = georegions
         if fused is not None:
             self.pre_ops = constants_for(fused.ops, self.dtype)

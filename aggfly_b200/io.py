@@ -114,15 +114,9 @@ def _is_netcdf3(path: str) -> bool:
 
 
 def select_time(ds: Dataset, time_sel) -> Dataset:
-    """``da.sel(time=time_sel)`` for a year / ``"YYYY"`` / ``slice(start, end)`` on a datetime axis."""
-    t = pd.DatetimeIndex(ds.time)
-    if isinstance(time_sel, slice):
-        a = 0 if time_sel.start is None else int(t.searchsorted(pd.Timestamp(time_sel.start), "left"))
-        b = len(t) if time_sel.stop is None else int(t.searchsorted(pd.Timestamp(time_sel.stop), "right"))
-    else:
-        year = int(str(time_sel)[:4])
-        idx = np.nonzero(t.year == year)[0]
-        a, b = (int(idx[0]), int(idx[-1]) + 1) if len(idx) else (0, 0)
+    """``da.sel(time=time_sel)``: a partial date string ("2001", "2001-06"), a timestamp or a slice."""
+    from .dataset import time_selection
+    a, b = time_selection(ds.time, time_sel)
     return ds.isel_time(a, b)
 
 

@@ -170,3 +170,18 @@ def test_csr_lowering_is_cached_on_disk_by_content(tmp_path):
     wdf2 = wdf.assign(weight=wdf["weight"] * 2)
     W.lower_to_csr_cached(wdf2, np.arange(4), 2, 2, lon_order, str(tmp_path))
     assert len(list(tmp_path.rglob("*.npz"))) == 2                                     # different content, new key
+
+
+def test_time_sel_selects_like_pandas_partial_string_indexing():
+    import aggfly_b200 as af
+    from aggfly_b200.timeaxis import CalendarIndex
+    t = pd.date_range("2000-11-01", "2002-02-28 23:00", freq="h")
+    arr = np.arange(len(t), dtype=np.float32)[:, None, None] * np.ones((1, 2, 2), np.float32)
+    ra = af.RasterArray(arr, ("time", "latitude", "longitude"), {"time": t, "latitude": [1.0, 0.0], "longitude": [0.0, 1.0]})
+    ds = af.Dataset(ra, time_sel="2001")
+    assert len(ds.time) == 8760 and ds.time[0] == pd.Timestamp("2001-01-01") and ds.values.shape[0] == 8760
+    assert float(ds.values[0, 0, 0]) == float(t.get_loc("2001-01-01 00:00"))
+    assert len(af.Dataset(ra, time_sel="2001-06").time) == 720
+    assert len(af.Dataset(ra, time_sel=slice("2001-01-01", "2001-01-02")).time) == 48          # both ends inclusive
+    from aggfly_b200.dataset import time_selection
+    assert time_selection(CalendarIndex.range("noleap", 2000, 365 * 3), "2001") == (365, 730)
