@@ -58,7 +58,7 @@ class ProgramInfo(C.Structure):
                 ("out_dtype", C.c_int32), ("n_out_groups", C.c_int64), ("partial_bytes", C.c_int64),
                 ("out_bytes", C.c_int64), ("valid_bytes", C.c_int64), ("kernel_lanes", C.c_int32),
                 ("kernel_slots", C.c_int32), ("kernel_mode", C.c_int32), ("uses_tma", C.c_int32),
-                ("kernel_kinds", C.c_int32), ("pad_", C.c_int32)]
+                ("kernel_kinds", C.c_int32), ("direct_out", C.c_int32)]
 
 
 class AgfError(RuntimeError):

@@ -366,6 +366,11 @@ extern "C" int agf_program_create(agf_program_t **out, const agf_program_desc_t 
     p->g2_rec_idx = plan.g2_rec_idx;
     p->n_recs = plan.n_recs;
 
+    if (desc->n_slots > 0 && p->stripes.size() == 1) {
+        p->direct_out = 1;  // nothing to merge: the kernel finalizes (see K1Params::direct_out)
+        for (size_t g = 0; g + 1 < p->b2.size(); ++g)
+            if (p->b2[g + 1] == p->b2[g]) p->direct_out = 0;  // an empty outer period gets its NaN from agf_finalize
+    }
     if ((rc = upload(&p->d_b1, p->b1)) || (rc = upload(&p->d_b2, p->b2)) ||
         (rc = upload(&p->d_stripes, p->stripes)) || (rc = upload(&p->d_g2_rec_ptr, p->g2_rec_ptr)) ||
         (rc = upload(&p->d_g2_rec_idx, p->g2_rec_idx))) {
@@ -388,7 +393,8 @@ extern "C" int agf_program_info(const agf_program_t *p, agf_program_info_t *info
     info->n_cols = p->desc.n_cols;
     info->out_dtype = p->desc.out_dtype;
     info->n_out_groups = out_groups(p);
-    info->partial_bytes = (int64_t)p->n_recs * p->desc.n_slots * p->n_cells * 8;
+    info->partial_bytes = p->direct_out ? 0 : (int64_t)p->n_recs * p->desc.n_slots * p->n_cells * 8;
+    info->direct_out = p->direct_out;
     info->out_bytes = info->n_out_groups * p->desc.n_cols * p->n_cells * (p->desc.out_dtype == AGF_F64 ? 8 : 4);
     info->valid_bytes = info->n_out_groups * p->n_cells;
     info->kernel_lanes = p->kernel_lanes;
@@ -462,9 +468,9 @@ extern "C" int agf_temporal_run(const agf_program_t *p, const void *d_x, int64_t
     if (ld < p->n_cells) return fail(AGF_E_INVALID, "ld < n_cells");
     if (row0 < 0 || row0 > p->b1[p->stripes[stripe_begin].g1_begin])
         return fail(AGF_E_INVALID, "row0 is past the first row of the stripe range");
-    if (p->desc.n_slots > 0 && !d_partial) return fail(AGF_E_INVALID, "two-level program needs d_partial");
-    if (p->desc.n_slots == 0 && (!d_out || !d_valid))
-        return fail(AGF_E_INVALID, "single-level program needs d_out and d_valid");
+    if (p->desc.n_slots > 0 && !p->direct_out && !d_partial) return fail(AGF_E_INVALID, "two-level program needs d_partial");
+    if ((p->desc.n_slots == 0 || p->direct_out) && (!d_out || !d_valid))
+        return fail(AGF_E_INVALID, "this program writes X / V from agf_temporal_run: d_out and d_valid are required");
     for (int c = 0; c < p->desc.n_cols; ++c)
         if (p->desc.cols[c].dst >= out_ncols) return fail(AGF_E_INVALID, "col %d: dst outside X (out_ncols=%d)", c, out_ncols);
     const int esz = p->desc.in_dtype == AGF_F64 ? 8 : 4;
@@ -478,7 +484,7 @@ extern "C" int agf_temporal_run(const agf_program_t *p, const void *d_x, int64_t
 extern "C" int agf_temporal_finalize(const agf_program_t *p, const double *d_partial, void *d_out,
                                      uint8_t *d_valid, int32_t out_ncols, int32_t valid_and, uintptr_t stream) {
     if (!p) return fail(AGF_E_INVALID, "null program");
-    if (p->desc.n_slots == 0) return 0;
+    if (p->desc.n_slots == 0 || p->direct_out) return 0;
     if (!d_partial || !d_out || !d_valid) return fail(AGF_E_INVALID, "null buffer");
     int rc = check_device(p->device);
     if (rc) return rc;

@@ -21,6 +21,7 @@ struct agf_program {
     int n_bin_slots = 0;      // slots of kind SK_BINS
     int uniform_gl = 0;       // rows per level-1 group when every group has the same size, else 0
     int max_group_rows = 0;   // longest level-1 group
+    int direct_out = 0;       // two-level, one stripe, no empty level-2 group: agf_temporal_run writes X / V itself
     int diag_ok = 0;     // columns (single-level) / slots (two-level) map 1:1 onto lanes
     int need_nan = 0, need_cnt = 0, has_sine = 0;
     // device copies

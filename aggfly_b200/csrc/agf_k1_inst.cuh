@@ -198,6 +198,25 @@ static int launch_k1(const K1Launch &a) {
             C.dst = d.cols[c].dst;
         }
     }
+    if (NS > 0) {
+        // direct output: one stripe covers the whole time axis, so every level-2 group is reduced inside one
+        // thread -- the kernel writes X / V itself; columns then name KERNEL slots (typed kernels reorder them)
+        kp.direct_out = p->direct_out;
+        if (kp.direct_out) {
+            for (int c = 0; c < d.n_cols; ++c) {
+                int ks = -1;
+                for (int j = 0; j < NS; ++j)
+                    if (kp.slots[j].dst == d.cols[c].src) ks = j;
+                ColP &C = kp.cols[c];
+                C.src = ks;
+                C.xform = d.cols[c].xform;
+                C.xparam = d.cols[c].xparam;
+                C.x_f64 = d.cols[c].x_f64;
+                C.dst = d.cols[c].dst;
+                if (ks < 0) kp.direct_out = 0;  // cannot happen for a validated descriptor
+            }
+        }
+    }
     if constexpr (TMA) {
         // rows of the view the stripes of this launch can touch
         const int64_t row_end = p->b1[p->stripes[a.s1 - 1].g1_end];

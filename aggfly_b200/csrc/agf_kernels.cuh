@@ -160,10 +160,12 @@ struct K1Params {
     int pre_linear;  // the chain has the form (v + b0) * a + b1 (identity fillers: -0.0, 1): inlined as 3 ops
     T pre_b0, pre_a, pre_b1;
     int stage_out;  // single-level: stage a warp's X[g, 32 cells, :] block in shared memory, store it coalesced
+    int direct_out;  // two-level program launched as ONE stripe: write X / V straight from the slots (no partial
+                     // records, no finalize launch -- the records of a single stripe have nothing to merge with)
     PreP<T> pre[AGF_MAX_PRE];
     LaneP<T> lanes[NL];
     SlotP slots[NS > 0 ? NS : 1];
-    ColP cols[NS > 0 ? 1 : AGF_MAX_COLS];
+    ColP cols[AGF_MAX_COLS];  // NS == 0: columns read lanes; NS > 0 (direct output only): src = KERNEL slot index
 };
 
 // ------------------------------------------------------------------------------------------
@@ -825,8 +827,36 @@ __device__ __forceinline__ void l1_flush(const K1Params<T, NL, NS> &p, ST &s, in
 
 // one partial record: slot values of a finished (stripe, level-2 group) intersection
 template <int NB, typename T, int NL, int NS, typename ST>
-__device__ __forceinline__ void l2_write_rec(const K1Params<T, NL, NS> &p, const ST &s, int rec, int cell) {
+__device__ __forceinline__ void l2_write_rec(const K1Params<T, NL, NS> &p, const ST &s, int rec, int cell, int g2) {
     if constexpr (NS > 0) {
+        if (p.direct_out) {
+            // the whole level-2 group g2 was reduced by this thread: do what agf_finalize would do
+            const int n2 = p.b2[g2 + 1] - p.b2[g2];
+            bool ok = true;
+            for (int c = 0; c < p.n_cols; ++c) {
+                const ColP &C = p.cols[c];
+                const SlotP &S = p.slots[C.src];
+                double v = 0.0;
+#pragma unroll
+                for (int j = 0; j < NS; ++j) {  // slot registers are picked by a select chain, never indexed
+                    double sj;
+                    if constexpr (NB >= 0)
+                        sj = (j < NB) ? (double)s.c[j < NB ? j : 0] : s.b[j >= NB ? j - NB : 0];
+                    else
+                        sj = s.b[j];
+                    v = (j == C.src) ? sj : v;
+                }
+                if (S.calc == AGF_CALC_MEAN) v = v / (double)n2;
+                const bool slot_f64 = S.x_f64 || p.in_f64;
+                if (!slot_f64) v = (double)(float)v;  // stored in the dtype of the slot's input series
+                if (C.xform != AGF_XF_NONE) v = slot_f64 ? apply_xform64(v, C.xform, C.xparam) : apply_xform<float>(v, C.xform, C.xparam, C.x_f64);
+                ok &= (v == v);
+                store_col<T>(p.out, p.out_f64, ((size_t)g2 * p.n_cells + cell) * p.out_ncols + C.dst, v);
+            }
+            unsigned char *vp = p.valid + (size_t)g2 * p.n_cells + cell;
+            *vp = (p.valid_and ? (*vp != 0) && ok : ok) ? 1 : 0;
+            return;
+        }
         if constexpr (NB >= 0) {
 #pragma unroll
             for (int j = 0; j < NS; ++j) {
@@ -902,7 +932,7 @@ __global__ void __launch_bounds__(K1_THREADS)
             if (NS > 0) {
                 // close every level-2 group that ends with level-1 group g
                 if (g + 1 == next_b2 || g + 1 == g_end) {
-                    l2_write_rec<NB>(p, s, rec, cell);
+                    l2_write_rec<NB>(p, s, rec, cell, g2);
                     l2_init<NB>(p, s);
                     ++rec;
                     if (g + 1 < g_end && g + 1 == next_b2) {
@@ -1051,7 +1081,7 @@ __global__ void __launch_bounds__(TMA_THREADS, MINB)
         l1_init<KINDS>(p, s);
         if constexpr (NS > 0) {
             if (g + 1 == next_b2 || g + 1 == g_end) {
-                if (active) l2_write_rec<NB>(p, s, rec, cell);
+                if (active) l2_write_rec<NB>(p, s, rec, cell, g2);
                 l2_init<NB>(p, s);
                 ++rec;
                 if (g + 1 < g_end && g + 1 == next_b2) {
@@ -1203,7 +1233,7 @@ __global__ void __launch_bounds__(TMA_THREADS, MINB)
         l1_init<KINDS>(p, s);
         if constexpr (NS > 0) {
             if (g + 1 == next_b2 || g + 1 == g_end) {
-                if (active) l2_write_rec<NB>(p, s, rec, cell);
+                if (active) l2_write_rec<NB>(p, s, rec, cell, g2);
                 l2_init<NB>(p, s);
                 ++rec;
                 if (g + 1 < g_end && g + 1 == next_b2) {

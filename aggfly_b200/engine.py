@@ -173,7 +173,8 @@ class StageRunner:
     @property
     def launches_per_run(self) -> int:
         n = sum(r.launches_per_run for r in self.inputs)
-        return n + sum(2 if p.spec.two_level else 1 for p in self.programs) + (1 if self.stage.elementwise else 0)
+        return (n + sum(2 if (p.spec.two_level and not p.info.direct_out) else 1 for p in self.programs)
+                + (1 if self.stage.elementwise else 0))
 
     def algorithmic_input_bytes(self) -> int:
         """Bytes of raster the temporal kernels of this stage must read (each program reads its
@@ -190,7 +191,7 @@ class StageRunner:
         n = 0
         for p in self.programs:
             if getattr(p.spec, "_source", None) is None:
-                if p.spec.two_level:
+                if p.spec.two_level and not p.info.direct_out:
                     n += int(p.info.partial_bytes)
                 else:
                     G = len(self.stage.labels)

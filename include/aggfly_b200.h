@@ -172,7 +172,8 @@ typedef struct {
     int32_t kernel_lanes, kernel_slots, kernel_mode; /* which instantiation will run */
     int32_t uses_tma;     /* 16-byte aligned rasters run the TMA / shared-memory-ring variant */
     int32_t kernel_kinds; /* compile-time lane-kind set of the chosen instantiation */
-    int32_t pad_;
+    int32_t direct_out;   /* two-level program cut into ONE stripe: agf_temporal_run writes X / V itself
+                             (partial_bytes == 0, agf_temporal_finalize is a no-op) */
 } agf_program_info_t;
 
 typedef struct agf_program agf_program_t;
@@ -205,7 +206,8 @@ int agf_program_stripe_rows(const agf_program_t *prog, int32_t stripe, int64_t *
 /* Run stripes [stripe_begin, stripe_end) of the fused temporal kernel.  d_x points at the
  * raster row `row0` (so a streamed chunk can be passed on its own), `ld` is the row stride in
  * elements.  Single-level programs write X / V directly; two-level programs write partial
- * records that agf_temporal_finalize merges.
+ * records that agf_temporal_finalize merges -- unless the program has a single stripe
+ * (info.direct_out), in which case there is nothing to merge and this call writes X / V.
  * Several programs of one call may share X / V: column c of this program goes to
  * X[:, :, cols[c].dst] of an X with `out_ncols` columns, and with valid_and != 0 its validity
  * is AND-ed into V instead of overwriting it. */

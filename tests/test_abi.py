@@ -35,7 +35,7 @@ def test_struct_layouts_match_the_header_as_gcc_sees_it(tmp_path):
                                                         "cols", "n_pre", "pre"]),
               "agf_program_info_t": (_lib.ProgramInfo, ["n_stripes", "n_recs", "n_cols", "out_dtype", "n_out_groups",
                                                         "partial_bytes", "out_bytes", "valid_bytes", "kernel_lanes",
-                                                        "kernel_slots", "kernel_mode", "uses_tma", "kernel_kinds"])}
+                                                        "kernel_slots", "kernel_mode", "uses_tma", "kernel_kinds", "direct_out"])}
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "aggfly_b200.h"', "int main(void) {"]
     for st, (_, names) in fields.items():
         lines.append(f'printf("{st} %zu\\n", sizeof({st}));')
