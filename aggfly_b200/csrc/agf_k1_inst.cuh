@@ -186,6 +186,7 @@ static int launch_k1(const K1Launch &a) {
             }
         } else {
             for (int j = 0; j < d.n_slots; ++j) fill(kp.slots[j], j);
+            for (int j = d.n_slots; j < NS; ++j) kp.slots[j].dst = -1;  // unused kernel slots name no program slot
         }
     } else {
         for (int c = 0; c < d.n_cols; ++c) {

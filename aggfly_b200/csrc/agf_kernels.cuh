@@ -1253,14 +1253,34 @@ __global__ void __launch_bounds__(TMA_THREADS, MINB)
         mbar_wait(&full[stg], ph);
         const T *col = tiles + (size_t)stg * (TMA_TILE_BYTES / sizeof(T)) + threadIdx.x;
         if constexpr (GPT == 1) {
-            // one group per tile: pull the column into registers, hand the stage back, then reduce
-            T v[TT];
+            // one group per tile: pull the column into registers, reduce it, hand the stage back, THEN
+            // flush.  The stage must not be released right after the loads are ISSUED: the arrive does
+            // not wait for the shared-memory reads to return (no register dependence), and once all 8
+            // warps have arrived the producer's next TMA may overwrite rows whose reads are still in
+            // flight.  That showed as a few cells per launch with a wrong daily value (non-repeatable
+            // sums, exact bins) in one instantiation.  The reduction consumes every loaded register,
+            // so by its end the reads have completed; only the group-end flush stays overlapped.
+            if constexpr (CellState<T, NL, NS, NB>::TL || TT % 2 != 0) {
+                T v[TT];  // typed lanes cull their bins on the min / max of the whole group
 #pragma unroll
-            for (int r = 0; r < TT; ++r) v[r] = col[r * TMA_CW];
+                for (int r = 0; r < TT; ++r) v[r] = col[r * TMA_CW];
+                pre_apply_batch(p, v);
+                l1_acc_group<KINDS>(p, s, v);
+            } else {
+                // two half-columns: 12 value registers live instead of 24 (the 20-slot kernel sits at the
+                // 72-register cap of three CTAs per SM)
+                constexpr int H = TT / 2;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    T v[H];
+#pragma unroll
+                    for (int r = 0; r < H; ++r) v[r] = col[(h * H + r) * TMA_CW];
+                    pre_apply_batch(p, v);
+                    l1_acc_group<KINDS>(p, s, v);
+                }
+            }
             __syncwarp();
             if ((threadIdx.x & 31) == 0) mbar_arrive(&empty[stg]);
-            pre_apply_batch(p, v);
-            l1_acc_group<KINDS>(p, s, v);
             group_end();
         } else {
             const int ng = min(GPT, g_end - g);

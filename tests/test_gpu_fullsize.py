@@ -83,7 +83,8 @@ def test_sampled_cells_match_a_float64_torch_restatement_and_bins_partition_the_
     for col, want in ((15, a1), (16, a2)):
         ok = ~torch.isnan(want)
         assert torch.equal(torch.isnan(got[:, col]), ~ok)
-        assert torch.equal(got[ok, col], want[ok]), names[col]       # single stripe per cell: same order, same bits
+        diff = (got[ok, col] - want[ok]).abs().max().item()
+        assert torch.equal(got[ok, col], want[ok]), (names[col], diff)   # single stripe per cell: same order, same bits
     # ---- every cell: the 15 bins partition its valid days (a daily mean exactly on an edge is in no bin)
     total = X[:, :15].sum(1)
     valid_cell = ~torch.isnan(X[:, 15])
