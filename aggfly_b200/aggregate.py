@@ -19,8 +19,8 @@ from . import engine as _engine
 from . import stream as _stream
 from .dataset import Dataset
 from .spec import Graph, Planner, TemporalAggregator, compile_spec
-from .timeaxis import CalendarIndex, label_values, labels_equal
-from .weights import GridWeights, lower_to_csr, lower_to_csr_cached
+from .timeaxis import label_values, labels_equal
+from .weights import GridWeights, lower_to_csr_cached
 
 ALLOWED_ENGINE = ("auto", "cuda", "dask", "numba")          # reference: cli/config.py:27 + "cuda"
 

@@ -6,7 +6,7 @@ number is produced by the kernels in ``csrc/`` (no torch math on the data path, 
 from __future__ import annotations
 
 import ctypes as C
-from typing import Dict, List, Optional, Tuple
+from typing import List, Tuple
 
 import numpy as np
 

@@ -11,8 +11,8 @@ path) and is reproducible from ``(seed, year)``.
 """
 from __future__ import annotations
 
-from dataclasses import dataclass, field
-from typing import Dict, Optional
+from dataclasses import dataclass
+from typing import Dict
 
 import numpy as np
 import pandas as pd

@@ -22,7 +22,6 @@ module keeps exactly that contract:
 from __future__ import annotations
 
 import warnings
-from copy import deepcopy
 from dataclasses import dataclass
 from typing import Optional
 

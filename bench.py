@@ -180,7 +180,6 @@ def host_mem_available_gb() -> float:
 
 def cpu_sample(wl, raster_dev, n_rows_lat: int):
     """A lat band of the same raster + the weights of the regions inside it (host arrays)."""
-    import pandas as pd
     from aggfly_b200 import synthetic as syn
     from aggfly_b200.dataset import Dataset
     lat = wl.grid.latitude

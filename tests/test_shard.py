@@ -83,7 +83,7 @@ def _worker(rank, world, port, out_dir):
             return list(out), res, None
 
         class _Csr:
-            host = agg.lower_to_csr(wdf, w.grid.cell_id, 3, 4, ds.lon_sort_order())
+            host = af.lower_to_csr(wdf, w.grid.cell_id, 3, 4, ds.lon_sort_order())
 
         def fake_spmm(csr, res):
             h = csr.host
