@@ -225,7 +225,9 @@ static int launch_k1(const K1Launch &a) {
         // C3 program: 3 CTAs x 3 stages 6.87 TB/s, 2 x 4 6.01 TB/s, 4 x 2 6.68 TB/s; tiles of 8 or
         // 12 rows lose 20-40% to per-tile synchronisation): three 9-warp CTAs per SM need <= 72
         // registers per thread, two need <= 112.
-        constexpr int state_regs = TL ? NB + 2 * (NL - NB) : 2 * NL + (NB >= 0 ? NB + 2 * (NS - NB) : 2 * NS);
+        // (a double raster holds its value batches and thresholds in register pairs: +27)
+        constexpr int state_regs = (TL ? NB + 2 * (NL - NB) : 2 * NL + (NB >= 0 ? NB + 2 * (NS - NB) : 2 * NS)) +
+                                   (sizeof(T) == 8 ? 27 : 0);
         constexpr int MINB = state_regs <= 30 ? 3 : (state_regs <= 48 ? 2 : 1);
         // kernels that stage their output block (single-level, several columns) give one ring stage
         // back to the staging area so that MINB CTAs still fit in the SM's 227 KB
