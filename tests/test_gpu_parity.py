@@ -28,9 +28,15 @@ def _variant(request):
         os.environ["AGF_DISABLE_TMA"] = "1"
     else:
         os.environ.pop("AGF_DISABLE_TMA", None)
+        assert _lib_tma_eligible(60, 4) and _lib_tma_eligible(60, 8) and not _lib_tma_eligible(45, 4)
     yield
     os.environ.pop("AGF_DISABLE_TMA", None)
     engine.OPTIONS["target_stripes"] = 0
+
+
+def _lib_tma_eligible(n_cells, esz):
+    """The library's rule: a 16-byte aligned base (torch allocations are) and a row pitch that is a multiple of 16."""
+    return (n_cells * esz) % 16 == 0
 
 
 def _exact(a, b):
@@ -180,7 +186,10 @@ SPECS = {
 INEXACT = {"spline_and_pow": 1e-6, "sine": 1e-5, "mix_bins_poly_dd": 1e-14}   # pow: libm vs exact products     # powf / libm transcendental differences only
 
 
-def _raster(dtype, nan, T=24 * 75 + 7, Y=5, X=9, seed=0):
+def _raster(dtype, nan, T=24 * 75 + 7, Y=5, X=12, seed=0):
+    """Seeded test raster.  The default 5 x 12 = 60 cells make the row pitch a multiple of 16 bytes for both
+    dtypes, so the "tma" variant of every test really runs the TMA kernels (a 45-cell raster silently fell back
+    to the direct-load kernel)."""
     rng = np.random.default_rng(seed)
     t = pd.date_range("2001-11-20 03:00", periods=T, freq="h")
     hours = np.arange(T)
@@ -320,7 +329,7 @@ def test_no_spec_aggregates_the_raw_series():
     arr, t, lat, lon = _raster("float32", True, T=30, seed=5)
     rng = np.random.default_rng(8)
     wdf, shp = _weights_case(lat, lon, rng)
-    want = orc.aggregate_dataset(orc.OWeights(wdf, np.arange(45), shp, "geoid", "area"), orc.ODataset(arr, t, lat, lon, True))
+    want = orc.aggregate_dataset(orc.OWeights(wdf, np.arange(arr.shape[1] * arr.shape[2]), shp, "geoid", "area"), orc.ODataset(arr, t, lat, lon, True))
     ds = af.Dataset.from_arrays(arr, t, lat, lon, True)
     w = af.weights_from_objects(ds, af.GeoRegions(shp, "geoid"), zero_weight="area"); w.weights = wdf
     got = af.aggregate_dataset(weights=w, dataset=ds)
@@ -430,7 +439,7 @@ def test_hourly_bins_and_mean_by_date_typed_lanes_many_shapes():
                     tavg=[("aggregate", {"calc": "mean", "groupby": "date"})],
                     tsum=[("aggregate", {"calc": "sum", "groupby": "date"})])
         for T in (24 * 12, 24 * 12 + 7):
-            arr, t, lat, lon = _raster("float32", True, T=T, Y=3, X=70, seed=nb)
+            arr, t, lat, lon = _raster("float32", True, T=T, Y=3, X=172, seed=nb)            # 516 cells: two full CTAs + a partial one
             if T % 24 == 0:
                 t = pd.date_range("2001-11-20 00:00", periods=T, freq="h")       # uniform 24-row groups
             got, want = _both_time(arr, t, lat, lon, spec)
@@ -471,13 +480,13 @@ def test_sharded_call_world1_nccl_equals_plain_call():
 def test_every_spmm_variant_matches_oracle(gs, monkeypatch):
     """K2 picks lanes-per-(period, region) from the problem size; pin each variant in turn."""
     monkeypatch.setenv("AGF_SPMM_GS", gs)
-    arr, t, lat, lon = _raster("float32", True, T=24 * 40, Y=6, X=11, seed=23)
+    arr, t, lat, lon = _raster("float32", True, T=24 * 40, Y=6, X=12, seed=23)
     rng = np.random.default_rng(6)
     wdf, shp = _weights_case(lat, lon, rng, n_regions=9)
-    big = pd.DataFrame({"cell_id": rng.permutation(66)[:50], "index_right": 10 + 3 * 8, "weight": rng.random(50)})
+    big = pd.DataFrame({"cell_id": rng.permutation(72)[:50], "index_right": 10 + 3 * 8, "weight": rng.random(50)})
     wdf = pd.concat([wdf, big], ignore_index=True)                  # one region with more entries than a warp
     for name in ("c3b_daily", "c3_bins_and_poly", "monthly_mix", "c1_tavg_poly"):     # float2, double, float4, double2 loads
-        want = orc.aggregate_dataset(orc.OWeights(wdf, np.arange(66), shp, "geoid", "nan"),
+        want = orc.aggregate_dataset(orc.OWeights(wdf, np.arange(72), shp, "geoid", "nan"),
                                      orc.ODataset(arr, t, lat, lon, True), aggregator_dict=SPECS[name])
         ds = af.Dataset.from_arrays(arr, t, lat, lon, True)
         w = af.weights_from_objects(ds, af.GeoRegions(shp, "geoid"), zero_weight="nan")
@@ -510,12 +519,12 @@ def test_fused_preprocess_equals_numpy_then_aggregate(name, dtype, expr):
 
 # ---- transforms the fused programs cannot carry: materialised by elementwise passes (never the CPU) ------
 def test_materialised_transforms_and_interactions_match_oracle():
-    arr, t, lat, lon = _raster("float32", True, T=24 * 45 + 3, Y=3, X=5, seed=31)
+    arr, t, lat, lon = _raster("float32", True, T=24 * 45 + 3, Y=3, X=8, seed=31)
     rng = np.random.default_rng(12)
     n_days = len(pd.DatetimeIndex(t).normalize().unique())
-    precip = rng.gamma(2.0, 1.5, (n_days, 3, 5)).astype(np.float32)              # a second daily variable
+    precip = rng.gamma(2.0, 1.5, (n_days, 3, 8)).astype(np.float32)              # a second daily variable
     precip64 = precip.astype(np.float64)
-    hourly_w = rng.random((len(t), 3, 5)).astype(np.float32)
+    hourly_w = rng.random((len(t), 3, 8)).astype(np.float32)
     spec = dict(
         poly=[("transform", {"transform": "power", "exp": np.arange(1, 3)}),      # powers of the HOURLY values
               ("aggregate", {"calc": "mean", "groupby": "month"})],
@@ -535,7 +544,7 @@ def test_materialised_transforms_and_interactions_match_oracle():
             _close(got[k].values, want[k][0], 1e-6 if got[k].values.dtype == np.float32 else 1e-12)
     # and end to end (the streamed host path runs the elementwise stages after the last chunk)
     wdf, shp = _weights_case(lat, lon, np.random.default_rng(1))
-    want = orc.aggregate_dataset(orc.OWeights(wdf, np.arange(15), shp, "geoid", "nan"), orc.ODataset(arr, t, lat, lon, True),
+    want = orc.aggregate_dataset(orc.OWeights(wdf, np.arange(24), shp, "geoid", "nan"), orc.ODataset(arr, t, lat, lon, True),
                                  aggregator_dict=spec)
     ds = af.Dataset.from_arrays(arr, t, lat, lon, True)
     w = af.weights_from_objects(ds, af.GeoRegions(shp, "geoid"), zero_weight="nan")
@@ -593,7 +602,7 @@ def test_three_and_six_hourly_rasters_uniform_groups_of_8_and_4(name, step_h):
 
 def test_preprocess_reaches_transforms_that_read_the_raster_directly():
     from aggfly_b200 import preprocess as pp
-    arr, t, lat, lon = _raster("float32", True, T=24 * 20, Y=3, X=5, seed=43)
+    arr, t, lat, lon = _raster("float32", True, T=24 * 20, Y=3, X=8, seed=43)
     raw = arr + np.float32(273.15)
     spec = dict(poly=[("transform", {"transform": "power", "exp": np.arange(1, 3)}),
                       ("aggregate", {"calc": "mean", "groupby": "date"})],
