@@ -357,7 +357,10 @@ def main_ours(args, rank, world, local_rank):
             step_ms.append((time.perf_counter() - ts) * 1e3)
             step_phases.append({k: round(v, 1) for k, v in _agg_mod.LAST_TRACE.get("phases_ms", {}).items()})
         torch.cuda.synchronize()
-        dt = (time.perf_counter() - t0) / e2e_steps
+        mean_dt = (time.perf_counter() - t0) / e2e_steps
+        # the box's PCIe / host memory is shared with other tenants: single calls range from 0.67 s to 1.4 s on
+        # the same code, so the typical (median) call is reported and the mean kept beside it
+        dt = float(np.median(step_ms)) * 1e-3
         tt = torch.tensor([dt], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -365,6 +368,7 @@ def main_ours(args, rank, world, local_rank):
         st = dict(_stream.LAST_STATS)
         h2d_ms = st["copy_events"][0].elapsed_time(st["copy_events"][1]) if "copy_events" in st else None
         e2e = {"value": world * wl.cell_steps / dt, "unit": UNIT,
+               "statistic": f"median of {e2e_steps} calls (max over ranks)", "mean_ms_per_step": mean_dt * 1e3,
                "step_ms": [round(x, 1) for x in step_ms], "phases_ms": step_phases,
                "feed": {"chunks": st.get("chunks"), "pinned": st.get("pinned"), "k1_launches": st.get("k1_launches"),
                         "h2d_ms": h2d_ms,
@@ -418,7 +422,7 @@ def main():
     ap.add_argument("--seed", type=int, default=1218)
     ap.add_argument("--cpu-rows", type=int, default=0,
                     help="latitude rows in the CPU-baseline sample (0: one per host thread, 24..192)")
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
