@@ -574,13 +574,9 @@ extern "C" int agf_spmm_run(const agf_csr_t *c, const void *d_x, int32_t x_dtype
     CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
     // enough pairs for >= 2048 threads on every SM: one thread per pair (no cross-lane reduction)
     int gs = pairs >= 2048LL * sms ? 1 : (mean_row <= 8.0 ? 8 : (mean_row <= 16.0 ? 16 : 32));
-    bool forced = false;
-    if (const char *force = getenv("AGF_SPMM_GS")) {  // test hook: pin the variant (0 = column-parallel, 1, 8, 16, 32)
+    if (const char *force = getenv("AGF_SPMM_GS")) {  // test hook: pin the variant (1, 8, 16 or 32)
         const int f = atoi(force);
-        if (f == 0 || f == 1 || f == 8 || f == 16 || f == 32) {
-            gs = f;
-            forced = true;
-        }
+        if (f == 1 || f == 8 || f == 16 || f == 32) gs = f;
     }
     const long long blocks = (pairs * gs + 255) / 256;
     if (blocks > 0x7fffffffLL) return fail(AGF_E_UNSUPPORTED, "panel too large for one launch");
@@ -595,39 +591,6 @@ extern "C" int agf_spmm_run(const agf_csr_t *c, const void *d_x, int32_t x_dtype
             break;
         }
     const int ev = vb / esz;
-    // big multi-column panels: LP lanes per pair, EV columns per lane (see agf_spmm_cols); AGF_SPMM_GS = 0
-    // pins this form in tests
-    if ((gs == 1 && !forced && n_cols / ev >= 4 && n_cols / ev <= 16) || gs == 0) {
-        if (gs == 0 && (n_cols / ev > 16)) return fail(AGF_E_UNSUPPORTED, "column-parallel form: too many columns");
-        int lp = 1;
-        while (lp * ev < n_cols) lp <<= 1;
-        const long long cblocks = (pairs * lp + 255) / 256;
-        if (cblocks > 0x7fffffffLL) return fail(AGF_E_UNSUPPORTED, "panel too large for one launch");
-#define AGF_SPMM_C(TX, LP, EV)                                                                                   \
-    agf_spmm_cols<TX, LP, EV><<<(unsigned)cblocks, 256, 0, st>>>(c->d_row_ptr, c->d_cell_idx, c->d_w,            \
-                                                                 (const TX *)d_x, d_valid, c->n_cells, n_groups, \
-                                                                 n_cols, c->n_regions, d_panel, d_den)
-#define AGF_SPMM_CL(TX, EV)                \
-    do {                                   \
-        if (lp == 1) AGF_SPMM_C(TX, 1, EV);      \
-        else if (lp == 2) AGF_SPMM_C(TX, 2, EV); \
-        else if (lp == 4) AGF_SPMM_C(TX, 4, EV); \
-        else if (lp == 8) AGF_SPMM_C(TX, 8, EV); \
-        else AGF_SPMM_C(TX, 16, EV);       \
-    } while (0)
-        if (x_dtype == AGF_F64) {
-            if (ev == 2) AGF_SPMM_CL(double, 2);
-            else AGF_SPMM_CL(double, 1);
-        } else {
-            if (ev == 4) AGF_SPMM_CL(float, 4);
-            else if (ev == 2) AGF_SPMM_CL(float, 2);
-            else AGF_SPMM_CL(float, 1);
-        }
-#undef AGF_SPMM_CL
-#undef AGF_SPMM_C
-        CU(cudaGetLastError());
-        return 0;
-    }
     const bool wide = n_cols > 4;
 #define AGF_SPMM_W(TX, GS, EV, W)                                                                                    \
     agf_spmm<TX, GS, EV, W><<<(unsigned)blocks, 256, 0, st>>>(c->d_row_ptr, c->d_cell_idx, c->d_w, (const TX *)d_x, \

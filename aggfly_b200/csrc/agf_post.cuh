@@ -75,6 +75,9 @@ __global__ void __launch_bounds__(256) agf_finalize(const __grid_constant__ FinP
 // the same period, so their gathers fall into a few shared sectors that stay in L1 while the
 // threads walk their rows.  Measured on the C3b daily panel (45 000 x 365 pairs x 14 columns): the
 // warp-per-pair form was instruction-bound (25e9 warp instructions, 43.7 ms, 5 % of DRAM peak).
+// (A column-parallel form -- LP lanes per pair, each owning a few columns, one load per cell row -- was
+// measured too: 10.8 ms, 8.5 ms with a 4-entry unroll, against 7.5 ms for this one; it has one row load in
+// flight per lane where this form has n_cols / EV, and the walk is latency-bound.)
 // columns accumulated per pass over a region's entries: WIDE = false for panels of <= 4 columns (a
 // 16-wide unrolled, guarded accumulator block cost 1900 instructions per warp on the one-column C5
 // panel), else 16 for the thread-per-pair form and 8 for the group forms
@@ -160,52 +163,6 @@ __global__ void __launch_bounds__(256)
             if (c0 == 0 && den_out) den_out[(size_t)r * G + g] = den;
         }
     }
-}
-
-// K2, column-parallel form for big multi-column panels: LP lanes share one (period, region) pair and each
-// owns EV consecutive columns, so one load instruction fetches a whole cell row (n_cols values, 2-3
-// sectors) for 32 / LP pairs at once and nothing is reduced across lanes -- every lane walks the region's
-// entries in weights-frame order and keeps its own columns (and a redundant copy of the denominator).
-// The thread-per-pair form issues n_cols / EV loads per entry, each touching one sector per lane: L1 tag
-// lookups were its bound on the daily panel (ncu r1i: L1 74 %, 22 sectors per request).
-template <typename TX, int LP, int EV>
-__global__ void __launch_bounds__(256)
-    agf_spmm_cols(const int *__restrict__ row_ptr, const int *__restrict__ cell_idx, const double *__restrict__ w,
-                  const TX *__restrict__ X, const unsigned char *__restrict__ V, long long n_cells, long long G,
-                  int n_cols, int n_regions, double *__restrict__ panel, double *__restrict__ den_out) {
-    const long long gid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / LP;
-    const int sub = threadIdx.x % LP;
-    if (gid >= (long long)n_regions * G) return;
-    const long long g = gid / n_regions;
-    const int r = (int)(gid % n_regions);
-    const int c0 = sub * EV;                 // first column of this lane (n_cols is a multiple of EV)
-    const bool has_cols = c0 < n_cols;
-    const int e0 = row_ptr[r], e1 = row_ptr[r + 1];
-    const unsigned char *Vg = V + (size_t)g * n_cells;
-    const TX *Xg = X + (size_t)g * n_cols * n_cells;
-    double acc[EV];
-#pragma unroll
-    for (int k = 0; k < EV; ++k) acc[k] = 0.0;
-    double den = 0.0;
-    for (int e = e0; e < e1; ++e) {
-        const int cell = cell_idx[e];        // the same address in all LP lanes of the pair: one broadcast sector
-        const double we = w[e];
-        if (Vg[cell]) {
-            den += we;
-            if (has_cols) {
-                double x[EV];
-                load_cols<TX, EV>(Xg + (size_t)cell * n_cols + c0, x);
-#pragma unroll
-                for (int k = 0; k < EV; ++k) acc[k] += we * x[k];
-            }
-        }
-    }
-    if (has_cols) {
-#pragma unroll
-        for (int k = 0; k < EV; ++k)
-            panel[((size_t)r * G + g) * n_cols + c0 + k] = (den != 0.0) ? acc[k] / den : agf_nan();
-    }
-    if (sub == 0 && den_out) den_out[(size_t)r * G + g] = den;
 }
 
 // shared validity mask of an existing X: V[g, cell] = AND_c !isnan(X[g, c, cell])  (spatial.py:114-119)

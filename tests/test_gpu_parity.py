@@ -476,7 +476,7 @@ def test_sharded_call_world1_nccl_equals_plain_call():
     _exact(sharded[vals].values, plain[vals].values)
 
 
-@pytest.mark.parametrize("gs", ["0", "1", "8", "16", "32"])
+@pytest.mark.parametrize("gs", ["1", "8", "16", "32"])
 def test_every_spmm_variant_matches_oracle(gs, monkeypatch):
     """K2 picks lanes-per-(period, region) from the problem size; pin each variant in turn."""
     monkeypatch.setenv("AGF_SPMM_GS", gs)
