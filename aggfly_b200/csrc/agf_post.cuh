@@ -132,10 +132,22 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
         for (int c = 0; c < SPMM_NCB; ++c) acc[c] = 0.0;
         double den = 0.0;
-        for (int e = e0 + lane; e < e1; e += GS) {
-            const int cell = cell_idx[e];
-            const double we = w[e];
-            if (Vg[cell]) {
+        // software pipeline: the next entry's index, weight and mask byte are requested before this entry's
+        // rows are consumed -- the walk is a chain of dependent loads (index -> mask -> row) otherwise
+        int e = e0 + lane;
+        int cell_n = e < e1 ? cell_idx[e] : 0;
+        double we_n = e < e1 ? w[e] : 0.0;
+        unsigned char ok_n = e < e1 ? Vg[cell_n] : (unsigned char)0;
+        for (; e < e1; e += GS) {
+            const int cell = cell_n;
+            const double we = we_n;
+            const unsigned char ok = ok_n;
+            if (e + GS < e1) {
+                cell_n = cell_idx[e + GS];
+                we_n = w[e + GS];
+                ok_n = Vg[cell_n];
+            }
+            if (ok) {
                 const TX *Xc = Xg + (size_t)cell * n_cols;
                 den += we;
 #pragma unroll
