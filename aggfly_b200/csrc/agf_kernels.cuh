@@ -998,6 +998,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
+// (An L2 evict-first cache hint on these loads was measured: C3 5.40 ms against 5.23 ms without it, the small
+// CONUS grid 0.130 against 0.133 ms -- not kept.)
 __device__ __forceinline__ void tma_load_2d(void *dst, const void *tmap, int c0, int c1, uint64_t *bar) {
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
