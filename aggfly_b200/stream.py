@@ -32,6 +32,7 @@ OPTIONS = {
     "staging_chunk_bytes": 64 << 20,   # ... pageable sources (also the size of a staging slot)
     "staging_slots": 8,                # pinned ring depth for pageable sources
     "staging_threads": 8,              # host threads filling the ring
+    "keep_device_raster": True,        # keep the device copy's buffer between calls (see _device_raster)
 }
 
 
@@ -107,7 +108,7 @@ def feed_and_run(runner, values, n_cells: int, stream=None, k1_events: Optional[
     dev = runner.device
     comp = torch.cuda.current_stream(dev) if stream is None else stream
     copy = _copy_stream(dev)
-    raster = torch.empty((T, n_cells), dtype=tdtype, device=dev)
+    raster = _device_raster(torch, dev, tdtype, T, n_cells)
     row_bytes = n_cells * raster.element_size()
     chunks = chunk_rows(T, row_bytes, chunk_bytes or OPTIONS["chunk_bytes" if pinned else "staging_chunk_bytes"])
     staging = None
@@ -161,6 +162,32 @@ def feed_and_run(runner, values, n_cells: int, stream=None, k1_events: Optional[
 
 
 LAST_STATS: dict = {}          # what the most recent feed did (tests, bench bookkeeping)
+
+
+_DEVICE_RASTERS = {}     # (device, dtype, elements) -> the device copy of the last host raster of that shape
+
+
+def _device_raster(torch, dev, tdtype, T: int, n_cells: int):
+    """Device buffer for a host raster.  A yearly loop feeds same-shaped rasters again and again; taking the
+    36 GB block from torch's caching allocator each time worked until a smaller buffer (partial records, X)
+    was carved out of the cached block between two calls -- the next call then paid a fresh cudaMalloc /
+    cudaFree of tens of GB (0.3-1.2 s, seen as sporadic slow calls in bench e2e).  The buffer of the most
+    recent shape is therefore kept here; ``release_device_rasters()`` returns it."""
+    if not OPTIONS.get("keep_device_raster", True):
+        return torch.empty((T, n_cells), dtype=tdtype, device=dev)
+    key = (dev.index, str(tdtype), T * n_cells)
+    buf = _DEVICE_RASTERS.get(key)
+    if buf is None:
+        _DEVICE_RASTERS.clear()                  # one shape at a time
+        buf = torch.empty(T * n_cells, dtype=tdtype, device=dev)
+        _DEVICE_RASTERS[key] = buf
+    return buf.view(T, n_cells)
+
+
+def release_device_rasters() -> None:
+    """Give the cached device raster (and the pinned staging ring) back."""
+    _DEVICE_RASTERS.clear()
+    _RINGS.clear()
 
 
 _COPY_STREAMS = {}
