@@ -129,13 +129,24 @@ def _temporal_device(dataset: Dataset, aggregator_dict, target_stripes: int = 0)
         # stripes of about four copy chunks: the kernels of a stripe start when its rows have landed
         nbytes = int(np.prod(dataset.shape)) * dataset.dtype.itemsize
         target_stripes = -int(min(64, nbytes // (4 * _stream.OPTIONS["chunk_bytes"])))
+    import time
+    t0 = time.perf_counter()
     runner = _engine.StageRunner(stage, n_cells, target_stripes=target_stripes)
+    t1 = time.perf_counter()
     try:
         res, raster = _stream.feed_and_run(runner, dataset.values, n_cells)
+        t2 = time.perf_counter()
     finally:
         torch.cuda.current_stream().synchronize()
+        t3 = time.perf_counter()
         runner.close()
+    global LAST_FEED_TRACE
+    LAST_FEED_TRACE = {"runner_ms": (t1 - t0) * 1e3, "issue_ms": (t2 - t1) * 1e3, "drain_ms": (t3 - t2) * 1e3,
+                       "close_ms": (time.perf_counter() - t3) * 1e3}
     return names, res, raster
+
+
+LAST_FEED_TRACE: dict = {}
 
 
 def aggregate_time(dataset: Dataset, weights: GridWeights = None,

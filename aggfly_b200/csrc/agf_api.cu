@@ -310,22 +310,42 @@ extern "C" int agf_program_plan(const agf_program_desc_t *desc, int64_t n_cells,
     return 0;
 }
 
+// The small device tables of a handle come from the device's stream-ordered memory pool, which is told to
+// keep what is freed: a yearly loop creates and destroys programs every call, and cudaFree -- a device-wide
+// synchronisation that also unmaps -- took 0.2-1.5 s now and then next to a 36 GB raster and its pinned host
+// copy (bench e2e: runner.close() accounted for every slow call).
+static int table_pool_ready(int dev) {
+    static bool done[64] = {false};
+    if (dev < 0 || dev >= 64 || done[dev]) return 0;
+    cudaMemPool_t pool;
+    CU(cudaDeviceGetDefaultMemPool(&pool, dev));
+    unsigned long long keep = ~0ULL;
+    CU(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    done[dev] = true;
+    return 0;
+}
+
 template <typename V>
 static int upload(V **dst, const std::vector<V> &src) {
     *dst = nullptr;
     if (src.empty()) return 0;
-    CU(cudaMalloc((void **)dst, src.size() * sizeof(V)));
-    CU(cudaMemcpy(*dst, src.data(), src.size() * sizeof(V), cudaMemcpyHostToDevice));
+    CU(cudaMallocAsync((void **)dst, src.size() * sizeof(V), (cudaStream_t)0));
+    CU(cudaMemcpyAsync(*dst, src.data(), src.size() * sizeof(V), cudaMemcpyHostToDevice, (cudaStream_t)0));
     return 0;
+}
+
+static void release_table(void *p) {
+    if (p) cudaFreeAsync(p, (cudaStream_t)0);
 }
 
 extern "C" int agf_program_destroy(agf_program_t *p) {
     if (!p) return 0;
-    cudaFree(p->d_b1);
-    cudaFree(p->d_b2);
-    cudaFree(p->d_g2_rec_ptr);
-    cudaFree(p->d_g2_rec_idx);
-    cudaFree(p->d_stripes);
+    // the caller has waited for the launches that used this handle (see the header)
+    release_table(p->d_b1);
+    release_table(p->d_b2);
+    release_table(p->d_g2_rec_ptr);
+    release_table(p->d_g2_rec_idx);
+    release_table(p->d_stripes);
     delete p;
     return 0;
 }
@@ -371,11 +391,17 @@ extern "C" int agf_program_create(agf_program_t **out, const agf_program_desc_t 
         for (size_t g = 0; g + 1 < p->b2.size(); ++g)
             if (p->b2[g + 1] == p->b2[g]) p->direct_out = 0;  // an empty outer period gets its NaN from agf_finalize
     }
-    if ((rc = upload(&p->d_b1, p->b1)) || (rc = upload(&p->d_b2, p->b2)) ||
+    if ((rc = table_pool_ready(dev)) || (rc = upload(&p->d_b1, p->b1)) || (rc = upload(&p->d_b2, p->b2)) ||
         (rc = upload(&p->d_stripes, p->stripes)) || (rc = upload(&p->d_g2_rec_ptr, p->g2_rec_ptr)) ||
         (rc = upload(&p->d_g2_rec_idx, p->g2_rec_idx))) {
         agf_program_destroy(p);
         return rc;
+    }
+    // the tables must be resident before a launch on ANY stream reads them (the copies ran on stream 0)
+    cudaError_t e_sync = cudaStreamSynchronize((cudaStream_t)0);
+    if (e_sync != cudaSuccess) {
+        agf_program_destroy(p);
+        return agf_cuda_fail(e_sync, "cudaStreamSynchronize");
     }
     *out = p;
     return 0;

@@ -355,7 +355,12 @@ def main_ours(args, rank, world, local_rank):
             ts = time.perf_counter()
             df = af.aggregate_dataset(weights=w, dataset=hds, aggregator_dict=wl.spec)
             step_ms.append((time.perf_counter() - ts) * 1e3)
-            step_phases.append({k: round(v, 1) for k, v in _agg_mod.LAST_TRACE.get("phases_ms", {}).items()})
+            ph = {k: round(v, 1) for k, v in _agg_mod.LAST_TRACE.get("phases_ms", {}).items()}
+            evs = _stream.LAST_STATS.get("copy_events")
+            if evs is not None:
+                ph["h2d (copy stream, first to last chunk)"] = round(evs[0].elapsed_time(evs[1]), 1)
+            ph.update({k: round(v, 1) for k, v in _agg_mod.LAST_FEED_TRACE.items()})
+            step_phases.append(ph)
         torch.cuda.synchronize()
         mean_dt = (time.perf_counter() - t0) / e2e_steps
         # the box's PCIe / host memory is shared with other tenants: single calls range from 0.67 s to 1.4 s on

@@ -190,6 +190,8 @@ const char *agf_last_error(void);
  * the host wants stripes of a few copy chunks, so that stripes can start before the copy ends). */
 int agf_program_create(agf_program_t **out, const agf_program_desc_t *desc, int64_t n_cells,
                        int32_t target_stripes);
+/* Destroy a handle.  The launches that used it must have completed (synchronise their stream first): its
+ * device tables go back to a stream-ordered pool and may be handed to the next program at once. */
 int agf_program_destroy(agf_program_t *prog);
 /* Host-only planning (no device needed): validates the descriptor, picks the kernel
  * instantiation and cuts the time axis into stripes.  stripes_out (may be NULL) receives
