@@ -228,19 +228,21 @@ def _zero_weight_regions(weights) -> np.ndarray:
 
 def _assemble_panel(panel: np.ndarray, names: List[str], labels, region_ids: np.ndarray,
                     weights: GridWeights) -> pd.DataFrame:
-    """spatial.py:136-153: long frame, then the row-drop rules."""
+    """spatial.py:136-153: long frame (regions outer, periods inner), then the row-drop rules.  The kept rows
+    are selected first and the frame is built once from them (a daily panel has 16 M candidate rows)."""
     R, G, NC = panel.shape
-    out = pd.DataFrame({"region_id": np.repeat(region_ids, G),
-                        "time": np.tile(label_values(labels), R)})
     flat = panel.reshape(R * G, NC)
-    for c, nm in enumerate(names):
-        out[nm] = flat[:, c]
-    ok = ~np.isnan(flat).any(axis=1)
+    keep = ~np.isnan(flat).any(axis=1)
     if getattr(weights, "zero_weight", "area") == "nan":
-        keep = np.isin(out["region_id"].to_numpy(), _zero_weight_regions(weights)) | ok
-    else:
-        keep = ok
-    return out.loc[keep].reset_index(drop=True)
+        zero = _zero_weight_regions(weights)
+        if len(zero):
+            keep |= np.repeat(np.isin(region_ids, zero), G)
+    idx = np.flatnonzero(keep)
+    data = {"region_id": np.asarray(region_ids)[idx // G], "time": label_values(labels)[idx % G]}
+    sel = flat[idx]
+    for c, nm in enumerate(names):
+        data[nm] = sel[:, c]
+    return pd.DataFrame(data)
 
 
 class SpatialAggregator:
