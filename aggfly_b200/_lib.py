@@ -12,7 +12,7 @@ from typing import Optional
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libaggfly_b200.so")
 
-ABI_VERSION = 2                      # AGF_ABI_VERSION of include/aggfly_b200.h
+ABI_VERSION = 3                      # AGF_ABI_VERSION of include/aggfly_b200.h
 MAX_LANES, MAX_SLOTS, MAX_COLS = 32, 32, 64
 E_INVALID, E_UNSUPPORTED, E_NOMEM, E_STATE = -1, -2, -3, -4
 
@@ -20,6 +20,7 @@ CALC = {"mean": 0, "sum": 1, "min": 2, "max": 3, "nanmean": 4, "dd": 5, "bins": 
         "_hidden_sum": 8, "_hidden_min": 9, "_hidden_max": 10, "dd_r": 11}
 XF_NONE, XF_POWI, XF_POW, XF_SPLINE2 = 0, 1, 2, 3
 F32, F64 = 0, 1
+I16, I32, U8, I8, U16 = 2, 3, 4, 5, 6          # storage dtypes of chunked sources (agf_tile_place_run)
 
 
 class Lane(C.Structure):
@@ -77,7 +78,7 @@ _lib: Optional[C.CDLL] = None
 SYMBOLS = ("agf_version", "agf_last_error", "agf_program_create", "agf_program_destroy",
            "agf_program_plan", "agf_program_info", "agf_program_stripe_rows", "agf_temporal_run",
            "agf_temporal_finalize", "agf_csr_create", "agf_csr_destroy", "agf_spmm_run",
-           "agf_valid_mask_run", "agf_elementwise_run", "agf_overlap_create", "agf_overlap_fetch", "agf_overlap_destroy")
+           "agf_valid_mask_run", "agf_elementwise_run", "agf_tile_place_run", "agf_overlap_create", "agf_overlap_fetch", "agf_overlap_destroy")
 
 
 def lib() -> C.CDLL:
@@ -106,6 +107,8 @@ def lib() -> C.CDLL:
     L.agf_spmm_run.argtypes = [vp, vp, i32, vp, i64, i32, vp, vp, u64]
     L.agf_valid_mask_run.argtypes = [vp, i32, i64, i32, i64, vp, u64]
     L.agf_elementwise_run.argtypes = [vp, i32, vp, i32, i64, i32, C.c_double, vp, i32, vp, i32, C.POINTER(Pre), u64]
+    L.agf_tile_place_run.argtypes = [vp, i32, i64, i64, i64, i64, i64, i64, vp, i32, i64, i64, i64, i64, i64,
+                                     i32, C.c_double, C.c_double, i32, C.c_double, u64]
     dp, i64p, i32p = C.POINTER(C.c_double), C.POINTER(i64), C.POINTER(i32)
     L.agf_overlap_create.argtypes = [C.POINTER(vp), i32, i64p, i64p, dp, i32, dp, C.c_double, i32, dp, C.c_double, i64p]
     L.agf_overlap_fetch.argtypes = [vp, i32p, i64p, dp]

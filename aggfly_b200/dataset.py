@@ -138,7 +138,7 @@ class Dataset:
                 order = np.argsort(time.values, kind="stable")
             time = time[order]
             values = values[order] if not _is_torch(values) else values[list(order)]
-        if not _is_torch(values):
+        if not _is_torch(values) and not getattr(values, "is_chunked_raster", False):
             values = np.asarray(values)
             if values.dtype not in (np.float32, np.float64):
                 values = values.astype(np.float64)

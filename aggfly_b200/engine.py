@@ -35,6 +35,11 @@ def to_device(values, device=None):
     """Raster -> contiguous device tensor [T, cells...] (numpy, CPU tensor or CUDA tensor)."""
     torch = _torch()
     device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+    if getattr(values, "is_chunked_raster", False):                # zarr store: chunks decoded + placed on the device
+        from . import stream as _stream
+        T, Y, X = values.shape
+        _, raster = _stream.feed_chunked(None, values, Y * X, device=device)
+        return raster.view(T, Y, X).clone()                         # the streamed buffer is recycled by the next feed
     if isinstance(values, np.ndarray):
         if values.dtype not in (np.float32, np.float64):
             values = values.astype(np.float64)

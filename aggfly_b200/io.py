@@ -12,7 +12,9 @@ read natively, and xarray is used only if it happens to be importable:
 ``.npy``               the raster alone, memory-mapped; axes from ``<path>.axes.npz``
 ``.nc`` (NetCDF-3)     ``scipy.io.netcdf_file`` (memory-mapped); CF ``units = "<unit> since <date>"``
                        time axes, ``scale_factor`` / ``add_offset`` unpacked like xarray (float64)
-anything else          ``xarray.open_dataset`` / ``open_zarr`` when xarray is installed
+zarr directory store   v2 / v3, any axis order and chunking (aggfly_b200.zarrio): opened lazily, chunks
+                       are decoded by host threads and placed on the device (``stream.feed_chunked``)
+anything else          ``xarray.open_dataset`` when xarray is installed
 ``.shp``               polygons (+ ``.dbf`` attributes), aggfly_b200.geometry
 ``.geojson`` / ``.json``  FeatureCollection of Polygon / MultiPolygon features
 =====================  =========================================================================
@@ -29,6 +31,7 @@ import pandas as pd
 from .dataset import Dataset
 from .geometry import orient_polygon
 from .weights import GeoRegions, SecondaryWeights
+from .zarrio import looks_like_zarr, open_raster, write_dataset
 
 
 # ---------------------------------------------------------------------------------------------
@@ -89,23 +92,76 @@ def dataset_from_path(path: str, var: Optional[str] = None, xycoords: Sequence[s
         time = _cf_time(tv.data, units, cal.decode() if isinstance(cal, bytes) else cal)
         lat, lon = np.array(f.variables[ydim].data, dtype=float), np.array(f.variables[xdim].data, dtype=float)
         keepalive = f                                                # the raster is a view of the mapped file
+    elif kwargs.get("engine") in (None, "zarr") and looks_like_zarr(path):      # dataset.py:697-701
+        values, time, lat, lon = open_raster(path, var, xycoords, timecoord)
     else:
         try:
             import xarray as xr                                      # optional dependency
         except Exception as exc:
             raise ImportError(f"{path}: reading this format needs xarray (not installed); natively supported: "
-                              ".npz, .npy (+ .axes.npz), NetCDF-3 .nc") from exc
-        dsx = xr.open_zarr(path, **kwargs) if ext == ".zarr" else xr.open_dataset(path, **kwargs)
+                              ".npz, .npy (+ .axes.npz), NetCDF-3 .nc, zarr directory stores") from exc
+        kwargs.pop("chunks", None)
+        dsx = xr.open_dataset(path, **kwargs)
         return Dataset(dsx[var], xycoords=xycoords, timecoord=timecoord, time_sel=time_sel, lon_is_360=lon_is_360,
                        preprocess=preprocess, name=name)
     ds = Dataset.from_arrays(values, time, lat, lon, lon_is_360=lon_is_360, name=name or var,
                              preprocess=preprocess if isinstance(preprocess, str) else None)
     ds._keepalive = keepalive
     if preprocess is not None and not isinstance(preprocess, str):
-        ds.values = preprocess(np.asarray(ds.values))
+        ds.values = np.asarray(preprocess(np.asarray(ds.values)))
     if time_sel is not None:
         ds = select_time(ds, time_sel)
     return ds
+
+
+def _auto_chunks(sizes: dict, itemsize: int, target_mb: float) -> dict:
+    """Chunking policy of the reference's converter (aggfly/dataset/zarr_convert.py:31-47): keep the time
+    axis whole when a square spatial tile of at least 32 cells fits the byte budget (tile capped at 256),
+    otherwise 128-cell tiles and as many time steps as the budget allows."""
+    T, Y, X = sizes["time"], sizes["latitude"], sizes["longitude"]
+    budget = max(1, int(target_mb * 1024 * 1024 / itemsize))
+    side = int((budget / T) ** 0.5)
+    if side >= 32:
+        side = int(min(side, 256, Y, X))
+        return {"time": -1, "latitude": side, "longitude": side}
+    side = int(min(128, Y, X))
+    return {"time": int(min(max(1, budget // (side * side)), T)), "latitude": side, "longitude": side}
+
+
+def dataset_to_zarr(dataset: Dataset, store: str, chunking="auto", target_mb: float = 256, overwrite: bool = False,
+                    return_dataset: bool = True, zarr_format: int = 3, compressor: Optional[str] = "zstd"):
+    """``af.dataset_to_zarr`` (aggfly/dataset/zarr_convert.py:50-121): write the raster as a time-contiguous
+    store with dims ``(latitude, longitude, time)`` and reopen it lazily."""
+    import shutil
+    values = np.asarray(dataset.values.cpu() if hasattr(dataset.values, "cpu") else dataset.values)
+    name = dataset.name or "variable"
+    sizes = {"time": values.shape[0], "latitude": values.shape[1], "longitude": values.shape[2]}
+    if isinstance(chunking, str) and chunking == "auto":
+        chunks = _auto_chunks(sizes, values.dtype.itemsize, target_mb)
+    elif isinstance(chunking, dict):
+        chunks = dict(chunking)
+    else:
+        raise ValueError("chunking must be 'auto' or a dict of chunk sizes")
+    if os.path.exists(store):
+        if not overwrite:
+            raise FileExistsError(f"{store} exists; pass overwrite=True to replace it")
+        shutil.rmtree(store)
+    write_dataset(store, values, dataset.time, dataset.latitude, dataset.longitude, var=name,
+                  dims=("latitude", "longitude", "time"), chunks=chunks, zarr_format=zarr_format, compressor=compressor)
+    if not return_dataset:
+        return None
+    new = dataset_from_path(store, var=name, lon_is_360=dataset.lon_is_360)
+    new.pre_ops = list(getattr(dataset, "pre_ops", []))
+    return new
+
+
+def zarr_from_path(path: str, var: str, store: str, *, xycoords=("longitude", "latitude"), timecoord: str = "time",
+                   lon_is_360: bool = True, preprocess=None, chunking="auto", target_mb: float = 256,
+                   overwrite: bool = False, **kwargs):
+    """Load any readable source and convert it in one call (aggfly/dataset/zarr_convert.py:124-155)."""
+    ds = dataset_from_path(path, var=var, xycoords=xycoords, timecoord=timecoord, lon_is_360=lon_is_360,
+                           preprocess=preprocess, **kwargs)
+    return dataset_to_zarr(ds, store, chunking=chunking, target_mb=target_mb, overwrite=overwrite)
 
 
 def _is_netcdf3(path: str) -> bool:

@@ -33,6 +33,7 @@ OPTIONS = {
     "staging_slots": 8,                # pinned ring depth for pageable sources
     "staging_threads": 8,              # host threads filling the ring
     "keep_device_raster": True,        # keep the device copy's buffer between calls (see _device_raster)
+    "chunked_ring_bytes": 2 << 30,     # pinned (and device) staging for chunked stores: slots x decoded chunk size
 }
 
 
@@ -95,6 +96,8 @@ def feed_and_run(runner, values, n_cells: int, stream=None, k1_events: Optional[
     Returns (StageResult, device raster [T, n_cells]).  Everything is asynchronous with respect to
     the host except the staging memcpys of a pageable source."""
     import torch
+    if getattr(values, "is_chunked_raster", False):
+        return feed_chunked(runner, values, n_cells, stream, k1_events, stats)
     host, host_np = _host_source(values)
     pinned = host is not None
     T = int(host.shape[0] if pinned else host_np.shape[0])
@@ -164,6 +167,134 @@ def feed_and_run(runner, values, n_cells: int, stream=None, k1_events: Optional[
 LAST_STATS: dict = {}          # what the most recent feed did (tests, bench bookkeeping)
 
 
+# ---------------------------------------------------------------------------------------------
+# chunked stores (zarr): decode on host threads -> pinned slot -> device slot -> placement kernel
+# ---------------------------------------------------------------------------------------------
+_CHUNK_RINGS = {}        # (device, slot_bytes, n_slots) -> (pinned slots, device slots), kept across calls
+
+_TILE_DTYPES = {"f4": 0, "f8": 1, "i2": 2, "i4": 3, "u1": 4, "i1": 5, "u2": 6}      # AGF_F32 .. AGF_U16
+
+
+def _chunk_ring(torch, dev, slot_bytes: int, n_slots: int):
+    key = (dev.index, int(slot_bytes), int(n_slots))
+    if key not in _CHUNK_RINGS:
+        _CHUNK_RINGS.clear()
+        _CHUNK_RINGS[key] = ([torch.empty(slot_bytes, dtype=torch.uint8, pin_memory=True) for _ in range(n_slots)],
+                             [torch.empty(slot_bytes, dtype=torch.uint8, device=dev) for _ in range(n_slots)])
+    return _CHUNK_RINGS[key]
+
+
+def feed_chunked(runner, src, n_cells: int, stream=None, k1_events: Optional[list] = None,
+                 stats: Optional[dict] = None, device=None):
+    """``feed_and_run`` for a ``zarrio.ChunkedRaster``: every storage chunk is decoded by a host thread
+    into a pinned slot (file read, decompression and the copy all release the GIL), copied to the device
+    as it is stored, and placed into the time-major raster by ``agf_tile_place_run`` (axis permutation,
+    CF unpacking and fill -> NaN on the device).  Chunks that are runs of whole raster rows and need no
+    decoding are copied straight into the raster.  Tiles arrive time chunk by time chunk, so for a
+    time-major store the temporal kernels of a stripe start as soon as its rows are complete; a
+    time-contiguous store (chunks ``[s, s, T]``) is scanned once its last tile has landed.
+    ``runner=None`` only builds the device raster (``engine.to_device``)."""
+    import torch
+    from . import _lib
+    L = _lib.lib()
+    T, Y, X = (int(v) for v in src.shape)
+    if Y * X != n_cells:
+        raise ValueError(f"raster of shape {src.shape} does not have {n_cells} cells per step")
+    dev = runner.device if runner is not None else (device or torch.device("cuda", torch.cuda.current_device()))
+    comp = torch.cuda.current_stream(dev) if stream is None else stream
+    copy = _copy_stream(dev)
+    tdtype = torch.float64 if src.dtype == np.float64 else torch.float32
+    raster = _device_raster(torch, dev, tdtype, T, n_cells)
+    sdt = src.array.dtype.newbyteorder("=")
+    code = _TILE_DTYPES.get(sdt.str[1:])
+    if code is None:
+        raise NotImplementedError(f"no tile decoder for stored dtype {sdt}")
+    tiles = src.tiles()
+    slot_bytes = src.slot_elems * sdt.itemsize
+    n_slots = int(max(2, min(OPTIONS["staging_slots"], OPTIONS["chunked_ring_bytes"] // max(1, slot_bytes))))
+    pinned, dslots = _chunk_ring(torch, dev, slot_bytes, n_slots)
+    views = [p.numpy().view(sdt) for p in pinned]
+    tviews = [p.view(tdtype) for p in pinned] if sdt == src.dtype else None
+    h2d_done = [None] * n_slots          # last copy out of the pinned slot
+    placed = [None] * n_slots            # last placement kernel reading the device slot
+    fill_scalar = None
+
+    def fill(i):
+        slot = i % n_slots
+        ev = h2d_done[slot]
+        if ev is not None:
+            ev.synchronize()
+        return src.load(tiles[i], views[slot])
+
+    copy.wait_stream(comp)
+    ev_first, ev_last = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev_first.record(copy)
+    if runner is not None:
+        runner.begin_streamed(comp)
+    launches = places = direct = absent = 0
+    h2d_bytes = 0
+    pool = ThreadPoolExecutor(max_workers=max(1, int(OPTIONS["staging_threads"])))
+    try:
+        futs = {i: pool.submit(fill, i) for i in range(min(n_slots, len(tiles)))}
+        for i, tile in enumerate(tiles):
+            slot = i % n_slots
+            present = futs.pop(i).result()
+            nt, ny, nx = tile.extent
+            if not present:
+                if fill_scalar is None:
+                    fv = src.array.fill_value
+                    fill_scalar = float(src.decode_host(np.full(1, 0 if fv is None else fv, sdt))[0])
+                with torch.cuda.stream(comp):
+                    raster.view(T, Y, X)[tile.t0:tile.t1, tile.y0:tile.y1, tile.x0:tile.x1] = fill_scalar
+                absent += 1
+            elif tviews is not None and src.direct_rows(tile):
+                with torch.cuda.stream(copy):
+                    raster[tile.t0:tile.t1].copy_(tviews[slot][tile.offset: tile.offset + nt * n_cells].view(nt, n_cells),
+                                                  non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(copy)
+                h2d_done[slot] = ev
+                comp.wait_event(ev)
+                h2d_bytes += nt * n_cells * sdt.itemsize
+                direct += 1
+            else:
+                with torch.cuda.stream(copy):
+                    if placed[slot] is not None:
+                        copy.wait_event(placed[slot])
+                    dslots[slot].copy_(pinned[slot], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(copy)
+                h2d_done[slot] = ev
+                comp.wait_event(ev)
+                _lib.check(L.agf_tile_place_run(
+                    dslots[slot].data_ptr() + tile.offset * sdt.itemsize, code, nt, ny, nx, tile.st, tile.sy, tile.sx,
+                    raster.data_ptr(), _lib.F64 if tdtype == torch.float64 else _lib.F32, n_cells, X,
+                    tile.t0, tile.y0, tile.x0, int(src.packed), float(src.scale), float(src.offset),
+                    int(src.fill is not None), float(src.fill if src.fill is not None else 0.0), comp.cuda_stream))
+                pe = torch.cuda.Event()
+                pe.record(comp)
+                placed[slot] = pe
+                h2d_bytes += slot_bytes
+                places += 1
+            if i + n_slots < len(tiles):
+                futs[i + n_slots] = pool.submit(fill, i + n_slots)
+            last_of_rows = i + 1 == len(tiles) or tiles[i + 1].t0 != tile.t0
+            if runner is not None and last_of_rows:
+                launches += runner.feed(raster, tile.t1, comp, k1_events)
+        ev_last.record(copy)
+        res = runner.finish_streamed(raster, comp) if runner is not None else None
+    finally:
+        pool.shutdown(wait=True)
+    raster.record_stream(comp)
+    global LAST_STATS
+    LAST_STATS = dict(chunks=len(tiles), pinned=False, chunked=True, h2d_bytes=h2d_bytes, k1_launches=launches,
+                      place_launches=places, direct_copies=direct, absent_chunks=absent, ring_slots=n_slots,
+                      copy_events=(ev_first, ev_last))
+    if stats is not None:
+        stats.update(LAST_STATS)
+    return res, raster
+
+
 _DEVICE_RASTERS = {}     # (device, dtype, elements) -> the device copy of the last host raster of that shape
 
 
@@ -188,6 +319,7 @@ def release_device_rasters() -> None:
     """Give the cached device raster (and the pinned staging ring) back."""
     _DEVICE_RASTERS.clear()
     _RINGS.clear()
+    _CHUNK_RINGS.clear()
 
 
 _COPY_STREAMS = {}

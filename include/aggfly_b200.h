@@ -47,7 +47,7 @@
 extern "C" {
 #endif
 
-#define AGF_ABI_VERSION 2
+#define AGF_ABI_VERSION 3
 
 #define AGF_MAX_LANES 32  /* level-1 reducers per program */
 #define AGF_MAX_SLOTS 32  /* level-2 reducers per program */
@@ -85,7 +85,9 @@ enum {
     AGF_XF_SPLINE2 = 3  /* (x > 20) * (x - 20), in the value's own dtype */
 };
 
-enum { AGF_F32 = 0, AGF_F64 = 1 };
+enum { AGF_F32 = 0, AGF_F64 = 1,
+       /* storage dtypes of chunked sources (agf_tile_place_run only) */
+       AGF_I16 = 2, AGF_I32 = 3, AGF_U8 = 4, AGF_I8 = 5, AGF_U16 = 6 };
 
 /* Elementwise preprocess of every raster value, applied in the raster dtype before any reducer
  * sees it (the reference's Dataset(preprocess=...): aggfly/cli/preprocess.py:24-30 named
@@ -250,6 +252,22 @@ int agf_valid_mask_run(const void *d_x, int32_t x_dtype, int64_t n_groups, int32
 int agf_elementwise_run(const void *d_in, int32_t in_dtype, void *d_out, int32_t out_dtype, int64_t n,
                         int32_t xform, double xparam, const void *d_other, int32_t other_dtype,
                         uint8_t *d_valid, int32_t n_pre, const agf_pre_t *pre, uintptr_t stream);
+
+/* ---- chunked sources: storage chunk -> time-major raster ------------------------------------------ */
+
+/* Place one decoded storage chunk (zarr / netCDF chunk, any axis order) into the device raster:
+ *     dst[(t0 + t) * ld + (y0 + y) * n_lon + (x0 + x)] = decode(src[t * st + y * sy + x * sx])
+ * for t < nt, y < ny, x < nx; st / sy / sx are ELEMENT strides of the stored chunk (a time-contiguous
+ * store written by the reference's dataset_to_zarr, aggfly/dataset/zarr_convert.py:31-47, has st = 1;
+ * the reference transposes such arrays to (time, y, x) in dask, aggfly/aggregate/nb_kernels.py:280).
+ * decode: if has_fill and src == fill -> NaN; if packed -> (double)src * scale + offset (CF
+ * scale_factor / add_offset, what xarray's decode_cf does on open, aggfly/dataset/dataset.py:700-707);
+ * then converted to dst_dtype (AGF_F32 | AGF_F64).  src_dtype: any AGF_* dtype; float64 sources need a
+ * float64 raster.  d_src and d_dst are caller-owned device buffers. */
+int agf_tile_place_run(const void *d_src, int32_t src_dtype, int64_t nt, int64_t ny, int64_t nx,
+                       int64_t st, int64_t sy, int64_t sx, void *d_dst, int32_t dst_dtype, int64_t ld,
+                       int64_t n_lon, int64_t t0, int64_t y0, int64_t x0, int32_t packed, double scale,
+                       double offset, int32_t has_fill, double fill, uintptr_t stream);
 
 /* ---- weights builder geometry (host only; replaces the GEOS work of calculate_weights) ---------- */
 

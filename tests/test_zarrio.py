@@ -1,0 +1,287 @@
+"""Zarr reader (aggfly_b200/zarrio.py) on the CPU: stores assembled BY HAND from the published v2 / v3
+layouts (independent of the package's own writer), every codec the reader claims, CF decoding, the
+lazy raster's tiles.  The reference reaches the same data through xarray's zarr backend
+(aggfly/dataset/dataset.py:585-615, 697-707; aggfly/dataset/zarr_convert.py:50-121)."""
+import gzip
+import itertools
+import json
+import os
+import struct
+import zlib
+
+import numpy as np
+import pandas as pd
+import pyarrow as pa
+import pytest
+
+import aggfly_b200 as af
+from aggfly_b200 import zarrio
+from aggfly_b200.io import _auto_chunks
+
+
+def _dump(path, obj):
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    with open(path, "w") as f:
+        json.dump(obj, f)
+
+
+def _put(path, raw: bytes):
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    with open(path, "wb") as f:
+        f.write(raw)
+
+
+def test_hand_built_v2_store(tmp_path):
+    """A 3 x 4 int32 array in 2 x 3 chunks, big-endian, '/' separator, zlib; one chunk left out."""
+    root = str(tmp_path / "a")
+    _dump(root + "/.zarray", {"zarr_format": 2, "shape": [3, 4], "chunks": [2, 3], "dtype": ">i4", "order": "C",
+                             "compressor": {"id": "zlib", "level": 1}, "fill_value": -1, "filters": None,
+                             "dimension_separator": "/"})
+    _dump(root + "/.zattrs", {"_ARRAY_DIMENSIONS": ["y", "x"], "units": "K"})
+    full = np.arange(12, dtype=np.int32).reshape(3, 4)
+    for (i, j) in [(0, 0), (0, 1), (1, 0)]:                                   # chunk (1, 1) is absent -> fill value
+        block = np.full((2, 3), -1, ">i4")
+        part = full[2 * i: 2 * i + 2, 3 * j: 3 * j + 3]
+        block[: part.shape[0], : part.shape[1]] = part
+        _put(f"{root}/{i}/{j}", zlib.compress(block.tobytes()))
+    a = zarrio.ZarrArray(root)
+    assert a.shape == (3, 4) and a.chunks == (2, 3) and a.dims == ("y", "x") and a.attrs["units"] == "K"
+    want = full.copy()
+    want[2:, 3:] = -1
+    assert np.array_equal(a.read(), want) and a.read().dtype == np.int32
+    assert np.array_equal(a[1:3, 2:4], want[1:3, 2:4]) and a[2, 0] == 8 and np.array_equal(a[-1], want[-1])
+
+
+def test_hand_built_v3_store(tmp_path):
+    """A 4 x 3 float32 array, chunks 2 x 3, codecs transpose([1, 0]) -> bytes(little) -> gzip -> crc32c."""
+    root = str(tmp_path / "g")
+    _dump(root + "/zarr.json", {"zarr_format": 3, "node_type": "group", "attributes": {"title": "t"}})
+    _dump(root + "/v/zarr.json", {
+        "zarr_format": 3, "node_type": "array", "shape": [4, 3], "data_type": "float32",
+        "chunk_grid": {"name": "regular", "configuration": {"chunk_shape": [2, 3]}},
+        "chunk_key_encoding": {"name": "default", "configuration": {"separator": "/"}}, "fill_value": "NaN",
+        "codecs": [{"name": "transpose", "configuration": {"order": [1, 0]}},
+                   {"name": "bytes", "configuration": {"endian": "little"}},
+                   {"name": "gzip", "configuration": {"level": 1}}, {"name": "crc32c"}],
+        "attributes": {"long_name": "x"}, "dimension_names": ["a", "b"]})
+    full = np.arange(12, dtype="<f4").reshape(4, 3) / 4
+    for i in range(2):
+        stored = np.ascontiguousarray(full[2 * i: 2 * i + 2].T)                # transpose codec: axis order [1, 0]
+        _put(f"{root}/v/c/{i}/0", gzip.compress(stored.tobytes()) + b"\0\0\0\0")
+    g = zarrio.ZarrGroup(root)
+    assert g.names() == ["v"] and g.attrs == {"title": "t"}
+    a = g["v"]
+    assert a.storage_axes == (1, 0) and a.dims == ("a", "b") and np.isnan(a.fill_value)
+    assert np.array_equal(a.read(), full)
+    # v2-style keys inside a v3 array
+    meta = json.load(open(root + "/v/zarr.json"))
+    meta["chunk_key_encoding"] = {"name": "v2", "configuration": {"separator": "."}}
+    meta["codecs"] = [{"name": "bytes", "configuration": {"endian": "big"}}]
+    _dump(root + "/w/zarr.json", meta)
+    for i in range(2):
+        _put(f"{root}/w/{i}.0", full[2 * i: 2 * i + 2].astype(">f4").tobytes())
+    assert np.array_equal(zarrio.ZarrArray(root + "/w").read(), full)
+
+
+def _blosc_frame(data: bytes, typesize: int, blocksize: int, cname: str, shuffle: int, split: bool = True) -> bytes:
+    """A Blosc-1 frame assembled from the published layout (header, block offsets, per-split streams)."""
+    comp_id = {"lz4": 1, "zlib": 3, "zstd": 4}[cname]
+    enc = {"lz4": lambda b: pa.Codec("lz4_raw").compress(b, asbytes=True), "zlib": lambda b: zlib.compress(b, 1),
+           "zstd": lambda b: pa.Codec("zstd").compress(b, asbytes=True)}[cname]
+    nbytes = len(data)
+    nblocks = -(-nbytes // blocksize)
+    can_split = split and typesize <= 16 and blocksize // typesize >= 128
+    flags = (comp_id << 5) | (0x10 if not can_split else 0) | {0: 0, 1: 0x1, 2: 0x4}[shuffle]
+    body, bstarts = b"", []
+    arr = np.frombuffer(data, np.uint8)
+    for b in range(nblocks):
+        blk = arr[b * blocksize: (b + 1) * blocksize]
+        n = blk.size // typesize
+        if shuffle == 1 and typesize > 1:
+            blk = np.concatenate([blk[: n * typesize].reshape(n, typesize).T.reshape(-1), blk[n * typesize:]])
+        elif shuffle == 2:
+            n8 = n & ~7
+            bits = np.unpackbits(blk[: n8 * typesize].reshape(n8, typesize), axis=1, bitorder="little")
+            blk = np.concatenate([np.packbits(bits.T, axis=1, bitorder="little").reshape(-1), blk[n8 * typesize:]])
+        leftover = blk.size != blocksize
+        nsplits = typesize if (can_split and not leftover) else 1
+        ne = blk.size // nsplits
+        bstarts.append(16 + 4 * nblocks + len(body))
+        for s in range(nsplits):
+            raw = blk[s * ne: (s + 1) * ne].tobytes()
+            c = enc(raw)
+            if len(c) >= len(raw):
+                c = raw                                                         # stored uncompressed
+            body += struct.pack("<i", len(c)) + c
+    head = struct.pack("<4B3I", 2, 1, flags, typesize, nbytes, blocksize, 16 + 4 * nblocks + len(body))
+    return head + struct.pack(f"<{nblocks}i", *bstarts) + body
+
+
+@pytest.mark.parametrize("cname,shuffle,split", [("lz4", 1, True), ("lz4", 0, False), ("zstd", 1, True), ("zlib", 2, False),
+                                                 ("zstd", 2, True)])
+def test_blosc_frames(cname, shuffle, split):
+    rng = np.random.default_rng(5)
+    data = (np.cumsum(rng.integers(-3, 4, 5000)) / 8).astype(np.float32).tobytes() + b"xyz"      # ragged tail
+    frame = _blosc_frame(data, 4, 4096, cname, shuffle, split)
+    assert zarrio.blosc_decompress(frame).tobytes() == data
+    memcpyed = struct.pack("<4B3I", 2, 1, 0x2, 4, len(data), len(data), len(data) + 16) + data
+    assert zarrio.blosc_decompress(memcpyed).tobytes() == data
+
+
+def test_v2_blosc_and_filters(tmp_path):
+    vals = np.arange(6 * 5, dtype="<i2").reshape(6, 5) * 3
+    root = str(tmp_path / "b")
+    _dump(root + "/.zarray", {"zarr_format": 2, "shape": [6, 5], "chunks": [6, 5], "dtype": "<i2", "order": "F",
+                             "compressor": {"id": "blosc", "cname": "lz4", "clevel": 5, "shuffle": 1, "blocksize": 0},
+                             "fill_value": 0, "filters": [{"id": "delta", "dtype": "<i2"}]})
+    stored = vals.tobytes(order="F")
+    delta = np.diff(np.frombuffer(stored, "<i2"), prepend=np.int16(0)).astype("<i2")
+    _put(root + "/0.0", _blosc_frame(delta.tobytes(), 2, 64, "lz4", 1))
+    assert np.array_equal(zarrio.ZarrArray(root).read(), vals)
+    # numcodecs Shuffle filter + bz2
+    root = str(tmp_path / "c")
+    _dump(root + "/.zarray", {"zarr_format": 2, "shape": [30], "chunks": [30], "dtype": "<f8", "order": "C",
+                             "compressor": {"id": "bz2", "level": 1}, "fill_value": "NaN",
+                             "filters": [{"id": "shuffle", "elementsize": 8}]})
+    import bz2
+    v = np.linspace(0, 1, 30)
+    _put(root + "/0", bz2.compress(np.frombuffer(v.tobytes(), np.uint8).reshape(30, 8).T.tobytes()))
+    assert np.array_equal(zarrio.ZarrArray(root).read(), v)
+    _dump(root + "/.zarray", dict(json.load(open(root + "/.zarray")), filters=[{"id": "quantize", "digits": 2}]))
+    with pytest.raises(NotImplementedError):
+        zarrio.ZarrArray(root)
+
+
+def _raster(T=50, Y=7, X=9, seed=0):
+    rng = np.random.default_rng(seed)
+    vals = rng.normal(10, 5, (T, Y, X)).astype(np.float32)
+    vals[3, 2, :] = np.nan
+    return vals, pd.date_range("2001-01-01", periods=T, freq="h"), np.linspace(40, 37, Y), np.linspace(230, 234, X)
+
+
+@pytest.mark.parametrize("fmt,comp", [(2, None), (2, "zlib"), (2, "zstd"), (2, "lz4"), (2, "gzip"), (3, None), (3, "zstd"), (3, "gzip")])
+def test_dataset_roundtrip_all_layouts(tmp_path, fmt, comp):
+    vals, t, lat, lon = _raster()
+    T, Y, X = vals.shape
+    dim_orders = [("time", "latitude", "longitude"), ("latitude", "longitude", "time"), ("longitude", "time", "latitude")]
+    chunkings = [{"time": 24}, {"latitude": 3, "longitude": 4}, {"time": 7, "latitude": 2, "longitude": 5}]
+    for n, (order, dims, chunks) in enumerate(itertools.product("CF", dim_orders, chunkings)):
+        store = zarrio.write_dataset(str(tmp_path / f"s{n}.zarr"), vals, t, lat, lon, var="t2m", dims=dims, chunks=chunks,
+                                     zarr_format=fmt, compressor=comp, order=order)
+        ds = af.dataset_from_path(store, var="t2m")
+        assert ds.shape == (T, Y, X) and ds.dtype == np.float32 and getattr(ds.values, "is_chunked_raster", False)
+        assert np.array_equal(np.asarray(ds.values), vals, equal_nan=True)
+        assert (ds.time == t).all() and np.array_equal(ds.latitude, lat) and np.array_equal(ds.longitude, lon)
+        cover = np.zeros(vals.shape, int)
+        buf = np.empty(ds.values.slot_elems, np.float32)
+        for tl in ds.values.tiles():                                  # what stream.feed_chunked hands to the device
+            cover[tl.t0:tl.t1, tl.y0:tl.y1, tl.x0:tl.x1] += 1
+            assert ds.values.load(tl, buf)
+            nt, ny, nx = tl.extent
+            blk = np.lib.stride_tricks.as_strided(buf[tl.offset:], (nt, ny, nx), (tl.st * 4, tl.sy * 4, tl.sx * 4))
+            assert np.array_equal(blk, vals[tl.t0:tl.t1, tl.y0:tl.y1, tl.x0:tl.x1], equal_nan=True)
+        assert (cover == 1).all()
+        t0s = [tl.t0 for tl in ds.values.tiles()]
+        assert t0s == sorted(t0s)                                     # time chunk by time chunk
+        win = ds.values[:, 1:5, 2:8][3:, :, 1:]                       # lazy windows compose
+        assert getattr(win, "is_chunked_raster", False) and np.array_equal(np.asarray(win), vals[3:, 1:5, 3:8], equal_nan=True)
+
+
+def test_time_sel_and_clip_stay_lazy(tmp_path):
+    vals, _, lat, lon = _raster(T=72)
+    t = pd.date_range("2001-12-31", periods=72, freq="h")
+    store = zarrio.write_dataset(str(tmp_path / "y.zarr"), vals, t, lat, lon, var="t2m", chunks={"time": 24})
+    ds = af.dataset_from_path(store, var="t2m", time_sel="2002")
+    assert ds.shape[0] == 48 and getattr(ds.values, "is_chunked_raster", False)
+    assert np.array_equal(np.asarray(ds.values), vals[24:], equal_nan=True)
+    from aggfly_b200.io import clip_to_extent
+    cl = clip_to_extent(ds, -129.0, -128.0, 38.0, 39.0)
+    assert getattr(cl.values, "is_chunked_raster", False) and cl.shape[1] < 7 and cl.shape[2] < 9
+    iy = [int(np.argmin(np.abs(lat - v))) for v in cl.latitude]
+    ix = [int(np.argmin(np.abs(lon - v))) for v in cl.longitude]
+    assert np.array_equal(np.asarray(cl.values), vals[24:][:, iy][:, :, ix], equal_nan=True)
+
+
+def test_cf_packing_fill_and_missing_chunks(tmp_path):
+    T, Y, X = 10, 4, 6
+    rng = np.random.default_rng(2)
+    packed = rng.integers(-3000, 3000, (T, Y, X)).astype(np.int16)
+    packed[2, 1, 1] = -32767
+    packed[5:] = -32767                                               # a whole time chunk of fill -> chunk files skipped
+    root = str(tmp_path / "p.zarr")
+    t = pd.date_range("2001-01-01", periods=T, freq="D")
+    zarrio.write_dataset(root, np.zeros((T, Y, X), np.float32), t, np.arange(Y), np.arange(X), var="t2m", time_units="days")
+    import shutil
+    shutil.rmtree(root + "/t2m")
+    zarrio.write_array(root + "/t2m", packed, [5, 2, 6], ["time", "latitude", "longitude"],
+                       {"scale_factor": 0.01, "add_offset": 273.15, "_FillValue": -32767}, zarr_format=2, compressor="zlib",
+                       fill_value=-32767, skip_fill_chunks=True)
+    assert not os.path.exists(root + "/t2m/1.0.0")
+    ds = af.dataset_from_path(root, var="t2m")
+    want = packed.astype(np.float64) * 0.01 + 273.15
+    want[packed == -32767] = np.nan
+    assert ds.dtype == np.float64 and ds.values.packed and ds.values.fill == -32767.0
+    assert np.array_equal(np.asarray(ds.values), want, equal_nan=True)
+    assert (ds.time == t).all()
+    loaded = [ds.values.load(tl, np.empty(ds.values.slot_elems, np.int16)) for tl in ds.values.tiles()]
+    assert loaded == [True, True, False, False]
+    # a v2 float array whose fill_value is a number and no _FillValue attribute: xarray masks it
+    zarrio.write_array(root + "/f", np.array([[1.0, -9.0], [3.0, 4.0]], np.float32)[None], [1, 2, 2],
+                       ["time", "latitude", "longitude"], None, zarr_format=2, compressor=None, fill_value=-9.0)
+    r = zarrio.ChunkedRaster(zarrio.ZarrArray(root + "/f"), (0, 1, 2))
+    assert np.array_equal(np.asarray(r)[0], [[1.0, np.nan], [3.0, 4.0]], equal_nan=True)
+
+
+def test_calendar_time_axes(tmp_path):
+    vals = np.zeros((800, 2, 2), np.float32)
+    for cal in ("noleap", "360_day"):
+        t = af.CalendarIndex.range(cal, 2001, 800, "D")
+        store = zarrio.write_dataset(str(tmp_path / f"{cal}.zarr"), vals, t, [0.0, 1.0], [0.0, 1.0], var="tas", chunks={"time": 365})
+        ds = af.dataset_from_path(store, var="tas")
+        assert isinstance(ds.time, af.CalendarIndex) and ds.time.calendar == cal
+        for f in ("year", "month", "day", "hour"):
+            assert np.array_equal(getattr(ds.time, f), getattr(t, f))
+    # fractional days since an origin on the standard calendar
+    root = str(tmp_path / "frac.zarr")
+    zarrio.write_dataset(root, vals[:4], pd.date_range("2001-01-01", periods=4, freq="6h"), [0.0, 1.0], [0.0, 1.0], var="tas",
+                         time_units="days")
+    a = zarrio.ZarrArray(root + "/time")
+    assert a.dtype.kind == "f" and a.attrs["units"].startswith("days since 2001-01-01")
+    assert (zarrio.decode_time(a) == pd.date_range("2001-01-01", periods=4, freq="6h")).all()
+
+
+def test_errors(tmp_path):
+    vals, t, lat, lon = _raster(T=5)
+    store = zarrio.write_dataset(str(tmp_path / "e.zarr"), vals, t, lat, lon, var="t2m")
+    with pytest.raises(KeyError):
+        af.dataset_from_path(store, var="nope")
+    with pytest.raises(ValueError):
+        af.dataset_from_path(store, var="t2m", xycoords=("lon", "lat"))
+    assert zarrio.looks_like_zarr(store) and not zarrio.looks_like_zarr(str(tmp_path))
+    os.rename(store, str(tmp_path / "plain"))
+    assert zarrio.looks_like_zarr(str(tmp_path / "plain"))                      # no ".zarr" in the name: the markers decide
+    meta = json.load(open(str(tmp_path / "plain/t2m/.zarray")))
+    meta["compressor"] = {"id": "pcodec"}
+    _dump(str(tmp_path / "plain/t2m/.zarray"), meta)
+    with pytest.raises(NotImplementedError):
+        af.dataset_from_path(str(tmp_path / "plain"), var="t2m")
+
+
+def test_auto_chunks_policy():
+    """aggfly/dataset/zarr_convert.py:31-47."""
+    assert _auto_chunks({"time": 8760, "latitude": 721, "longitude": 1440}, 4, 256) == {"time": -1, "latitude": 87, "longitude": 87}
+    assert _auto_chunks({"time": 8760, "latitude": 20, "longitude": 30}, 4, 256) == {"time": -1, "latitude": 20, "longitude": 20}
+    got = _auto_chunks({"time": 350640, "latitude": 721, "longitude": 1440}, 4, 64)
+    assert got == {"time": 1024, "latitude": 128, "longitude": 128}
+
+
+def test_dataset_to_zarr_reopens_time_contiguous(tmp_path):
+    vals, t, lat, lon = _raster()
+    ds = af.Dataset.from_arrays(vals, t, lat, lon, name="t2m", preprocess="x - 273.15")
+    out = af.dataset_to_zarr(ds, str(tmp_path / "tc.zarr"), chunking={"time": -1, "latitude": 4, "longitude": 4})
+    arr = out.values.array
+    assert arr.dims == ("latitude", "longitude", "time") and arr.chunks == (4, 4, 50) and arr.zarr_format == 3
+    assert np.array_equal(np.asarray(out.values), vals, equal_nan=True) and out.pre_ops == ds.pre_ops
+    with pytest.raises(FileExistsError):
+        af.dataset_to_zarr(ds, str(tmp_path / "tc.zarr"))
+    assert af.dataset_to_zarr(ds, str(tmp_path / "tc.zarr"), overwrite=True, return_dataset=False) is None
