@@ -78,7 +78,8 @@ _lib: Optional[C.CDLL] = None
 SYMBOLS = ("agf_version", "agf_last_error", "agf_program_create", "agf_program_destroy",
            "agf_program_plan", "agf_program_info", "agf_program_stripe_rows", "agf_temporal_run",
            "agf_temporal_finalize", "agf_csr_create", "agf_csr_destroy", "agf_spmm_run",
-           "agf_valid_mask_run", "agf_elementwise_run", "agf_tile_place_run", "agf_overlap_create", "agf_overlap_fetch", "agf_overlap_destroy")
+           "agf_valid_mask_run", "agf_elementwise_run", "agf_tile_place_run", "agf_decompress_caps", "agf_decompress_lz4_run",
+           "agf_unshuffle_run", "agf_copy_segments_run", "agf_overlap_create", "agf_overlap_fetch", "agf_overlap_destroy")
 
 
 def lib() -> C.CDLL:
@@ -109,6 +110,10 @@ def lib() -> C.CDLL:
     L.agf_elementwise_run.argtypes = [vp, i32, vp, i32, i64, i32, C.c_double, vp, i32, vp, i32, C.POINTER(Pre), u64]
     L.agf_tile_place_run.argtypes = [vp, i32, i64, i64, i64, i64, i64, i64, vp, i32, i64, i64, i64, i64, i64,
                                      i32, C.c_double, C.c_double, i32, C.c_double, u64]
+    L.agf_decompress_caps.argtypes = [C.POINTER(i32), C.POINTER(i64)]
+    L.agf_decompress_lz4_run.argtypes = [vp, C.POINTER(i64), C.POINTER(i64), vp, C.POINTER(i64), C.POINTER(i64), i64, vp, u64]
+    L.agf_unshuffle_run.argtypes = [vp, vp, i64, i32, i64, u64]
+    L.agf_copy_segments_run.argtypes = [vp, vp, vp, i64, u64]
     dp, i64p, i32p = C.POINTER(C.c_double), C.POINTER(i64), C.POINTER(i32)
     L.agf_overlap_create.argtypes = [C.POINTER(vp), i32, i64p, i64p, dp, i32, dp, C.c_double, i32, dp, C.c_double, i64p]
     L.agf_overlap_fetch.argtypes = [vp, i32p, i64p, dp]

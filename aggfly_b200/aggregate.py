@@ -140,6 +140,7 @@ def _temporal_device(dataset: Dataset, aggregator_dict, target_stripes: int = 0)
         torch.cuda.current_stream().synchronize()
         t3 = time.perf_counter()
         runner.close()
+    _stream.check_device_decompress()
     global LAST_FEED_TRACE
     LAST_FEED_TRACE = {"runner_ms": (t1 - t0) * 1e3, "issue_ms": (t2 - t1) * 1e3, "drain_ms": (t3 - t2) * 1e3,
                        "close_ms": (time.perf_counter() - t3) * 1e3}

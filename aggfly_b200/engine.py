@@ -39,6 +39,8 @@ def to_device(values, device=None):
         from . import stream as _stream
         T, Y, X = values.shape
         _, raster = _stream.feed_chunked(None, values, Y * X, device=device)
+        torch.cuda.current_stream(device).synchronize()
+        _stream.check_device_decompress()
         return raster.view(T, Y, X).clone()                         # the streamed buffer is recycled by the next feed
     if isinstance(values, np.ndarray):
         if values.dtype not in (np.float32, np.float64):

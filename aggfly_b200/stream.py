@@ -34,6 +34,10 @@ OPTIONS = {
     "staging_threads": 8,              # host threads filling the ring
     "keep_device_raster": True,        # keep the device copy's buffer between calls (see _device_raster)
     "chunked_ring_bytes": 2 << 30,     # pinned (and device) staging for chunked stores: slots x decoded chunk size
+    "device_decompress": True,         # Blosc-LZ4 chunks: inflate on the GPU's decompression engine when it has one
+    # Blosc packs its streams back to back at arbitrary byte offsets.  0: hand them to the engine where they are;
+    # n > 1: first move every stream to an n-byte aligned offset of a second device buffer (one segment-copy launch)
+    "device_decompress_align": int(__import__("os").environ.get("AGF_DE_ALIGN", "0")),
 }
 
 
@@ -175,25 +179,65 @@ _CHUNK_RINGS = {}        # (device, slot_bytes, n_slots) -> (pinned slots, devic
 _TILE_DTYPES = {"f4": 0, "f8": 1, "i2": 2, "i4": 3, "u1": 4, "i1": 5, "u2": 6}      # AGF_F32 .. AGF_U16
 
 
-def _chunk_ring(torch, dev, slot_bytes: int, n_slots: int):
-    key = (dev.index, int(slot_bytes), int(n_slots))
+def _chunk_ring(torch, dev, slot_bytes: int, n_slots: int, de: bool):
+    """Staging of ``n_slots`` chunks: pinned host bytes + a device copy; with ``de`` (device decompression)
+    the pinned / first device buffer hold the COMPRESSED file (a little headroom for incompressible
+    chunks) and two more device buffers hold the inflated and the unshuffled chunk."""
+    key = (dev.index, int(slot_bytes), int(n_slots), bool(de))
     if key not in _CHUNK_RINGS:
         _CHUNK_RINGS.clear()
-        _CHUNK_RINGS[key] = ([torch.empty(slot_bytes, dtype=torch.uint8, pin_memory=True) for _ in range(n_slots)],
-                             [torch.empty(slot_bytes, dtype=torch.uint8, device=dev) for _ in range(n_slots)])
+        cap = slot_bytes + (slot_bytes // 64 + 65536 if de else 0)
+        cap = (cap + 15) // 16 * 16
+        ring = {"cap": cap,
+                "pinned": [torch.empty(cap, dtype=torch.uint8, pin_memory=True) for _ in range(n_slots)],
+                "dev": [torch.empty(cap, dtype=torch.uint8, device=dev) for _ in range(n_slots)]}
+        if de:
+            ring["inflated"] = [torch.empty(slot_bytes, dtype=torch.uint8, device=dev) for _ in range(n_slots)]
+            ring["plain"] = [torch.empty(slot_bytes, dtype=torch.uint8, device=dev) for _ in range(n_slots)]
+            ring["aligned_cap"] = cap + cap // 4 + (1 << 20)
+            ring["aligned"] = None                     # allocated on first use (device_decompress_align)
+        _CHUNK_RINGS[key] = ring
     return _CHUNK_RINGS[key]
+
+
+_PENDING_CHECKS = []     # device booleans "every engine operation produced the bytes its frame promised"
+
+
+def check_device_decompress() -> None:
+    """Call after synchronising the stream a chunked feed ran on: raises if any decompression-engine
+    operation of the feeds since the last call wrote a different number of bytes than its Blosc frame said."""
+    pending, _PENDING_CHECKS[:] = list(_PENDING_CHECKS), []
+    for ok, what in pending:
+        if not bool(ok):
+            raise IOError(f"{what}: the decompression engine produced a stream of unexpected length (corrupt chunk?)")
+
+
+def device_decompress_caps():
+    """(algorithm mask, bytes per operation) of the device's decompression engine (0, 0: none)."""
+    import ctypes as C
+    from . import _lib
+    mask, mx = C.c_int32(0), C.c_int64(0)
+    _lib.check(_lib.lib().agf_decompress_caps(C.byref(mask), C.byref(mx)))
+    return int(mask.value), int(mx.value)
 
 
 def feed_chunked(runner, src, n_cells: int, stream=None, k1_events: Optional[list] = None,
                  stats: Optional[dict] = None, device=None):
-    """``feed_and_run`` for a ``zarrio.ChunkedRaster``: every storage chunk is decoded by a host thread
-    into a pinned slot (file read, decompression and the copy all release the GIL), copied to the device
-    as it is stored, and placed into the time-major raster by ``agf_tile_place_run`` (axis permutation,
-    CF unpacking and fill -> NaN on the device).  Chunks that are runs of whole raster rows and need no
-    decoding are copied straight into the raster.  Tiles arrive time chunk by time chunk, so for a
-    time-major store the temporal kernels of a stripe start as soon as its rows are complete; a
-    time-contiguous store (chunks ``[s, s, T]``) is scanned once its last tile has landed.
+    """``feed_and_run`` for a ``zarrio.ChunkedRaster``: every storage chunk is brought into a pinned slot by
+    a host thread (file read, decompression and copies all release the GIL), copied to the device as it is
+    stored, and placed into the time-major raster by ``agf_tile_place_run`` (axis permutation, CF unpacking
+    and fill -> NaN on the device).
+
+    * Chunks that are runs of whole raster rows and need no decoding are copied straight into the raster.
+    * Blosc-LZ4 chunks (zarr v2's default compressor) are NOT inflated on the host when the device has a
+      decompression engine (``OPTIONS["device_decompress"]``): the compressed file crosses PCIe, its LZ4
+      streams are inflated by ``agf_decompress_lz4_run`` and un-shuffled by ``agf_unshuffle_run``.
+    * Tiles arrive time chunk by time chunk, so for a time-major store the temporal kernels of a stripe
+      start as soon as its rows are complete; a time-contiguous store (chunks ``[s, s, T]``) is scanned once
+      its last tile has landed.
+
     ``runner=None`` only builds the device raster (``engine.to_device``)."""
+    import ctypes as C
     import torch
     from . import _lib
     L = _lib.lib()
@@ -204,6 +248,7 @@ def feed_chunked(runner, src, n_cells: int, stream=None, k1_events: Optional[lis
     comp = torch.cuda.current_stream(dev) if stream is None else stream
     copy = _copy_stream(dev)
     tdtype = torch.float64 if src.dtype == np.float64 else torch.float32
+    dst_code = _lib.F64 if tdtype == torch.float64 else _lib.F32
     raster = _device_raster(torch, dev, tdtype, T, n_cells)
     sdt = src.array.dtype.newbyteorder("=")
     code = _TILE_DTYPES.get(sdt.str[1:])
@@ -211,12 +256,18 @@ def feed_chunked(runner, src, n_cells: int, stream=None, k1_events: Optional[lis
         raise NotImplementedError(f"no tile decoder for stored dtype {sdt}")
     tiles = src.tiles()
     slot_bytes = src.slot_elems * sdt.itemsize
+    de, max_len = False, 0
+    if OPTIONS.get("device_decompress", True) and src.array.blosc_only:
+        mask, max_len = device_decompress_caps()
+        de = bool(mask & 4) and max_len > 0
     n_slots = int(max(2, min(OPTIONS["staging_slots"], OPTIONS["chunked_ring_bytes"] // max(1, slot_bytes))))
-    pinned, dslots = _chunk_ring(torch, dev, slot_bytes, n_slots)
-    views = [p.numpy().view(sdt) for p in pinned]
-    tviews = [p.view(tdtype) for p in pinned] if sdt == src.dtype else None
+    ring = _chunk_ring(torch, dev, slot_bytes, n_slots, de)
+    pinned, dslots = ring["pinned"], ring["dev"]
+    bytes_np = [p.numpy() for p in pinned]
+    views = [b[:slot_bytes].view(sdt) for b in bytes_np]
+    tviews = [p[:slot_bytes].view(tdtype) for p in pinned] if sdt == src.dtype else None
     h2d_done = [None] * n_slots          # last copy out of the pinned slot
-    placed = [None] * n_slots            # last placement kernel reading the device slot
+    placed = [None] * n_slots            # last kernel reading the slot's device buffers
     fill_scalar = None
 
     def fill(i):
@@ -224,30 +275,41 @@ def feed_chunked(runner, src, n_cells: int, stream=None, k1_events: Optional[lis
         ev = h2d_done[slot]
         if ev is not None:
             ev.synchronize()
-        return src.load(tiles[i], views[slot])
+        if de:
+            return src.load_stored(tiles[i], bytes_np[slot], max_len)
+        return ("host",) if src.load(tiles[i], views[slot]) else None
 
+    def place(ptr, tile):
+        nt, ny, nx = tile.extent
+        _lib.check(L.agf_tile_place_run(
+            ptr + tile.offset * sdt.itemsize, code, nt, ny, nx, tile.st, tile.sy, tile.sx, raster.data_ptr(), dst_code,
+            n_cells, X, tile.t0, tile.y0, tile.x0, int(src.packed), float(src.scale), float(src.offset),
+            int(src.fill is not None), float(src.fill if src.fill is not None else 0.0), comp.cuda_stream))
+
+    i64p = C.POINTER(C.c_int64)
+    align = int(OPTIONS.get("device_decompress_align", 0) or 0)
     copy.wait_stream(comp)
     ev_first, ev_last = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev_first.record(copy)
     if runner is not None:
         runner.begin_streamed(comp)
-    launches = places = direct = absent = 0
+    launches = places = direct = absent = inflated = engine_ops = raw_copies = 0
     h2d_bytes = 0
     pool = ThreadPoolExecutor(max_workers=max(1, int(OPTIONS["staging_threads"])))
     try:
         futs = {i: pool.submit(fill, i) for i in range(min(n_slots, len(tiles)))}
         for i, tile in enumerate(tiles):
             slot = i % n_slots
-            present = futs.pop(i).result()
+            got = futs.pop(i).result()
             nt, ny, nx = tile.extent
-            if not present:
+            if got is None:
                 if fill_scalar is None:
                     fv = src.array.fill_value
                     fill_scalar = float(src.decode_host(np.full(1, 0 if fv is None else fv, sdt))[0])
                 with torch.cuda.stream(comp):
                     raster.view(T, Y, X)[tile.t0:tile.t1, tile.y0:tile.y1, tile.x0:tile.x1] = fill_scalar
                 absent += 1
-            elif tviews is not None and src.direct_rows(tile):
+            elif got[0] == "host" and tviews is not None and src.direct_rows(tile):
                 with torch.cuda.stream(copy):
                     raster[tile.t0:tile.t1].copy_(tviews[slot][tile.offset: tile.offset + nt * n_cells].view(nt, n_cells),
                                                   non_blocking=True)
@@ -258,23 +320,64 @@ def feed_chunked(runner, src, n_cells: int, stream=None, k1_events: Optional[lis
                 h2d_bytes += nt * n_cells * sdt.itemsize
                 direct += 1
             else:
+                n_up = slot_bytes if got[0] == "host" else got[1]
                 with torch.cuda.stream(copy):
                     if placed[slot] is not None:
                         copy.wait_event(placed[slot])
-                    dslots[slot].copy_(pinned[slot], non_blocking=True)
+                    dslots[slot][:n_up].copy_(pinned[slot][:n_up], non_blocking=True)
                     ev = torch.cuda.Event()
                     ev.record(copy)
                 h2d_done[slot] = ev
                 comp.wait_event(ev)
-                _lib.check(L.agf_tile_place_run(
-                    dslots[slot].data_ptr() + tile.offset * sdt.itemsize, code, nt, ny, nx, tile.st, tile.sy, tile.sx,
-                    raster.data_ptr(), _lib.F64 if tdtype == torch.float64 else _lib.F32, n_cells, X,
-                    tile.t0, tile.y0, tile.x0, int(src.packed), float(src.scale), float(src.offset),
-                    int(src.fill is not None), float(src.fill if src.fill is not None else 0.0), comp.cuda_stream))
+                h2d_bytes += n_up
+                if got[0] == "host":
+                    place(dslots[slot].data_ptr(), tile)
+                else:
+                    plan = got[2]
+                    if plan.kind == "memcpy":
+                        place(dslots[slot].data_ptr() + 16, tile)
+                    else:
+                        infl, plain = ring["inflated"][slot], ring["plain"][slot]
+                        n_ops = len(plan.src_off)
+                        with torch.cuda.stream(comp):
+                            if n_ops:
+                                src_ptr, src_off = dslots[slot].data_ptr(), plan.src_off
+                                if align > 1:
+                                    padded = (plan.src_len + (align - 1)) // align * align
+                                    src_off = np.ascontiguousarray(np.concatenate([[0], np.cumsum(padded)[:-1]]).astype(np.int64))
+                                    if int(src_off[-1] + padded[-1]) <= ring["aligned_cap"]:
+                                        if ring["aligned"] is None:
+                                            ring["aligned"] = [torch.empty(ring["aligned_cap"], dtype=torch.uint8, device=dev)
+                                                               for _ in range(n_slots)]
+                                        moved = torch.from_numpy(np.stack([plan.src_off, src_off, plan.src_len])).to(dev, non_blocking=True)
+                                        _lib.check(L.agf_copy_segments_run(src_ptr, ring["aligned"][slot].data_ptr(), moved.data_ptr(),
+                                                                           n_ops, comp.cuda_stream))
+                                        src_ptr = ring["aligned"][slot].data_ptr()
+                                    else:
+                                        src_off = plan.src_off
+                                actual = torch.empty(n_ops, dtype=torch.int32, device=dev)
+                                _lib.check(L.agf_decompress_lz4_run(
+                                    src_ptr, src_off.ctypes.data_as(i64p), plan.src_len.ctypes.data_as(i64p),
+                                    infl.data_ptr(), plan.dst_off.ctypes.data_as(i64p), plan.dst_len.ctypes.data_as(i64p),
+                                    n_ops, actual.data_ptr(), comp.cuda_stream))
+                                want = torch.from_numpy(plan.dst_len.astype(np.int32)).to(dev, non_blocking=True)
+                                _PENDING_CHECKS.append(((actual == want).all(), src.array.chunk_path(tile.index)))
+                            if plan.raw.shape[1]:                          # streams Blosc stored uncompressed
+                                table = torch.from_numpy(plan.raw).to(dev, non_blocking=True)
+                                _lib.check(L.agf_copy_segments_run(dslots[slot].data_ptr(), infl.data_ptr(), table.data_ptr(),
+                                                                   plan.raw.shape[1], comp.cuda_stream))
+                                raw_copies += int(plan.raw.shape[1])
+                        if plan.shuffled:
+                            _lib.check(L.agf_unshuffle_run(infl.data_ptr(), plain.data_ptr(), plan.nbytes, plan.typesize,
+                                                           plan.blocksize, comp.cuda_stream))
+                            place(plain.data_ptr(), tile)
+                        else:
+                            place(infl.data_ptr(), tile)
+                        inflated += 1
+                        engine_ops += n_ops
                 pe = torch.cuda.Event()
                 pe.record(comp)
                 placed[slot] = pe
-                h2d_bytes += slot_bytes
                 places += 1
             if i + n_slots < len(tiles):
                 futs[i + n_slots] = pool.submit(fill, i + n_slots)
@@ -289,6 +392,7 @@ def feed_chunked(runner, src, n_cells: int, stream=None, k1_events: Optional[lis
     global LAST_STATS
     LAST_STATS = dict(chunks=len(tiles), pinned=False, chunked=True, h2d_bytes=h2d_bytes, k1_launches=launches,
                       place_launches=places, direct_copies=direct, absent_chunks=absent, ring_slots=n_slots,
+                      device_decompress=bool(de), inflated_on_device=inflated, engine_ops=engine_ops, raw_streams=raw_copies,
                       copy_events=(ev_first, ev_last))
     if stats is not None:
         stats.update(LAST_STATS)

@@ -148,6 +148,118 @@ def blosc_decompress(buf, nbytes_hint: int = 0) -> np.ndarray:
     return out
 
 
+class BloscPlan:
+    """What the device needs to decode one Blosc frame whose bytes sit in a buffer: raw-LZ4 streams for the
+    decompression engine (offsets into the frame / into the decoded chunk), streams stored uncompressed (plain
+    copies), and the shuffle parameters.  ``kind == "memcpy"``: the frame is a 16-byte header + plain data."""
+    __slots__ = ("kind", "nbytes", "typesize", "blocksize", "shuffled", "src_off", "src_len", "dst_off", "dst_len", "raw")
+
+
+def blosc_device_plan(u8: np.ndarray, max_len: int) -> Optional[BloscPlan]:
+    """Parse a Blosc-1 frame (uint8 view) without touching its payload.  None: not decodable on the device
+    (inner codec other than LZ4, bit shuffle, streams above the engine's limit, malformed) -- the caller
+    decodes on the host instead.  Vectorised over blocks: a 256 MB chunk has ~1000 blocks x typesize streams."""
+    if u8.size < 16:
+        return None
+    flags, typesize = int(u8[2]), int(u8[3])
+    nbytes, blocksize, cbytes = (int(v) for v in np.frombuffer(u8[4:16], "<u4"))
+    plan = BloscPlan()
+    plan.nbytes, plan.typesize, plan.blocksize = nbytes, typesize, blocksize
+    plan.shuffled = bool(flags & 0x1) and typesize > 1
+    if cbytes > u8.size or blocksize <= 0 or typesize <= 0:
+        return None
+    if flags & 0x2:
+        plan.kind = "memcpy"
+        return plan if 16 + nbytes <= u8.size else None
+    if (flags >> 5) != 1 or flags & 0x4 or (plan.shuffled and typesize not in (2, 4, 8)):
+        return None
+    nblocks = -(-nbytes // blocksize)
+    if 16 + 4 * nblocks > cbytes:
+        return None
+    bstarts = np.frombuffer(u8[16:16 + 4 * nblocks], "<i4").astype(np.int64)
+    leftover = nbytes % blocksize
+    nfull = nblocks - (1 if leftover else 0)
+    split = (not flags & 0x10) and typesize <= 16 and blocksize // typesize >= 128
+    nsplits = typesize if split else 1
+    if blocksize % nsplits:
+        return None
+    four = np.arange(4, dtype=np.int64)
+
+    def lengths(pos):
+        if (pos < 0).any() or (pos + 4 > cbytes).any():
+            return None
+        return np.ascontiguousarray(u8[pos[:, None] + four]).view("<i4").ravel().astype(np.int64)
+
+    so, sl, do, dl = [], [], [], []
+    if nfull:
+        ne = blocksize // nsplits
+        pos = bstarts[:nfull].copy()
+        base = np.arange(nfull, dtype=np.int64) * blocksize
+        for k in range(nsplits):
+            c = lengths(pos)
+            if c is None or (c <= 0).any() or (pos + 4 + c > cbytes).any():
+                return None
+            so.append(pos + 4), sl.append(c), do.append(base + k * ne), dl.append(np.full(nfull, ne, np.int64))
+            pos = pos + 4 + c
+    if leftover:
+        pos = bstarts[nfull:nfull + 1]
+        c = lengths(pos)
+        if c is None or c[0] <= 0 or pos[0] + 4 + c[0] > cbytes:
+            return None
+        so.append(pos + 4), sl.append(c), do.append(np.array([nfull * blocksize], np.int64)), dl.append(np.array([leftover], np.int64))
+    if not so:
+        return None
+    src_off, src_len, dst_off, dst_len = (np.concatenate(v) for v in (so, sl, do, dl))
+    raw = src_len == dst_len                                             # stream stored uncompressed
+    if (src_len > dst_len).any() or (dst_len[~raw] > max_len).any():
+        return None
+    plan.kind = "lz4"
+    plan.raw = np.ascontiguousarray(np.stack([src_off[raw], dst_off[raw], dst_len[raw]]))      # int64[3, n_raw]
+    keep = ~raw
+    plan.src_off, plan.src_len = np.ascontiguousarray(src_off[keep]), np.ascontiguousarray(src_len[keep])
+    plan.dst_off, plan.dst_len = np.ascontiguousarray(dst_off[keep]), np.ascontiguousarray(dst_len[keep])
+    return plan
+
+
+def blosc_compress(data: bytes, typesize: int, cname: str = "lz4", shuffle: int = 1, blocksize: int = 0,
+                   split: bool = True) -> bytes:
+    """A Blosc-1 frame assembled from the published layout (the inverse of ``blosc_decompress``): blocks of
+    ``blocksize`` bytes (0: 256 KB), optional byte (1) / bit (2) shuffle, each full block split into
+    ``typesize`` streams when ``split``.  For fixtures and for stores this package writes; not c-blosc."""
+    comp_id = {"lz4": 1, "zlib": 3, "zstd": 4}[cname]
+    enc = {"lz4": lambda b: _arrow("lz4_raw").compress(b, asbytes=True), "zlib": lambda b: zlib.compress(b, 1),
+           "zstd": lambda b: _arrow("zstd").compress(b, asbytes=True)}[cname]
+    nbytes = len(data)
+    blocksize = int(blocksize) or (256 << 10)
+    blocksize = max(typesize, min(blocksize, max(nbytes, typesize)) // typesize * typesize)
+    nblocks = -(-nbytes // blocksize) if nbytes else 0
+    can_split = split and typesize <= 16 and blocksize // typesize >= 128
+    flags = (comp_id << 5) | (0 if can_split else 0x10) | {0: 0, 1: 0x1, 2: 0x4}[shuffle]
+    arr = np.frombuffer(data, np.uint8)
+    body, bstarts, pos = [], [], 16 + 4 * nblocks
+    for b in range(nblocks):
+        blk = arr[b * blocksize: (b + 1) * blocksize]
+        n = blk.size // typesize
+        if shuffle == 1 and typesize > 1:
+            blk = np.concatenate([blk[: n * typesize].reshape(n, typesize).T.reshape(-1), blk[n * typesize:]])
+        elif shuffle == 2:
+            n8 = n & ~7
+            bits = np.unpackbits(blk[: n8 * typesize].reshape(n8, typesize), axis=1, bitorder="little")
+            blk = np.concatenate([np.packbits(bits.T, axis=1, bitorder="little").reshape(-1), blk[n8 * typesize:]])
+        nsplits = typesize if (can_split and blk.size == blocksize) else 1
+        ne = blk.size // nsplits
+        bstarts.append(pos)
+        for k in range(nsplits):
+            raw = blk[k * ne: (k + 1) * ne].tobytes()
+            c = enc(raw)
+            if len(c) >= len(raw):
+                c = raw                                                         # stored uncompressed
+            body.append(struct.pack("<i", len(c)) + c)
+            pos += 4 + len(c)
+    head = struct.pack("<4B3I", 2, 1, flags, typesize, nbytes, blocksize, pos)
+    return head + struct.pack(f"<{nblocks}i", *bstarts) + b"".join(body)
+
+
 def _blosc(buf, nbytes: int):
     return memoryview(blosc_decompress(buf, nbytes))
 
@@ -291,16 +403,26 @@ class ZarrArray:
             key = self._prefix + (self._sep + key if key else "")
         return os.path.join(self.path, *key.split("/"))
 
-    def read_chunk_storage(self, idx: Sequence[int], out: Optional[np.ndarray] = None) -> Optional[np.ndarray]:
-        """Decoded chunk as stored: a C-contiguous array of ``storage_shape`` (native byte order), written
-        into ``out`` (flat, same dtype, e.g. a pinned staging slot) when given.  None: the chunk file does
-        not exist (all fill value)."""
+    def read_chunk_bytes(self, idx: Sequence[int], into: Optional[np.ndarray] = None):
+        """The chunk file as stored: ``bytes``, or -- when ``into`` (uint8 array, e.g. a pinned slot) is
+        large enough -- the number of bytes read straight into it.  None: no such file (all fill value)."""
         p = self.chunk_path(idx)
         try:
             with open(p, "rb") as f:
-                buf = f.read()
+                if into is not None:
+                    size = os.fstat(f.fileno()).st_size
+                    if size <= into.size:
+                        got = f.readinto(memoryview(into)[:size])
+                        if got != size:
+                            raise IOError(f"{p}: short read ({got} of {size} bytes)")
+                        return size
+                return f.read()
         except FileNotFoundError:
             return None
+
+    def decode_chunk(self, buf, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """Stored bytes -> C-contiguous array of ``storage_shape`` (native byte order), written into ``out``
+        (flat, same dtype, e.g. a pinned staging slot) when given."""
         n = self.chunk_nbytes
         for dec in self._decoders:
             buf = dec(buf, n)
@@ -317,6 +439,18 @@ class ZarrArray:
         dst = out[: arr.size]
         np.copyto(dst, arr, casting="unsafe" if not self.dtype.isnative else "same_kind")   # byteswaps if needed
         return dst.reshape(self.storage_shape)
+
+    def read_chunk_storage(self, idx: Sequence[int], out: Optional[np.ndarray] = None) -> Optional[np.ndarray]:
+        """Decoded chunk as stored, or None when the chunk file does not exist (all fill value)."""
+        buf = self.read_chunk_bytes(idx)
+        return None if buf is None else self.decode_chunk(buf, out)
+
+    @property
+    def blosc_only(self) -> bool:
+        """The stored bytes of a chunk are exactly one Blosc frame of native little-endian values: the
+        frame's LZ4 streams can be inflated on the device (``blosc_device_plan``)."""
+        return (len(self._decoders) == 1 and self._decoders[0] is _blosc and not self._filters
+                and (self.dtype.byteorder in "<|" or (self.dtype.byteorder == "=" and np.little_endian)))
 
     def read_chunk(self, idx: Sequence[int]) -> np.ndarray:
         """Chunk in logical axis order (a transposed view of the stored chunk), padded to ``chunks``."""
@@ -540,6 +674,23 @@ class ChunkedRaster:
     def slot_elems(self) -> int:
         return int(np.prod(self.array.chunks))
 
+    def load_stored(self, tile: Tile, slot_u8: np.ndarray, max_len: int):
+        """Device-decode variant of ``load``: read the chunk FILE into ``slot_u8`` (pinned bytes) and plan its
+        decoding on the device.  Returns None (chunk absent), ("de", n_bytes, BloscPlan), or ("host",) after
+        decoding on the host into the same slot (frames the engine cannot take)."""
+        arr = self.array
+        got = arr.read_chunk_bytes(tile.index, into=slot_u8)
+        if got is None:
+            return None
+        sdt = arr.dtype.newbyteorder("=")
+        if isinstance(got, int):
+            plan = blosc_device_plan(slot_u8[:got], max_len)
+            if plan is not None and plan.nbytes == arr.chunk_nbytes and plan.typesize in (1, sdt.itemsize):
+                return ("de", got, plan)
+            got = bytes(slot_u8[:got])                                       # the decoder writes into the same slot
+        arr.decode_chunk(got, slot_u8[: arr.chunk_nbytes].view(sdt))
+        return ("host",)
+
     def load(self, tile: Tile, out: np.ndarray) -> bool:
         """Decode the tile's chunk into ``out`` (flat array of the STORED dtype, >= slot_elems).  False: the
         chunk is absent from the store (every value is the fill value)."""
@@ -628,9 +779,11 @@ def open_raster(path: str, var: Optional[str], xycoords=("longitude", "latitude"
 # ---------------------------------------------------------------------------------------------
 # writer (fixtures, examples, dataset_to_zarr)
 # ---------------------------------------------------------------------------------------------
-def _compress(buf: bytes, compressor: Optional[str], level: int) -> bytes:
+def _compress(buf: bytes, compressor: Optional[str], level: int, typesize: int = 1) -> bytes:
     if compressor is None:
         return buf
+    if compressor == "blosc":                                              # Blosc(cname="lz4", shuffle=SHUFFLE): zarr v2's default
+        return blosc_compress(buf, typesize, "lz4", 1)
     if compressor in ("zlib",):
         return zlib.compress(buf, level)
     if compressor == "gzip":
@@ -640,7 +793,7 @@ def _compress(buf: bytes, compressor: Optional[str], level: int) -> bytes:
         return _arrow("zstd").compress(buf, asbytes=True)
     if compressor == "lz4":
         return struct.pack("<I", len(buf)) + _arrow("lz4_raw").compress(buf, asbytes=True)
-    raise ValueError(f"compressor {compressor!r} not in [None, 'zlib', 'gzip', 'zstd', 'lz4']")
+    raise ValueError(f"compressor {compressor!r} not in [None, 'zlib', 'gzip', 'zstd', 'lz4', 'blosc']")
 
 
 def write_array(path: str, data: np.ndarray, chunks: Sequence[int], dims: Sequence[str], attrs: Optional[dict] = None,
@@ -664,6 +817,8 @@ def write_array(path: str, data: np.ndarray, chunks: Sequence[int], dims: Sequen
             comp = {"id": "lz4", "acceleration": 1}
         elif compressor == "zstd":
             comp = {"id": "zstd", "level": level}
+        elif compressor == "blosc":
+            comp = {"id": "blosc", "cname": "lz4", "clevel": 5, "shuffle": 1, "blocksize": 0}
         else:
             comp = None if compressor is None else {"id": compressor, "level": level}
         meta = {"zarr_format": 2, "shape": list(data.shape), "chunks": list(chunks), "dtype": data.dtype.str,
@@ -672,8 +827,8 @@ def write_array(path: str, data: np.ndarray, chunks: Sequence[int], dims: Sequen
         json.dump(dict(attrs, _ARRAY_DIMENSIONS=list(dims)), open(os.path.join(path, ".zattrs"), "w"))
         key = lambda idx: os.path.join(path, ".".join(map(str, idx)) if n else "0")          # noqa: E731
     elif zarr_format == 3:
-        if compressor not in (None, "gzip", "zstd"):
-            raise ValueError("zarr v3 stores written here use None, 'gzip' or 'zstd'")
+        if compressor not in (None, "gzip", "zstd", "blosc"):
+            raise ValueError("zarr v3 stores written here use None, 'gzip', 'zstd' or 'blosc'")
         inv = {"?": "bool", "i1": "int8", "i2": "int16", "i4": "int32", "i8": "int64", "u1": "uint8", "u2": "uint16",
                "u4": "uint32", "u8": "uint64", "f4": "float32", "f8": "float64"}
         codecs = []
@@ -684,6 +839,9 @@ def write_array(path: str, data: np.ndarray, chunks: Sequence[int], dims: Sequen
             codecs.append({"name": "zstd", "configuration": {"level": level, "checksum": False}})
         elif compressor == "gzip":
             codecs.append({"name": "gzip", "configuration": {"level": level}})
+        elif compressor == "blosc":
+            codecs.append({"name": "blosc", "configuration": {"cname": "lz4", "clevel": 5, "shuffle": "shuffle",
+                                                              "typesize": data.dtype.itemsize, "blocksize": 0}})
         meta = {"zarr_format": 3, "node_type": "array", "shape": list(data.shape), "data_type": inv[data.dtype.str[1:]],
                 "chunk_grid": {"name": "regular", "configuration": {"chunk_shape": list(chunks)}},
                 "chunk_key_encoding": {"name": "default", "configuration": {"separator": "/"}},
@@ -706,7 +864,7 @@ def write_array(path: str, data: np.ndarray, chunks: Sequence[int], dims: Sequen
         p = key(idx)
         os.makedirs(os.path.dirname(p), exist_ok=True)
         with open(p, "wb") as f:
-            f.write(_compress(raw, compressor, level))
+            f.write(_compress(raw, compressor, level, data.dtype.itemsize))
 
 
 def write_dataset(store: str, values: np.ndarray, time, latitude, longitude, var: str = "variable",

@@ -269,6 +269,32 @@ int agf_tile_place_run(const void *d_src, int32_t src_dtype, int64_t nt, int64_t
                        int64_t n_lon, int64_t t0, int64_t y0, int64_t x0, int32_t packed, double scale,
                        double offset, int32_t has_fill, double fill, uintptr_t stream);
 
+/* ---- compressed chunks: Blackwell decompression engine --------------------------------------------- */
+
+/* Bit mask of the algorithms the device's hardware decompression engine offers (1 deflate, 2 snappy,
+ * 4 lz4; 0: none / driver too old) and the largest number of bytes one operation may read or write. */
+int agf_decompress_caps(int32_t *algo_mask, int64_t *max_length);
+
+/* Inflate n independent raw-LZ4 streams with the decompression engine, stream-ordered:
+ *     d_dst[dst_off[i] .. + dst_len[i]) = lz4_block_decode(d_src[src_off[i] .. + src_len[i]))
+ * The offset / length arrays are HOST arrays; d_actual[n] (device, uint32) receives the bytes each
+ * operation produced, for the caller to compare with dst_len.  d_src / d_dst / d_actual must come from
+ * cudaMalloc (torch's default allocator qualifies).  This is what Blosc-compressed zarr chunks need: one
+ * stream per (block, byte plane); see aggfly_b200/zarrio.py.  AGF_E_UNSUPPORTED without an LZ4 engine. */
+int agf_decompress_lz4_run(const void *d_src, const int64_t *src_off, const int64_t *src_len, void *d_dst,
+                           const int64_t *dst_off, const int64_t *dst_len, int64_t n, uint32_t *d_actual,
+                           uintptr_t stream);
+
+/* d_dst[dst_off[i] .. + len[i]) = d_src[src_off[i] .. + len[i]) for n byte segments; d_table is a DEVICE
+ * array int64[3 * n] = src_off[n], dst_off[n], len[n].  For the streams Blosc stored uncompressed (the noisy
+ * low-mantissa byte planes of float data), which bypass the decompression engine. */
+int agf_copy_segments_run(const void *d_src, void *d_dst, const int64_t *d_table, int64_t n, uintptr_t stream);
+
+/* Undo Blosc's byte shuffle of a decoded chunk (blocks of `blocksize` bytes, the last one shorter):
+ * out[b * blocksize + i * typesize + j] = in[b * blocksize + j * n_b + i].  typesize 2, 4 or 8. */
+int agf_unshuffle_run(const void *d_src, void *d_dst, int64_t nbytes, int32_t typesize, int64_t blocksize,
+                      uintptr_t stream);
+
 /* ---- weights builder geometry (host only; replaces the GEOS work of calculate_weights) ---------- */
 
 /* For every region the fraction of each grid cell's rectangle that it covers -- what

@@ -204,3 +204,105 @@ def test_reference_converter_layout_end_to_end(tmp_path):
                                 aggregator_dict=spec)
     assert len(got) == len(want) > 0
     _exact(got[["tavg_1", "tavg_2"]].values, want[["tavg_1", "tavg_2"]].values)
+
+
+# ---- Blosc-LZ4 chunks inflated by the decompression engine -----------------------------------------------
+def _engine():
+    mask, max_len = stream.device_decompress_caps()
+    return bool(mask & 4) and max_len > 0, max_len
+
+
+@pytest.mark.parametrize("ts", [2, 4, 8])
+def test_unshuffle_and_segment_copy_match_numpy(ts):
+    import torch
+    rng = np.random.default_rng(ts)
+    L = _lib.lib()
+    s = torch.cuda.current_stream().cuda_stream
+    for nbytes, bs in [(10_007 * ts + 3, 512 * ts), (4096 * ts, 4096 * ts), (77, 64 * ts)]:
+        data = rng.integers(0, 256, nbytes, dtype=np.uint8)
+        want = np.concatenate([zarrio._unshuffle(data[b:b + bs], ts) for b in range(0, nbytes, bs)])
+        src, dst = torch.from_numpy(data).cuda(), torch.zeros(nbytes, dtype=torch.uint8, device="cuda")
+        _lib.check(L.agf_unshuffle_run(src.data_ptr(), dst.data_ptr(), nbytes, ts, bs, s))
+        assert np.array_equal(dst.cpu().numpy(), want)
+    assert L.agf_unshuffle_run(src.data_ptr(), dst.data_ptr(), 10, 3, 64, s) == -2
+    table = np.array([[3, 1000, 4097], [500, 0, 2000], [77, 333, 1]], np.int64).T.copy()       # src_off, dst_off, len
+    src = torch.from_numpy(rng.integers(0, 256, 6000, dtype=np.uint8)).cuda()
+    dst = torch.zeros(3000, dtype=torch.uint8, device="cuda")
+    _lib.check(L.agf_copy_segments_run(src.data_ptr(), dst.data_ptr(), torch.from_numpy(table).cuda().data_ptr(), 3, s))
+    want = np.zeros(3000, np.uint8)
+    h = src.cpu().numpy()
+    for a, d, m in table.T:
+        want[d:d + m] = h[a:a + m]
+    assert np.array_equal(dst.cpu().numpy(), want)
+
+
+def test_decompression_engine_inflates_blosc_frames():
+    """agf_decompress_lz4_run + agf_copy_segments_run + agf_unshuffle_run on a Blosc frame == the host decoder."""
+    import ctypes as C
+    import torch
+    have, max_len = _engine()
+    if not have:
+        pytest.skip("no LZ4 decompression engine on this device / driver")
+    rng = np.random.default_rng(3)
+    vals = (20 + np.cumsum(rng.normal(0, 0.05, 700_001))).astype(np.float32)               # noisy low mantissa bytes
+    data = vals.tobytes()
+    frame = zarrio.blosc_compress(data, 4, "lz4", 1, 64 << 10)
+    u8 = np.frombuffer(frame, np.uint8)
+    plan = zarrio.blosc_device_plan(u8, max_len)
+    assert plan is not None and plan.kind == "lz4" and len(plan.src_off) > 0 and plan.raw.shape[1] > 0
+    L = _lib.lib()
+    s = torch.cuda.current_stream().cuda_stream
+    d_frame = torch.from_numpy(u8.copy()).cuda()
+    infl = torch.zeros(len(data), dtype=torch.uint8, device="cuda")
+    plain = torch.zeros(len(data), dtype=torch.uint8, device="cuda")
+    act = torch.zeros(len(plan.src_off), dtype=torch.int32, device="cuda")
+    p64 = C.POINTER(C.c_int64)
+    _lib.check(L.agf_decompress_lz4_run(d_frame.data_ptr(), plan.src_off.ctypes.data_as(p64), plan.src_len.ctypes.data_as(p64),
+                                        infl.data_ptr(), plan.dst_off.ctypes.data_as(p64), plan.dst_len.ctypes.data_as(p64),
+                                        len(plan.src_off), act.data_ptr(), s))
+    _lib.check(L.agf_copy_segments_run(d_frame.data_ptr(), infl.data_ptr(), torch.from_numpy(plan.raw).cuda().data_ptr(),
+                                       plan.raw.shape[1], s))
+    _lib.check(L.agf_unshuffle_run(infl.data_ptr(), plain.data_ptr(), plan.nbytes, plan.typesize, plan.blocksize, s))
+    torch.cuda.synchronize()
+    assert np.array_equal(act.cpu().numpy(), plan.dst_len.astype(np.int32))
+    assert plain.cpu().numpy().tobytes() == data
+
+
+@pytest.mark.parametrize("device_decompress", [True, False])
+@pytest.mark.parametrize("layout", ["time_major_daily_chunks", "time_contiguous_tiles", "lon_time_lat_lz4"])
+def test_blosc_store_matches_in_memory_result(tmp_path, layout, device_decompress):
+    import torch
+    lay = LAYOUTS[layout]
+    arr, t, lat, lon = _raster("float32", True, T=24 * 40 + 5, seed=23)
+    rng = np.random.default_rng(6)
+    wdf, shp = _weights_case(lat, lon, rng)
+    store = zarrio.write_dataset(str(tmp_path / "b.zarr"), arr, t, lat, lon, var="t2m", dims=lay["dims"], chunks=lay["chunks"],
+                                 zarr_format=lay["fmt"], compressor="blosc", order=lay["order"])
+    name = "c3_bins_and_poly"
+
+    def run(ds):
+        w = af.weights_from_objects(ds, af.GeoRegions(shp, "geoid"), zero_weight="nan")
+        w.weights = wdf
+        return af.aggregate_dataset(weights=w, dataset=ds, aggregator_dict=SPECS[name])
+
+    old = dict(stream.OPTIONS)
+    try:
+        stream.OPTIONS.update(staging_slots=3, staging_threads=2, device_decompress=device_decompress)
+        resident = run(af.Dataset.from_arrays(torch.from_numpy(arr).cuda(), t, lat, lon, True))
+        ds = af.dataset_from_path(store, var="t2m")
+        assert ds.values.array.blosc_only
+        got = run(ds)
+        st = stream.LAST_STATS
+        have, _ = _engine()
+        assert st["device_decompress"] == (device_decompress and have)
+        if st["device_decompress"]:
+            assert st["inflated_on_device"] == st["chunks"] and st["engine_ops"] > 0 and st["h2d_bytes"] < arr.nbytes
+        else:
+            assert st["inflated_on_device"] == 0
+        dev_raster = engine.to_device(ds.values).cpu().numpy()
+    finally:
+        stream.OPTIONS.update(old)
+    _exact(dev_raster, arr)
+    vals = [c for c in resident.columns if c not in ("geoid", "time")]
+    assert len(got) == len(resident) > 0
+    _exact(got[vals].values, resident[vals].values)

@@ -128,6 +128,38 @@ def test_blosc_frames(cname, shuffle, split):
     assert zarrio.blosc_decompress(memcpyed).tobytes() == data
 
 
+@pytest.mark.parametrize("n,ts,bs,shuffle,split", [(1_000_003, 4, 65536, 1, True), (300_000, 4, 0, 1, True), (5000, 2, 256, 1, True),
+                                                   (40000, 8, 4096, 0, False), (100, 4, 64, 1, True), (70000, 4, 8192, 1, False)])
+def test_blosc_device_plan_describes_the_frame(n, ts, bs, shuffle, split):
+    """``blosc_device_plan`` is what the GPU path executes (LZ4 streams -> decompression engine, raw streams ->
+    segment copies, then the byte un-shuffle): emulate those three steps with NumPy and compare with the data.
+    Smooth high bytes + noisy low bytes, so that some byte planes are stored uncompressed like real float data."""
+    rng = np.random.default_rng(n)
+    smooth = (np.cumsum(rng.integers(-3, 4, n // 4 + 1)) * 1024 + rng.integers(0, 256, n // 4 + 1)).astype("<i4")
+    data = smooth.tobytes()[:n]
+    frame = zarrio.blosc_compress(data, ts, "lz4", shuffle, bs, split)
+    assert zarrio.blosc_decompress(frame).tobytes() == data
+    assert frame == _blosc_frame(data, ts, bs or (256 << 10), "lz4", shuffle, split) or bs == 0 or n < bs
+    u8 = np.frombuffer(frame, np.uint8)
+    plan = zarrio.blosc_device_plan(u8, 4 << 20)
+    assert plan is not None and plan.kind == "lz4" and plan.nbytes == n and plan.typesize == ts
+    out = np.zeros(n, np.uint8)
+    for a, l, d, m in zip(plan.src_off, plan.src_len, plan.dst_off, plan.dst_len):
+        out[d:d + m] = np.frombuffer(pa.Codec("lz4_raw").decompress(u8[a:a + l].tobytes(), decompressed_size=int(m)), np.uint8)
+    for a, d, m in plan.raw.T:
+        out[d:d + m] = u8[a:a + m]
+    if ts == 4 and n > 1000 and split:
+        assert plan.raw.shape[1] > 0                                     # the noisy byte plane
+    if plan.shuffled:
+        out = np.concatenate([zarrio._unshuffle(out[b:b + plan.blocksize], ts) for b in range(0, n, plan.blocksize)])
+    assert out.tobytes() == data
+    assert zarrio.blosc_device_plan(u8, 16) is None                      # streams above the engine's limit: host decode
+    assert zarrio.blosc_device_plan(np.frombuffer(zarrio.blosc_compress(data, ts, "zstd", shuffle, bs, split), np.uint8), 4 << 20) is None
+    mem = struct.pack("<4B3I", 2, 1, 0x2, ts, n, n, n + 16) + data
+    assert zarrio.blosc_device_plan(np.frombuffer(mem, np.uint8), 4 << 20).kind == "memcpy"
+    assert zarrio.blosc_device_plan(u8[: u8.size // 2], 4 << 20) is None   # truncated
+
+
 def test_v2_blosc_and_filters(tmp_path):
     vals = np.arange(6 * 5, dtype="<i2").reshape(6, 5) * 3
     root = str(tmp_path / "b")
@@ -159,7 +191,8 @@ def _raster(T=50, Y=7, X=9, seed=0):
     return vals, pd.date_range("2001-01-01", periods=T, freq="h"), np.linspace(40, 37, Y), np.linspace(230, 234, X)
 
 
-@pytest.mark.parametrize("fmt,comp", [(2, None), (2, "zlib"), (2, "zstd"), (2, "lz4"), (2, "gzip"), (3, None), (3, "zstd"), (3, "gzip")])
+@pytest.mark.parametrize("fmt,comp", [(2, None), (2, "zlib"), (2, "zstd"), (2, "lz4"), (2, "gzip"), (2, "blosc"), (3, None),
+                                      (3, "zstd"), (3, "gzip"), (3, "blosc")])
 def test_dataset_roundtrip_all_layouts(tmp_path, fmt, comp):
     vals, t, lat, lon = _raster()
     T, Y, X = vals.shape

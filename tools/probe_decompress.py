@@ -19,6 +19,8 @@ def main():
     ap.add_argument("--out", default=None)
     ap.add_argument("--mb", type=int, default=64, help="decoded bytes per operation batch")
     ap.add_argument("--block-kb", type=int, default=256, help="decoded bytes per independent block")
+    ap.add_argument("--cases", default="lz4", help="comma list of lz4, lz4_src_unaligned, lz4_dst_unaligned, snappy, deflate; "
+                    "a failing operation poisons the CUDA context, so run doubtful cases in separate processes")
     a = ap.parse_args()
     out = {}
     try:
@@ -64,13 +66,20 @@ def main():
     codecs = {"lz4": (4, lambda b: pa.Codec("lz4_raw").compress(b, asbytes=True)),
               "snappy": (2, lambda b: pa.Codec("snappy").compress(b, asbytes=True)),
               "deflate": (1, deflate_raw)}
-    for name, (algo, enc) in codecs.items():
+    for case in a.cases.split(","):
+        name = case.split("_")[0]
+        algo, enc = codecs[name]
         rec = {}
-        out[name] = rec
+        out[case] = rec
+        src_shift = 1 if case.endswith("src_unaligned") else 0          # every stream starts at an odd address
+        dst_shift = 1 if case.endswith("dst_unaligned") else 0
+        if dst_shift:
+            block -= 1                                                   # odd block size -> odd destination offsets
+            shuf = shuf[: n_blocks * block]
         try:
             parts = [enc(shuf[i * block:(i + 1) * block]) for i in range(n_blocks)]
-            offs = np.concatenate([[0], np.cumsum([(len(p) + 15) // 16 * 16 for p in parts])]).astype(np.int64)
-            comp = np.zeros(int(offs[-1]), np.uint8)
+            offs = np.concatenate([[0], np.cumsum([(len(p) + 15) // 16 * 16 + 16 for p in parts])]).astype(np.int64) + src_shift
+            comp = np.zeros(int(offs[-1]) + 16, np.uint8)
             for i, p in enumerate(parts):
                 comp[offs[i]: offs[i] + len(p)] = np.frombuffer(p, np.uint8)
             rec.update(blocks=n_blocks, block_bytes=block, decoded_bytes=len(shuf), compressed_bytes=int(sum(len(p) for p in parts)))
