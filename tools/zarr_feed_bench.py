@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--out", default=None)
+    ap.add_argument("--only", default=None, help="comma list of substrings of layout names")
     a = ap.parse_args()
     import torch
     import aggfly_b200 as af
@@ -58,7 +59,12 @@ def main():
         "time_major_24h_zstd": dict(dims=("time", "latitude", "longitude"), chunks={"time": 24}, zarr_format=3, compressor="zstd"),
         "time_major_24h_raw": dict(dims=("time", "latitude", "longitude"), chunks={"time": 24}, zarr_format=3, compressor=None),
         "reference_time_contiguous_zstd": dict(dims=("latitude", "longitude", "time"), chunks=tc, zarr_format=3, compressor="zstd"),
+        "time_major_24h_blosc_lz4": dict(dims=("time", "latitude", "longitude"), chunks={"time": 24}, zarr_format=2, compressor="blosc"),
+        "reference_time_contiguous_blosc_lz4": dict(dims=("latitude", "longitude", "time"), chunks=tc, zarr_format=2,
+                                                    compressor="blosc"),
     }
+    if a.only:
+        layouts = {k: v for k, v in layouts.items() if any(w in k for w in a.only.split(","))}
     out = {"grid": [Y, X], "hours": T, "raw_gb": arr.nbytes / 1e9, "threads": stream.OPTIONS["staging_threads"],
            "host_cpus": os.cpu_count(), "layouts": {}}
 
@@ -83,13 +89,17 @@ def main():
             wsec = time.perf_counter() - t0
             size = sum(os.path.getsize(os.path.join(d, f)) for d, _, fs in os.walk(store) for f in fs)
             ds = af.dataset_from_path(store, var="t2m")
-            got, ms = timed(ds)
-            same = bool(np.array_equal(got[["tavg_1", "tavg_2"]].values, want[["tavg_1", "tavg_2"]].values, equal_nan=True))
-            st = {k: v for k, v in stream.LAST_STATS.items() if k != "copy_events"}
-            best = min(ms)
-            out["layouts"][name] = {"chunks": list(ds.values.array.chunks), "store_gb": size / 1e9, "write_s": wsec, "ms": ms,
-                                    "raw_gbs": arr.nbytes / 1e6 / best, "cell_hours_per_s": arr.size / (best / 1e3),
-                                    "bitwise_equal_to_in_memory": same, "feed": st}
+            for dd in ([True, False] if lay["compressor"] == "blosc" else [True]):
+                stream.OPTIONS["device_decompress"] = dd
+                got, ms = timed(ds)
+                same = bool(np.array_equal(got[["tavg_1", "tavg_2"]].values, want[["tavg_1", "tavg_2"]].values, equal_nan=True))
+                st = {k: v for k, v in stream.LAST_STATS.items() if k != "copy_events"}
+                best = min(ms)
+                key = name if dd else name + "_host_decode"
+                out["layouts"][key] = {"chunks": list(ds.values.array.chunks), "store_gb": size / 1e9, "write_s": wsec, "ms": ms,
+                                       "raw_gbs": arr.nbytes / 1e6 / best, "cell_hours_per_s": arr.size / (best / 1e3),
+                                       "bitwise_equal_to_in_memory": same, "feed": st}
+            stream.OPTIONS["device_decompress"] = True
             shutil.rmtree(store)
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
