@@ -798,10 +798,13 @@ def _compress(buf: bytes, compressor: Optional[str], level: int, typesize: int =
 
 def write_array(path: str, data: np.ndarray, chunks: Sequence[int], dims: Sequence[str], attrs: Optional[dict] = None,
                 zarr_format: int = 2, compressor: Optional[str] = "zlib", level: int = 1, order: str = "C",
-                fill_value=None, skip_fill_chunks: bool = False) -> None:
+                fill_value=None, skip_fill_chunks: bool = False, threads: int = 1) -> None:
     """One array of a directory store (v2 or v3).  ``order="F"`` stores chunks with the first axis fastest
-    (v2 ``order``; a v3 ``transpose`` codec)."""
-    data = np.asarray(data)
+    (v2 ``order``; a v3 ``transpose`` codec).  ``data``: an array, or any object with ``shape``, ``dtype`` and
+    ``__getitem__(tuple of slices) -> ndarray`` whose ``lazy_blocks`` attribute is true (blocks are then fetched
+    chunk by chunk, e.g. from a device tensor); ``threads`` > 1 compresses / writes chunks concurrently."""
+    if not getattr(data, "lazy_blocks", False):
+        data = np.asarray(data)
     chunks = tuple(int(min(max(1, c), max(1, s))) if c > 0 else max(1, int(s)) for c, s in zip(chunks, data.shape))
     os.makedirs(path, exist_ok=True)
     attrs = dict(attrs or {})
@@ -848,23 +851,36 @@ def write_array(path: str, data: np.ndarray, chunks: Sequence[int], dims: Sequen
                 "fill_value": fv_json, "codecs": codecs, "attributes": attrs, "dimension_names": list(dims)}
         json.dump(meta, open(os.path.join(path, "zarr.json"), "w"))
         key = lambda idx: os.path.join(path, "c", *map(str, idx))                                 # noqa: E731
-        data = data.astype(data.dtype.newbyteorder("<"), copy=False)
+        if isinstance(data, np.ndarray):
+            data = data.astype(data.dtype.newbyteorder("<"), copy=False)
     else:
         raise ValueError("zarr_format must be 2 or 3")
     grid = [-(-s // c) for s, c in zip(data.shape, chunks)]
-    for idx in np.ndindex(*grid):
-        block = np.full(chunks, fill_value, data.dtype)
+
+    def one(idx):
         sl = tuple(slice(i * c, min((i + 1) * c, s)) for i, c, s in zip(idx, chunks, data.shape))
-        part = data[sl]
-        block[tuple(slice(0, p) for p in part.shape)] = part
+        part = np.asarray(data[sl])
+        if part.shape == tuple(chunks):
+            block = part
+        else:                                                            # edge chunks are stored full-size
+            block = np.full(chunks, fill_value, data.dtype)
+            block[tuple(slice(0, p) for p in part.shape)] = part
         if skip_fill_chunks and (np.isnan(block).all() if data.dtype.kind == "f" and np.isnan(fill_value)
                                  else (block == fill_value).all()):
-            continue
+            return
         raw = block.tobytes(order="F" if order == "F" else "C")
         p = key(idx)
         os.makedirs(os.path.dirname(p), exist_ok=True)
         with open(p, "wb") as f:
             f.write(_compress(raw, compressor, level, data.dtype.itemsize))
+
+    if threads > 1:
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=int(threads)) as ex:
+            list(ex.map(one, np.ndindex(*grid)))
+    else:
+        for idx in np.ndindex(*grid):
+            one(idx)
 
 
 def write_dataset(store: str, values: np.ndarray, time, latitude, longitude, var: str = "variable",

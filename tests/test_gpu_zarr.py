@@ -225,11 +225,11 @@ def test_unshuffle_and_segment_copy_match_numpy(ts):
         _lib.check(L.agf_unshuffle_run(src.data_ptr(), dst.data_ptr(), nbytes, ts, bs, s))
         assert np.array_equal(dst.cpu().numpy(), want)
     assert L.agf_unshuffle_run(src.data_ptr(), dst.data_ptr(), 10, 3, 64, s) == -2
-    table = np.array([[3, 1000, 4097], [500, 0, 2000], [77, 333, 1]], np.int64).T.copy()       # src_off, dst_off, len
+    table = np.array([[3, 500, 77], [2100, 0, 5500], [3000, 2000, 1]], np.int64)                # src_off, dst_off, len
     src = torch.from_numpy(rng.integers(0, 256, 6000, dtype=np.uint8)).cuda()
-    dst = torch.zeros(3000, dtype=torch.uint8, device="cuda")
+    dst = torch.zeros(6000, dtype=torch.uint8, device="cuda")
     _lib.check(L.agf_copy_segments_run(src.data_ptr(), dst.data_ptr(), torch.from_numpy(table).cuda().data_ptr(), 3, s))
-    want = np.zeros(3000, np.uint8)
+    want = np.zeros(6000, np.uint8)
     h = src.cpu().numpy()
     for a, d, m in table.T:
         want[d:d + m] = h[a:a + m]
