@@ -125,8 +125,10 @@ def _temporal_device(dataset: Dataset, aggregator_dict, target_stripes: int = 0)
         return names, res, raster
     import torch
     n_cells = len(dataset.latitude) * len(dataset.longitude)
-    if not (target_stripes or _engine.OPTIONS["target_stripes"]):
-        # stripes of about four copy chunks: the kernels of a stripe start when its rows have landed
+    whole_time_chunks = getattr(dataset.values, "single_time_chunk", False)
+    if not (target_stripes or _engine.OPTIONS["target_stripes"]) and not whole_time_chunks:
+        # stripes of about four copy chunks: the kernels of a stripe start when its rows have landed.  (A store
+        # whose chunks span the whole time axis delivers every row at once: planned like a resident raster.)
         nbytes = int(np.prod(dataset.shape)) * dataset.dtype.itemsize
         target_stripes = -int(min(64, nbytes // (4 * _stream.OPTIONS["chunk_bytes"])))
     import time

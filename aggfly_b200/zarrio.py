@@ -607,6 +607,13 @@ class ChunkedRaster:
         return self.shape[0]
 
     @property
+    def single_time_chunk(self) -> bool:
+        """Every tile spans the view's whole time range (time-contiguous stores): no row is complete before the
+        last tile has landed, so there is nothing to gain from time stripes."""
+        (lo, hi), c = self.window[0], self.array.chunks[self.axes[0]]
+        return hi > lo and lo // c == (hi - 1) // c
+
+    @property
     def nbytes_stored(self) -> int:
         return int(np.prod(self.shape)) * self.array.dtype.itemsize
 

@@ -318,3 +318,40 @@ def test_dataset_to_zarr_reopens_time_contiguous(tmp_path):
     with pytest.raises(FileExistsError):
         af.dataset_to_zarr(ds, str(tmp_path / "tc.zarr"))
     assert af.dataset_to_zarr(ds, str(tmp_path / "tc.zarr"), overwrite=True, return_dataset=False) is None
+
+
+def test_writer_takes_lazy_block_sources_and_threads(tmp_path):
+    """write_array pulls blocks chunk by chunk from any object with shape / dtype / __getitem__ (the global
+    bench hands it a device tensor) and may compress chunks on several threads."""
+    vals, t, lat, lon = _raster(T=40, Y=9, X=11, seed=3)
+
+    class Blocks:
+        lazy_blocks = True
+        shape, dtype, ndim = (9, 11, 40), np.dtype(np.float32), 3
+        asked = []
+
+        def __getitem__(self, sl):
+            self.asked.append(sl)
+            return np.ascontiguousarray(np.transpose(vals, (1, 2, 0))[sl])
+
+    store = zarrio.write_dataset(str(tmp_path / "l.zarr"), vals[:1], t[:1], lat, lon, var="t2m", compressor=None)
+    import shutil
+    shutil.rmtree(store + "/t2m")
+    shutil.rmtree(store + "/time")
+    zarrio.write_array(store + "/time", np.arange(40, dtype=np.int64), [-1], ["time"],
+                       {"units": "hours since 2001-01-01 00:00:00", "calendar": "proleptic_gregorian"}, compressor=None)
+    src = Blocks()
+    zarrio.write_array(store + "/t2m", src, [4, 5, -1], ["latitude", "longitude", "time"], None, zarr_format=2,
+                       compressor="blosc", threads=3)
+    assert len(src.asked) == 9 and json.load(open(store + "/time/.zarray"))["fill_value"] is None
+    ds = af.dataset_from_path(store, var="t2m")
+    assert ds.values.array.blosc_only and (ds.time == t).all()
+    assert np.array_equal(np.asarray(ds.values), vals, equal_nan=True)
+    tile = ds.values.tiles()[-1]                                      # edge chunk, stored full-size
+    slot = np.zeros(ds.values.slot_elems * 4 + 70000, np.uint8)
+    kind, n, plan = ds.values.load_stored(tile, slot, 4 << 20)
+    assert kind == "de" and n == os.path.getsize(ds.values.array.chunk_path(tile.index)) and plan.nbytes == 4 * 5 * 40 * 4
+    assert ds.values.load_stored(tile, slot, 8) == ("host",)          # engine limit too small: decoded on the host instead
+    blk = np.lib.stride_tricks.as_strided(slot[: plan.nbytes].view(np.float32)[tile.offset:], tile.extent,
+                                          (tile.st * 4, tile.sy * 4, tile.sx * 4))
+    assert np.array_equal(blk, vals[tile.t0:tile.t1, tile.y0:tile.y1, tile.x0:tile.x1], equal_nan=True)
