@@ -163,3 +163,32 @@ def test_run_matches_the_hand_written_api(tmp_path, fmt):
     vals = [c for c in want.columns if c not in ("GEOID", "time")]
     # clipping (on in the CLI run, off in the hand-written one) never changes results (test_cli.py:461-476)
     assert np.allclose(got[vals].values.astype(float), want[vals].values, rtol=1e-12)
+
+
+@pytest.mark.gpu
+def test_run_from_zarr_stores_matches_the_npz_run(tmp_path):
+    """The reference's main workflow: ``aggfly run`` over one zarr store per year (one in the converter's
+    time-contiguous Blosc layout, one time-major zstd v3), clipped to the regions -- same panel as from the arrays."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from aggfly_b200 import zarrio
+    path, raw = _project(tmp_path)
+    r = CliRunner().invoke(cli.cli, ["run", path])
+    assert r.exit_code == 0, r.output
+    want = pd.read_parquet(tmp_path / "out.parquet")
+    layouts = {2001: dict(dims=("latitude", "longitude", "time"), chunks={"latitude": 3, "longitude": 4}, zarr_format=2, compressor="blosc"),
+               2002: dict(dims=("time", "latitude", "longitude"), chunks={"time": 24 * 7}, zarr_format=3, compressor="zstd")}
+    for y, lay in layouts.items():
+        z = np.load(tmp_path / f"t2m_{y}.npz")
+        zarrio.write_dataset(str(tmp_path / f"t2m_{y}.zarr"), z["t2m"], pd.DatetimeIndex(z["time"]), z["latitude"], z["longitude"],
+                             var="t2m", **lay)
+    raw["dataset"]["path"] = str(tmp_path / "t2m_{year}.zarr")
+    raw["output"]["path"] = str(tmp_path / "out_zarr.parquet")
+    (tmp_path / "config_zarr.yaml").write_text(yaml.safe_dump(raw))
+    r = CliRunner().invoke(cli.cli, ["run", str(tmp_path / "config_zarr.yaml")])
+    assert r.exit_code == 0, r.output
+    got = pd.read_parquet(tmp_path / "out_zarr.parquet")
+    assert list(got.columns) == list(want.columns) and list(got.GEOID) == list(want.GEOID) and list(got.time) == list(want.time)
+    vals = [c for c in want.columns if c not in ("GEOID", "time")]
+    assert np.allclose(got[vals].values.astype(float), want[vals].values.astype(float), rtol=1e-12, atol=0, equal_nan=True)

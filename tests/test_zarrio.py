@@ -233,6 +233,21 @@ def test_time_sel_and_clip_stay_lazy(tmp_path):
     iy = [int(np.argmin(np.abs(lat - v))) for v in cl.latitude]
     ix = [int(np.argmin(np.abs(lon - v))) for v in cl.longitude]
     assert np.array_equal(np.asarray(cl.values), vals[24:][:, iy][:, :, ix], equal_nan=True)
+    for layout in (dict(dims=("latitude", "longitude", "time"), chunks={"latitude": 2, "longitude": 4}),
+                   dict(dims=("time", "latitude", "longitude"), chunks={"time": 24, "latitude": 3, "longitude": 5})):
+        store = zarrio.write_dataset(str(tmp_path / "w.zarr"), vals, t, lat, lon, var="t2m", compressor="blosc", **layout)
+        win = clip_to_extent(af.dataset_from_path(store, var="t2m", time_sel="2002"), -129.0, -128.0, 38.0, 39.0).values
+        want = vals[24:][:, iy][:, :, ix]
+        cover = np.zeros(want.shape, int)
+        buf = np.empty(win.slot_elems, np.float32)
+        for tl in win.tiles():                                        # the windowed tiles the device feed uses
+            assert win.load(tl, buf)
+            blk = np.lib.stride_tricks.as_strided(buf[tl.offset:], tl.extent, (tl.st * 4, tl.sy * 4, tl.sx * 4))
+            assert np.array_equal(blk, want[tl.t0:tl.t1, tl.y0:tl.y1, tl.x0:tl.x1], equal_nan=True)
+            cover[tl.t0:tl.t1, tl.y0:tl.y1, tl.x0:tl.x1] += 1
+        assert (cover == 1).all() and win.single_time_chunk == (layout["dims"][0] == "latitude")
+        import shutil
+        shutil.rmtree(store)
 
 
 def test_cf_packing_fill_and_missing_chunks(tmp_path):
