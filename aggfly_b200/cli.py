@@ -224,6 +224,130 @@ def run(config, output, engine, years, project_dir, backend, n_workers, verbose)
         click.echo(f"Wrote {len(df)} rows to {cfg.output_path} ({cfg.output_format}).")
 
 
+# ---------------------------------------------------------------------------------------------
+# info: what a config author needs to know about a raster (aggfly/cli/info.py), metadata only
+# ---------------------------------------------------------------------------------------------
+_COORD_ALIASES = {"lon": ("longitude", "lon", "x", "nav_lon"), "lat": ("latitude", "lat", "y", "nav_lat"),
+                  "time": ("time", "valid_time", "t")}
+
+
+def _alias(names, kind):
+    lowered = {str(n).lower(): n for n in names}
+    return next((lowered[c] for c in _COORD_ALIASES[kind] if c in lowered), None)
+
+
+def describe_raster(path: str) -> dict:
+    """Variables (dims, shape, chunks, units) and coordinate facts of a raster file, reading coordinate
+    arrays only: zarr directory stores, .npz, NetCDF-3."""
+    import numpy as np
+    from . import zarrio
+    out = {"variables": {}, "coords": {}}
+    if zarrio.looks_like_zarr(path):
+        g = zarrio.ZarrGroup(path)
+        arrays = {n: g[n] for n in g.names()}
+        dims_all = {d for a in arrays.values() for d in (a.dims or ())}
+        for n, a in arrays.items():
+            if n in dims_all and a.ndim == 1:
+                out["coords"][n] = a
+            else:
+                out["variables"][n] = {"dims": a.dims or tuple(f"dim_{i}" for i in range(a.ndim)), "shape": a.shape,
+                                       "chunks": a.chunks, "units": a.attrs.get("units")}
+        tname = _alias(out["coords"], "time")
+        if tname is not None:
+            t = zarrio.decode_time(out["coords"][tname])
+            out["time"] = (tname, str(out["coords"][tname].attrs.get("calendar", "standard")).lower(), t)
+        out["coords"] = {n: (None if n == tname else np.asarray(a.read(), dtype=float)) for n, a in out["coords"].items()}
+        return out
+    ext = os.path.splitext(path)[1].lower()
+    if ext == ".npz":
+        z = np.load(path, allow_pickle=False)
+        one_d = {n: z[n] for n in z.files if z[n].ndim == 1}
+        for n in z.files:
+            if z[n].ndim > 1:
+                out["variables"][n] = {"dims": ("time", "latitude", "longitude")[-z[n].ndim:], "shape": z[n].shape, "chunks": None,
+                                       "units": None}
+        tname = _alias(one_d, "time")
+        if tname is not None:
+            tv = one_d.pop(tname)
+            t = pd.DatetimeIndex(tv.astype("datetime64[ns]") if tv.dtype.kind == "M" else pd.to_datetime(tv.astype(str)))
+            out["time"] = (tname, "standard", t)
+            out["coords"][tname] = None
+        out["coords"].update({n: np.asarray(v, dtype=float) for n, v in one_d.items()})
+        return out
+    if ext in (".nc", ".nc3", ".cdf") and _io._is_netcdf3(path):
+        from scipy.io import netcdf_file
+        with netcdf_file(path, "r", mmap=False, maskandscale=False) as f:
+            dec = lambda v: v.decode() if isinstance(v, bytes) else v                    # noqa: E731
+            for n, v in f.variables.items():
+                if len(v.dimensions) == 1 and v.dimensions[0] == n:
+                    out["coords"][n] = np.array(v.data, dtype=float)
+                else:
+                    out["variables"][n] = {"dims": tuple(v.dimensions), "shape": tuple(v.shape), "chunks": None,
+                                           "units": dec(getattr(v, "units", None))}
+            tname = _alias(out["coords"], "time")
+            if tname is not None:
+                tv = f.variables[tname]
+                cal = str(dec(getattr(tv, "calendar", "standard"))).lower()
+                t = _io._cf_time(out["coords"][tname], dec(tv.units), cal) if cal in ("standard", "gregorian", "proleptic_gregorian") else None
+                out["time"] = (tname, cal, t)
+                out["coords"][tname] = None
+        return out
+    raise click.ClickException(f"Could not open {path!r}: natively readable are zarr directory stores, .npz and NetCDF-3 files")
+
+
+@cli.command()
+@click.argument("path", type=str)
+@click.option("--var", default=None, help="Report only this data variable.")
+@click.option("--storage-options", default=None, help="JSON dict for a remote storage backend (validated; local paths only here).")
+def info(path, var, storage_options):
+    """Inspect a raster dataset (dims, calendar, lon convention, time span): the values a config needs
+    for ``xycoords``, ``timecoord``, ``lon_is_360`` and ``preprocess``."""
+    import json
+    import numpy as np
+    from .timeaxis import CalendarIndex
+    if storage_options is not None:
+        try:
+            json.loads(storage_options)
+        except json.JSONDecodeError as e:
+            raise click.ClickException(f"--storage-options is not valid JSON: {e}")
+    try:
+        d = describe_raster(path)
+    except click.ClickException:
+        raise
+    except Exception as e:
+        raise click.ClickException(f"Could not open {path!r}: {e}")
+    names = list(d["variables"])
+    if var is not None and var not in names:
+        raise click.ClickException(f"Variable {var!r} not found. Available: {', '.join(names) or '(none)'}")
+    click.echo(f"Dataset: {path}")
+    click.echo(f"  data variables : {', '.join(names) or '(none)'}")
+    for name in ([var] if var else names):
+        v = d["variables"][name]
+        click.echo(f"  {name}:")
+        click.echo("    dims   : " + ", ".join(f"{dn}={n}" for dn, n in zip(v["dims"], v["shape"])))
+        if v["chunks"] is not None:
+            click.echo("    chunks : " + ", ".join(f"{dn}={c}" for dn, c in zip(v["dims"], v["chunks"])))
+        if v["units"]:
+            click.echo(f"    units  : {v['units']}")
+    lon_name, lat_name = _alias(d["coords"], "lon"), _alias(d["coords"], "lat")
+    click.echo("  config hints:")
+    if lon_name and lat_name:
+        click.echo(f"    xycoords   : [{lon_name}, {lat_name}]")
+    if lon_name:
+        lo, hi = float(np.nanmin(d["coords"][lon_name])), float(np.nanmax(d["coords"][lon_name]))
+        click.echo(f"    lon range  : {lo:.4g} .. {hi:.4g}  \u2192 lon_is_360: {str(hi > 180.0).lower()}")
+    if "time" in d:
+        tname, calendar, t = d["time"]
+        nonstd = isinstance(t, CalendarIndex) or calendar not in ("standard", "gregorian", "proleptic_gregorian")
+        click.echo(f"    timecoord  : {tname}")
+        click.echo(f"    calendar   : {calendar}{'  (cftime / non-standard)' if nonstd else ''}")
+        if t is not None:
+            click.echo(f"    time steps : {len(t)}")
+            if len(t):
+                first, last = (t.to_objects()[[0, -1]] if isinstance(t, CalendarIndex) else (t[0], t[-1]))
+                click.echo(f"    time span  : {first} .. {last}")
+
+
 def main(argv=None):
     cli.main(args=argv, prog_name="aggfly")
 

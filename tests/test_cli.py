@@ -192,3 +192,43 @@ def test_run_from_zarr_stores_matches_the_npz_run(tmp_path):
     assert list(got.columns) == list(want.columns) and list(got.GEOID) == list(want.GEOID) and list(got.time) == list(want.time)
     vals = [c for c in want.columns if c not in ("GEOID", "time")]
     assert np.allclose(got[vals].values.astype(float), want[vals].values.astype(float), rtol=1e-12, atol=0, equal_nan=True)
+
+
+# ---- `aggfly info` (reference: aggfly/cli/info.py, tests aggfly/tests/test_cli.py:77-115) -------------------------------
+def _info_store(tmp_path, name, calendar="standard", lon_360=True, var="t2m", units="K", fmt=3):
+    from aggfly_b200 import zarrio
+    lon = (np.arange(0.0, 360.0, 90.0) if lon_360 else np.arange(-180.0, 180.0, 90.0))
+    lat = np.array([10.0, 0.0, -10.0])
+    t = pd.date_range("2001-01-01", periods=48, freq="h") if calendar == "standard" else af.CalendarIndex.range(calendar, 2001, 48, "D")
+    return zarrio.write_dataset(str(tmp_path / name), np.zeros((48, 3, 4), np.float32), t, lat, lon, var=var, chunks={"time": 24},
+                                zarr_format=fmt, compressor="zstd", attrs={"units": units} if units else None)
+
+
+def test_info_datetime64_era5_like(tmp_path):
+    r = CliRunner().invoke(cli.cli, ["info", _info_store(tmp_path, "era5.zarr")])
+    assert r.exit_code == 0, r.output
+    for needle in ("data variables : t2m", "dims   : time=48, latitude=3, longitude=4", "chunks : time=24, latitude=3, longitude=4",
+                   "xycoords   : [longitude, latitude]", "lon_is_360: true", "timecoord  : time", "units  : K", "time steps : 48",
+                   "time span  : 2001-01-01 00:00:00 .. 2001-01-02 23:00:00"):
+        assert needle in r.output, needle
+    assert "cftime" not in r.output                                    # a standard calendar is not flagged
+
+
+def test_info_360day_cmip6_like_and_errors(tmp_path):
+    path = _info_store(tmp_path, "cmip6.zarr", calendar="360_day", lon_360=False, var="tas", units="", fmt=2)
+    r = CliRunner().invoke(cli.cli, ["info", path, "--var", "tas"])
+    assert r.exit_code == 0, r.output
+    assert "calendar   : 360_day" in r.output and "cftime / non-standard" in r.output and "lon_is_360: false" in r.output
+    r = CliRunner().invoke(cli.cli, ["info", path, "--var", "nope"])
+    assert r.exit_code != 0 and "not found" in r.output
+    r = CliRunner().invoke(cli.cli, ["info", path, "--storage-options", "{not json}"])
+    assert r.exit_code != 0 and "not valid JSON" in r.output
+    r = CliRunner().invoke(cli.cli, ["info", str(tmp_path / "missing.tif")])
+    assert r.exit_code != 0 and "Could not open" in r.output
+
+
+def test_info_npz(tmp_path):
+    path, _ = _project(tmp_path, years=(2001,))
+    r = CliRunner().invoke(cli.cli, ["info", str(tmp_path / "t2m_2001.npz")])
+    assert r.exit_code == 0, r.output
+    assert "t2m:" in r.output and "lon_is_360: true" in r.output and "time steps : 2160" in r.output
