@@ -285,6 +285,21 @@ def _fill(value, dtype: np.dtype):
     return np.asarray(value).astype(dtype)[()]
 
 
+def _attr_fill(value: str, dtype: np.dtype):
+    """A ``_FillValue`` ATTRIBUTE spelled as a string: zarr's "NaN" / "Infinity" / a number, or -- what xarray
+    writes into zarr v3 stores for floating-point variables -- base64 of the little-endian float64."""
+    try:
+        return _fill(value, dtype)
+    except ValueError:
+        import base64
+        raw = base64.standard_b64decode(value)
+        if dtype.kind == "f" and len(raw) == 8:
+            return struct.unpack("<d", raw)[0]
+        if dtype.kind == "f" and len(raw) == 4:
+            return struct.unpack("<f", raw)[0]
+        raise
+
+
 # ---------------------------------------------------------------------------------------------
 # arrays
 # ---------------------------------------------------------------------------------------------
@@ -503,7 +518,7 @@ class ZarrArray:
         if isinstance(fv, list):
             fv = fv[0] if fv else None
         if isinstance(fv, str):
-            fv = _fill(fv, self.dtype)
+            fv = _attr_fill(fv, self.dtype)
         fv = None if fv is None else float(fv)
         if fv is not None and np.isnan(fv):
             fv = None                                                     # NaN stays NaN by itself

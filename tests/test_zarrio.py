@@ -280,6 +280,23 @@ def test_cf_packing_fill_and_missing_chunks(tmp_path):
     assert np.array_equal(np.asarray(r)[0], [[1.0, np.nan], [3.0, 4.0]], equal_nan=True)
 
 
+def test_xarray_style_v3_fill_value_attribute(tmp_path):
+    """xarray stores a float variable's ``_FillValue`` in zarr v3 attributes as base64 of the float64."""
+    import base64
+    root = str(tmp_path / "x.zarr")
+    data = np.array([[[1.0, -999.0], [3.0, np.nan]]], np.float32)
+    for enc, masked in ((base64.standard_b64encode(struct.pack("<d", -999.0)).decode(), True),
+                        (base64.standard_b64encode(struct.pack("<d", np.nan)).decode(), False), ("NaN", False), (-999.0, True)):
+        zarrio.write_array(root + "/v", data, [1, 2, 2], ["time", "latitude", "longitude"], {"_FillValue": enc}, zarr_format=3,
+                           compressor="zstd")
+        r = zarrio.ChunkedRaster(zarrio.ZarrArray(root + "/v"), (0, 1, 2))
+        assert (r.fill == -999.0) if masked else (r.fill is None)
+        want = data.copy()
+        if masked:
+            want[0, 0, 1] = np.nan
+        assert np.array_equal(np.asarray(r), want, equal_nan=True)
+
+
 def test_calendar_time_axes(tmp_path):
     vals = np.zeros((800, 2, 2), np.float32)
     for cal in ("noleap", "360_day"):
