@@ -35,6 +35,11 @@ OPTIONS = {
     "keep_device_raster": True,        # keep the device copy's buffer between calls (see _device_raster)
     "chunked_ring_bytes": 2 << 30,     # pinned (and device) staging for chunked stores: slots x decoded chunk size
     "device_decompress": True,         # Blosc-LZ4 chunks: inflate on the GPU's decompression engine when it has one
+    # The per-chunk tables of the device decode (expected stream lengths, raw-segment table) are uploaded from
+    # pageable memory, which makes the driver synchronise the compute stream twice per chunk (~0.4 ms per chunk:
+    # what bounds stores of small chunks).  True: the feed threads append them to the staged slot so that they ride
+    # the chunk's own copy.  Off until it has been measured on a GPU (round 2).
+    "inline_chunk_tables": False,
     # Blosc packs its streams back to back at arbitrary byte offsets.  0: hand them to the engine where they are;
     # n > 1: first move every stream to an n-byte aligned offset of a second device buffer (one segment-copy launch)
     "device_decompress_align": int(__import__("os").environ.get("AGF_DE_ALIGN", "0")),
@@ -276,7 +281,7 @@ def feed_chunked(runner, src, n_cells: int, stream=None, k1_events: Optional[lis
         if ev is not None:
             ev.synchronize()
         if de:
-            return src.load_stored(tiles[i], bytes_np[slot], max_len)
+            return src.load_stored(tiles[i], bytes_np[slot], max_len, bool(OPTIONS.get("inline_chunk_tables", False)))
         return ("host",) if src.load(tiles[i], views[slot]) else None
 
     def place(ptr, tile):
@@ -360,11 +365,18 @@ def feed_chunked(runner, src, n_cells: int, stream=None, k1_events: Optional[lis
                                     src_ptr, src_off.ctypes.data_as(i64p), plan.src_len.ctypes.data_as(i64p),
                                     infl.data_ptr(), plan.dst_off.ctypes.data_as(i64p), plan.dst_len.ctypes.data_as(i64p),
                                     n_ops, actual.data_ptr(), comp.cuda_stream))
-                                want = torch.from_numpy(plan.dst_len.astype(np.int32)).to(dev, non_blocking=True)
+                                if plan.inline is not None:
+                                    want = dslots[slot][plan.inline[0]: plan.inline[0] + 4 * n_ops].view(torch.int32)
+                                else:
+                                    want = torch.from_numpy(plan.dst_len.astype(np.int32)).to(dev, non_blocking=True)
                                 _PENDING_CHECKS.append(((actual == want).all(), src.array.chunk_path(tile.index)))
                             if plan.raw.shape[1]:                          # streams Blosc stored uncompressed
-                                table = torch.from_numpy(plan.raw).to(dev, non_blocking=True)
-                                _lib.check(L.agf_copy_segments_run(dslots[slot].data_ptr(), infl.data_ptr(), table.data_ptr(),
+                                if plan.inline is not None:
+                                    table_ptr = dslots[slot].data_ptr() + plan.inline[1]
+                                else:
+                                    table = torch.from_numpy(plan.raw).to(dev, non_blocking=True)
+                                    table_ptr = table.data_ptr()
+                                _lib.check(L.agf_copy_segments_run(dslots[slot].data_ptr(), infl.data_ptr(), table_ptr,
                                                                    plan.raw.shape[1], comp.cuda_stream))
                                 raw_copies += int(plan.raw.shape[1])
                         if plan.shuffled:

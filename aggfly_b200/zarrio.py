@@ -152,7 +152,11 @@ class BloscPlan:
     """What the device needs to decode one Blosc frame whose bytes sit in a buffer: raw-LZ4 streams for the
     decompression engine (offsets into the frame / into the decoded chunk), streams stored uncompressed (plain
     copies), and the shuffle parameters.  ``kind == "memcpy"``: the frame is a 16-byte header + plain data."""
-    __slots__ = ("kind", "nbytes", "typesize", "blocksize", "shuffled", "src_off", "src_len", "dst_off", "dst_len", "raw")
+    __slots__ = ("kind", "nbytes", "typesize", "blocksize", "shuffled", "src_off", "src_len", "dst_off", "dst_len", "raw",
+                 "inline")
+
+    def __init__(self):
+        self.inline = None          # (offset of int32 dst_len[n_ops], offset of int64 raw[3, n_raw]) inside the staged slot
 
 
 def blosc_device_plan(u8: np.ndarray, max_len: int) -> Optional[BloscPlan]:
@@ -696,10 +700,12 @@ class ChunkedRaster:
     def slot_elems(self) -> int:
         return int(np.prod(self.array.chunks))
 
-    def load_stored(self, tile: Tile, slot_u8: np.ndarray, max_len: int):
+    def load_stored(self, tile: Tile, slot_u8: np.ndarray, max_len: int, inline_tables: bool = False):
         """Device-decode variant of ``load``: read the chunk FILE into ``slot_u8`` (pinned bytes) and plan its
         decoding on the device.  Returns None (chunk absent), ("de", n_bytes, BloscPlan), or ("host",) after
-        decoding on the host into the same slot (frames the engine cannot take)."""
+        decoding on the host into the same slot (frames the engine cannot take).  ``inline_tables``: the plan's
+        small device-side tables (expected stream lengths, raw-segment table) are appended to the slot behind the
+        frame (``plan.inline``), so that they travel with the chunk's one host-to-device copy."""
         arr = self.array
         got = arr.read_chunk_bytes(tile.index, into=slot_u8)
         if got is None:
@@ -708,6 +714,15 @@ class ChunkedRaster:
         if isinstance(got, int):
             plan = blosc_device_plan(slot_u8[:got], max_len)
             if plan is not None and plan.nbytes == arr.chunk_nbytes and plan.typesize in (1, sdt.itemsize):
+                if inline_tables and plan.kind == "lz4":
+                    n_ops, n_raw = len(plan.src_off), plan.raw.shape[1]
+                    a = (got + 15) // 16 * 16
+                    b = (a + 4 * n_ops + 15) // 16 * 16
+                    if b + 24 * n_raw <= slot_u8.size:
+                        slot_u8[a:a + 4 * n_ops].view(np.int32)[:] = plan.dst_len
+                        slot_u8[b:b + 24 * n_raw].view(np.int64)[:] = plan.raw.ravel()
+                        plan.inline = (a, b)
+                        got = b + 24 * n_raw
                 return ("de", got, plan)
             got = bytes(slot_u8[:got])                                       # the decoder writes into the same slot
         arr.decode_chunk(got, slot_u8[: arr.chunk_nbytes].view(sdt))

@@ -268,9 +268,11 @@ def test_decompression_engine_inflates_blosc_frames():
     assert plain.cpu().numpy().tobytes() == data
 
 
-@pytest.mark.parametrize("device_decompress", [True, False])
+@pytest.mark.parametrize("device_decompress", [True, False] + (["inline"] if __import__("os").environ.get("AGF_TEST_INLINE_TABLES") else []))
 @pytest.mark.parametrize("layout", ["time_major_daily_chunks", "time_contiguous_tiles", "lon_time_lat_lz4"])
 def test_blosc_store_matches_in_memory_result(tmp_path, layout, device_decompress):
+    # "inline": OPTIONS["inline_chunk_tables"], not yet run on a GPU (AGF_TEST_INLINE_TABLES=1 enables the case)
+    inline, device_decompress = device_decompress == "inline", bool(device_decompress)
     import torch
     lay = LAYOUTS[layout]
     arr, t, lat, lon = _raster("float32", True, T=24 * 40 + 5, seed=23)
@@ -287,7 +289,7 @@ def test_blosc_store_matches_in_memory_result(tmp_path, layout, device_decompres
 
     old = dict(stream.OPTIONS)
     try:
-        stream.OPTIONS.update(staging_slots=3, staging_threads=2, device_decompress=device_decompress)
+        stream.OPTIONS.update(staging_slots=3, staging_threads=2, device_decompress=device_decompress, inline_chunk_tables=inline)
         resident = run(af.Dataset.from_arrays(torch.from_numpy(arr).cuda(), t, lat, lon, True))
         ds = af.dataset_from_path(store, var="t2m")
         assert ds.values.array.blosc_only

@@ -383,6 +383,12 @@ def test_writer_takes_lazy_block_sources_and_threads(tmp_path):
     slot = np.zeros(ds.values.slot_elems * 4 + 70000, np.uint8)
     kind, n, plan = ds.values.load_stored(tile, slot, 4 << 20)
     assert kind == "de" and n == os.path.getsize(ds.values.array.chunk_path(tile.index)) and plan.nbytes == 4 * 5 * 40 * 4
+    kind, n2, plan2 = ds.values.load_stored(tile, slot, 4 << 20, inline_tables=True)    # tables appended behind the frame
+    a, b = plan2.inline
+    assert a % 16 == 0 and b % 16 == 0 and n <= a < b <= n2 <= slot.size
+    assert np.array_equal(slot[a:a + 4 * len(plan2.dst_len)].view(np.int32), plan2.dst_len)
+    assert np.array_equal(slot[b:n2].view(np.int64).reshape(3, -1), plan2.raw)
+    assert ds.values.load_stored(tile, slot[: n + 8], 4 << 20, inline_tables=True)[2].inline is None      # no room: not inlined
     assert ds.values.load_stored(tile, slot, 8) == ("host",)          # engine limit too small: decoded on the host instead
     blk = np.lib.stride_tricks.as_strided(slot[: plan.nbytes].view(np.float32)[tile.offset:], tile.extent,
                                           (tile.st * 4, tile.sy * 4, tile.sx * 4))
