@@ -15,6 +15,7 @@ read natively, and xarray is used only if it happens to be importable:
 zarr directory store   v2 / v3, any axis order and chunking (aggfly_b200.zarrio): opened lazily, chunks
                        are decoded by host threads and placed on the device (``stream.feed_chunked``)
 anything else          ``xarray.open_dataset`` when xarray is installed
+``.tif`` / ``.tiff``   secondary rasters: north-up single-band GeoTIFF in geographic coordinates (Pillow)
 ``.shp``               polygons (+ ``.dbf`` attributes), aggfly_b200.geometry
 ``.geojson`` / ``.json``  FeatureCollection of Polygon / MultiPolygon features
 =====================  =========================================================================
@@ -232,11 +233,53 @@ def georegions_from_path(path: str, regionid: Optional[str] = None, region_list=
     raise ImportError(f"{path}: only .shp and .geojson region files are read natively (no geopandas here)")
 
 
+def _read_geotiff(path: str):
+    """(values[lat, lon], latitude, longitude, nodata) of a north-up, single-band GeoTIFF in geographic coordinates
+    (LandScan / GPW / cropland rasters: aggfly/weights/secondary_weights.py:201-245 opens them with rioxarray).
+    Pixels are decoded by Pillow's libtiff (strips / tiles, LZW / deflate); the georeferencing comes from the
+    ModelPixelScale + ModelTiepoint tags (or ModelTransformation without rotation), nodata from GDAL_NODATA."""
+    try:
+        from PIL import Image
+    except Exception as exc:                                         # pragma: no cover
+        raise ImportError(f"{path}: reading GeoTIFF needs Pillow") from exc
+    Image.MAX_IMAGE_PIXELS = None                                    # global rasters are far above Pillow's bomb guard
+    with Image.open(path) as img:
+        tags = img.tag_v2
+        scale, tie, xform = tags.get(33550), tags.get(33922), tags.get(34264)
+        nodata = tags.get(42113)
+        if getattr(img, "n_frames", 1) != 1 or len(img.getbands()) != 1:
+            raise ValueError(f"{path}: expected one band, found {len(img.getbands())} band(s) / {getattr(img, 'n_frames', 1)} page(s)")
+        values = np.asarray(img)
+    ny, nx = values.shape
+    if scale is not None and tie is not None:
+        sx, sy = float(scale[0]), float(scale[1])
+        i0, j0, x0, y0 = float(tie[0]), float(tie[1]), float(tie[3]), float(tie[4])
+        lon = x0 + (np.arange(nx) + 0.5 - i0) * sx                    # tiepoint = outer corner of pixel (i0, j0)
+        lat = y0 - (np.arange(ny) + 0.5 - j0) * sy
+    elif xform is not None:
+        m = [float(v) for v in xform]
+        if m[1] != 0.0 or m[4] != 0.0:
+            raise NotImplementedError(f"{path}: rotated / sheared GeoTIFF")
+        lon = m[3] + (np.arange(nx) + 0.5) * m[0]
+        lat = m[7] + (np.arange(ny) + 0.5) * m[5]
+    else:
+        raise ValueError(f"{path}: no georeferencing tags (ModelPixelScale / ModelTiepoint)")
+    if isinstance(nodata, (bytes, str)):
+        txt = (nodata.decode() if isinstance(nodata, bytes) else nodata).strip("\x00 ").strip()
+        nodata = float(txt) if txt else None
+    if abs(lat).max() > 90.0001 or abs(lon).max() > 360.0001:
+        raise NotImplementedError(f"{path}: projected coordinates (only geographic lat / lon rasters are averaged onto the grid)")
+    return values, lat, lon, nodata
+
+
 def secondary_weights_from_path(path: str, nodata: Optional[float] = None) -> SecondaryWeights:
+    """``.npz`` (values, latitude, longitude) or a geographic GeoTIFF (``.tif`` / ``.tiff``)."""
     ext = os.path.splitext(path)[1].lower()
+    if ext in (".tif", ".tiff"):
+        values, lat, lon, file_nodata = _read_geotiff(path)
+        return SecondaryWeights(values, lat, lon, nodata=file_nodata if nodata is None else nodata, name=os.path.basename(path))
     if ext != ".npz":
-        raise ImportError(f"{path}: secondary rasters are read from .npz (values, latitude, longitude); "
-                          "GeoTIFF needs rasterio, which is not installed")
+        raise ImportError(f"{path}: secondary rasters are read from .npz (values, latitude, longitude) or GeoTIFF")
     z = np.load(path, allow_pickle=False)
     return SecondaryWeights(z["values"], z["latitude"], z["longitude"], nodata=nodata, name=os.path.basename(path))
 

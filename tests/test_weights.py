@@ -261,3 +261,36 @@ def test_real_shapefile_if_available():
         inside = sum(_py_clip_area(r, -125.0, -66.0, 24.0, 50.0) for r in rings)
         got = wdf.loc[wdf.index_right == ridx, "area_weight"].sum() * 0.0625
         assert np.isclose(got, abs(inside), rtol=1e-9), (ridx, got, inside)
+
+
+def test_geotiff_secondary_raster_equals_the_npz_one(tmp_path):
+    """Secondary rasters usually come as GeoTIFF (aggfly/weights/secondary_weights.py:201-245; the reference's
+    example config points at a LandScan .tif): tiepoint / pixel-scale georeferencing, GDAL_NODATA, LZW / deflate."""
+    from PIL import Image, TiffImagePlugin
+    from aggfly_b200 import io
+    from aggfly_b200.dataset import Grid
+    rng = np.random.default_rng(4)
+    vals = rng.random((16, 20)).astype(np.float32) * 100
+    vals[3, 5] = -9999.0
+    lat, lon = 40.125 - 0.25 * np.arange(16), -110.125 + 0.25 * np.arange(20)
+    np.savez(tmp_path / "pop.npz", values=vals, latitude=lat, longitude=lon)
+    ifd = TiffImagePlugin.ImageFileDirectory_v2()
+    ifd[33550], ifd.tagtype[33550] = (0.25, 0.25, 0.0), 12                                  # ModelPixelScale
+    ifd[33922], ifd.tagtype[33922] = (0.0, 0.0, 0.0, -110.25, 40.25, 0.0), 12                # ModelTiepoint: outer corner
+    ifd[42113], ifd.tagtype[42113] = "-9999", 2                                             # GDAL_NODATA
+    grid = Grid(-110.0 + 0.5 * np.arange(9), 40.0 - 0.5 * np.arange(7))
+    want = io.secondary_weights_from_path(str(tmp_path / "pop.npz"), nodata=-9999.0)
+    for comp in ("tiff_lzw", "tiff_adobe_deflate", None):
+        path = str(tmp_path / f"pop_{comp}.tif")
+        Image.fromarray(vals).save(path, tiffinfo=ifd, compression=comp)
+        got = io.secondary_weights_from_path(path)
+        assert got.nodata == -9999.0 and np.array_equal(got.values, vals.astype(float))
+        assert np.allclose(got.latitude, lat) and np.allclose(got.longitude, lon)
+        assert np.array_equal(got.on_grid(grid), want.on_grid(grid), equal_nan=True)
+    Image.fromarray(vals).save(str(tmp_path / "bare.tif"))
+    with pytest.raises(ValueError, match="georeferencing"):
+        io.secondary_weights_from_path(str(tmp_path / "bare.tif"))
+    ifd[33922] = (0.0, 0.0, 0.0, 500000.0, 4400000.0, 0.0)                                   # UTM-like coordinates
+    Image.fromarray(vals).save(str(tmp_path / "utm.tif"), tiffinfo=ifd)
+    with pytest.raises(NotImplementedError, match="projected"):
+        io.secondary_weights_from_path(str(tmp_path / "utm.tif"))
