@@ -232,3 +232,20 @@ def test_info_npz(tmp_path):
     r = CliRunner().invoke(cli.cli, ["info", str(tmp_path / "t2m_2001.npz")])
     assert r.exit_code == 0, r.output
     assert "t2m:" in r.output and "lon_is_360: true" in r.output and "time steps : 2160" in r.output
+
+
+def test_regions_command(tmp_path):
+    """`aggfly regions` (aggfly/cli/main.py:50-81, aggfly/regions/georegions.py:326-428) from the file headers."""
+    _project(tmp_path, years=(2001,))
+    r = CliRunner().invoke(cli.cli, ["regions", str(tmp_path / "regions.shp"), "--uniqueness"])
+    assert r.exit_code == 0, r.output
+    for needle in ("geometry   : Polygon  features=3", "bounds     : lon -109.7000 .. -59.0000 | lat 0.0000 .. 38.7000",
+                   "fields     : 1", "GEOID", "first 3 row(s)", "08003", "regionid candidates", "crs        : NONE"):
+        assert needle in r.output, needle
+    d = cli.describe_regions(str(tmp_path / "regions.shp"), rows=0)
+    assert d["features"] == 3 and d["head"] is None and d["unique_columns"] is None
+    os.remove(tmp_path / "regions.dbf")
+    r = CliRunner().invoke(cli.cli, ["regions", str(tmp_path / "regions.shp")])
+    assert r.exit_code == 0 and "no column to use as regionid" in r.output
+    r = CliRunner().invoke(cli.cli, ["regions", str(tmp_path / "nope.gpkg")])
+    assert r.exit_code != 0 and "ValueError" in r.output
