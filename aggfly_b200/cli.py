@@ -148,16 +148,37 @@ def _load(config_path: str) -> _cfg.RunConfig:
         raise SystemExit(1)
 
 
+def check_paths(cfg: _cfg.RunConfig) -> List[str]:
+    """Local input paths that do not exist (aggfly/cli/main.py:118-127 reports them as warnings); URLs are skipped."""
+    missing = []
+    paths = [("regions.path", cfg.regions_path)] + [("dataset.path", p) for p in cfg.resolved_paths()]
+    if cfg.secondary is not None:
+        paths.append(("weights.secondary.path", cfg.secondary.path))
+    for label, p in paths:
+        if p and "://" not in str(p) and not os.path.exists(str(p)):
+            missing.append(f"{label}: {p} does not exist")
+    return missing
+
+
 @cli.command()
 @click.argument("config", type=click.Path())
-def validate(config):
-    """Check a config file (schema, step lists, preprocess) without reading any data."""
+@click.option("--strict", is_flag=True, help="Treat unresolved input paths as errors (exit nonzero), not warnings.")
+def validate(config, strict):
+    """Check a config file (schema, step lists, preprocess) without reading any data; local input paths are
+    checked for existence (warnings, or errors with --strict)."""
     cfg = _load(config)
     try:
         resolve_preprocess(cfg)
     except _pp.PreprocessError as e:
         raise click.ClickException(f"preprocess: {e}")
     n = len(cfg.resolved_paths())
+    problems = check_paths(cfg)
+    if problems:
+        click.echo("Errors:" if strict else "Warnings:", err=strict)
+        for msg in problems:
+            click.echo(f"  - {msg}", err=strict)
+        if strict:
+            raise SystemExit(1)
     click.echo(f"Config OK: {len(cfg.variables)} variable(s), {n} dataset path(s), engine={cfg.engine}, "
                f"output={cfg.output_path} ({cfg.output_format}).")
 

@@ -249,3 +249,15 @@ def test_regions_command(tmp_path):
     assert r.exit_code == 0 and "no column to use as regionid" in r.output
     r = CliRunner().invoke(cli.cli, ["regions", str(tmp_path / "nope.gpkg")])
     assert r.exit_code != 0 and "ValueError" in r.output
+
+
+def test_validate_reports_missing_paths(tmp_path):
+    path, raw = _project(tmp_path, years=(2001,))
+    r = CliRunner().invoke(cli.cli, ["validate", path, "--strict"])
+    assert r.exit_code == 0 and "Config OK" in r.output and "Warnings" not in r.output
+    raw["years"] = "2001:2002"                                        # 2002 was never written
+    (tmp_path / "c2.yaml").write_text(yaml.safe_dump(raw))
+    r = CliRunner().invoke(cli.cli, ["validate", str(tmp_path / "c2.yaml")])
+    assert r.exit_code == 0 and "Warnings:" in r.output and "t2m_2002.npz does not exist" in r.output and "Config OK" in r.output
+    r = CliRunner().invoke(cli.cli, ["validate", str(tmp_path / "c2.yaml"), "--strict"])
+    assert r.exit_code == 1 and "Config OK" not in r.output
