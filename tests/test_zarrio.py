@@ -393,3 +393,42 @@ def test_writer_takes_lazy_block_sources_and_threads(tmp_path):
     blk = np.lib.stride_tricks.as_strided(slot[: plan.nbytes].view(np.float32)[tile.offset:], tile.extent,
                                           (tile.st * 4, tile.sy * 4, tile.sx * 4))
     assert np.array_equal(blk, vals[tile.t0:tile.t1, tile.y0:tile.y1, tile.x0:tile.x1], equal_nan=True)
+
+
+def test_tiles_property_random_shapes_chunks_orders_windows(tmp_path):
+    """Property check of ChunkedRaster.tiles(): for random shapes / chunkings / axis orders / C-F storage / windows
+    the tiles partition the window and (offset, strides) address exactly the window's elements in the stored chunk."""
+    from hypothesis import given, settings, strategies as st
+
+    counter = [0]
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.tuples(st.integers(1, 9), st.integers(1, 7), st.integers(1, 8)), st.permutations(["time", "latitude", "longitude"]),
+           st.sampled_from("CF"), st.sampled_from([2, 3]), st.data())
+    def check(shape, dims, order, fmt, data):
+        T, Y, X = shape
+        chunks = {d: data.draw(st.integers(1, n + 1)) for d, n in zip(("time", "latitude", "longitude"), shape)}
+        vals = np.arange(T * Y * X, dtype=np.float32).reshape(T, Y, X)
+        counter[0] += 1
+        store = zarrio.write_dataset(str(tmp_path / f"h{counter[0]}.zarr"), vals, pd.date_range("2001-01-01", periods=T, freq="h"),
+                                     np.arange(Y, dtype=float), np.arange(X, dtype=float), var="v", dims=tuple(dims), chunks=chunks,
+                                     zarr_format=fmt, compressor=None, order=order)
+        r = af.dataset_from_path(store, var="v").values
+        lo = [data.draw(st.integers(0, n - 1)) for n in shape]
+        hi = [data.draw(st.integers(l + 1, n)) for l, n in zip(lo, shape)]
+        win = r[lo[0]:hi[0], lo[1]:hi[1], lo[2]:hi[2]]
+        want = vals[lo[0]:hi[0], lo[1]:hi[1], lo[2]:hi[2]]
+        assert win.shape == want.shape and np.array_equal(np.asarray(win), want)
+        cover = np.zeros(want.shape, int)
+        buf = np.empty(win.slot_elems, np.float32)
+        for tl in win.tiles():
+            assert win.load(tl, buf)
+            blk = np.lib.stride_tricks.as_strided(buf[tl.offset:], tl.extent, (tl.st * 4, tl.sy * 4, tl.sx * 4))
+            assert np.array_equal(blk, want[tl.t0:tl.t1, tl.y0:tl.y1, tl.x0:tl.x1])
+            cover[tl.t0:tl.t1, tl.y0:tl.y1, tl.x0:tl.x1] += 1
+            if win.direct_rows(tl):
+                assert tl.extent[1:] == want.shape[1:] and np.array_equal(
+                    buf[tl.offset: tl.offset + blk.size].reshape(blk.shape), blk)
+        assert (cover == 1).all()
+
+    check()
