@@ -65,6 +65,66 @@ class RasterArray:
         self.data, self.dims, self.coords = data, tuple(dims), dict(coords)
 
 
+class TimeConcat:
+    """Lazy concatenation along time of rasters ``[T_i, lat, lon]`` that live in different files (NumPy arrays,
+    memory maps, ``zarrio.ChunkedRaster``): what ``xr.open_mfdataset`` gives the reference for a list / glob of
+    paths (aggfly/dataset/dataset.py:686-695).  Slicing with step-1 slices stays lazy (a slice inside one part IS
+    that part's own slice); NumPy sees the data through ``__array__``, so the host feed's worker threads read /
+    decode only the rows of the chunk they stage."""
+
+    lazy_rows = True
+    ndim = 3
+
+    def __init__(self, parts):
+        parts = [p for p in parts if p.shape[0] > 0] or list(parts[:1])
+        if not parts:
+            raise ValueError("nothing to concatenate")
+        tail = {tuple(p.shape[1:]) for p in parts}
+        if len(tail) != 1:
+            raise ValueError(f"parts have different grids: {sorted(tail)}")
+        dts = {np.dtype(p.dtype) for p in parts}
+        self.dtype = np.dtype(np.float64) if (len(dts) > 1 or next(iter(dts)) not in (np.float32, np.float64)) else next(iter(dts))
+        self.parts = list(parts)
+        self.starts = np.concatenate([[0], np.cumsum([p.shape[0] for p in parts])]).astype(np.int64)
+
+    @property
+    def shape(self):
+        return (int(self.starts[-1]),) + tuple(self.parts[0].shape[1:])
+
+    @property
+    def size(self) -> int:
+        return int(np.prod(self.shape))
+
+    def __len__(self):
+        return self.shape[0]
+
+    def __getitem__(self, key):
+        if not isinstance(key, tuple):
+            key = (key,)
+        if len(key) <= 3 and all(isinstance(k, slice) and k.step in (None, 1) for k in key):
+            a, b, _ = key[0].indices(self.shape[0])
+            b = max(a, b)
+            rest = tuple(key[1:])
+            out = []
+            for p, s0, s1 in zip(self.parts, self.starts[:-1], self.starts[1:]):
+                lo, hi = max(a, int(s0)), min(b, int(s1))
+                if hi > lo:
+                    out.append(p[(slice(lo - int(s0), hi - int(s0)),) + rest])
+            if len(out) == 1 and np.dtype(out[0].dtype) == self.dtype:
+                return out[0]
+            if not out:
+                out = [self.parts[0][(slice(0, 0),) + rest]]
+            return TimeConcat(out)
+        return np.asarray(self)[key]
+
+    def __array__(self, dtype=None, copy=None):
+        out = np.concatenate([np.asarray(p, dtype=self.dtype) for p in self.parts], axis=0)
+        return out if dtype is None else out.astype(dtype, copy=False)
+
+    def __repr__(self):
+        return f"<TimeConcat {self.shape} {self.dtype} of {len(self.parts)} parts>"
+
+
 def time_selection(time, time_sel):
     """Row range [a, b) of ``.sel(time=time_sel)`` on a sorted axis: a partial date string ("2001",
     "2001-06", "2001-06-15"), a timestamp, or a slice of those (both ends inclusive, like pandas/xarray)."""
@@ -138,7 +198,7 @@ class Dataset:
                 order = np.argsort(time.values, kind="stable")
             time = time[order]
             values = values[order] if not _is_torch(values) else values[list(order)]
-        if not _is_torch(values) and not getattr(values, "is_chunked_raster", False):
+        if not _is_torch(values) and not getattr(values, "is_chunked_raster", False) and not getattr(values, "lazy_rows", False):
             values = np.asarray(values)
             if values.dtype not in (np.float32, np.float64):
                 values = values.astype(np.float64)

@@ -42,6 +42,8 @@ def to_device(values, device=None):
         torch.cuda.current_stream(device).synchronize()
         _stream.check_device_decompress()
         return raster.view(T, Y, X).clone()                         # the streamed buffer is recycled by the next feed
+    if getattr(values, "lazy_rows", False):
+        values = np.asarray(values)
     if isinstance(values, np.ndarray):
         if values.dtype not in (np.float32, np.float64):
             values = values.astype(np.float64)

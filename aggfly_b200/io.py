@@ -14,6 +14,7 @@ read natively, and xarray is used only if it happens to be importable:
                        time axes, ``scale_factor`` / ``add_offset`` unpacked like xarray (float64)
 zarr directory store   v2 / v3, any axis order and chunking (aggfly_b200.zarrio): opened lazily, chunks
                        are decoded by host threads and placed on the device (``stream.feed_chunked``)
+list / glob of paths   one dataset concatenated along time (``dataset.TimeConcat``, lazy), parts in any of the formats above
 anything else          ``xarray.open_dataset`` when xarray is installed
 ``.tif`` / ``.tiff``   secondary rasters: north-up single-band GeoTIFF in geographic coordinates (Pillow)
 ``.shp``               polygons (+ ``.dbf`` attributes), aggfly_b200.geometry
@@ -55,12 +56,14 @@ def _cf_time(values: np.ndarray, units: str, calendar: str = "standard"):
     return pd.DatetimeIndex(origin.value + np.round(vals * ns).astype(np.int64))
 
 
-def dataset_from_path(path: str, var: Optional[str] = None, xycoords: Sequence[str] = ("longitude", "latitude"),
+def dataset_from_path(path, var: Optional[str] = None, xycoords: Sequence[str] = ("longitude", "latitude"),
                       timecoord: str = "time", lon_is_360: bool = True, preprocess=None, time_sel=None,
                       name: Optional[str] = None, **kwargs) -> Dataset:
     """``af.dataset_from_path`` (aggfly/dataset/dataset.py:636-740) for the formats listed in the module
     docstring.  ``preprocess``: builtin name / expression in ``x`` (fused on the device) or a callable."""
     xdim, ydim = xycoords
+    if isinstance(path, (list, tuple)) or (isinstance(path, str) and any(c in path for c in "*?[")):
+        return _dataset_from_paths(path, var, xycoords, timecoord, lon_is_360, preprocess, time_sel, name, **kwargs)
     ext = os.path.splitext(path.rstrip("/"))[1].lower()
     keepalive = None
     if ext == ".npz":
@@ -110,6 +113,47 @@ def dataset_from_path(path: str, var: Optional[str] = None, xycoords: Sequence[s
     ds._keepalive = keepalive
     if preprocess is not None and not isinstance(preprocess, str):
         ds.values = np.asarray(preprocess(np.asarray(ds.values)))
+    if time_sel is not None:
+        ds = select_time(ds, time_sel)
+    return ds
+
+
+def _dataset_from_paths(paths, var, xycoords, timecoord, lon_is_360, preprocess, time_sel, name, **kwargs) -> Dataset:
+    """Several files of one variable (a list, or a glob pattern) as ONE dataset concatenated along time -- the
+    reference's ``xr.open_mfdataset`` branch (aggfly/dataset/dataset.py:686-695).  Every file is opened lazily
+    on its own; the parts are ordered by their first time stamp, must share the grid and must not overlap in time."""
+    import glob
+    from .dataset import TimeConcat
+    from .timeaxis import CalendarIndex
+    if isinstance(paths, str):
+        pattern, paths = paths, sorted(glob.glob(paths))
+        if not paths:
+            raise FileNotFoundError(f"no file matches {pattern!r}")
+    if not paths:
+        raise ValueError("empty list of paths")
+    fused = preprocess if isinstance(preprocess, str) else None
+    parts = [dataset_from_path(p, var=var, xycoords=xycoords, timecoord=timecoord, lon_is_360=lon_is_360,
+                               preprocess=preprocess, name=name, **kwargs) for p in paths]
+    cal = {type(d.time).__name__ + (d.time.calendar if isinstance(d.time, CalendarIndex) else "") for d in parts}
+    if len(cal) != 1:
+        raise ValueError(f"the files do not share one calendar: {sorted(cal)}")
+    key = (lambda d: int(d.time.ordinal_hours()[0])) if isinstance(parts[0].time, CalendarIndex) else (lambda d: d.time[0].value)
+    parts = sorted([d for d in parts if len(d.time)], key=key) or parts[:1]
+    first = parts[0]
+    for d in parts[1:]:
+        if not (np.array_equal(d.latitude, first.latitude) and np.array_equal(d.longitude, first.longitude)):
+            raise ValueError("the files are on different grids")
+    if isinstance(first.time, CalendarIndex):
+        time = CalendarIndex(first.time.calendar, *[np.concatenate([getattr(d.time, f) for d in parts])
+                                                     for f in ("year", "month", "day", "hour")])
+    else:
+        time = pd.DatetimeIndex(np.concatenate([d.time.values for d in parts]))
+    if not time.is_monotonic_increasing:
+        raise ValueError("the files overlap in time")
+    values = TimeConcat([d.values for d in parts]) if len(parts) > 1 else first.values
+    ds = Dataset.from_arrays(values, time, first.latitude, first.longitude, lon_is_360=lon_is_360, name=name or var,
+                             preprocess=fused)
+    ds._keepalive = [getattr(d, "_keepalive", None) for d in parts]
     if time_sel is not None:
         ds = select_time(ds, time_sel)
     return ds

@@ -51,6 +51,10 @@ def _host_source(values):
     everything else -- numpy arrays (any strides: memory maps, clipped views), pageable tensors -- goes
     through the pinned staging ring chunk by chunk, so no whole-raster host copy is ever made."""
     import torch
+    if getattr(values, "lazy_rows", False):
+        # dataset.TimeConcat (several files along time): row slices are NumPy views / lazy windows of the parts, turned
+        # into arrays by np.copyto inside the staging threads -- the whole raster is never materialised on the host
+        return None, values
     if isinstance(values, np.ndarray) or not type(values).__module__.startswith("torch"):
         arr = np.asarray(values)
         if arr.dtype not in (np.float32, np.float64) or not arr.dtype.isnative:

@@ -626,6 +626,10 @@ class ChunkedRaster:
         return self.shape[0]
 
     @property
+    def size(self) -> int:
+        return int(np.prod(self.shape))
+
+    @property
     def single_time_chunk(self) -> bool:
         """Every tile spans the view's whole time range (time-contiguous stores): no row is complete before the
         last tile has landed, so there is nothing to gain from time stripes."""

@@ -432,3 +432,40 @@ def test_tiles_property_random_shapes_chunks_orders_windows(tmp_path):
         assert (cover == 1).all()
 
     check()
+
+
+def test_multi_file_dataset_is_a_lazy_time_concat(tmp_path):
+    """A list / glob of files = one dataset along time (the reference's open_mfdataset branch,
+    aggfly/dataset/dataset.py:686-695); parts of different formats, opened lazily, ordered by time."""
+    import torch
+    from aggfly_b200 import stream
+    from aggfly_b200.dataset import TimeConcat
+    rng = np.random.default_rng(0)
+    lat, lon = np.linspace(40, 38, 5), np.linspace(250, 253, 7)
+    full = rng.normal(280, 5, (24 * 9, 5, 7)).astype(np.float32)
+    t = pd.date_range("2001-01-30", periods=24 * 9, freq="h")
+    d = str(tmp_path)
+    np.savez(d + "/b_2.npz", t2m=full[72:144], time=t[72:144].values, latitude=lat, longitude=lon)
+    zarrio.write_dataset(d + "/a_1.zarr", full[:72], t[:72], lat, lon, var="t2m", chunks={"time": 24}, compressor="zstd", zarr_format=3)
+    zarrio.write_dataset(d + "/c_3.zarr", full[144:], t[144:], lat, lon, var="t2m", chunks={"time": 24}, compressor="blosc")
+    ds = af.dataset_from_path([d + "/c_3.zarr", d + "/b_2.npz", d + "/a_1.zarr"], var="t2m", preprocess="kelvin_to_celsius")
+    assert isinstance(ds.values, TimeConcat) and ds.shape == full.shape and ds.dtype == np.float32 and len(ds.pre_ops) == 1
+    assert (ds.time == t).all() and np.array_equal(np.asarray(ds.values), full)
+    assert isinstance(ds.values[60:100], TimeConcat) and isinstance(ds.values[80:100], np.ndarray)
+    assert getattr(ds.values[10:30], "is_chunked_raster", False)                       # inside one zarr part: that part's window
+    assert np.array_equal(np.asarray(ds.values[:, 1:4, 2:6][100:200]), full[100:200, 1:4, 2:6])
+    assert af.dataset_from_path(d + "/*_?.zarr", var="t2m").shape == (144, 5, 7)       # glob: the two zarr parts
+    feb = af.dataset_from_path(d + "/*", var="t2m", time_sel="2001-02")
+    assert feb.shape[0] == 168 and np.array_equal(np.asarray(feb.values), full[48:])
+    with pytest.raises(ValueError, match="overlap"):
+        af.dataset_from_path([d + "/a_1.zarr", d + "/a_1.zarr"], var="t2m")
+    with pytest.raises(FileNotFoundError):
+        af.dataset_from_path(d + "/nothing_*.zarr", var="t2m")
+    # what the host feed does with it: row chunks staged by worker threads through np.copyto (stream._Staging.fill)
+    host, src = stream._host_source(ds.values)
+    assert host is None and src is ds.values
+    ring = stream._Staging.__new__(stream._Staging)
+    ring.slots, ring.events = [torch.empty(40 * 35, dtype=torch.float32)], [None]
+    for r0, r1 in stream.chunk_rows(full.shape[0], 35 * 4, 40 * 35 * 4):
+        got = ring.fill(0, src[r0:r1]).view(r1 - r0, 35).numpy()
+        assert np.array_equal(got, full[r0:r1].reshape(r1 - r0, 35))
