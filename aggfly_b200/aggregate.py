@@ -374,10 +374,19 @@ def aggregate_dataset(weights: GridWeights, dataset: Dataset = None,
     tr.mark("csr")
     names, res, raster = _temporal_device(dataset, aggregator_dict)
     tr.mark("temporal (+ host feed)")
-    panel = _engine.run_spmm(csr, res)
-    tr.mark("spmm (issue)")
-    df = _panel_frame(panel, names, res.labels, csr.host.region_ids, weights)
-    tr.mark("panel frame (row selection on the device, d2h, region join)")
+    if _engine.OPTIONS.get("device_panel_frame", False):
+        panel = _engine.run_spmm(csr, res)
+        tr.mark("spmm (issue)")
+        df = _panel_frame(panel, names, res.labels, csr.host.region_ids, weights)
+        tr.mark("panel frame (row selection on the device, d2h, region join)")
+    else:
+        panel = _engine.run_spmm(csr, res).cpu().numpy()
+        tr.mark("spmm + d2h")
+        df = _assemble_panel(panel, names, res.labels, csr.host.region_ids, weights)
+        tr.mark("assemble")
+        rid = weights.georegions.regionid
+        df = weights.georegions.shp[[rid]].merge(df, left_index=True, right_on="region_id").drop(columns="region_id")
+        tr.mark("merge")
     tr.done()
     return df
 

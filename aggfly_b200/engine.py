@@ -16,7 +16,13 @@ from .weights import HostCSR
 
 
 # Tunables (tests pin target_stripes to exercise the stripe/merge path; 0 = library heuristic).
-OPTIONS = {"target_stripes": 0}
+OPTIONS = {
+    "target_stripes": 0,
+    # aggregate._panel_frame: select / gather / transpose the panel's rows on the device and join the region ids without
+    # DataFrame.merge.  Frame-identical to the literal route on CPU tensors (tests/test_panel.py); stays off until it has run
+    # through the GPU tests on a device (AGF_DEVICE_PANEL=1 turns it on).
+    "device_panel_frame": bool(int(__import__("os").environ.get("AGF_DEVICE_PANEL", "0") or 0)),
+}
 
 
 def _torch():
