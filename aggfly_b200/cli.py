@@ -265,7 +265,12 @@ def describe_raster(path: str) -> dict:
     out = {"variables": {}, "coords": {}}
     if zarrio.looks_like_zarr(path):
         g = zarrio.ZarrGroup(path)
-        arrays = {n: g[n] for n in g.names()}
+        arrays = {}
+        for n in g.names():
+            try:
+                arrays[n] = g[n]
+            except NotImplementedError:                      # auxiliary arrays of types the reader does not decode (strings ...)
+                continue
         dims_all = {d for a in arrays.values() for d in (a.dims or ())}
         for n, a in arrays.items():
             if n in dims_all and a.ndim == 1:

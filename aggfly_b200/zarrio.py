@@ -798,7 +798,12 @@ def open_raster(path: str, var: Optional[str], xycoords=("longitude", "latitude"
     names = g.names()
     xdim, ydim = xycoords
     if var is None:
-        cands = [n for n in names if n not in (xdim, ydim, timecoord) and g[n].ndim == 3]
+        def _ndim(n):
+            try:
+                return g[n].ndim
+            except NotImplementedError:                      # e.g. a string-typed auxiliary variable
+                return -1
+        cands = [n for n in names if n not in (xdim, ydim, timecoord) and _ndim(n) == 3]
         if len(cands) != 1:
             raise KeyError(f"{path}: pass var= (3-D arrays: {cands})")
         var = cands[0]
