@@ -277,6 +277,103 @@ def georegions_from_path(path: str, regionid: Optional[str] = None, region_list=
     raise ImportError(f"{path}: only .shp and .geojson region files are read natively (no geopandas here)")
 
 
+def describe_regions(path: str, rows: int = 5, uniqueness: bool = False) -> dict:
+    """Fields, feature count, bounds and the first rows of a shapefile (from the .shp / .shx / .dbf HEADERS, no
+    geometry is read) or a GeoJSON file; ``uniqueness`` also lists the columns that could serve as ``regionid``."""
+    import struct
+    from .geometry import read_dbf
+    ext = os.path.splitext(path)[1].lower()
+    out = {"path": path, "fields": [], "dtypes": [], "head": None, "unique_columns": None, "crs": None}
+    if ext == ".shp":
+        with open(path, "rb") as f:
+            head = f.read(100)
+        if len(head) < 100 or struct.unpack(">i", head[:4])[0] != 9994:
+            raise ValueError(f"{path}: not an ESRI shapefile")
+        stype = struct.unpack("<i", head[32:36])[0]
+        out["geometry_type"] = {0: "Null", 1: "Point", 3: "LineString", 5: "Polygon", 15: "PolygonZ", 25: "PolygonM"}.get(stype, f"type {stype}")
+        out["total_bounds"] = struct.unpack("<4d", head[36:68])
+        base = os.path.splitext(path)[0]
+        if os.path.exists(base + ".shx"):
+            out["features"] = (os.path.getsize(base + ".shx") - 100) // 8
+        if out["total_bounds"][0] >= out["total_bounds"][2] or "features" not in out:
+            # a writer that left the header box empty / no index file: walk the record headers (each polygon record
+            # carries its own box; vertices are skipped)
+            boxes, n = [], 0
+            with open(path, "rb") as f:
+                f.seek(100)
+                while True:
+                    rh = f.read(8)
+                    if len(rh) < 8:
+                        break
+                    clen = struct.unpack(">ii", rh)[1]
+                    rec = f.read(36)
+                    if len(rec) >= 36 and struct.unpack("<i", rec[:4])[0] in (3, 5, 8, 13, 15, 18, 23, 25, 28):
+                        boxes.append(struct.unpack("<4d", rec[4:36]))
+                    f.seek(2 * clen - len(rec), 1)
+                    n += 1
+            out["features"] = n
+            if boxes:
+                b = np.asarray(boxes)
+                out["total_bounds"] = (b[:, 0].min(), b[:, 1].min(), b[:, 2].max(), b[:, 3].max())
+        if os.path.exists(base + ".prj"):
+            out["crs"] = open(base + ".prj").read().strip()[:60]
+        attrs = read_dbf(base + ".dbf") if os.path.exists(base + ".dbf") else None
+        out["driver"] = "ESRI Shapefile"
+    elif ext in (".geojson", ".json"):
+        gr = georegions_from_path(path)
+        attrs = gr.shp.drop(columns=[c for c in ("rings", "region_id") if c in gr.shp.columns])
+        pts = np.concatenate([r for rings in gr.shp["rings"] for r in rings])
+        out.update(geometry_type="Polygon", total_bounds=(pts[:, 0].min(), pts[:, 1].min(), pts[:, 0].max(), pts[:, 1].max()),
+                   features=len(gr.shp), driver="GeoJSON", crs="OGC:CRS84 (GeoJSON default)")
+        attrs = attrs if len(attrs.columns) else None
+    else:
+        raise ValueError(f"{path}: only .shp and .geojson region files are read natively")
+    if attrs is not None:
+        out.setdefault("features", len(attrs))
+        out["fields"], out["dtypes"] = list(attrs.columns), [str(attrs[c].dtype) for c in attrs.columns]
+        out["head"] = attrs.head(rows) if rows else None
+        if uniqueness:
+            out["unique_columns"] = [c for c in attrs.columns if attrs[c].notna().all() and not attrs[c].duplicated().any()]
+    return out
+
+
+def print_regions_info(d: dict, echo=print) -> None:
+    echo(f"{d['path']}")
+    echo(f"  driver     : {d.get('driver')}")
+    echo(f"  geometry   : {d.get('geometry_type')}  features={d.get('features')}")
+    echo(f"  crs        : {d['crs']}" if d["crs"] else "  crs        : NONE (no .prj); coordinates are taken as longitude / latitude")
+    xmin, ymin, xmax, ymax = d["total_bounds"]
+    echo(f"  bounds     : lon {xmin:.4f} .. {xmax:.4f} | lat {ymin:.4f} .. {ymax:.4f}")
+    if xmin >= 0 and xmax > 180:
+        echo("               longitudes run 0\u2013360, not -180\u2013180")
+    if not d["fields"]:
+        echo("  fields     : none \u2014 this file has no attribute table, so there is")
+        echo("               no column to use as regionid")
+        return
+    echo(f"  fields     : {len(d['fields'])}")
+    for f, t in zip(d["fields"], d["dtypes"]):
+        echo(f"      {f:<24} {t}")
+    if d["head"] is not None:
+        echo(f"  first {len(d['head'])} row(s) (geometry omitted):")
+        for line in d["head"].to_string().splitlines():
+            echo(f"      {line}")
+    if d["unique_columns"] is not None:
+        if d["unique_columns"]:
+            echo(f"  unique across all {d['features']} features (regionid candidates):")
+            echo(f"      {', '.join(d['unique_columns'])}")
+        else:
+            echo("  no column is unique across all features \u2014 none can serve as a")
+            echo("  regionid on its own")
+
+
+def shapefile_info(path: str, n: int = 5, uniqueness: bool = False) -> dict:
+    """``af.shapefile_info`` (aggfly/regions/georegions.py:326-428): print a summary of a regions file (fields, feature
+    count, bounds, the first ``n`` rows, optionally the columns that are unique across all features) and return it."""
+    d = describe_regions(path, n, uniqueness)
+    print_regions_info(d)
+    return d
+
+
 def _read_geotiff(path: str):
     """(values[lat, lon], latitude, longitude, nodata) of a north-up, single-band GeoTIFF in geographic coordinates
     (LandScan / GPW / cropland rasters: aggfly/weights/secondary_weights.py:201-245 opens them with rioxarray).
