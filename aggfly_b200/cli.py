@@ -81,7 +81,15 @@ def compute_weights(config: _cfg.RunConfig, log=lambda m: None):
     path0 = config.resolved_paths()[0]
     log(f"Building weights from sample layer: {path0}")
     sample = load_dataset(config, path0, georegions)
-    secondary = None if config.secondary is None else _io.secondary_weights_from_path(config.secondary.path)
+    secondary = None
+    if config.secondary is not None:                       # aggfly/cli/pipeline.py:60-73
+        sc = config.secondary
+        if sc.type == "pop":
+            secondary = _io.pop_weights_from_path(sc.path)
+        elif sc.type == "crop":
+            secondary = _io.crop_weights_from_path(sc.path, crop=sc.crop or "corn", feed=sc.feed)
+        else:
+            secondary = _io.secondary_weights_from_path(sc.path)
     w = weights_from_objects(sample, georegions, secondary_weights=secondary, project_dir=config.project_dir,
                              zero_weight=config.zero_weight)
     w.calculate_weights()

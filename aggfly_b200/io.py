@@ -413,16 +413,101 @@ def _read_geotiff(path: str):
     return values, lat, lon, nodata
 
 
-def secondary_weights_from_path(path: str, nodata: Optional[float] = None) -> SecondaryWeights:
-    """``.npz`` (values, latitude, longitude) or a geographic GeoTIFF (``.tif`` / ``.tiff``)."""
-    ext = os.path.splitext(path)[1].lower()
+_Y_NAMES, _X_NAMES = ("y", "latitude", "lat"), ("x", "longitude", "lon")
+
+
+def _select_2d(values, dims, coords, sel, path):
+    """``da.sel(**sel)`` on the non-spatial axes, then the single remaining band: -> (values[y, x], y name, x name)."""
+    dims = list(dims)
+    for dim, want in (sel or {}).items():
+        if dim not in dims:
+            raise KeyError(f"{path}: no dimension {dim!r} to select on (have {dims})")
+        labels = [v.decode() if isinstance(v, bytes) else str(v) for v in np.asarray(coords[dim]).tolist()] \
+            if np.asarray(coords[dim]).dtype.kind in "SUO" else np.asarray(coords[dim]).tolist()
+        key = str(want) if labels and isinstance(labels[0], str) else want
+        if key not in labels:
+            raise KeyError(f"{path}: {dim}={want!r} not found (have {labels})")
+        values = np.take(values, labels.index(key), axis=dims.index(dim))
+        dims.remove(dim)
+    ydim = next((d for d in dims if d.lower() in _Y_NAMES), None)
+    xdim = next((d for d in dims if d.lower() in _X_NAMES), None)
+    if ydim is None or xdim is None:
+        raise ValueError(f"{path}: no y / x (latitude / longitude) dimensions among {dims}")
+    for d in [d for d in dims if d not in (ydim, xdim)]:
+        if values.shape[dims.index(d)] != 1:
+            raise ValueError(f"{path}: dimension {d!r} has {values.shape[dims.index(d)]} entries; pass sel={{{d!r}: ...}}")
+        values = np.take(values, 0, axis=dims.index(d))
+        dims.remove(d)
+    if dims.index(ydim) > dims.index(xdim):
+        values = np.asarray(values).T
+    return np.asarray(values), ydim, xdim
+
+
+def secondary_weights_from_path(path: str, var: Optional[str] = None, sel: Optional[dict] = None, nodata: Optional[float] = None,
+                                wtype: str = "secondary", cache_identifier: Optional[str] = None, crs=None, name: Optional[str] = None,
+                                **kwargs) -> SecondaryWeights:
+    """``af.secondary_weights_from_path`` (aggfly/weights/secondary_weights.py:112-245): a raster on a regular
+    latitude / longitude grid from ``.npz`` (values, latitude, longitude), a geographic GeoTIFF, a zarr store or a
+    NetCDF-3 file (``var`` + ``sel={"crop": "corn"}`` coordinate selection like the reference's ``open_raster``).
+    ``wtype`` / ``cache_identifier`` label the weights (cache discrimination); ``crs`` is accepted for signature
+    compatibility -- only geographic rasters are supported, nothing is reprojected."""
+    ext = os.path.splitext(path.rstrip("/"))[1].lower()
+    label = name or os.path.basename(path.rstrip("/"))
     if ext in (".tif", ".tiff"):
         values, lat, lon, file_nodata = _read_geotiff(path)
-        return SecondaryWeights(values, lat, lon, nodata=file_nodata if nodata is None else nodata, name=os.path.basename(path))
-    if ext != ".npz":
-        raise ImportError(f"{path}: secondary rasters are read from .npz (values, latitude, longitude) or GeoTIFF")
-    z = np.load(path, allow_pickle=False)
-    return SecondaryWeights(z["values"], z["latitude"], z["longitude"], nodata=nodata, name=os.path.basename(path))
+        nodata = file_nodata if nodata is None else nodata
+    elif ext == ".npz":
+        z = np.load(path, allow_pickle=False)
+        values, lat, lon = z["values" if var is None or var not in z.files else var], z["latitude"], z["longitude"]
+    elif looks_like_zarr(path):
+        from .zarrio import ZarrGroup
+        g = ZarrGroup(path)
+        if var is None:
+            cands = [n for n in g.names() if g[n].dims and g[n].ndim >= 2 and n not in g[n].dims]
+            if len(cands) != 1:
+                raise KeyError(f"{path}: pass var= (arrays: {cands})")
+            var = cands[0]
+        a = g[var]
+        fv, scale, offset = a.cf_packing()
+        raw = a.read()
+        values = raw.astype(np.float64) * scale + offset if (scale != 1.0 or offset != 0.0) else raw.astype(np.float64)
+        if fv is not None:
+            values[raw.astype(np.float64) == fv] = np.nan
+        coords = {d: g[d].read() for d in a.dims if d in g}
+        values, ydim, xdim = _select_2d(values, a.dims, coords, sel, path)
+        lat, lon = np.asarray(coords[ydim], dtype=float), np.asarray(coords[xdim], dtype=float)
+    elif ext in (".nc", ".nc3", ".cdf") and _is_netcdf3(path):
+        from scipy.io import netcdf_file
+        with netcdf_file(path, "r", mmap=False, maskandscale=True) as f:
+            if var is None:
+                cands = [n for n, v in f.variables.items() if len(v.dimensions) >= 2]
+                if len(cands) != 1:
+                    raise KeyError(f"{path}: pass var= (variables: {cands})")
+                var = cands[0]
+            v = f.variables[var]
+            coords = {d: np.array(f.variables[d].data) for d in v.dimensions if d in f.variables}
+            values = np.ma.filled(np.ma.asarray(v[:], dtype=np.float64), np.nan)
+            values, ydim, xdim = _select_2d(values, v.dimensions, coords, sel, path)
+            lat, lon = np.asarray(coords[ydim], dtype=float), np.asarray(coords[xdim], dtype=float)
+    else:
+        raise NotImplementedError(f"Unsupported raster format: {path} (.npz, GeoTIFF, zarr and NetCDF-3 are read natively)")
+    out = SecondaryWeights(values, lat, lon, nodata=nodata, name=label)
+    out.wtype, out.cache_identifier, out.path = wtype, cache_identifier, path
+    return out
+
+
+def pop_weights_from_path(path: str, **kwargs) -> SecondaryWeights:
+    """``af.pop_weights_from_path`` (aggfly/weights/pop_weights.py): a population raster, ``wtype="pop"``."""
+    kwargs.setdefault("wtype", "pop")
+    return secondary_weights_from_path(path, **kwargs)
+
+
+def crop_weights_from_path(path: str, crop: str = "corn", feed: Optional[str] = "total", var: str = "layer", **kwargs) -> SecondaryWeights:
+    """``af.crop_weights_from_path`` (aggfly/weights/crop_weights.py): the ``crop`` layer of a cropland store; the feed
+    regime only discriminates caches."""
+    out = secondary_weights_from_path(path, var=var, sel={"crop": crop}, wtype=crop, cache_identifier=feed, **kwargs)
+    out.crop, out.feed = crop, feed
+    return out
 
 
 # ---------------------------------------------------------------------------------------------

@@ -146,3 +146,79 @@ def test_shapefile_info_handles_a_file_with_no_attributes(tmp_path):
         {"type": "Feature", "properties": {}, "geometry": {"type": "Polygon", "coordinates": [[[0, 0], [1, 0], [1, 1], [0, 1], [0, 0]]]}}]}))
     info = af.shapefile_info(str(path))
     assert info["fields"] == [] and info["head"] is None and info["features"] == 1
+
+
+# ---- secondary rasters (:1222-1322): GeoTIFF, zarr with variable + coordinate selection, NetCDF ----------------------------
+def _cropland_zarr(tmp_path):
+    """:1236-1253 -- a `layer` variable indexed by a `crop` coordinate (zarr v2, fixed-width unicode labels like xarray writes)."""
+    root = str(tmp_path / "cropland.zarr")
+    y = x = np.arange(0, 4.0) + 0.5
+    import json
+    os.makedirs(root)
+    json.dump({"zarr_format": 2}, open(root + "/.zgroup", "w"))
+    zarrio.write_array(root + "/layer", np.stack([np.ones((4, 4)), np.full((4, 4), 7.0)]), [1, 4, 4], ["crop", "y", "x"])
+    zarrio.write_array(root + "/crop", np.array(["corn", "soybeans"], dtype="<U8"), [-1], ["crop"], compressor=None, fill_value=0)
+    json.dump(dict(json.load(open(root + "/crop/.zarray")), fill_value=""), open(root + "/crop/.zarray", "w"))
+    zarrio.write_array(root + "/y", y, [-1], ["y"])
+    zarrio.write_array(root + "/x", x, [-1], ["x"])
+    return root
+
+
+def _pop_tif(tmp_path):
+    """:1222-1233."""
+    from PIL import Image, TiffImagePlugin
+    ifd = TiffImagePlugin.ImageFileDirectory_v2()
+    ifd[33550], ifd.tagtype[33550] = (1.0, 1.0, 0.0), 12
+    ifd[33922], ifd.tagtype[33922] = (0.0, 0.0, 0.0, 0.0, 4.0, 0.0), 12
+    path = str(tmp_path / "pop.tif")
+    Image.fromarray(np.arange(16, dtype=np.float32).reshape(4, 4)).save(path, tiffinfo=ifd)
+    return path
+
+
+def test_pop_and_crop_wrappers_equal_the_generic_loader(tmp_path):
+    """:1256-1300."""
+    tif = _pop_tif(tmp_path)
+    pop, gen = af.pop_weights_from_path(tif), af.secondary_weights_from_path(tif, wtype="pop")
+    assert pop.wtype == gen.wtype == "pop" and np.array_equal(pop.values, gen.values)
+    assert np.array_equal(pop.latitude, [3.5, 2.5, 1.5, 0.5]) and np.array_equal(pop.longitude, [0.5, 1.5, 2.5, 3.5])
+    store = _cropland_zarr(tmp_path)
+    crop = af.crop_weights_from_path(store, crop="soybeans", feed="rainfed", crs="WGS84")
+    gen = af.secondary_weights_from_path(store, var="layer", sel={"crop": "soybeans"}, wtype="soybeans", cache_identifier="rainfed",
+                                         crs="WGS84")
+    assert np.array_equal(crop.values, gen.values) and (crop.wtype, crop.cache_identifier) == (gen.wtype, gen.cache_identifier)
+    assert float(crop.values.max()) == 7.0                                       # soybeans == 7.0, corn == 1.0
+    assert float(af.crop_weights_from_path(store, crop="corn", crs="WGS84").values.max()) == 1.0
+    rain, irr = (af.crop_weights_from_path(store, crop="corn", feed=f, crs="WGS84") for f in ("rainfed", "irrigated"))
+    assert (rain.feed, irr.feed) == ("rainfed", "irrigated") and rain.cache_identifier != irr.cache_identifier
+    with pytest.raises(KeyError, match="wheat"):
+        af.crop_weights_from_path(store, crop="wheat")
+
+
+def test_open_raster_supports_tif_zarr_and_netcdf(tmp_path):
+    """:1304-1322."""
+    from scipy.io import netcdf_file
+    assert af.secondary_weights_from_path(_pop_tif(tmp_path)).values.shape == (4, 4)
+    z = af.secondary_weights_from_path(_cropland_zarr(tmp_path), var="layer", sel={"crop": "corn"})
+    assert float(z.values.max()) == 1.0 and z.values.shape == (4, 4)
+    nc = str(tmp_path / "x.nc")
+    with netcdf_file(nc, "w") as f:
+        f.createDimension("y", 2), f.createDimension("x", 2)
+        f.createVariable("y", "f8", ("y",))[:] = [0.5, 1.5]
+        f.createVariable("x", "f8", ("x",))[:] = [0.5, 1.5]
+        f.createVariable("layer", "f8", ("y", "x"))[:] = np.ones((2, 2))
+    got = af.secondary_weights_from_path(nc, var="layer")
+    assert np.array_equal(got.values, np.ones((2, 2))) and np.array_equal(got.latitude, [0.5, 1.5])
+    with pytest.raises(NotImplementedError, match="Unsupported raster format"):
+        af.secondary_weights_from_path(str(tmp_path / "x.bogus"))
+
+
+def test_cropland_weights_flow_into_the_weight_frame(tmp_path):
+    """A cropland layer from a zarr store weights the cells of a region like an in-memory raster does."""
+    store = _cropland_zarr(tmp_path)
+    lat = lon = np.arange(0, 4.0) + 0.5
+    ds = af.Dataset.from_arrays(np.ones((3, 4, 4)), pd.date_range("2000-01-01", periods=3), lat, lon, lon_is_360=False)
+    regions = af.GeoRegions.from_rectangles(["r1"], lon_min=[0.0], lon_max=[4.0], lat_min=[0.0], lat_max=[4.0])
+    a = af.weights_from_objects(ds, regions, secondary_weights=af.crop_weights_from_path(store, crop="soybeans"))
+    b = af.weights_from_objects(ds, regions, secondary_weights=af.SecondaryWeights(np.full((4, 4), 7.0), lat, lon))
+    a.calculate_weights(), b.calculate_weights()
+    assert len(a.weights) == 16 and np.allclose(a.weights.sort_values("cell_id").weight.values, b.weights.sort_values("cell_id").weight.values)
