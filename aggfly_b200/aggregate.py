@@ -35,6 +35,51 @@ def resolve_engine(engine: str, da=None, calc: str = None) -> str:
 
 
 # ---------------------------------------------------------------------------------------------
+# dask client helpers of the reference (aggfly/aggregate/aggregate_utils.py:9-102, exported at
+# aggfly/__init__.py:1-11).  There is no dask cluster behind this engine: scripts that bracket their calls with
+# start_dask_client() / shutdown_dask_client() keep running, each helper says so ONCE and does nothing.
+# ---------------------------------------------------------------------------------------------
+_SHIM_WARNED = set()
+_SHIM_ARGS = None          # what start_dask_client was called with (shutdown_dask_client returns it, like :89-102)
+
+
+def _shim_warn(name: str) -> None:
+    if name not in _SHIM_WARNED:
+        _SHIM_WARNED.add(name)
+        warnings.warn(f"aggfly_b200.{name}() is a no-op: the CUDA engine of the current device replaces the dask cluster "
+                      "(multi-GPU runs are launched with torchrun, see aggregate_dataset_sharded)", UserWarning, stacklevel=3)
+
+
+def is_distributed() -> bool:
+    """aggregate_utils.py:9-23 -- True when a dask client is running; never the case here."""
+    _shim_warn("is_distributed")
+    return False
+
+
+def distributed_client():
+    """aggregate_utils.py:25-35 -- the global dask client; always None here."""
+    _shim_warn("distributed_client")
+    return None
+
+
+def start_dask_client(n_workers: int = 2, threads_per_worker: int = 2, cap_numba_threads: int = 1, **kwargs):
+    """aggregate_utils.py:38-86 -- accepted for drop-in compatibility, starts nothing, returns None."""
+    global _SHIM_ARGS
+    _shim_warn("start_dask_client")
+    _SHIM_ARGS = {"n_workers": n_workers, "threads_per_worker": threads_per_worker,
+                  "cap_numba_threads": cap_numba_threads, **kwargs}
+    return None
+
+
+def shutdown_dask_client():
+    """aggregate_utils.py:89-102 -- returns the arguments of the matching start_dask_client() call, or None."""
+    global _SHIM_ARGS
+    _shim_warn("shutdown_dask_client")
+    args, _SHIM_ARGS = _SHIM_ARGS, None
+    return args
+
+
+# ---------------------------------------------------------------------------------------------
 # temporal
 # ---------------------------------------------------------------------------------------------
 class _DeviceRaster:
@@ -58,10 +103,14 @@ def _compile(dataset: Dataset, aggregator_dict: Optional[Dict[str, list]]):
 
 
 def _spec_fingerprint(aggregator_dict) -> Optional[tuple]:
-    """Hashable identity of a spec (None: not cacheable)."""
+    """Hashable identity of a spec by CONTENT (None: not cacheable).  A spec that carries an opaque object -- an
+    ``inter`` Dataset / tensor, a large array -- is never cached: its identity (``id``) says nothing about its
+    contents, which the caller may have reassigned or mutated since the plan captured them."""
     def fp(v):
         if isinstance(v, np.ndarray):
-            return ("arr", v.dtype.str, v.shape, v.tobytes()) if v.size <= 64 else ("id", id(v))
+            if v.size > 64:
+                raise TypeError("large array: not cacheable")
+            return ("arr", v.dtype.str, v.shape, v.tobytes())
         if isinstance(v, (list, tuple)):
             return tuple(fp(x) for x in v)
         if isinstance(v, dict):
@@ -70,7 +119,7 @@ def _spec_fingerprint(aggregator_dict) -> Optional[tuple]:
             return ("agg", v.calc, v.groupby, fp(v.ddargs))
         if isinstance(v, (str, int, float, bool, type(None), np.integer, np.floating)):
             return (type(v).__name__, v)
-        return ("id", id(v))
+        raise TypeError("opaque value: not cacheable")
     try:
         return None if aggregator_dict is None else tuple((k, fp(v)) for k, v in aggregator_dict.items())
     except Exception:

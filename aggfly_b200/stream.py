@@ -36,10 +36,10 @@ OPTIONS = {
     "chunked_ring_bytes": 2 << 30,     # pinned (and device) staging for chunked stores: slots x decoded chunk size
     "device_decompress": True,         # Blosc-LZ4 chunks: inflate on the GPU's decompression engine when it has one
     # The per-chunk tables of the device decode (expected stream lengths, raw-segment table) are uploaded from
-    # pageable memory, which makes the driver synchronise the compute stream twice per chunk (~0.4 ms per chunk:
-    # what bounds stores of small chunks).  True: the feed threads append them to the staged slot so that they ride
-    # the chunk's own copy.  Off until it has been measured on a GPU (round 2).
-    "inline_chunk_tables": False,
+    # pageable memory, which makes the driver synchronise the compute stream twice per chunk.  True: the feed threads append them to the staged slot so that they ride the chunk's own copy.
+    # Validated on a B200 in round 2 (GPU suite green both ways; the 24-hour-chunk Blosc store feeds in 156 ms either
+    # way, so the uploads were not its bound) and kept on: one copy per chunk instead of three.
+    "inline_chunk_tables": True,
     # Blosc packs its streams back to back at arbitrary byte offsets.  0: hand them to the engine where they are;
     # n > 1: first move every stream to an n-byte aligned offset of a second device buffer (one segment-copy launch)
     "device_decompress_align": int(__import__("os").environ.get("AGF_DE_ALIGN", "0")),
@@ -285,7 +285,7 @@ def feed_chunked(runner, src, n_cells: int, stream=None, k1_events: Optional[lis
         if ev is not None:
             ev.synchronize()
         if de:
-            return src.load_stored(tiles[i], bytes_np[slot], max_len, bool(OPTIONS.get("inline_chunk_tables", False)))
+            return src.load_stored(tiles[i], bytes_np[slot], max_len, bool(OPTIONS.get("inline_chunk_tables", True)))
         return ("host",) if src.load(tiles[i], views[slot]) else None
 
     def place(ptr, tile):

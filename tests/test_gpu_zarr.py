@@ -268,11 +268,11 @@ def test_decompression_engine_inflates_blosc_frames():
     assert plain.cpu().numpy().tobytes() == data
 
 
-@pytest.mark.parametrize("device_decompress", [True, False] + (["inline"] if __import__("os").environ.get("AGF_TEST_INLINE_TABLES") else []))
+@pytest.mark.parametrize("device_decompress", [True, False, "tables_uploaded"])
 @pytest.mark.parametrize("layout", ["time_major_daily_chunks", "time_contiguous_tiles", "lon_time_lat_lz4"])
 def test_blosc_store_matches_in_memory_result(tmp_path, layout, device_decompress):
-    # "inline": OPTIONS["inline_chunk_tables"], not yet run on a GPU (AGF_TEST_INLINE_TABLES=1 enables the case)
-    inline, device_decompress = device_decompress == "inline", bool(device_decompress)
+    # "tables_uploaded": the per-chunk tables as separate pageable uploads instead of riding the chunk's own copy (the default)
+    inline, device_decompress = device_decompress != "tables_uploaded", bool(device_decompress)
     import torch
     lay = LAYOUTS[layout]
     arr, t, lat, lon = _raster("float32", True, T=24 * 40 + 5, seed=23)
@@ -310,9 +310,6 @@ def test_blosc_store_matches_in_memory_result(tmp_path, layout, device_decompres
     _exact(got[vals].values, resident[vals].values)
 
 
-@pytest.mark.skipif(not __import__("os").environ.get("AGF_TEST_UNVALIDATED"),
-                    reason="multi-file feed written after the round's GPU budget was spent; host side covered by "
-                           "tests/test_zarrio.py::test_multi_file_dataset_is_a_lazy_time_concat")
 def test_multi_file_dataset_matches_single_array(tmp_path):
     import torch
     arr, t, lat, lon = _raster("float32", True, T=24 * 30, seed=31)

@@ -185,3 +185,33 @@ def test_time_sel_selects_like_pandas_partial_string_indexing():
     assert len(af.Dataset(ra, time_sel=slice("2001-01-01", "2001-01-02")).time) == 48          # both ends inclusive
     from aggfly_b200.dataset import time_selection
     assert time_selection(CalendarIndex.range("noleap", 2000, 365 * 3), "2001") == (365, 730)
+
+
+def test_dask_client_helpers_are_warn_once_noops():
+    """aggfly/__init__.py:1-11 exports start_dask_client / shutdown_dask_client / is_distributed /
+    distributed_client (aggregate_utils.py:9-102); scripts that call them must keep running."""
+    import warnings
+    import aggfly_b200 as af
+    from aggfly_b200 import aggregate as agg
+    agg._SHIM_WARNED.clear()
+    with warnings.catch_warnings(record=True) as rec:
+        warnings.simplefilter("always")
+        assert af.start_dask_client(n_workers=4, threads_per_worker=1, processes=False) is None
+        assert af.start_dask_client() is None                                  # second call: silent
+        assert af.is_distributed() is False and af.distributed_client() is None
+        assert af.shutdown_dask_client() == {"n_workers": 2, "threads_per_worker": 2, "cap_numba_threads": 1}
+        assert af.shutdown_dask_client() is None
+    assert sorted(str(w.message).split("(")[0] for w in rec) == [
+        "aggfly_b200.distributed_client", "aggfly_b200.is_distributed", "aggfly_b200.shutdown_dask_client",
+        "aggfly_b200.start_dask_client"]
+
+
+def test_specs_with_opaque_values_are_never_plan_cached():
+    """A plan captures an ``inter`` array by value; keying the cache on id() would hand back a stale plan."""
+    from aggfly_b200.aggregate import _spec_fingerprint
+    small = {"a": [("aggregate", {"calc": "mean", "groupby": "date"}), ("transform", {"transform": "power", "exp": np.arange(1, 3)})]}
+    assert _spec_fingerprint(small) is not None and _spec_fingerprint(small) == _spec_fingerprint(
+        {"a": [("aggregate", {"calc": "mean", "groupby": "date"}), ("transform", {"transform": "power", "exp": np.arange(1, 3)})]})
+    big = {"a": [("aggregate", {"calc": "mean", "groupby": "date"}), ("transform", {"inter": np.zeros((3, 5, 5))})]}
+    assert _spec_fingerprint(big) is None
+    assert _spec_fingerprint({"a": [("transform", {"inter": object()})]}) is None
