@@ -12,7 +12,7 @@ from typing import Optional
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libaggfly_b200.so")
 
-ABI_VERSION = 3                      # AGF_ABI_VERSION of include/aggfly_b200.h
+ABI_VERSION = 4                      # AGF_ABI_VERSION of include/aggfly_b200.h
 MAX_LANES, MAX_SLOTS, MAX_COLS = 32, 32, 64
 E_INVALID, E_UNSUPPORTED, E_NOMEM, E_STATE = -1, -2, -3, -4
 
@@ -62,6 +62,18 @@ class ProgramInfo(C.Structure):
                 ("kernel_kinds", C.c_int32), ("direct_out", C.c_int32)]
 
 
+class RPlanInfo(C.Structure):
+    _fields_ = [("n_tiles", C.c_int32), ("n_active_tiles", C.c_int32), ("n_slots", C.c_int32),
+                ("max_slots_per_tile", C.c_int32), ("n_entries", C.c_int64), ("tile_lat", C.c_int32),
+                ("tile_lon", C.c_int32), ("n_empty_regions", C.c_int32), ("pad_", C.c_int32), ("table_bytes", C.c_int64)]
+
+
+class RegionalInfo(C.Structure):
+    _fields_ = [("supported", C.c_int32), ("lanes_per_slot", C.c_int32), ("periods_per_unit", C.c_int32),
+                ("ring_blocks", C.c_int32), ("workspace_bytes", C.c_int64), ("n_units", C.c_int64),
+                ("kernel_lanes", C.c_int32), ("smem_bytes", C.c_int32)]
+
+
 class AgfError(RuntimeError):
     def __init__(self, code: int, msg: str):
         super().__init__(f"libaggfly_b200 error {code}: {msg}")
@@ -79,7 +91,9 @@ SYMBOLS = ("agf_version", "agf_last_error", "agf_program_create", "agf_program_d
            "agf_program_plan", "agf_program_info", "agf_program_stripe_rows", "agf_temporal_run",
            "agf_temporal_finalize", "agf_csr_create", "agf_csr_destroy", "agf_spmm_run",
            "agf_valid_mask_run", "agf_elementwise_run", "agf_tile_place_run", "agf_decompress_caps", "agf_decompress_lz4_run",
-           "agf_unshuffle_run", "agf_copy_segments_run", "agf_overlap_create", "agf_overlap_fetch", "agf_overlap_destroy")
+           "agf_unshuffle_run", "agf_copy_segments_run", "agf_overlap_create", "agf_overlap_fetch", "agf_overlap_destroy",
+           "agf_rplan_create", "agf_rplan_destroy", "agf_rplan_info", "agf_rplan_tables", "agf_temporal_regional_plan",
+           "agf_temporal_regional_run")
 
 
 def lib() -> C.CDLL:
@@ -118,6 +132,12 @@ def lib() -> C.CDLL:
     L.agf_overlap_create.argtypes = [C.POINTER(vp), i32, i64p, i64p, dp, i32, dp, C.c_double, i32, dp, C.c_double, i64p]
     L.agf_overlap_fetch.argtypes = [vp, i32p, i64p, dp]
     L.agf_overlap_destroy.argtypes = [vp]
+    L.agf_rplan_create.argtypes = [C.POINTER(vp), i32, i32, i32, i64, vp, vp, vp]
+    L.agf_rplan_destroy.argtypes = [vp]
+    L.agf_rplan_tables.argtypes = [i32, i32, i32, i64, vp, vp, vp, C.POINTER(RPlanInfo)] + [vp] * 8
+    L.agf_rplan_info.argtypes = [vp, C.POINTER(RPlanInfo)]
+    L.agf_temporal_regional_plan.argtypes = [vp, vp, i64, i64, i32, i32, C.POINTER(RegionalInfo)]
+    L.agf_temporal_regional_run.argtypes = [vp, vp, vp, i64, i64, i64, i64, i32, i32, vp, i64, vp, i64, i32, vp, u64]
     for name in SYMBOLS:
         fn = getattr(L, name)
         if name not in ("agf_version", "agf_last_error"):

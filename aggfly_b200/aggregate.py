@@ -15,6 +15,7 @@ from typing import Dict, List, Optional, Union
 import numpy as np
 import pandas as pd
 
+from . import _lib as _lib_mod
 from . import engine as _engine
 from . import stream as _stream
 from .dataset import Dataset
@@ -199,6 +200,35 @@ def _temporal_device(dataset: Dataset, aggregator_dict, target_stripes: int = 0)
 
 
 LAST_FEED_TRACE: dict = {}
+
+
+def _temporal_regional(dataset: Dataset, aggregator_dict, csr):
+    """Many-period panels: temporal scan + regional average in one kernel (engine.RegionalRunner), no per-cell X.
+    Returns (names, PanelResult) or None when the call is not a candidate / the library has no instantiation for it --
+    the caller then runs the two-kernel path."""
+    names, stage = _plan(dataset, aggregator_dict)
+    n_lat, n_lon = len(dataset.latitude), len(dataset.longitude)
+    if not _engine.regional_candidate(stage, n_lon):
+        return None
+    import torch
+    runner = _engine.RegionalRunner(stage, csr, n_lat, n_lon)
+    try:
+        if not runner.supported:
+            return None
+        try:
+            if _is_device_tensor(dataset.values):
+                raster = _DeviceRaster(dataset)
+                res = runner.run(raster.flat)
+            else:
+                res, raster = _stream.feed_and_run(runner, dataset.values, n_lat * n_lon)
+        except _lib_mod.AgfUnsupported:                     # e.g. a raster view that is not 16-byte aligned
+            return None
+        finally:
+            torch.cuda.current_stream().synchronize()
+    finally:
+        runner.close()
+    _stream.check_device_decompress()
+    return names, res
 
 
 def aggregate_time(dataset: Dataset, weights: GridWeights = None,
@@ -421,6 +451,19 @@ def aggregate_dataset(weights: GridWeights, dataset: Dataset = None,
     tr = _Trace()
     csr = _device_csr(weights, dataset)               # cached on the weights object after the first call
     tr.mark("csr")
+    fused = _temporal_regional(dataset, aggregator_dict, csr)
+    if fused is not None:
+        names, pres = fused
+        tr.mark("temporal + regional, one kernel (+ host feed)")
+        if _engine.OPTIONS.get("device_panel_frame", False):
+            df = _panel_frame(pres.panel, names, pres.labels, csr.host.region_ids, weights)
+        else:
+            df = _assemble_panel(pres.panel.cpu().numpy(), names, pres.labels, csr.host.region_ids, weights)
+            rid = weights.georegions.regionid
+            df = weights.georegions.shp[[rid]].merge(df, left_index=True, right_on="region_id").drop(columns="region_id")
+        tr.mark("panel frame")
+        tr.done()
+        return df
     names, res, raster = _temporal_device(dataset, aggregator_dict)
     tr.mark("temporal (+ host feed)")
     if _engine.OPTIONS.get("device_panel_frame", False):

@@ -58,6 +58,45 @@ struct K1Launch {
     int use_tma;
 };
 
+// ---- K1R: temporal scan + regional average in one kernel (agf_regional.cuh, agf_rplan.cu) ----
+// A CSR lowered onto 8 x 32 cell tiles of a lat x lon grid: per-tile slots (one per region the tile touches) and their
+// entries, plus for every region the slots that contribute to it.  Device tables are owned by the handle.
+struct agf_rplan {
+    int n_regions = 0, n_lat = 0, n_lon = 0;
+    int tiles_x = 0, tiles_y = 0, n_active = 0, n_gslots = 0, max_slots = 0;
+    int64_t n_entries = 0;
+    int n_empty_regions = 0;
+    int device = -1;
+    int *d_tile_ids = nullptr, *d_tile_slot_ptr = nullptr, *d_slot_region = nullptr, *d_slot_ent_ptr = nullptr;
+    int *d_region_slot_ptr = nullptr, *d_region_slots = nullptr;
+    void *d_entries = nullptr;
+    int64_t table_bytes = 0;
+};
+
+struct RegionalLaunch {
+    K1Launch k;              // program, raster view, stream (stripe / X / V fields unused)
+    const agf_rplan *plan;
+    int64_t g_begin, g_end;  // periods of this launch
+    int D, ring;             // periods per unit; day-blocks the partial buffer holds
+    void *d_workspace;
+    int64_t workspace_bytes;
+    double *d_panel, *d_den;
+    int64_t G;               // periods of the whole panel (row pitch)
+    int out_ncols;
+};
+
+struct RegionalChoice {
+    int lanes, typed_bins, lps;   // instantiation: kernel lanes, NB, lanes per slot
+    int smem_bytes, ctas_per_sm, grid;
+    int64_t workspace_bytes;
+    int64_t n_units;
+};
+
+// mode 0: launch; mode 1: only report the instantiation / workspace in *choice.  Returns 1 if nothing fits.
+int agf_k1_f32_regional(const RegionalLaunch &a, int mode, RegionalChoice *choice, int *rc);
+int agf_make_tensor_map3(agf::TensorMap *out, const void *base, int elem_size, uint64_t n_lon, uint64_t n_lat,
+                         uint64_t n_rows, uint64_t ld, int box_lon, int box_lat, int box_rows);
+
 struct K1Choice {
     int lanes, slots, diag;
     unsigned kinds;

@@ -29,10 +29,10 @@ static inline void set_thresholds(LaneP<double> &L, double t0, double t1) {
     L.hi = t1;
 }
 
-template <typename T, int NL, int NS, bool DIAG, unsigned KINDS, int NB, int GL, bool TMA>
-static int launch_k1(const K1Launch &a) {
+// descriptor + launch arguments -> the kernel's parameter block (lane / slot / column tables in KERNEL order)
+template <typename T, int NL, int NS, bool DIAG, unsigned KINDS, int NB>
+static void k1_fill_params(K1Params<T, NL, NS> &kp, const K1Launch &a) {
     const agf_program *p = a.p;
-    K1Params<T, NL, NS> kp;
     memset(&kp, 0, sizeof(kp));
     const agf_program_desc_t &d = p->desc;
     kp.x = (const T *)a.d_x;
@@ -218,6 +218,15 @@ static int launch_k1(const K1Launch &a) {
             }
         }
     }
+}
+
+template <typename T, int NL, int NS, bool DIAG, unsigned KINDS, int NB, int GL, bool TMA>
+static int launch_k1(const K1Launch &a) {
+    const agf_program *p = a.p;
+    const agf_program_desc_t &d = p->desc;
+    K1Params<T, NL, NS> kp;
+    k1_fill_params<T, NL, NS, DIAG, KINDS, NB>(kp, a);
+    constexpr bool TL = typed_lanes<NS, NB>();
     if constexpr (TMA) {
         // rows of the view the stripes of this launch can touch
         const int64_t row_end = p->b1[p->stripes[a.s1 - 1].g1_end];
@@ -290,6 +299,7 @@ static inline bool k1_fits(const agf_program *p, int NL, int NS, bool DG, unsign
     return (p->kinds & ~KINDS) == 0;
 }
 
+#ifdef AGF_LIST
 int AGF_FN(const K1Launch &a, int mode, K1Choice *choice, int *rc) {
     const agf_program *p = a.p;
 #define K1CASE(NL, NS, DG, KINDS, NB, GL)                                             \
@@ -302,3 +312,4 @@ int AGF_FN(const K1Launch &a, int mode, K1Choice *choice, int *rc) {
 #undef K1CASE
     return 1;
 }
+#endif  // AGF_LIST

@@ -1,0 +1,338 @@
+// agf_rplan.cu -- host side of K1R (agf_regional.cuh): lowers a CSR weights matrix onto the cell tiles of a
+// lat x lon grid, and the C-ABI entry points agf_rplan_* / agf_temporal_regional_*.
+//
+// Reference semantics: _weight_triplets (aggfly/aggregate/spatial.py:157-178) fixes the order of a region's entries
+// (weights-frame order); the tables below keep that order inside every (tile, region) slot, so the in-kernel sums add
+// the same terms in the same order as np.add.at for every region that lies inside one tile.
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include <cuda.h>
+
+#include "agf_host.h"
+#include "agf_regional.cuh"
+
+using namespace agf;
+
+template <typename V>
+static int upload_vec(V **dst, const std::vector<V> &src, int64_t *bytes) {
+    *dst = nullptr;
+    const size_t n = std::max<size_t>(src.size(), 1);
+    CU(cudaMalloc((void **)dst, n * sizeof(V)));
+    if (!src.empty()) CU(cudaMemcpy(*dst, src.data(), src.size() * sizeof(V), cudaMemcpyHostToDevice));
+    *bytes += (int64_t)(n * sizeof(V));
+    return 0;
+}
+
+extern "C" int agf_rplan_destroy(agf_rplan_t *p) {
+    if (!p) return 0;
+    cudaFree(p->d_tile_ids);
+    cudaFree(p->d_tile_slot_ptr);
+    cudaFree(p->d_slot_region);
+    cudaFree(p->d_slot_ent_ptr);
+    cudaFree(p->d_region_slot_ptr);
+    cudaFree(p->d_region_slots);
+    cudaFree(p->d_entries);
+    delete p;
+    return 0;
+}
+
+namespace {
+struct HostTables {
+    std::vector<int32_t> tile_ids, tile_slot_ptr, slot_region, slot_ent_ptr, region_slot_ptr, region_slots;
+    std::vector<RgEntry> entries;
+    int tiles_x = 0, tiles_y = 0, max_slots = 0, n_empty = 0;
+};
+}  // namespace
+
+static int build_tables(HostTables &t, int32_t n_regions, int32_t n_lat, int32_t n_lon, int64_t nnz,
+                        const int32_t *row_ptr, const int32_t *cell_idx, const double *w) {
+    if (n_regions <= 0 || n_lat <= 0 || n_lon <= 0 || nnz < 0 || nnz > 0x7fffffff)
+        return agf_fail(AGF_E_INVALID, "bad sizes");
+    if (!row_ptr || (nnz > 0 && (!cell_idx || !w))) return agf_fail(AGF_E_INVALID, "null CSR array");
+    if (row_ptr[0] != 0 || row_ptr[n_regions] != nnz) return agf_fail(AGF_E_INVALID, "row_ptr does not span nnz");
+    const int64_t n_cells = (int64_t)n_lat * n_lon;
+    const int tiles_x = (n_lon + RG_TW - 1) / RG_TW, tiles_y = (n_lat + RG_TH - 1) / RG_TH;
+    const int64_t n_tiles = (int64_t)tiles_x * tiles_y;
+    t.tiles_x = tiles_x;
+    t.tiles_y = tiles_y;
+
+    // counting sort of the entries by tile; visiting regions in ascending order and their entries in CSR order keeps
+    // (region ascending, weights-frame order) inside every tile
+    std::vector<int32_t> tile_of(nnz);
+    std::vector<int64_t> tile_cnt(n_tiles + 1, 0);
+    for (int64_t e = 0; e < nnz; ++e) {
+        const int64_t c = cell_idx[e];
+        if (c < 0 || c >= n_cells) return agf_fail(AGF_E_INVALID, "cell_idx[%lld] = %lld outside the grid", (long long)e, (long long)c);
+        const int lat = (int)(c / n_lon), lon = (int)(c % n_lon);
+        tile_of[e] = (lat / RG_TH) * tiles_x + lon / RG_TW;
+        ++tile_cnt[tile_of[e] + 1];
+    }
+    for (int64_t k = 0; k < n_tiles; ++k) tile_cnt[k + 1] += tile_cnt[k];
+    std::vector<int64_t> pos(tile_cnt.begin(), tile_cnt.end() - 1);
+    std::vector<int32_t> ent_region(nnz);
+    t.entries.resize(nnz);
+    for (int32_t r = 0; r < n_regions; ++r) {
+        if (row_ptr[r] > row_ptr[r + 1]) return agf_fail(AGF_E_INVALID, "row_ptr not monotonic");
+        for (int64_t e = row_ptr[r]; e < row_ptr[r + 1]; ++e) {
+            const int64_t c = cell_idx[e];
+            const int lat = (int)(c / n_lon), lon = (int)(c % n_lon);
+            const int64_t k = pos[tile_of[e]]++;
+            ent_region[k] = r;
+            t.entries[k].w = w[e];
+            t.entries[k].cell = (lat % RG_TH) * RG_TW + (lon % RG_TW);
+            t.entries[k].pad = 0;
+        }
+    }
+    // slots: runs of one region inside a tile
+    t.tile_slot_ptr.assign(1, 0);
+    for (int64_t tl = 0; tl < n_tiles; ++tl) {
+        if (tile_cnt[tl + 1] == tile_cnt[tl]) continue;
+        int ns = 0;
+        for (int64_t k = tile_cnt[tl]; k < tile_cnt[tl + 1]; ++k) {
+            if (k == tile_cnt[tl] || ent_region[k] != ent_region[k - 1]) {
+                t.slot_region.push_back(ent_region[k]);
+                t.slot_ent_ptr.push_back((int32_t)k);
+                ++ns;
+            }
+        }
+        t.tile_ids.push_back((int32_t)tl);
+        t.tile_slot_ptr.push_back((int32_t)t.slot_region.size());
+        t.max_slots = std::max(t.max_slots, ns);
+    }
+    t.slot_ent_ptr.push_back((int32_t)nnz);
+    const int n_gslots = (int)t.slot_region.size();
+    // slots of every region in ascending slot (== tile) order
+    t.region_slot_ptr.assign(n_regions + 1, 0);
+    t.region_slots.resize(n_gslots);
+    for (int s = 0; s < n_gslots; ++s) ++t.region_slot_ptr[t.slot_region[s] + 1];
+    for (int r = 0; r < n_regions; ++r) t.region_slot_ptr[r + 1] += t.region_slot_ptr[r];
+    {
+        std::vector<int32_t> at(t.region_slot_ptr.begin(), t.region_slot_ptr.end() - 1);
+        for (int s = 0; s < n_gslots; ++s) t.region_slots[at[t.slot_region[s]]++] = s;
+    }
+    for (int r = 0; r < n_regions; ++r) t.n_empty += t.region_slot_ptr[r + 1] == t.region_slot_ptr[r];
+    return 0;
+}
+
+static void fill_info(agf_rplan_info_t *info, const HostTables &t, int64_t table_bytes) {
+    memset(info, 0, sizeof(*info));
+    info->n_tiles = t.tiles_x * t.tiles_y;
+    info->n_active_tiles = (int32_t)t.tile_ids.size();
+    info->n_slots = (int32_t)t.slot_region.size();
+    info->max_slots_per_tile = t.max_slots;
+    info->n_entries = (int64_t)t.entries.size();
+    info->tile_lat = RG_TH;
+    info->tile_lon = RG_TW;
+    info->n_empty_regions = t.n_empty;
+    info->table_bytes = table_bytes;
+}
+
+// host-only: the tables agf_rplan_create would upload (no device needed; used by the CPU tests of the lowering)
+extern "C" int agf_rplan_tables(int32_t n_regions, int32_t n_lat, int32_t n_lon, int64_t nnz, const int32_t *row_ptr,
+                                const int32_t *cell_idx, const double *w, agf_rplan_info_t *info, int32_t *tile_ids,
+                                int32_t *tile_slot_ptr, int32_t *slot_region, int32_t *slot_ent_ptr, int32_t *entry_cell,
+                                double *entry_w, int32_t *region_slot_ptr, int32_t *region_slots) {
+    HostTables t;
+    int rc = build_tables(t, n_regions, n_lat, n_lon, nnz, row_ptr, cell_idx, w);
+    if (rc) return rc;
+    if (info) fill_info(info, t, 0);
+    auto put = [](int32_t *dst, const std::vector<int32_t> &src) {
+        if (dst && !src.empty()) memcpy(dst, src.data(), src.size() * sizeof(int32_t));
+    };
+    put(tile_ids, t.tile_ids);
+    put(tile_slot_ptr, t.tile_slot_ptr);
+    put(slot_region, t.slot_region);
+    put(slot_ent_ptr, t.slot_ent_ptr);
+    put(region_slot_ptr, t.region_slot_ptr);
+    put(region_slots, t.region_slots);
+    for (size_t k = 0; k < t.entries.size(); ++k) {
+        if (entry_cell) entry_cell[k] = t.entries[k].cell;
+        if (entry_w) entry_w[k] = t.entries[k].w;
+    }
+    return 0;
+}
+
+extern "C" int agf_rplan_create(agf_rplan_t **out, int32_t n_regions, int32_t n_lat, int32_t n_lon, int64_t nnz,
+                                const int32_t *row_ptr, const int32_t *cell_idx, const double *w) {
+    if (!out) return agf_fail(AGF_E_INVALID, "null out");
+    *out = nullptr;
+    HostTables t;
+    int rc = build_tables(t, n_regions, n_lat, n_lon, nnz, row_ptr, cell_idx, w);
+    if (rc) return rc;
+    agf_rplan *p = new agf_rplan();
+    p->n_regions = n_regions;
+    p->n_lat = n_lat;
+    p->n_lon = n_lon;
+    p->tiles_x = t.tiles_x;
+    p->tiles_y = t.tiles_y;
+    p->n_active = (int)t.tile_ids.size();
+    p->n_gslots = (int)t.slot_region.size();
+    p->max_slots = t.max_slots;
+    p->n_entries = nnz;
+    p->n_empty_regions = t.n_empty;
+    cudaError_t e0 = cudaGetDevice(&p->device);
+    if (e0 != cudaSuccess) {
+        delete p;
+        return agf_cuda_fail(e0, "cudaGetDevice");
+    }
+    if ((rc = upload_vec(&p->d_tile_ids, t.tile_ids, &p->table_bytes)) ||
+        (rc = upload_vec(&p->d_tile_slot_ptr, t.tile_slot_ptr, &p->table_bytes)) ||
+        (rc = upload_vec(&p->d_slot_region, t.slot_region, &p->table_bytes)) ||
+        (rc = upload_vec(&p->d_slot_ent_ptr, t.slot_ent_ptr, &p->table_bytes)) ||
+        (rc = upload_vec(&p->d_region_slot_ptr, t.region_slot_ptr, &p->table_bytes)) ||
+        (rc = upload_vec(&p->d_region_slots, t.region_slots, &p->table_bytes)) ||
+        (rc = upload_vec((RgEntry **)&p->d_entries, t.entries, &p->table_bytes))) {
+        agf_rplan_destroy(p);
+        return rc;
+    }
+    *out = p;
+    return 0;
+}
+
+extern "C" int agf_rplan_info(const agf_rplan_t *p, agf_rplan_info_t *info) {
+    if (!p || !info) return agf_fail(AGF_E_INVALID, "null argument");
+    memset(info, 0, sizeof(*info));
+    info->n_tiles = p->tiles_x * p->tiles_y;
+    info->n_active_tiles = p->n_active;
+    info->n_slots = p->n_gslots;
+    info->max_slots_per_tile = p->max_slots;
+    info->n_entries = p->n_entries;
+    info->tile_lat = RG_TH;
+    info->tile_lon = RG_TW;
+    info->n_empty_regions = p->n_empty_regions;
+    info->table_bytes = p->table_bytes;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// 3-D tensor map over the raster [rows, n_lat, n_lon]
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn3)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int agf_make_tensor_map3(agf::TensorMap *out, const void *base, int elem_size, uint64_t n_lon, uint64_t n_lat,
+                         uint64_t n_rows, uint64_t ld, int box_lon, int box_lat, int box_rows) {
+    static EncodeTiledFn3 fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn3)ptr;
+    }
+    if (!fn) return agf_fail(AGF_E_UNSUPPORTED, "cuTensorMapEncodeTiled not available");
+    cuuint64_t dims[3] = {n_lon, n_lat, n_rows};
+    cuuint64_t strides[2] = {n_lon * (cuuint64_t)elem_size, ld * (cuuint64_t)elem_size};
+    cuuint32_t box[3] = {(cuuint32_t)box_lon, (cuuint32_t)box_lat, (cuuint32_t)box_rows};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn((CUtensorMap *)out, elem_size == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+                    3, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return agf_fail(AGF_E_UNSUPPORTED, "cuTensorMapEncodeTiled (3-D) failed (%d)", (int)r);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// C-ABI
+// ------------------------------------------------------------------------------------------
+static int regional_args(const agf_program_t *p, const agf_rplan_t *plan, int64_t g0, int64_t g1) {
+    if (!p || !plan) return agf_fail(AGF_E_INVALID, "null argument");
+    int dev = -1;
+    CU(cudaGetDevice(&dev));
+    if (dev != p->device || dev != plan->device)
+        return agf_fail(AGF_E_STATE, "handles belong to devices %d / %d, current device is %d", p->device, plan->device, dev);
+    if ((int64_t)plan->n_lat * plan->n_lon != p->n_cells)
+        return agf_fail(AGF_E_INVALID, "plan grid %d x %d does not match the program's %lld cells", plan->n_lat, plan->n_lon,
+                        (long long)p->n_cells);
+    if (g0 < 0 || g1 > p->desc.n_groups1 || g0 >= g1) return agf_fail(AGF_E_INVALID, "bad period range [%lld, %lld)", (long long)g0, (long long)g1);
+    return 0;
+}
+
+static int default_D() {
+    if (const char *e = getenv("AGF_REGIONAL_D")) {
+        const int v = atoi(e);
+        if (v >= 1 && v <= 64) return v;
+    }
+    return 4;
+}
+
+extern "C" int agf_temporal_regional_plan(const agf_program_t *p, const agf_rplan_t *plan, int64_t group_begin,
+                                          int64_t group_end, int32_t periods_per_unit, int32_t ring_blocks,
+                                          agf_regional_info_t *info) {
+    if (!info) return agf_fail(AGF_E_INVALID, "null info");
+    memset(info, 0, sizeof(*info));
+    int rc = regional_args(p, plan, group_begin, group_end);
+    if (rc) return rc;
+    RegionalLaunch a{};
+    a.k.p = p;
+    a.k.use_tma = 1;
+    a.plan = plan;
+    a.g_begin = group_begin;
+    a.g_end = group_end;
+    a.D = periods_per_unit > 0 ? periods_per_unit : default_D();
+    a.ring = ring_blocks;
+    RegionalChoice ch{};
+    int krc = 0;
+    if (p->desc.in_dtype != AGF_F32 || agf_k1_f32_regional(a, 1, &ch, &krc)) {
+        agf_fail(AGF_E_UNSUPPORTED, "no regional instantiation for this program (single-level float32 programs with 24-row "
+                                    "periods are covered); run agf_temporal_run + agf_spmm_run");
+        return 0;  // info->supported stays 0
+    }
+    info->supported = 1;
+    info->lanes_per_slot = ch.lps;
+    info->periods_per_unit = a.D;
+    const int64_t n_blocks = (group_end - group_begin + a.D - 1) / a.D;
+    info->ring_blocks = (int32_t)((ring_blocks > 0 && ring_blocks < n_blocks) ? ring_blocks : n_blocks);
+    info->workspace_bytes = ch.workspace_bytes;
+    info->n_units = ch.n_units;
+    info->kernel_lanes = ch.lanes;
+    info->smem_bytes = ch.smem_bytes;
+    return 0;
+}
+
+extern "C" int agf_temporal_regional_run(const agf_program_t *p, const agf_rplan_t *plan, const void *d_x, int64_t ld,
+                                         int64_t row0, int64_t group_begin, int64_t group_end, int32_t periods_per_unit,
+                                         int32_t ring_blocks, void *d_workspace, int64_t workspace_bytes, double *d_panel,
+                                         int64_t panel_groups, int32_t out_ncols, double *d_den, uintptr_t stream) {
+    int rc = regional_args(p, plan, group_begin, group_end);
+    if (rc) return rc;
+    if (!d_x || !d_workspace || !d_panel) return agf_fail(AGF_E_INVALID, "null buffer");
+    if (ld < p->n_cells) return agf_fail(AGF_E_INVALID, "ld < n_cells");
+    if (row0 < 0 || row0 > p->b1[group_begin]) return agf_fail(AGF_E_INVALID, "row0 is past the first row of the period range");
+    if (panel_groups < group_end) return agf_fail(AGF_E_INVALID, "panel has %lld periods, the range ends at %lld", (long long)panel_groups, (long long)group_end);
+    for (int c = 0; c < p->desc.n_cols; ++c)
+        if (p->desc.cols[c].dst >= out_ncols) return agf_fail(AGF_E_INVALID, "col %d: dst outside the panel (out_ncols=%d)", c, out_ncols);
+    if (p->desc.in_dtype != AGF_F32) return agf_fail(AGF_E_UNSUPPORTED, "regional kernel: float32 rasters only");
+    if (((uintptr_t)d_x % 16) != 0 || (ld % 4) != 0 || (plan->n_lon % 4) != 0)
+        return agf_fail(AGF_E_UNSUPPORTED, "regional kernel needs a 16-byte aligned raster whose row and latitude pitches are "
+                                           "multiples of 16 bytes (n_lon %% 4 == 0)");
+    RegionalLaunch a{};
+    a.k.p = p;
+    a.k.d_x = d_x;
+    a.k.ld = ld;
+    a.k.row0 = row0;
+    a.k.ncols = out_ncols;
+    a.k.stream = (cudaStream_t)stream;
+    a.k.use_tma = 1;
+    a.plan = plan;
+    a.g_begin = group_begin;
+    a.g_end = group_end;
+    a.D = periods_per_unit > 0 ? periods_per_unit : default_D();
+    a.ring = ring_blocks;
+    a.d_workspace = d_workspace;
+    a.workspace_bytes = workspace_bytes;
+    a.d_panel = d_panel;
+    a.d_den = d_den;
+    a.G = panel_groups;
+    a.out_ncols = out_ncols;
+    int krc = 0;
+    if (agf_k1_f32_regional(a, 0, nullptr, &krc))
+        return agf_fail(AGF_E_UNSUPPORTED, "no regional instantiation for this program");
+    return krc;
+}

@@ -23,6 +23,13 @@ OPTIONS = {
     # suite ran green through it on a B200 in round 2, daily-panel call 3.97 s -> 1.84 s).  AGF_DEVICE_PANEL=0 selects the
     # literal route (kept as the cross-check the tests compare against).
     "device_panel_frame": bool(int(__import__("os").environ.get("AGF_DEVICE_PANEL", "1") or 0)),
+    # Panels with many periods (hourly raster -> daily panel): temporal scan + regional average in ONE kernel
+    # (agf_temporal_regional_run, csrc/agf_regional.cuh) instead of K1 -> X -> K2.  "auto": when the program has a regional
+    # instantiation and the panel has at least ``regional_min_periods`` periods; True / False force it on / off.
+    "regional": {"0": False, "1": True}.get(__import__("os").environ.get("AGF_REGIONAL", ""), "auto"),
+    "regional_min_periods": 32,
+    "regional_periods_per_unit": 0,      # 0: library default (4)
+    "regional_ring_blocks": 0,           # 0: partial rows for the whole range (no reuse); n: a ring of n period blocks
 }
 
 
@@ -112,6 +119,161 @@ class DeviceCSR:
             self.close()
         except Exception:
             pass
+
+
+class RegionalPlan:
+    """``agf_rplan_t``: a CSR lowered onto the 8 x 32 cell tiles of the raster's lat x lon grid (kept on the DeviceCSR)."""
+
+    def __init__(self, host: HostCSR, n_lat: int, n_lon: int):
+        _torch()
+        self.n_lat, self.n_lon = int(n_lat), int(n_lon)
+        self.handle = C.c_void_p()
+        rp, ci, w = (np.ascontiguousarray(host.row_ptr, dtype=np.int32), np.ascontiguousarray(host.cell_idx, dtype=np.int32),
+                     np.ascontiguousarray(host.w, dtype=np.float64))
+        _lib.check(_lib.lib().agf_rplan_create(C.byref(self.handle), host.n_regions, self.n_lat, self.n_lon, host.nnz,
+                                               rp.ctypes.data, ci.ctypes.data, w.ctypes.data))
+        self.info = _lib.RPlanInfo()
+        _lib.check(_lib.lib().agf_rplan_info(self.handle, C.byref(self.info)))
+
+    def close(self):
+        if self.handle:
+            _lib.lib().agf_rplan_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def regional_plan_of(csr: "DeviceCSR", n_lat: int, n_lon: int) -> RegionalPlan:
+    cache = csr.__dict__.setdefault("_rplans", {})
+    key = (int(n_lat), int(n_lon))
+    if key not in cache:
+        if int(n_lat) * int(n_lon) != csr.host.n_cells:
+            raise ValueError(f"grid {n_lat} x {n_lon} does not match the CSR's {csr.host.n_cells} cells")
+        cache[key] = RegionalPlan(csr.host, n_lat, n_lon)
+    return cache[key]
+
+
+class PanelResult:
+    """What a regional run leaves on the device: the panel itself (no per-cell X / V)."""
+
+    def __init__(self, panel, den, labels, nodes):
+        self.panel, self.den, self.labels, self.nodes = panel, den, labels, nodes
+
+
+def regional_candidate(stage: Stage, n_lon: int) -> bool:
+    """Cheap host-side test: one raster-reading single-level float32 program fills the whole stage."""
+    opt = OPTIONS.get("regional", "auto")
+    if opt is False or stage.inputs or stage.elementwise is not None or len(stage.programs) != 1:
+        return False
+    spec = stage.programs[0]
+    if spec.two_level or getattr(spec, "_source", None) is not None or np.dtype(spec.in_dtype) != np.float32:
+        return False
+    b1 = np.asarray(spec.bounds1)
+    if len(b1) < 2 or not np.all(np.diff(b1) == 24) or n_lon % 4 != 0:
+        return False
+    return opt is True or len(stage.labels) >= int(OPTIONS.get("regional_min_periods", 32))
+
+
+class RegionalRunner:
+    """One program + one regional plan -> the panel, without X.  Same streamed interface as ``StageRunner``
+    (``begin_streamed`` / ``feed`` / ``finish_streamed``), so ``stream.feed_and_run`` drives either."""
+
+    GROUP_QUANTUM = 16          # periods per launch of a streamed feed (a few period blocks: amortises the launch)
+
+    def __init__(self, stage: Stage, csr: "DeviceCSR", n_lat: int, n_lon: int, device=None, want_den: bool = False):
+        torch = _torch()
+        self.stage, self.csr = stage, csr
+        self.n_cells = int(n_lat) * int(n_lon)
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+        self.plan = regional_plan_of(csr, n_lat, n_lon)
+        self.program = Program(stage.programs[0], stage.dtype, self.n_cells, 1)
+        self.programs = [self.program]
+        self.G, self.n_cols = len(stage.labels), len(stage.nodes)
+        self.D = int(OPTIONS.get("regional_periods_per_unit", 0))
+        self.ring = int(OPTIONS.get("regional_ring_blocks", 0))
+        self.info = _lib.RegionalInfo()
+        _lib.check(_lib.lib().agf_temporal_regional_plan(self.program.handle, self.plan.handle, 0, self.G, self.D, self.ring,
+                                                         C.byref(self.info)))
+        self.supported = bool(self.info.supported)
+        self.workspace = self.panel = self.den = None
+        self.want_den = want_den
+        self.b1 = np.asarray(stage.programs[0].bounds1, dtype=np.int64)
+        self._cursor = 0
+
+    def _buffers(self):
+        torch = _torch()
+        if self.workspace is None:
+            self.workspace = torch.empty(int(self.info.workspace_bytes) + 256, dtype=torch.uint8, device=self.device)
+        R = self.csr.host.n_regions
+        self.panel = torch.empty((R, self.G, self.n_cols), dtype=torch.float64, device=self.device)
+        self.den = torch.empty((R, self.G), dtype=torch.float64, device=self.device) if self.want_den else None
+
+    def _launch(self, raster, g0: int, g1: int, stream, k1_events=None) -> None:
+        torch = _torch()
+        if raster.dtype != torch.float32:
+            raise TypeError(f"raster dtype {raster.dtype} does not match the planned float32")
+        ev = None
+        if k1_events is not None:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record(stream)
+        with torch.cuda.stream(stream):
+            _lib.check(_lib.lib().agf_temporal_regional_run(
+                self.program.handle, self.plan.handle, raster.data_ptr(), self.n_cells, 0, g0, g1, self.D, self.ring,
+                self.workspace.data_ptr(), self.workspace.numel(), self.panel.data_ptr(), self.G, self.n_cols,
+                self.den.data_ptr() if self.den is not None else None, stream.cuda_stream))
+        if ev is not None:
+            ev[1].record(stream)
+            k1_events.append(ev)
+
+    @property
+    def launches_per_run(self) -> int:
+        return 1 + 1                                # the kernel + the memset of its arrival counters
+
+    def algorithmic_input_bytes(self) -> int:
+        """Raster bytes the kernel must read: the tiles that hold at least one weighted cell (cells no region
+        touches cannot change the panel and are never loaded)."""
+        T = int(self.b1[-1] - self.b1[0])
+        return T * int(self.plan.info.n_active_tiles) * 256 * 4
+
+    def algorithmic_output_bytes(self) -> int:
+        return self.csr.host.n_regions * self.G * self.n_cols * 8
+
+    def run(self, raster, stream=None, k1_events=None) -> PanelResult:
+        """Device-resident raster [T, n_cells]: one launch for the whole period range."""
+        torch = _torch()
+        st = torch.cuda.current_stream() if stream is None else stream
+        self._buffers()
+        self._launch(raster, 0, self.G, st, k1_events)
+        return PanelResult(self.panel, self.den, self.stage.labels, self.stage.nodes)
+
+    # ---- streamed execution (stream.feed_and_run) ----
+    def begin_streamed(self, stream) -> None:
+        self._buffers()
+        self._cursor = 0
+
+    def feed(self, raster, rows_ready: int, stream, k1_events=None) -> int:
+        g_ready = int(np.searchsorted(self.b1, rows_ready, side="right")) - 1     # complete periods
+        g_ready = min(g_ready, self.G)
+        if g_ready < self.G:
+            g_ready = self._cursor + (g_ready - self._cursor) // self.GROUP_QUANTUM * self.GROUP_QUANTUM
+        if g_ready <= self._cursor:
+            return 0
+        self._launch(raster, self._cursor, g_ready, stream, k1_events)
+        self._cursor = g_ready
+        return 1
+
+    def finish_streamed(self, raster, stream) -> PanelResult:
+        if self._cursor != self.G:
+            raise RuntimeError(f"streamed run ended with periods {self._cursor}..{self.G} not launched "
+                               "(raster shorter than the time axis?)")
+        return PanelResult(self.panel, self.den, self.stage.labels, self.stage.nodes)
+
+    def close(self):
+        self.program.close()
 
 
 class StageResult:

@@ -47,7 +47,7 @@
 extern "C" {
 #endif
 
-#define AGF_ABI_VERSION 3
+#define AGF_ABI_VERSION 4
 
 #define AGF_MAX_LANES 32  /* level-1 reducers per program */
 #define AGF_MAX_SLOTS 32  /* level-2 reducers per program */
@@ -237,6 +237,70 @@ int agf_csr_destroy(agf_csr_t *csr);
 int agf_spmm_run(const agf_csr_t *csr, const void *d_x, int32_t x_dtype, const uint8_t *d_valid,
                  int64_t n_groups, int32_t n_cols, double *d_panel, double *d_den,
                  uintptr_t stream);
+
+/* ---- temporal scan + regional average in ONE kernel (daily / many-period panels) ------------------------ */
+
+/* For panels with many periods the per-cell columns X are as large as the raster (hourly -> daily: 21.6 GB written
+ * and read back next to a 36.4 GB raster).  agf_temporal_regional_run produces the panel of
+ *     numba_resample (aggfly/aggregate/nb_kernels.py:253-305)  ->  _scatter_block + divide
+ *                                                    (aggfly/aggregate/spatial.py:114-133, 181-186)
+ * without materialising X: cells are scanned in 8 x 32 (lat x lon) tiles, every period's columns are contracted
+ * with the weights inside the tile (entries in weights-frame order), and regions that straddle tiles are
+ * completed by the last tile to arrive, adding the per-tile partial sums in ascending tile order -- so the result
+ * does not depend on scheduling (bit-identical from run to run), equals agf_temporal_run + agf_spmm_run bit for
+ * bit for regions that lie inside one tile, and differs from it by the re-association of one sum otherwise
+ * (rel ~1e-16).  Covered: single-level float32 programs whose periods have 24 rows (hourly -> date). */
+
+/* A CSR lowered onto the cell tiles of a n_lat x n_lon grid (cell = lat * n_lon + lon, the raster's memory order).
+ * row_ptr / cell_idx / w are HOST arrays (the arrays agf_csr_create takes on the device); the handle owns its
+ * device tables (about 16 bytes per entry). */
+typedef struct agf_rplan agf_rplan_t;
+typedef struct {
+    int32_t n_tiles, n_active_tiles; /* tiles of the grid / tiles that hold at least one entry (only those are read) */
+    int32_t n_slots;                 /* (tile, region) pairs */
+    int32_t max_slots_per_tile;
+    int64_t n_entries;
+    int32_t tile_lat, tile_lon;      /* 8, 32 */
+    int32_t n_empty_regions;         /* regions without any entry on this grid (their rows are NaN) */
+    int32_t pad_;
+    int64_t table_bytes;
+} agf_rplan_info_t;
+int agf_rplan_create(agf_rplan_t **out, int32_t n_regions, int32_t n_lat, int32_t n_lon, int64_t nnz,
+                     const int32_t *row_ptr, const int32_t *cell_idx, const double *w);
+int agf_rplan_destroy(agf_rplan_t *plan);
+/* Host-only twin of agf_rplan_create (no device needed): fills *info and copies the tables into the non-NULL
+ * outputs -- tile_ids[n_active_tiles], tile_slot_ptr[n_active_tiles + 1], slot_region[n_slots],
+ * slot_ent_ptr[n_slots + 1], entry_cell[n_entries] (cell inside its tile: (lat % 8) * 32 + lon % 32),
+ * entry_w[n_entries], region_slot_ptr[n_regions + 1], region_slots[n_slots].  Call once with NULL outputs for the
+ * sizes. */
+int agf_rplan_tables(int32_t n_regions, int32_t n_lat, int32_t n_lon, int64_t nnz, const int32_t *row_ptr,
+                     const int32_t *cell_idx, const double *w, agf_rplan_info_t *info, int32_t *tile_ids,
+                     int32_t *tile_slot_ptr, int32_t *slot_region, int32_t *slot_ent_ptr, int32_t *entry_cell,
+                     double *entry_w, int32_t *region_slot_ptr, int32_t *region_slots);
+int agf_rplan_info(const agf_rplan_t *plan, agf_rplan_info_t *info);
+
+typedef struct {
+    int32_t supported;        /* 0: this program has no regional instantiation -- use agf_temporal_run + agf_spmm_run */
+    int32_t lanes_per_slot;
+    int32_t periods_per_unit; /* periods (days) a tile processes before it merges */
+    int32_t ring_blocks;      /* blocks of periods_per_unit periods the partial buffer holds */
+    int64_t workspace_bytes;  /* size of d_workspace for this (range, periods_per_unit, ring_blocks) */
+    int64_t n_units;          /* (tile, period block) units of work */
+    int32_t kernel_lanes, smem_bytes;
+} agf_regional_info_t;
+/* periods_per_unit = 0 and ring_blocks = 0 select the defaults (4 periods per unit; a partial buffer that covers the
+ * whole range, i.e. no reuse and no waiting between period blocks). */
+int agf_temporal_regional_plan(const agf_program_t *prog, const agf_rplan_t *plan, int64_t group_begin,
+                               int64_t group_end, int32_t periods_per_unit, int32_t ring_blocks,
+                               agf_regional_info_t *info);
+/* P[r, g, cols[c].dst] for g in [group_begin, group_end) (and D[r, g] when d_den != NULL) of a panel
+ * P[n_regions, panel_groups, out_ncols].  d_x points at raster row `row0` (row stride ld elements) and must hold
+ * the rows of the period range; d_workspace is caller-owned scratch of workspace_bytes (its contents need not
+ * survive the call).  Stream-ordered, no host synchronisation. */
+int agf_temporal_regional_run(const agf_program_t *prog, const agf_rplan_t *plan, const void *d_x, int64_t ld,
+                              int64_t row0, int64_t group_begin, int64_t group_end, int32_t periods_per_unit,
+                              int32_t ring_blocks, void *d_workspace, int64_t workspace_bytes, double *d_panel,
+                              int64_t panel_groups, int32_t out_ncols, double *d_den, uintptr_t stream);
 
 /* V[g, cell] = 1 iff no column of X[g, :, cell] is NaN -- for callers that bring their own
  * temporally-reduced X (aggregate_space / SpatialAggregator, aggfly/aggregate/spatial.py:114-119). */

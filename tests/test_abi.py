@@ -19,7 +19,7 @@ def test_library_exports_every_declared_symbol():
     L = _lib.lib()
     for name in declared:
         assert hasattr(L, name), name
-    assert L.agf_version() == 3          # AGF_ABI_VERSION
+    assert L.agf_version() == 4          # AGF_ABI_VERSION
 
 
 def test_struct_layouts_match_the_header_as_gcc_sees_it(tmp_path):
@@ -35,7 +35,11 @@ def test_struct_layouts_match_the_header_as_gcc_sees_it(tmp_path):
                                                         "cols", "n_pre", "pre"]),
               "agf_program_info_t": (_lib.ProgramInfo, ["n_stripes", "n_recs", "n_cols", "out_dtype", "n_out_groups",
                                                         "partial_bytes", "out_bytes", "valid_bytes", "kernel_lanes",
-                                                        "kernel_slots", "kernel_mode", "uses_tma", "kernel_kinds", "direct_out"])}
+                                                        "kernel_slots", "kernel_mode", "uses_tma", "kernel_kinds", "direct_out"]),
+              "agf_rplan_info_t": (_lib.RPlanInfo, ["n_tiles", "n_active_tiles", "n_slots", "max_slots_per_tile", "n_entries",
+                                                    "tile_lat", "tile_lon", "n_empty_regions", "table_bytes"]),
+              "agf_regional_info_t": (_lib.RegionalInfo, ["supported", "lanes_per_slot", "periods_per_unit", "ring_blocks",
+                                                          "workspace_bytes", "n_units", "kernel_lanes", "smem_bytes"])}
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "aggfly_b200.h"', "int main(void) {"]
     for st, (_, names) in fields.items():
         lines.append(f'printf("{st} %zu\\n", sizeof({st}));')

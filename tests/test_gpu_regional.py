@@ -1,0 +1,237 @@
+"""The one-kernel temporal + regional path (agf_temporal_regional_run, csrc/agf_regional.cuh) against the two-kernel path
+(agf_temporal_run -> X -> agf_spmm_run) and against the CPU oracle.
+
+Parity bar: identical rows, region ids and time labels; every value rel 1e-12 against the two-kernel path and rel 1e-11
+against the oracle (north_star: 1e-5); BIT-identical to the two-kernel path for regions whose cells lie inside one 8 x 32
+tile (same terms, same order); bit-identical from run to run (the cross-tile merge adds partial rows in a fixed order)."""
+import numpy as np
+import pandas as pd
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import aggfly_b200 as af
+from aggfly_b200 import aggregate as agg_mod, engine, synthetic as syn
+from oracle import oracle as orc
+
+BINS13 = syn.BINS13
+SPECS = {
+    "daily_bins_mean": syn.SPECS["daily_bins_mean"],                                              # 13 bin lanes + mean (typed, LPS 8)
+    "tavg": dict(tavg=[("aggregate", {"calc": "mean", "groupby": "date"})]),                     # one lane
+    "tsum": dict(tsum=[("aggregate", {"calc": "sum", "groupby": "date"})]),
+    "gdd": dict(gdd=[("aggregate", {"calc": "dd", "groupby": "date", "ddargs": [10, 30, 0]})]),   # degree days per date
+    "tavg_gdd": dict(tavg=[("aggregate", {"calc": "mean", "groupby": "date"})],                  # mixed mean + dd lanes
+                     gdd=[("aggregate", {"calc": "dd", "groupby": "date", "ddargs": [10, 30, 0]})]),
+    "tavg_3dd": dict(tavg=[("aggregate", {"calc": "mean", "groupby": "date"})],
+                     dd=[("aggregate", {"calc": "dd", "groupby": "date", "ddargs": [[0, 10, 0], [10, 20, 0], [20, 99, 1]]})]),
+    "bins6_mean_sum": dict(b=[("aggregate", {"calc": "bins", "groupby": "date", "ddargs": BINS13[3:9]})],
+                           tavg=[("aggregate", {"calc": "mean", "groupby": "date"})],
+                           tsum=[("aggregate", {"calc": "sum", "groupby": "date"})]),
+    "bins14_two_sums": dict(b=[("aggregate", {"calc": "bins", "groupby": "date",
+                                               "ddargs": [[-99, -20, 0]] + BINS13})],
+                            tavg=[("aggregate", {"calc": "mean", "groupby": "date"})],
+                            tsum=[("aggregate", {"calc": "sum", "groupby": "date"})]),
+    "tavg_poly": dict(tavg=[("aggregate", {"calc": "mean", "groupby": "date"}),                   # columns transformed from one lane
+                            ("transform", {"transform": "power", "exp": np.arange(1, 4)})]),
+}
+
+
+@pytest.fixture(autouse=True)
+def _gpu():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    saved = dict(engine.OPTIONS)
+    yield
+    engine.OPTIONS.clear()
+    engine.OPTIONS.update(saved)
+
+
+def _case(n_lat, n_lon, days, seed, ocean=0.2, regions=(9, 5), zero_weight="nan"):
+    rng = np.random.default_rng(seed)
+    T = 24 * days
+    t = pd.date_range("2001-03-01", periods=T, freq="h")
+    lat = 49.75 - 0.25 * np.arange(n_lat)
+    lon = 235.0 + 0.25 * np.arange(n_lon)
+    arr = (12 + 14 * np.sin(np.arange(T) / 24.0 * 0.7)[:, None, None] + 5 * np.sin(2 * np.pi * (np.arange(T) % 24) / 24)[:, None, None]
+           + rng.normal(0, 4, (T, n_lat, n_lon))).astype(np.float32)
+    if ocean:
+        tiles = rng.random(((n_lat + 3) // 4, (n_lon + 3) // 4)) < ocean
+        mask = np.repeat(np.repeat(tiles, 4, 0), 4, 1)[:n_lat, :n_lon]
+        arr[:, mask] = np.nan
+    arr[30:33, n_lat // 2, n_lon // 2] = np.nan                    # a cell that is invalid on ONE day only
+    gd = syn.GridDef(lat, lon, True, (regions[0], regions[1], -125.125, -125.125 + 0.25 * n_lon, 49.875 - 0.25 * n_lat, 49.875))
+    ds = af.Dataset.from_arrays(arr, t, lat, lon, lon_is_360=True)
+    w = af.weights_from_objects(ds, syn.tessellation(gd), zero_weight=zero_weight)
+    w.calculate_weights()
+    return arr, t, lat, lon, ds, w
+
+
+def _frames(ds, w, spec, device=True):
+    import torch
+    d = ds
+    if device:
+        d = af.Dataset.from_arrays(torch.from_numpy(np.asarray(ds.values)).cuda(), ds.time, ds.latitude, ds.longitude,
+                                   lon_is_360=ds.lon_is_360)
+    engine.OPTIONS["regional"] = False
+    two = af.aggregate_dataset(weights=w, dataset=d, aggregator_dict=spec)
+    assert "spmm (issue)" in agg_mod.LAST_TRACE["phases_ms"] or "spmm + d2h" in agg_mod.LAST_TRACE["phases_ms"]
+    engine.OPTIONS["regional"] = True
+    one = af.aggregate_dataset(weights=w, dataset=d, aggregator_dict=spec)
+    assert any(k.startswith("temporal + regional") for k in agg_mod.LAST_TRACE["phases_ms"]), agg_mod.LAST_TRACE
+    return one, two
+
+
+def _same_frame(a, b, rtol):
+    assert list(a.columns) == list(b.columns) and len(a) == len(b) > 0
+    rid = a.columns[0]
+    assert np.array_equal(np.asarray(a[rid]), np.asarray(b[rid]))
+    assert np.array_equal(np.asarray(a["time"]).astype("datetime64[ns]"), np.asarray(b["time"]).astype("datetime64[ns]"))
+    cols = [c for c in a.columns if c not in (rid, "time")]
+    x, y = a[cols].to_numpy(float), b[cols].to_numpy(float)
+    assert np.array_equal(np.isnan(x), np.isnan(y))
+    ok = ~np.isnan(y)
+    err = np.abs(x[ok] - y[ok]) / np.maximum(np.abs(y[ok]), 1e-300)
+    assert float(err.max(initial=0.0)) <= rtol, float(err.max())
+
+
+def _single_tile_regions(w, ds):
+    """Region ids (shapefile row index) whose cells all lie inside one 8 x 32 tile of the raster."""
+    n_lon = len(ds.longitude)
+    order = ds.lon_sort_order()
+    cid = w.weights["cell_id"].to_numpy()
+    li, rj = cid // n_lon, order[cid % n_lon]
+    tile = (li // 8) * 1000 + rj // 32
+    n_tiles = pd.Series(tile).groupby(w.weights["index_right"].to_numpy()).nunique()
+    return set(n_tiles.index[n_tiles.to_numpy() == 1])
+
+
+@pytest.mark.parametrize("name", list(SPECS))
+@pytest.mark.parametrize("shape", [(40, 64), (21, 100), (13, 36)])
+def test_one_kernel_path_matches_two_kernel_path_and_oracle(name, shape):
+    spec = SPECS[name]
+    arr, t, lat, lon, ds, w = _case(shape[0], shape[1], days=9, seed=shape[0] + len(name))
+    one, two = _frames(ds, w, spec)
+    _same_frame(one, two, 1e-12)
+    rid = w.georegions.regionid
+    want = orc.aggregate_dataset(orc.OWeights(w.weights, w.grid.cell_id, w.georegions.shp, rid, w.zero_weight),
+                                 orc.ODataset(arr, t, lat, lon, True), aggregator_dict=spec)
+    _same_frame(one.reset_index(drop=True), want.reset_index(drop=True), 1e-11)
+    # regions inside one tile: the very same bits as the two-kernel path
+    inside = _single_tile_regions(w, ds)
+    ids = set(w.georegions.shp.loc[sorted(inside), rid]) if inside else set()
+    if ids:
+        a, b = one[one[rid].isin(ids)], two[two[rid].isin(ids)]
+        cols = [c for c in a.columns if c not in (rid, "time")]
+        assert np.array_equal(a[cols].to_numpy(float), b[cols].to_numpy(float), equal_nan=True)
+
+
+@pytest.mark.parametrize("zero_weight", ["nan", "area"])
+def test_host_fed_raster_and_zero_weight_rows(zero_weight):
+    """The streamed feed (pageable NumPy raster -> staging ring -> launches per period range) and the row-drop rules."""
+    from aggfly_b200 import stream
+    arr, t, lat, lon, ds, w = _case(40, 64, days=40, seed=5, ocean=0.45, regions=(6, 4), zero_weight=zero_weight)
+    saved = dict(stream.OPTIONS)
+    stream.OPTIONS.update(staging_chunk_bytes=1 << 20, chunk_bytes=1 << 20)        # many chunks -> several launches
+    try:
+        one, two = _frames(ds, w, SPECS["daily_bins_mean"], device=False)
+    finally:
+        stream.OPTIONS.clear()
+        stream.OPTIONS.update(saved)
+    _same_frame(one, two, 1e-12)
+    assert len(one) < 24 * 40                                                       # some (region, day) rows were dropped
+
+
+@pytest.mark.parametrize("d_ring", [(1, 0), (2, 2), (3, 1), (4, 2), (16, 0)])
+def test_period_blocks_and_partial_ring_do_not_change_the_result(d_ring):
+    import torch
+    arr, t, lat, lon, ds, w = _case(48, 128, days=21, seed=11, regions=(14, 9))
+    spec = SPECS["daily_bins_mean"]
+    dsd = af.Dataset.from_arrays(torch.from_numpy(arr).cuda(), t, lat, lon, lon_is_360=True)
+    engine.OPTIONS["regional"] = True
+    ref = af.aggregate_dataset(weights=w, dataset=dsd, aggregator_dict=spec)
+    engine.OPTIONS["regional_periods_per_unit"], engine.OPTIONS["regional_ring_blocks"] = d_ring
+    got = af.aggregate_dataset(weights=w, dataset=dsd, aggregator_dict=spec)
+    cols = [c for c in ref.columns if c not in ("geoid", "time")]
+    assert np.array_equal(ref[cols].to_numpy(float), got[cols].to_numpy(float), equal_nan=True)   # bit for bit
+    assert np.array_equal(np.asarray(ref["time"]), np.asarray(got["time"]))
+
+
+def test_runner_denominators_and_repeatability():
+    import torch
+    from aggfly_b200.aggregate import _device_csr, _plan
+    arr, t, lat, lon, ds, w = _case(48, 128, days=12, seed=3, regions=(14, 9))
+    spec = SPECS["daily_bins_mean"]
+    dsd = af.Dataset.from_arrays(torch.from_numpy(arr).cuda(), t, lat, lon, lon_is_360=True)
+    csr = _device_csr(w, dsd)
+    names, stage = _plan(dsd, spec)
+    flat = dsd.values.reshape(len(t), -1)
+    rr = engine.RegionalRunner(stage, csr, len(lat), len(lon), want_den=True)
+    assert rr.supported and rr.info.lanes_per_slot == 8
+    res = rr.run(flat)
+    torch.cuda.synchronize()
+    p0, d0 = res.panel.clone(), res.den.clone()
+    two = engine.StageRunner(stage, len(lat) * len(lon))
+    r2 = two.run(flat)
+    p2, d2 = engine.run_spmm(csr, r2, want_den=True)
+    torch.cuda.synchronize()
+    assert torch.equal(torch.isnan(p0), torch.isnan(p2))
+    ok = ~torch.isnan(p2)
+    assert float(((p0[ok] - p2[ok]).abs() / p2[ok].abs().clamp_min(1e-300)).max()) <= 1e-12
+    assert float(((d0 - d2).abs() / d2.abs().clamp_min(1e-300))[d2 > 0].max()) <= 1e-12 and torch.equal(d0 == 0, d2 == 0)
+    for _ in range(5):
+        res = rr.run(flat)
+        torch.cuda.synchronize()
+        assert torch.equal(res.panel.view(torch.int64), p0.view(torch.int64)) and torch.equal(res.den, d0)
+    rr.close(); two.close()
+
+
+def test_unsupported_programs_fall_back_to_the_two_kernel_path():
+    """Two-level chains, float64 rasters, ragged periods: no regional instantiation -> same answer through K1 + K2."""
+    import torch
+    arr, t, lat, lon, ds, w = _case(16, 64, days=40, seed=8)
+    engine.OPTIONS["regional"] = True
+    spec = dict(tavg=[("aggregate", {"calc": "mean", "groupby": "date"}), ("aggregate", {"calc": "mean", "groupby": "month"})])
+    df = af.aggregate_dataset(weights=w, dataset=ds, aggregator_dict=spec)
+    assert len(df) > 0 and not any(k.startswith("temporal + regional") for k in agg_mod.LAST_TRACE["phases_ms"])
+    ds64 = af.Dataset.from_arrays(arr.astype(np.float64), t, lat, lon, lon_is_360=True)
+    df = af.aggregate_dataset(weights=w, dataset=ds64, aggregator_dict=SPECS["tavg"])
+    assert len(df) > 0 and not any(k.startswith("temporal + regional") for k in agg_mod.LAST_TRACE["phases_ms"])
+    # min / max lanes have no regional instantiation: the library says so, the host falls back
+    spec = dict(tmin=[("aggregate", {"calc": "min", "groupby": "date"})])
+    df = af.aggregate_dataset(weights=w, dataset=ds, aggregator_dict=spec)
+    assert len(df) > 0 and not any(k.startswith("temporal + regional") for k in agg_mod.LAST_TRACE["phases_ms"])
+
+
+def test_full_size_daily_panel_is_repeatable_and_matches_the_two_kernel_path():
+    """C3b at its BASELINE size: 721 x 1440 x 8760 -> 45 000 regions x 365 days x 14 columns."""
+    import torch
+    if torch.cuda.get_device_properties(0).total_memory < 100e9:
+        pytest.skip("needs a GPU that holds the 36.4 GB raster and the 21 GB of columns of the two-kernel path")
+    from aggfly_b200.aggregate import _device_csr, _plan
+    wl = syn.make_workload("c3b_global_daily")
+    raster = wl.raster(torch.device("cuda", 0), seed=1218)
+    ds = wl.dataset(raster)
+    w = wl.weights(ds)
+    csr = _device_csr(w, ds)
+    names, stage = _plan(ds, wl.spec)
+    flat = raster.reshape(wl.n_time, wl.n_cells)
+    rr = engine.RegionalRunner(stage, csr, 721, 1440)
+    assert rr.supported
+    first = None
+    for it in range(10):
+        res = rr.run(flat)
+        torch.cuda.synchronize()
+        if first is None:
+            first = res.panel.clone()
+        else:
+            assert torch.equal(res.panel.view(torch.int64), first.view(torch.int64)), f"launch {it} differs"
+    rr.close()
+    two = engine.StageRunner(stage, wl.n_cells)
+    p2 = engine.run_spmm(csr, two.run(flat))
+    torch.cuda.synchronize()
+    two.close()
+    assert torch.equal(torch.isnan(first), torch.isnan(p2))
+    ok = ~torch.isnan(p2)
+    assert float(((first[ok] - p2[ok]).abs() / p2[ok].abs().clamp_min(1e-300)).max()) <= 1e-12
+    assert float((first[ok] == p2[ok]).double().mean()) > 0.2          # regions inside one tile: identical bits
