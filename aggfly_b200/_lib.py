@@ -65,13 +65,12 @@ class ProgramInfo(C.Structure):
 class RPlanInfo(C.Structure):
     _fields_ = [("n_tiles", C.c_int32), ("n_active_tiles", C.c_int32), ("n_slots", C.c_int32),
                 ("max_slots_per_tile", C.c_int32), ("n_entries", C.c_int64), ("tile_lat", C.c_int32),
-                ("tile_lon", C.c_int32), ("n_empty_regions", C.c_int32), ("pad_", C.c_int32), ("table_bytes", C.c_int64)]
+                ("tile_lon", C.c_int32), ("n_empty_regions", C.c_int32), ("n_partial_rows", C.c_int32), ("table_bytes", C.c_int64)]
 
 
 class RegionalInfo(C.Structure):
-    _fields_ = [("supported", C.c_int32), ("lanes_per_slot", C.c_int32), ("periods_per_unit", C.c_int32),
-                ("ring_blocks", C.c_int32), ("workspace_bytes", C.c_int64), ("n_units", C.c_int64),
-                ("kernel_lanes", C.c_int32), ("smem_bytes", C.c_int32)]
+    _fields_ = [("supported", C.c_int32), ("lanes_per_slot", C.c_int32), ("kernel_lanes", C.c_int32),
+                ("smem_bytes", C.c_int32), ("ctas_per_sm", C.c_int32), ("pad_", C.c_int32), ("workspace_bytes", C.c_int64)]
 
 
 class AgfError(RuntimeError):
@@ -134,10 +133,10 @@ def lib() -> C.CDLL:
     L.agf_overlap_destroy.argtypes = [vp]
     L.agf_rplan_create.argtypes = [C.POINTER(vp), i32, i32, i32, i64, vp, vp, vp]
     L.agf_rplan_destroy.argtypes = [vp]
-    L.agf_rplan_tables.argtypes = [i32, i32, i32, i64, vp, vp, vp, C.POINTER(RPlanInfo)] + [vp] * 8
+    L.agf_rplan_tables.argtypes = [i32, i32, i32, i64, vp, vp, vp, C.POINTER(RPlanInfo)] + [vp] * 9
     L.agf_rplan_info.argtypes = [vp, C.POINTER(RPlanInfo)]
-    L.agf_temporal_regional_plan.argtypes = [vp, vp, i64, i64, i32, i32, C.POINTER(RegionalInfo)]
-    L.agf_temporal_regional_run.argtypes = [vp, vp, vp, i64, i64, i64, i64, i32, i32, vp, i64, vp, i64, i32, vp, u64]
+    L.agf_temporal_regional_plan.argtypes = [vp, vp, i64, C.POINTER(RegionalInfo)]
+    L.agf_temporal_regional_run.argtypes = [vp, vp, vp, i64, i64, i64, i64, vp, i64, vp, i64, i32, vp, u64]
     for name in SYMBOLS:
         fn = getattr(L, name)
         if name not in ("agf_version", "agf_last_error"):

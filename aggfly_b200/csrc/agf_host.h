@@ -64,11 +64,13 @@ struct K1Launch {
 struct agf_rplan {
     int n_regions = 0, n_lat = 0, n_lon = 0;
     int tiles_x = 0, tiles_y = 0, n_active = 0, n_gslots = 0, max_slots = 0;
+    int n_partial_rows = 0;  // slots of regions that straddle tiles
+    int n_multi = 0;         // such regions
     int64_t n_entries = 0;
     int n_empty_regions = 0;
     int device = -1;
-    int *d_tile_ids = nullptr, *d_tile_slot_ptr = nullptr, *d_slot_region = nullptr, *d_slot_ent_ptr = nullptr;
-    int *d_region_slot_ptr = nullptr, *d_region_slots = nullptr;
+    int *d_tile_ids = nullptr, *d_tile_slot_ptr = nullptr, *d_slot_dst = nullptr, *d_slot_ent_ptr = nullptr;
+    int *d_region_slot_ptr = nullptr, *d_region_slots = nullptr, *d_multi_regions = nullptr;
     void *d_entries = nullptr;
     int64_t table_bytes = 0;
 };
@@ -77,7 +79,6 @@ struct RegionalLaunch {
     K1Launch k;              // program, raster view, stream (stripe / X / V fields unused)
     const agf_rplan *plan;
     int64_t g_begin, g_end;  // periods of this launch
-    int D, ring;             // periods per unit; day-blocks the partial buffer holds
     void *d_workspace;
     int64_t workspace_bytes;
     double *d_panel, *d_den;
@@ -87,12 +88,10 @@ struct RegionalLaunch {
 
 struct RegionalChoice {
     int lanes, typed_bins, lps;   // instantiation: kernel lanes, NB, lanes per slot
-    int smem_bytes, ctas_per_sm, grid;
-    int64_t workspace_bytes;
-    int64_t n_units;
+    int smem_bytes, ctas_per_sm;
 };
 
-// mode 0: launch; mode 1: only report the instantiation / workspace in *choice.  Returns 1 if nothing fits.
+// mode 0: launch; mode 1: only report the instantiation in *choice.  Returns 1 if nothing fits.
 int agf_k1_f32_regional(const RegionalLaunch &a, int mode, RegionalChoice *choice, int *rc);
 int agf_make_tensor_map3(agf::TensorMap *out, const void *base, int elem_size, uint64_t n_lon, uint64_t n_lat,
                          uint64_t n_rows, uint64_t ld, int box_lon, int box_lat, int box_rows);

@@ -1,6 +1,8 @@
 // K1R instantiations: float raster, 24-row periods (hourly -> date), single-level programs; see agf_regional.cuh.
 // Rows are RCASE(kernel lanes, diagonal, lane kinds, NB, lanes per slot), tried in order, cheapest first.
 #define AGF_T float
+#include <algorithm>
+
 #include "agf_k1_inst.cuh"
 #include "agf_regional.cuh"
 
@@ -38,56 +40,37 @@ int launch_regional(const RegionalLaunch &a, int mode, RegionalChoice *choice) {
     constexpr int MINB0 = state_regs <= 30 ? 3 : (state_regs <= 48 ? 2 : 1);
     constexpr int TT = R_GL;
     constexpr int TILE = TT * TMA_CW * (int)sizeof(T);
-    // shared memory: ring + barriers + staged rows + merge lists; three CTAs per SM need <= 75 KB each
-    constexpr int fixed3 = 2 * TILE + 128 + stage_bytes<LPS>() + 16;
-    constexpr int MINB = (MINB0 == 3 && fixed3 + 2 * 4 * 64 <= 75 * 1024) ? 3 : (MINB0 >= 2 ? 2 : 1);
+    // shared memory: ring + barriers + staged rows; three CTAs per SM need <= 75 KB each
+    constexpr int MINB = (MINB0 == 3 && 2 * TILE + 128 + stage_bytes<LPS>() <= 75 * 1024) ? 3 : (MINB0 >= 2 ? 2 : 1);
     constexpr int STAGES = MINB == 3 ? 2 : (MINB == 2 ? 3 : 6);
-    const int smem = STAGES * TILE + 128 + stage_bytes<LPS>() + 16 + 2 * plan->max_slots * 4;
+    constexpr int smem = STAGES * TILE + 128 + stage_bytes<LPS>();
     auto kern = agf_k1_regional<T, NL, DIAG, KINDS, NB, LPS, R_GL, TT, STAGES, MINB>;
 
-    const int D = a.D;
-    const int64_t n_blocks = (a.g_end - a.g_begin + D - 1) / D;
-    const int64_t ring = (a.ring > 0 && a.ring < n_blocks) ? a.ring : n_blocks;
-    const int64_t n_units = n_blocks * plan->n_active;
-    const int64_t partial_bytes = ring * plan->n_gslots * (int64_t)D * LPS * 16;
-    const int64_t cnt_bytes = ((ring * plan->n_regions * 4 + 255) / 256) * 256;
-    const int64_t done_bytes = ((n_blocks * 4 + 255) / 256) * 256;
-    const int64_t ws_bytes = partial_bytes + cnt_bytes + done_bytes + 256;
-    if (n_units > 0x7fffffffLL) return agf_fail(AGF_E_UNSUPPORTED, "too many units of work for one launch");
-    if (smem > 200 * 1024) return agf_fail(AGF_E_UNSUPPORTED, "a tile touches %d regions: merge lists do not fit", plan->max_slots);
-
     static int ctas_per_sm = 0;  // per instantiation
-    static int smem_set = 0;
     int sms = 148;
-    if (mode == 0 || choice) {
+    {
         int dev = -1;
         CU(cudaGetDevice(&dev));
         CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        if (smem > smem_set) {
-            CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            smem_set = smem;
-            ctas_per_sm = 0;
-        }
         if (ctas_per_sm == 0) {
+            CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
             CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, TMA_THREADS, smem));
             if (ctas_per_sm < 1) return agf_fail(AGF_E_UNSUPPORTED, "regional kernel does not fit on an SM");
         }
     }
-    // the grid must be entirely resident (tiles wait for earlier day-blocks when the partial ring is reused)
-    const int grid = (int)std::min<int64_t>((int64_t)ctas_per_sm * sms, n_units);
     if (choice) {
         choice->lanes = NL;
         choice->typed_bins = NB;
         choice->lps = LPS;
         choice->smem_bytes = smem;
         choice->ctas_per_sm = ctas_per_sm;
-        choice->grid = grid;
-        choice->workspace_bytes = ws_bytes;
-        choice->n_units = n_units;
     }
     if (mode != 0) return 0;
-    if (a.workspace_bytes < ws_bytes)
-        return agf_fail(AGF_E_INVALID, "workspace of %lld bytes, %lld needed", (long long)a.workspace_bytes, (long long)ws_bytes);
+    const int64_t n_groups = a.g_end - a.g_begin;
+    const int64_t ws_bytes = (int64_t)plan->n_partial_rows * a.G * LPS * 16;
+    unsigned char *ws = (unsigned char *)(((uintptr_t)a.d_workspace + 255) & ~(uintptr_t)255);
+    if (plan->n_partial_rows > 0 && a.workspace_bytes - (ws - (unsigned char *)a.d_workspace) < ws_bytes)
+        return agf_fail(AGF_E_INVALID, "workspace of %lld bytes, %lld needed", (long long)a.workspace_bytes, (long long)ws_bytes + 256);
 
     K1Params<T, NL, 0> kp;
     k1_fill_params<T, NL, 0, DIAG, KINDS, NB>(kp, a.k);
@@ -95,30 +78,19 @@ int launch_regional(const RegionalLaunch &a, int mode, RegionalChoice *choice) {
     memset(&q, 0, sizeof(q));
     q.tile_ids = plan->d_tile_ids;
     q.tile_slot_ptr = plan->d_tile_slot_ptr;
-    q.slot_region = plan->d_slot_region;
+    q.slot_dst = plan->d_slot_dst;
     q.slot_ent_ptr = plan->d_slot_ent_ptr;
     q.entries = (const RgEntry *)plan->d_entries;
-    q.region_slot_ptr = plan->d_region_slot_ptr;
-    q.region_slots = plan->d_region_slots;
     q.n_active = plan->n_active;
     q.tiles_x = plan->tiles_x;
-    q.n_regions = plan->n_regions;
-    q.n_gslots = plan->n_gslots;
-    q.max_slots = plan->max_slots;
     q.g_begin = (int)a.g_begin;
-    q.g_end = (int)a.g_end;
-    q.D = D;
-    q.n_blocks = (int)n_blocks;
-    q.ring = (int)ring;
-    unsigned char *ws = (unsigned char *)(((uintptr_t)a.d_workspace + 255) & ~(uintptr_t)255);
+    q.n_groups = (int)n_groups;
+    q.row_begin = (long long)p->b1[a.g_begin] - a.k.row0;
     q.partial = (double *)ws;
-    q.cnt = (int *)(ws + partial_bytes);
-    q.done = (int *)(ws + partial_bytes + cnt_bytes);
     q.panel = a.d_panel;
     q.den_out = a.d_den;
     q.G = a.G;
     q.n_cols = a.out_ncols;
-    q.n_int = S::N_INT;
     q.n_int_units = S::N_INT_UNITS;
     q.den_unit = (S::N_INT - 1) >> 1;
     q.den_half = (S::N_INT - 1) & 1;
@@ -132,21 +104,53 @@ int launch_regional(const RegionalLaunch &a, int mode, RegionalChoice *choice) {
     } else {
         for (int c = 0; c < kp.n_cols && c < 16; ++c) q.dst_dbl[c] = kp.cols[c].dst;
     }
-    CU(cudaMemsetAsync(q.cnt, 0, (size_t)(cnt_bytes + done_bytes), a.k.stream));
     if (plan->n_empty_regions > 0) {
         agf_regional_fill_empty<<<plan->n_regions, 256, 0, a.k.stream>>>(plan->d_region_slot_ptr, plan->n_regions, q.g_begin,
-                                                                           q.g_end, q.G, q.n_cols, q.panel, q.den_out);
+                                                                           q.n_groups, q.G, q.n_cols, q.panel, q.den_out);
         CU(cudaGetLastError());
     }
-    if (n_units == 0) return 0;
+    if (plan->n_active == 0) return 0;
+    // periods per CTA: enough CTAs for ~8 waves of the resident grid, at least 8 periods each (the ring's ramp-up
+    // and the tile's tables are paid once per CTA)
+    const int64_t want_ctas = 8LL * ctas_per_sm * sms;
+    int64_t stripes = std::max<int64_t>(1, std::min<int64_t>((want_ctas + plan->n_active - 1) / plan->n_active, n_groups / 8));
+    stripes = std::min<int64_t>(stripes, 65535);
+    q.groups_per_cta = (int)((n_groups + stripes - 1) / stripes);
+    stripes = (n_groups + q.groups_per_cta - 1) / q.groups_per_cta;
     // rows of the raster view this launch can touch
     const int64_t row_end = p->b1[a.g_end];
     TensorMap tm;
     int rc = agf_make_tensor_map3(&tm, a.k.d_x, (int)sizeof(T), (uint64_t)plan->n_lon, (uint64_t)plan->n_lat,
                                   (uint64_t)(row_end - a.k.row0), (uint64_t)a.k.ld, RG_TW, RG_TH, TT);
     if (rc) return rc;
+    dim3 grid((unsigned)plan->n_active, (unsigned)stripes);
     kern<<<grid, TMA_THREADS, smem, a.k.stream>>>(kp, q, tm);
     CU(cudaGetLastError());
+    if (plan->n_multi > 0) {
+        MergeP m;
+        memset(&m, 0, sizeof(m));
+        m.multi_regions = plan->d_multi_regions;
+        m.region_slot_ptr = plan->d_region_slot_ptr;
+        m.region_slots = plan->d_region_slots;
+        m.slot_dst = plan->d_slot_dst;
+        m.n_multi = plan->n_multi;
+        m.g_begin = q.g_begin;
+        m.n_groups = q.n_groups;
+        m.partial = q.partial;
+        m.panel = q.panel;
+        m.den_out = q.den_out;
+        m.G = q.G;
+        m.n_cols = q.n_cols;
+        m.n_int_units = q.n_int_units;
+        m.den_unit = q.den_unit;
+        m.den_half = q.den_half;
+        memcpy(m.dst_int, q.dst_int, sizeof(m.dst_int));
+        memcpy(m.dst_dbl, q.dst_dbl, sizeof(m.dst_dbl));
+        const int64_t items = (int64_t)plan->n_multi * n_groups;
+        const int64_t blocks = std::min<int64_t>((items + (256 / LPS) - 1) / (256 / LPS), 64LL * sms);
+        agf_regional_merge<LPS><<<(unsigned)blocks, 256, 0, a.k.stream>>>(m);
+        CU(cudaGetLastError());
+    }
     return 0;
 }
 

@@ -30,7 +30,8 @@ extern "C" int agf_rplan_destroy(agf_rplan_t *p) {
     if (!p) return 0;
     cudaFree(p->d_tile_ids);
     cudaFree(p->d_tile_slot_ptr);
-    cudaFree(p->d_slot_region);
+    cudaFree(p->d_slot_dst);
+    cudaFree(p->d_multi_regions);
     cudaFree(p->d_slot_ent_ptr);
     cudaFree(p->d_region_slot_ptr);
     cudaFree(p->d_region_slots);
@@ -42,8 +43,9 @@ extern "C" int agf_rplan_destroy(agf_rplan_t *p) {
 namespace {
 struct HostTables {
     std::vector<int32_t> tile_ids, tile_slot_ptr, slot_region, slot_ent_ptr, region_slot_ptr, region_slots;
+    std::vector<int32_t> slot_dst, multi_regions;
     std::vector<RgEntry> entries;
-    int tiles_x = 0, tiles_y = 0, max_slots = 0, n_empty = 0;
+    int tiles_x = 0, tiles_y = 0, max_slots = 0, n_empty = 0, n_partial_rows = 0;
 };
 }  // namespace
 
@@ -73,7 +75,7 @@ static int build_tables(HostTables &t, int32_t n_regions, int32_t n_lat, int32_t
     for (int64_t k = 0; k < n_tiles; ++k) tile_cnt[k + 1] += tile_cnt[k];
     std::vector<int64_t> pos(tile_cnt.begin(), tile_cnt.end() - 1);
     std::vector<int32_t> ent_region(nnz);
-    t.entries.resize(nnz);
+    std::vector<RgEntry> ent(nnz);
     for (int32_t r = 0; r < n_regions; ++r) {
         if (row_ptr[r] > row_ptr[r + 1]) return agf_fail(AGF_E_INVALID, "row_ptr not monotonic");
         for (int64_t e = row_ptr[r]; e < row_ptr[r + 1]; ++e) {
@@ -81,30 +83,37 @@ static int build_tables(HostTables &t, int32_t n_regions, int32_t n_lat, int32_t
             const int lat = (int)(c / n_lon), lon = (int)(c % n_lon);
             const int64_t k = pos[tile_of[e]]++;
             ent_region[k] = r;
-            t.entries[k].w = w[e];
-            t.entries[k].cell = (lat % RG_TH) * RG_TW + (lon % RG_TW);
-            t.entries[k].pad = 0;
+            ent[k].w = w[e];
+            ent[k].cell = (lat % RG_TH) * RG_TW + (lon % RG_TW);
+            ent[k].pad = 0;
         }
     }
-    // slots: runs of one region inside a tile
+    // slots: runs of one region inside a tile, re-ordered LONGEST FIRST inside the tile (the kernel hands neighbouring
+    // slots to the lane groups of one warp: rows of similar length keep the warp's lanes busy together)
     t.tile_slot_ptr.assign(1, 0);
+    t.entries.reserve(nnz);
+    struct Run { int64_t k0, k1; int32_t region; };
+    std::vector<Run> runs;
     for (int64_t tl = 0; tl < n_tiles; ++tl) {
         if (tile_cnt[tl + 1] == tile_cnt[tl]) continue;
-        int ns = 0;
+        runs.clear();
         for (int64_t k = tile_cnt[tl]; k < tile_cnt[tl + 1]; ++k) {
-            if (k == tile_cnt[tl] || ent_region[k] != ent_region[k - 1]) {
-                t.slot_region.push_back(ent_region[k]);
-                t.slot_ent_ptr.push_back((int32_t)k);
-                ++ns;
-            }
+            if (k == tile_cnt[tl] || ent_region[k] != ent_region[k - 1]) runs.push_back(Run{k, k, ent_region[k]});
+            runs.back().k1 = k + 1;
+        }
+        std::stable_sort(runs.begin(), runs.end(), [](const Run &a, const Run &b) { return a.k1 - a.k0 > b.k1 - b.k0; });
+        for (const Run &r : runs) {
+            t.slot_region.push_back(r.region);
+            t.slot_ent_ptr.push_back((int32_t)t.entries.size());
+            t.entries.insert(t.entries.end(), ent.begin() + r.k0, ent.begin() + r.k1);
         }
         t.tile_ids.push_back((int32_t)tl);
         t.tile_slot_ptr.push_back((int32_t)t.slot_region.size());
-        t.max_slots = std::max(t.max_slots, ns);
+        t.max_slots = std::max(t.max_slots, (int)runs.size());
     }
     t.slot_ent_ptr.push_back((int32_t)nnz);
     const int n_gslots = (int)t.slot_region.size();
-    // slots of every region in ascending slot (== tile) order
+    // slots of every region in ascending slot order (tiles in raster order)
     t.region_slot_ptr.assign(n_regions + 1, 0);
     t.region_slots.resize(n_gslots);
     for (int s = 0; s < n_gslots; ++s) ++t.region_slot_ptr[t.slot_region[s] + 1];
@@ -113,6 +122,14 @@ static int build_tables(HostTables &t, int32_t n_regions, int32_t n_lat, int32_t
         std::vector<int32_t> at(t.region_slot_ptr.begin(), t.region_slot_ptr.end() - 1);
         for (int s = 0; s < n_gslots; ++s) t.region_slots[at[t.slot_region[s]]++] = s;
     }
+    // where a slot's sums go: the panel row of its region when the slot holds the whole region, else a partial row
+    t.slot_dst.resize(n_gslots);
+    for (int s = 0; s < n_gslots; ++s) {
+        const int r = t.slot_region[s];
+        t.slot_dst[s] = (t.region_slot_ptr[r + 1] - t.region_slot_ptr[r] == 1) ? r : -(++t.n_partial_rows);
+    }
+    for (int r = 0; r < n_regions; ++r)
+        if (t.region_slot_ptr[r + 1] - t.region_slot_ptr[r] > 1) t.multi_regions.push_back(r);
     for (int r = 0; r < n_regions; ++r) t.n_empty += t.region_slot_ptr[r + 1] == t.region_slot_ptr[r];
     return 0;
 }
@@ -127,6 +144,7 @@ static void fill_info(agf_rplan_info_t *info, const HostTables &t, int64_t table
     info->tile_lat = RG_TH;
     info->tile_lon = RG_TW;
     info->n_empty_regions = t.n_empty;
+    info->n_partial_rows = t.n_partial_rows;
     info->table_bytes = table_bytes;
 }
 
@@ -134,7 +152,7 @@ static void fill_info(agf_rplan_info_t *info, const HostTables &t, int64_t table
 extern "C" int agf_rplan_tables(int32_t n_regions, int32_t n_lat, int32_t n_lon, int64_t nnz, const int32_t *row_ptr,
                                 const int32_t *cell_idx, const double *w, agf_rplan_info_t *info, int32_t *tile_ids,
                                 int32_t *tile_slot_ptr, int32_t *slot_region, int32_t *slot_ent_ptr, int32_t *entry_cell,
-                                double *entry_w, int32_t *region_slot_ptr, int32_t *region_slots) {
+                                double *entry_w, int32_t *region_slot_ptr, int32_t *region_slots, int32_t *slot_dst) {
     HostTables t;
     int rc = build_tables(t, n_regions, n_lat, n_lon, nnz, row_ptr, cell_idx, w);
     if (rc) return rc;
@@ -148,6 +166,7 @@ extern "C" int agf_rplan_tables(int32_t n_regions, int32_t n_lat, int32_t n_lon,
     put(slot_ent_ptr, t.slot_ent_ptr);
     put(region_slot_ptr, t.region_slot_ptr);
     put(region_slots, t.region_slots);
+    put(slot_dst, t.slot_dst);
     for (size_t k = 0; k < t.entries.size(); ++k) {
         if (entry_cell) entry_cell[k] = t.entries[k].cell;
         if (entry_w) entry_w[k] = t.entries[k].w;
@@ -171,6 +190,8 @@ extern "C" int agf_rplan_create(agf_rplan_t **out, int32_t n_regions, int32_t n_
     p->n_active = (int)t.tile_ids.size();
     p->n_gslots = (int)t.slot_region.size();
     p->max_slots = t.max_slots;
+    p->n_partial_rows = t.n_partial_rows;
+    p->n_multi = (int)t.multi_regions.size();
     p->n_entries = nnz;
     p->n_empty_regions = t.n_empty;
     cudaError_t e0 = cudaGetDevice(&p->device);
@@ -180,7 +201,8 @@ extern "C" int agf_rplan_create(agf_rplan_t **out, int32_t n_regions, int32_t n_
     }
     if ((rc = upload_vec(&p->d_tile_ids, t.tile_ids, &p->table_bytes)) ||
         (rc = upload_vec(&p->d_tile_slot_ptr, t.tile_slot_ptr, &p->table_bytes)) ||
-        (rc = upload_vec(&p->d_slot_region, t.slot_region, &p->table_bytes)) ||
+        (rc = upload_vec(&p->d_slot_dst, t.slot_dst, &p->table_bytes)) ||
+        (rc = upload_vec(&p->d_multi_regions, t.multi_regions, &p->table_bytes)) ||
         (rc = upload_vec(&p->d_slot_ent_ptr, t.slot_ent_ptr, &p->table_bytes)) ||
         (rc = upload_vec(&p->d_region_slot_ptr, t.region_slot_ptr, &p->table_bytes)) ||
         (rc = upload_vec(&p->d_region_slots, t.region_slots, &p->table_bytes)) ||
@@ -203,6 +225,7 @@ extern "C" int agf_rplan_info(const agf_rplan_t *p, agf_rplan_info_t *info) {
     info->tile_lat = RG_TH;
     info->tile_lon = RG_TW;
     info->n_empty_regions = p->n_empty_regions;
+    info->n_partial_rows = p->n_partial_rows;
     info->table_bytes = p->table_bytes;
     return 0;
 }
@@ -254,29 +277,20 @@ static int regional_args(const agf_program_t *p, const agf_rplan_t *plan, int64_
     return 0;
 }
 
-static int default_D() {
-    if (const char *e = getenv("AGF_REGIONAL_D")) {
-        const int v = atoi(e);
-        if (v >= 1 && v <= 64) return v;
-    }
-    return 4;
-}
-
-extern "C" int agf_temporal_regional_plan(const agf_program_t *p, const agf_rplan_t *plan, int64_t group_begin,
-                                          int64_t group_end, int32_t periods_per_unit, int32_t ring_blocks,
+extern "C" int agf_temporal_regional_plan(const agf_program_t *p, const agf_rplan_t *plan, int64_t panel_groups,
                                           agf_regional_info_t *info) {
     if (!info) return agf_fail(AGF_E_INVALID, "null info");
     memset(info, 0, sizeof(*info));
-    int rc = regional_args(p, plan, group_begin, group_end);
+    int rc = regional_args(p, plan, 0, p ? p->desc.n_groups1 : 0);
     if (rc) return rc;
+    if (panel_groups < p->desc.n_groups1) return agf_fail(AGF_E_INVALID, "panel_groups < the program's periods");
     RegionalLaunch a{};
     a.k.p = p;
     a.k.use_tma = 1;
     a.plan = plan;
-    a.g_begin = group_begin;
-    a.g_end = group_end;
-    a.D = periods_per_unit > 0 ? periods_per_unit : default_D();
-    a.ring = ring_blocks;
+    a.g_begin = 0;
+    a.g_end = p->desc.n_groups1;
+    a.G = panel_groups;
     RegionalChoice ch{};
     int krc = 0;
     if (p->desc.in_dtype != AGF_F32 || agf_k1_f32_regional(a, 1, &ch, &krc)) {
@@ -284,25 +298,23 @@ extern "C" int agf_temporal_regional_plan(const agf_program_t *p, const agf_rpla
                                     "periods are covered); run agf_temporal_run + agf_spmm_run");
         return 0;  // info->supported stays 0
     }
+    if (krc) return krc;
     info->supported = 1;
     info->lanes_per_slot = ch.lps;
-    info->periods_per_unit = a.D;
-    const int64_t n_blocks = (group_end - group_begin + a.D - 1) / a.D;
-    info->ring_blocks = (int32_t)((ring_blocks > 0 && ring_blocks < n_blocks) ? ring_blocks : n_blocks);
-    info->workspace_bytes = ch.workspace_bytes;
-    info->n_units = ch.n_units;
     info->kernel_lanes = ch.lanes;
     info->smem_bytes = ch.smem_bytes;
+    info->ctas_per_sm = ch.ctas_per_sm;
+    info->workspace_bytes = (int64_t)plan->n_partial_rows * panel_groups * ch.lps * 16 + 256;
     return 0;
 }
 
 extern "C" int agf_temporal_regional_run(const agf_program_t *p, const agf_rplan_t *plan, const void *d_x, int64_t ld,
-                                         int64_t row0, int64_t group_begin, int64_t group_end, int32_t periods_per_unit,
-                                         int32_t ring_blocks, void *d_workspace, int64_t workspace_bytes, double *d_panel,
-                                         int64_t panel_groups, int32_t out_ncols, double *d_den, uintptr_t stream) {
+                                         int64_t row0, int64_t group_begin, int64_t group_end, void *d_workspace,
+                                         int64_t workspace_bytes, double *d_panel, int64_t panel_groups,
+                                         int32_t out_ncols, double *d_den, uintptr_t stream) {
     int rc = regional_args(p, plan, group_begin, group_end);
     if (rc) return rc;
-    if (!d_x || !d_workspace || !d_panel) return agf_fail(AGF_E_INVALID, "null buffer");
+    if (!d_x || !d_panel || (!d_workspace && plan->n_partial_rows > 0)) return agf_fail(AGF_E_INVALID, "null buffer");
     if (ld < p->n_cells) return agf_fail(AGF_E_INVALID, "ld < n_cells");
     if (row0 < 0 || row0 > p->b1[group_begin]) return agf_fail(AGF_E_INVALID, "row0 is past the first row of the period range");
     if (panel_groups < group_end) return agf_fail(AGF_E_INVALID, "panel has %lld periods, the range ends at %lld", (long long)panel_groups, (long long)group_end);
@@ -323,8 +335,6 @@ extern "C" int agf_temporal_regional_run(const agf_program_t *p, const agf_rplan
     a.plan = plan;
     a.g_begin = group_begin;
     a.g_end = group_end;
-    a.D = periods_per_unit > 0 ? periods_per_unit : default_D();
-    a.ring = ring_blocks;
     a.d_workspace = d_workspace;
     a.workspace_bytes = workspace_bytes;
     a.d_panel = d_panel;

@@ -28,8 +28,6 @@ OPTIONS = {
     # instantiation and the panel has at least ``regional_min_periods`` periods; True / False force it on / off.
     "regional": {"0": False, "1": True}.get(__import__("os").environ.get("AGF_REGIONAL", ""), "auto"),
     "regional_min_periods": 32,
-    "regional_periods_per_unit": 0,      # 0: library default (4)
-    "regional_ring_blocks": 0,           # 0: partial rows for the whole range (no reuse); n: a ring of n period blocks
 }
 
 
@@ -193,11 +191,8 @@ class RegionalRunner:
         self.program = Program(stage.programs[0], stage.dtype, self.n_cells, 1)
         self.programs = [self.program]
         self.G, self.n_cols = len(stage.labels), len(stage.nodes)
-        self.D = int(OPTIONS.get("regional_periods_per_unit", 0))
-        self.ring = int(OPTIONS.get("regional_ring_blocks", 0))
         self.info = _lib.RegionalInfo()
-        _lib.check(_lib.lib().agf_temporal_regional_plan(self.program.handle, self.plan.handle, 0, self.G, self.D, self.ring,
-                                                         C.byref(self.info)))
+        _lib.check(_lib.lib().agf_temporal_regional_plan(self.program.handle, self.plan.handle, self.G, C.byref(self.info)))
         self.supported = bool(self.info.supported)
         self.workspace = self.panel = self.den = None
         self.want_den = want_den
@@ -207,7 +202,7 @@ class RegionalRunner:
     def _buffers(self):
         torch = _torch()
         if self.workspace is None:
-            self.workspace = torch.empty(int(self.info.workspace_bytes) + 256, dtype=torch.uint8, device=self.device)
+            self.workspace = torch.empty(int(self.info.workspace_bytes), dtype=torch.uint8, device=self.device)
         R = self.csr.host.n_regions
         self.panel = torch.empty((R, self.G, self.n_cols), dtype=torch.float64, device=self.device)
         self.den = torch.empty((R, self.G), dtype=torch.float64, device=self.device) if self.want_den else None
@@ -222,7 +217,7 @@ class RegionalRunner:
             ev[0].record(stream)
         with torch.cuda.stream(stream):
             _lib.check(_lib.lib().agf_temporal_regional_run(
-                self.program.handle, self.plan.handle, raster.data_ptr(), self.n_cells, 0, g0, g1, self.D, self.ring,
+                self.program.handle, self.plan.handle, raster.data_ptr(), self.n_cells, 0, g0, g1,
                 self.workspace.data_ptr(), self.workspace.numel(), self.panel.data_ptr(), self.G, self.n_cols,
                 self.den.data_ptr() if self.den is not None else None, stream.cuda_stream))
         if ev is not None:
@@ -231,7 +226,11 @@ class RegionalRunner:
 
     @property
     def launches_per_run(self) -> int:
-        return 1 + 1                                # the kernel + the memset of its arrival counters
+        return 1 + (1 if self.plan.info.n_partial_rows else 0) + (1 if self.plan.info.n_empty_regions else 0)
+
+    def partial_bytes(self) -> int:
+        """Scratch rows of the regions that straddle tiles: written by the scan kernel, read once by the merge kernel."""
+        return int(self.plan.info.n_partial_rows) * self.G * int(self.info.lanes_per_slot) * 16
 
     def algorithmic_input_bytes(self) -> int:
         """Raster bytes the kernel must read: the tiles that hold at least one weighted cell (cells no region

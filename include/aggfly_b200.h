@@ -245,11 +245,11 @@ int agf_spmm_run(const agf_csr_t *csr, const void *d_x, int32_t x_dtype, const u
  *     numba_resample (aggfly/aggregate/nb_kernels.py:253-305)  ->  _scatter_block + divide
  *                                                    (aggfly/aggregate/spatial.py:114-133, 181-186)
  * without materialising X: cells are scanned in 8 x 32 (lat x lon) tiles, every period's columns are contracted
- * with the weights inside the tile (entries in weights-frame order), and regions that straddle tiles are
- * completed by the last tile to arrive, adding the per-tile partial sums in ascending tile order -- so the result
- * does not depend on scheduling (bit-identical from run to run), equals agf_temporal_run + agf_spmm_run bit for
- * bit for regions that lie inside one tile, and differs from it by the re-association of one sum otherwise
- * (rel ~1e-16).  Covered: single-level float32 programs whose periods have 24 rows (hourly -> date). */
+ * with the weights inside the tile (entries in weights-frame order); a region that lies inside one tile gets its
+ * panel row from that tile -- the same bits as agf_temporal_run + agf_spmm_run -- and a region that straddles tiles
+ * gets per-tile partial sums that a second small kernel adds in ascending tile order (rel ~1e-16 from the two-kernel
+ * path: one sum re-associated).  No atomics: results are bit-identical from run to run.  Tiles without a weighted
+ * cell are never read.  Covered: single-level float32 programs whose periods have 24 rows (hourly -> date). */
 
 /* A CSR lowered onto the cell tiles of a n_lat x n_lon grid (cell = lat * n_lon + lon, the raster's memory order).
  * row_ptr / cell_idx / w are HOST arrays (the arrays agf_csr_create takes on the device); the handle owns its
@@ -262,7 +262,7 @@ typedef struct {
     int64_t n_entries;
     int32_t tile_lat, tile_lon;      /* 8, 32 */
     int32_t n_empty_regions;         /* regions without any entry on this grid (their rows are NaN) */
-    int32_t pad_;
+    int32_t n_partial_rows;          /* slots of regions that straddle tiles (one scratch row per slot and period) */
     int64_t table_bytes;
 } agf_rplan_info_t;
 int agf_rplan_create(agf_rplan_t **out, int32_t n_regions, int32_t n_lat, int32_t n_lon, int64_t nnz,
@@ -271,36 +271,31 @@ int agf_rplan_destroy(agf_rplan_t *plan);
 /* Host-only twin of agf_rplan_create (no device needed): fills *info and copies the tables into the non-NULL
  * outputs -- tile_ids[n_active_tiles], tile_slot_ptr[n_active_tiles + 1], slot_region[n_slots],
  * slot_ent_ptr[n_slots + 1], entry_cell[n_entries] (cell inside its tile: (lat % 8) * 32 + lon % 32),
- * entry_w[n_entries], region_slot_ptr[n_regions + 1], region_slots[n_slots].  Call once with NULL outputs for the
- * sizes. */
+ * entry_w[n_entries], region_slot_ptr[n_regions + 1], region_slots[n_slots], slot_dst[n_slots] (region r >= 0 when
+ * the slot holds the whole region, else -(partial row + 1)).  Call once with NULL outputs for the sizes. */
 int agf_rplan_tables(int32_t n_regions, int32_t n_lat, int32_t n_lon, int64_t nnz, const int32_t *row_ptr,
                      const int32_t *cell_idx, const double *w, agf_rplan_info_t *info, int32_t *tile_ids,
                      int32_t *tile_slot_ptr, int32_t *slot_region, int32_t *slot_ent_ptr, int32_t *entry_cell,
-                     double *entry_w, int32_t *region_slot_ptr, int32_t *region_slots);
+                     double *entry_w, int32_t *region_slot_ptr, int32_t *region_slots, int32_t *slot_dst);
 int agf_rplan_info(const agf_rplan_t *plan, agf_rplan_info_t *info);
 
 typedef struct {
     int32_t supported;        /* 0: this program has no regional instantiation -- use agf_temporal_run + agf_spmm_run */
     int32_t lanes_per_slot;
-    int32_t periods_per_unit; /* periods (days) a tile processes before it merges */
-    int32_t ring_blocks;      /* blocks of periods_per_unit periods the partial buffer holds */
-    int64_t workspace_bytes;  /* size of d_workspace for this (range, periods_per_unit, ring_blocks) */
-    int64_t n_units;          /* (tile, period block) units of work */
-    int32_t kernel_lanes, smem_bytes;
+    int32_t kernel_lanes, smem_bytes, ctas_per_sm;
+    int32_t pad_;
+    int64_t workspace_bytes;  /* size of d_workspace for a panel of panel_groups periods */
 } agf_regional_info_t;
-/* periods_per_unit = 0 and ring_blocks = 0 select the defaults (4 periods per unit; a partial buffer that covers the
- * whole range, i.e. no reuse and no waiting between period blocks). */
-int agf_temporal_regional_plan(const agf_program_t *prog, const agf_rplan_t *plan, int64_t group_begin,
-                               int64_t group_end, int32_t periods_per_unit, int32_t ring_blocks,
+int agf_temporal_regional_plan(const agf_program_t *prog, const agf_rplan_t *plan, int64_t panel_groups,
                                agf_regional_info_t *info);
 /* P[r, g, cols[c].dst] for g in [group_begin, group_end) (and D[r, g] when d_den != NULL) of a panel
  * P[n_regions, panel_groups, out_ncols].  d_x points at raster row `row0` (row stride ld elements) and must hold
- * the rows of the period range; d_workspace is caller-owned scratch of workspace_bytes (its contents need not
- * survive the call).  Stream-ordered, no host synchronisation. */
+ * the rows of the period range; d_workspace is caller-owned scratch of workspace_bytes (partial rows of straddling
+ * regions, indexed by period: ranges of one panel may share it).  Stream-ordered, no host synchronisation. */
 int agf_temporal_regional_run(const agf_program_t *prog, const agf_rplan_t *plan, const void *d_x, int64_t ld,
-                              int64_t row0, int64_t group_begin, int64_t group_end, int32_t periods_per_unit,
-                              int32_t ring_blocks, void *d_workspace, int64_t workspace_bytes, double *d_panel,
-                              int64_t panel_groups, int32_t out_ncols, double *d_den, uintptr_t stream);
+                              int64_t row0, int64_t group_begin, int64_t group_end, void *d_workspace,
+                              int64_t workspace_bytes, double *d_panel, int64_t panel_groups, int32_t out_ncols,
+                              double *d_den, uintptr_t stream);
 
 /* V[g, cell] = 1 iff no column of X[g, :, cell] is NaN -- for callers that bring their own
  * temporally-reduced X (aggregate_space / SpatialAggregator, aggfly/aggregate/spatial.py:114-119). */

@@ -37,9 +37,9 @@ def test_struct_layouts_match_the_header_as_gcc_sees_it(tmp_path):
                                                         "partial_bytes", "out_bytes", "valid_bytes", "kernel_lanes",
                                                         "kernel_slots", "kernel_mode", "uses_tma", "kernel_kinds", "direct_out"]),
               "agf_rplan_info_t": (_lib.RPlanInfo, ["n_tiles", "n_active_tiles", "n_slots", "max_slots_per_tile", "n_entries",
-                                                    "tile_lat", "tile_lon", "n_empty_regions", "table_bytes"]),
-              "agf_regional_info_t": (_lib.RegionalInfo, ["supported", "lanes_per_slot", "periods_per_unit", "ring_blocks",
-                                                          "workspace_bytes", "n_units", "kernel_lanes", "smem_bytes"])}
+                                                    "tile_lat", "tile_lon", "n_empty_regions", "n_partial_rows", "table_bytes"]),
+              "agf_regional_info_t": (_lib.RegionalInfo, ["supported", "lanes_per_slot", "kernel_lanes", "smem_bytes",
+                                                          "ctas_per_sm", "workspace_bytes"])}
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "aggfly_b200.h"', "int main(void) {"]
     for st, (_, names) in fields.items():
         lines.append(f'printf("{st} %zu\\n", sizeof({st}));')

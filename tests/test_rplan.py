@@ -18,13 +18,15 @@ def _tables(n_regions, n_lat, n_lon, row_ptr, cell_idx, w):
     rp, ci, ww = (np.ascontiguousarray(row_ptr, np.int32), np.ascontiguousarray(cell_idx, np.int32),
                   np.ascontiguousarray(w, np.float64))
     args = (n_regions, n_lat, n_lon, len(ci), rp.ctypes.data, ci.ctypes.data, ww.ctypes.data)
-    _lib.check(L.agf_rplan_tables(*args, C.byref(info), *([None] * 8)))
+    _lib.check(L.agf_rplan_tables(*args, C.byref(info), *([None] * 9)))
     t = dict(tile_ids=np.zeros(info.n_active_tiles, np.int32), tile_slot_ptr=np.zeros(info.n_active_tiles + 1, np.int32),
              slot_region=np.zeros(info.n_slots, np.int32), slot_ent_ptr=np.zeros(info.n_slots + 1, np.int32),
              entry_cell=np.zeros(info.n_entries, np.int32), entry_w=np.zeros(info.n_entries, np.float64),
-             region_slot_ptr=np.zeros(n_regions + 1, np.int32), region_slots=np.zeros(info.n_slots, np.int32))
+             region_slot_ptr=np.zeros(n_regions + 1, np.int32), region_slots=np.zeros(info.n_slots, np.int32),
+             slot_dst=np.zeros(info.n_slots, np.int32))
     _lib.check(L.agf_rplan_tables(*args, C.byref(info), *[t[k].ctypes.data for k in (
-        "tile_ids", "tile_slot_ptr", "slot_region", "slot_ent_ptr", "entry_cell", "entry_w", "region_slot_ptr", "region_slots")]))
+        "tile_ids", "tile_slot_ptr", "slot_region", "slot_ent_ptr", "entry_cell", "entry_w", "region_slot_ptr", "region_slots",
+        "slot_dst")]))
     return info, t
 
 
@@ -86,6 +88,15 @@ def test_tables_reproduce_the_scatter(shape):
         ws = t["entry_w"][t["slot_ent_ptr"][s]:t["slot_ent_ptr"][s + 1]]
         ks = [np.flatnonzero(w[row_ptr[r]:row_ptr[r + 1]] == v)[0] for v in ws]
         assert ks == sorted(ks)
+    # slots of a tile come longest first; a slot that holds its whole region names the region, the others a partial row
+    for ti in range(info.n_active_tiles):
+        lens = np.diff(t["slot_ent_ptr"][t["tile_slot_ptr"][ti]:t["tile_slot_ptr"][ti + 1] + 1])
+        assert np.all(np.diff(lens) <= 0) and np.all(lens > 0)
+    n_slots_of = np.diff(t["region_slot_ptr"])
+    whole = n_slots_of[t["slot_region"]] == 1
+    assert np.array_equal(t["slot_dst"][whole], t["slot_region"][whole])
+    assert np.array_equal(np.sort(-t["slot_dst"][~whole] - 1), np.arange(info.n_partial_rows))
+    assert info.n_partial_rows == int((~whole).sum())
     # regions: partial rows in ascending slot order; one-tile regions match the sequential sum bit for bit
     n_single = 0
     for r in range(R):
@@ -115,7 +126,7 @@ def test_bad_arguments_are_rejected():
     w = np.ones(2)
     info = _lib.RPlanInfo()
     with pytest.raises(_lib.AgfError, match="outside the grid"):
-        _lib.check(L.agf_rplan_tables(1, 4, 8, 2, rp.ctypes.data, ci.ctypes.data, w.ctypes.data, C.byref(info), *([None] * 8)))
+        _lib.check(L.agf_rplan_tables(1, 4, 8, 2, rp.ctypes.data, ci.ctypes.data, w.ctypes.data, C.byref(info), *([None] * 9)))
     rp2 = np.array([0, 1], np.int32)
     with pytest.raises(_lib.AgfError, match="row_ptr"):
-        _lib.check(L.agf_rplan_tables(1, 4, 8, 2, rp2.ctypes.data, ci.ctypes.data, w.ctypes.data, C.byref(info), *([None] * 8)))
+        _lib.check(L.agf_rplan_tables(1, 4, 8, 2, rp2.ctypes.data, ci.ctypes.data, w.ctypes.data, C.byref(info), *([None] * 9)))
