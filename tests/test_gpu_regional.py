@@ -138,6 +138,7 @@ def test_host_fed_raster_and_zero_weight_rows(zero_weight):
     """The streamed feed (pageable NumPy raster -> staging ring -> launches per period range) and the row-drop rules."""
     from aggfly_b200 import stream
     arr, t, lat, lon, ds, w = _case(40, 64, days=40, seed=5, ocean=0.45, regions=(6, 4), zero_weight=zero_weight)
+    arr[:, :11, :12] = np.nan                     # every cell of the north-west region is ocean: its rows are dropped
     saved = dict(stream.OPTIONS)
     stream.OPTIONS.update(staging_chunk_bytes=1 << 20, chunk_bytes=1 << 20)        # many chunks -> several launches
     try:
