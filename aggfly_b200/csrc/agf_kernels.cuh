@@ -998,6 +998,34 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
+// The producer lane's wait for a free stage.  try_wait returns after a few cycles when the phase has not completed
+// (ncu r2d: ~900 polls per wait, YIELD + TRYWAIT + BRA each -- a quarter of all warp instructions the daily-panel
+// kernel issued came from its three producer warps per SM spinning, on an SM whose issue slots are the scarce
+// resource).  A stage frees up once per tile, microseconds apart: sleep between polls.
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t *bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    while (!done) {
+        __nanosleep(256);
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    }
+}
 // (An L2 evict-first cache hint on these loads was measured: C3 5.40 ms against 5.23 ms without it, the small
 // CONUS grid 0.130 against 0.133 ms -- not kept.)
 __device__ __forceinline__ void tma_load_2d(void *dst, const void *tmap, int c0, int c1, uint64_t *bar) {
@@ -1048,7 +1076,7 @@ __global__ void __launch_bounds__(TMA_THREADS, MINB)
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
             for (int i = 0; i < n_tiles; ++i) {
                 const int s = i % TMA_STAGES;
-                if (i >= TMA_STAGES) mbar_wait(&empty[s], ((i / TMA_STAGES) - 1) & 1);
+                if (i >= TMA_STAGES) mbar_wait_backoff(&empty[s], ((i / TMA_STAGES) - 1) & 1);
                 mbar_expect_tx(&full[s], TMA_TILE_BYTES);
                 tma_load_2d(smem_raw + s * TMA_TILE_BYTES, &tmap, cell0, (int)(k_begin + i * TT - p.row0), &full[s]);
             }
@@ -1201,7 +1229,7 @@ __global__ void __launch_bounds__(TMA_THREADS, MINB)
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
             int s = 0, ph = 0;
             for (int i = 0; i < n_tiles; ++i) {
-                if (i >= TMA_STAGES) mbar_wait(&empty[s], ph ^ 1);
+                if (i >= TMA_STAGES) mbar_wait_backoff(&empty[s], ph ^ 1);
                 mbar_expect_tx(&full[s], TMA_TILE_BYTES);
                 tma_load_2d(smem_raw + s * TMA_TILE_BYTES, &tmap, cell0, (int)(k_begin + i * TT - p.row0), &full[s]);
                 if (++s == TMA_STAGES) {
