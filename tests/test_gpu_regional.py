@@ -129,6 +129,15 @@ def test_host_fed_raster_and_zero_weight_rows(zero_weight):
     assert len(one) < 24 * 40                                                       # some (region, day) rows were dropped
 
 
+@pytest.mark.parametrize("name", ["daily_bins_mean", "tavg_gdd"])
+def test_tiles_with_hundreds_of_tiny_regions_read_their_tables_from_global_memory(name):
+    """2 560 one-cell regions on a 40 x 64 grid: 256 slots per tile, more than the kernel's shared-memory tables hold."""
+    arr, t, lat, lon, ds, w = _case(40, 64, days=6, seed=21, regions=(64, 40))
+    one, two = _frames(ds, w, SPECS[name])
+    _same_frame(one, two, 1e-12)
+    assert one["geoid"].nunique() > 1500
+
+
 def test_period_ranges_launched_separately_do_not_change_the_result():
     """A streamed feed launches the kernel per period range as rows land: same bits as one launch."""
     import torch
