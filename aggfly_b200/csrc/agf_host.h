@@ -89,7 +89,6 @@ struct RegionalLaunch {
 struct RegionalChoice {
     int lanes, typed_bins, lps;   // instantiation: kernel lanes, NB, lanes per slot
     int smem_bytes, ctas_per_sm;
-    int partial_row_bytes;        // scratch bytes per (partial row, period)
 };
 
 // mode 0: launch; mode 1: only report the instantiation in *choice.  Returns 1 if nothing fits.

@@ -1,5 +1,5 @@
 // K1R instantiations: float raster, 24-row periods (hourly -> date), single-level programs; see agf_regional.cuh.
-// Rows are RCASE(kernel lanes, diagonal, lane kinds, NB, float4 quads per staged row), tried in order, cheapest first.
+// Rows are RCASE(kernel lanes, diagonal, lane kinds, NB, lanes per slot), tried in order, cheapest first.
 #define AGF_T float
 #include <algorithm>
 
@@ -10,29 +10,29 @@ namespace {
 
 constexpr int R_GL = 24;
 
-template <int NL, bool DIAG, unsigned KINDS, int NB, int NQ>
+template <int NL, bool DIAG, unsigned KINDS, int NB, int LPS>
 struct RShape {
     static constexpr bool TL = typed_lanes<0, NB>();
     static constexpr int NBL = TL ? NB : 0;
-    static constexpr int NA = TL ? NL - NB : NL;   // mean / sum / dd lanes
-    static constexpr int CAP = NQ * 4;             // float32 columns a staged row holds (one of them: validity)
+    static constexpr int NA = TL ? NL - NB : NL;          // float64 lanes
+    static constexpr int N_INT = NBL + 1;                  // bin lanes + the denominator's 0 / 1
+    static constexpr int N_INT_UNITS = (N_INT + 1) / 2;
+    static constexpr int MAX_DBL = LPS - N_INT_UNITS;      // float64 units that fit behind the integers
 };
 
-template <int NL, bool DIAG, unsigned KINDS, int NB, int NQ>
+template <int NL, bool DIAG, unsigned KINDS, int NB, int LPS>
 bool regional_fits(const agf_program *p) {
-    using S = RShape<NL, DIAG, KINDS, NB, NQ>;
+    using S = RShape<NL, DIAG, KINDS, NB, LPS>;
     if (!k1_fits(p, NL, 0, DIAG, KINDS, NB, R_GL)) return false;
     const agf_program_desc_t &d = p->desc;
-    if (d.out_dtype != AGF_F32) return false;  // staged columns are float32, like the X they replace
-    if (S::TL) return S::NBL + 1 + S::NA <= S::CAP;
-    if (DIAG) return 1 + NL <= S::CAP;
-    return 1 + d.n_cols <= S::CAP;  // columns transformed from the lanes
+    if (S::TL || DIAG) return S::NA <= S::MAX_DBL;
+    return d.n_cols <= S::MAX_DBL;  // columns transformed from the lanes: one float64 unit per column
 }
 
-template <int NL, bool DIAG, unsigned KINDS, int NB, int NQ>
+template <int NL, bool DIAG, unsigned KINDS, int NB, int LPS>
 int launch_regional(const RegionalLaunch &a, int mode, RegionalChoice *choice) {
     using T = float;
-    using S = RShape<NL, DIAG, KINDS, NB, NQ>;
+    using S = RShape<NL, DIAG, KINDS, NB, LPS>;
     const agf_program *p = a.k.p;
     const agf_rplan *plan = a.plan;
     // ring shape by register budget, like launch_k1
@@ -44,14 +44,14 @@ int launch_regional(const RegionalLaunch &a, int mode, RegionalChoice *choice) {
     // enough for three CTAs per SM: a stage is handed back as soon as its 24 values per thread sit in registers, and the
     // scan is bound by instruction issue, not by bytes in flight (13.5 KB per SM cover DRAM latency at 2 TB/s).
     constexpr int budget3 = 74 * 1024, budget2 = 110 * 1024;
-    constexpr int fixed1 = TILE + 128 + 2 * stage_bytes<NQ>() + RG_SM_SLOTS * 16;
+    constexpr int fixed1 = TILE + 128 + 2 * stage_bytes<LPS>() + RG_SM_SLOTS * 16;
     constexpr int MINB = (MINB0 == 3 && fixed1 + 256 * 16 <= budget3) ? 3 : (MINB0 >= 2 ? 2 : 1);
-    constexpr int STAGES = (MINB != 3 && 2 * TILE + 128 + 2 * stage_bytes<NQ>() + RG_SM_SLOTS * 16 + 1024 * 16 <= budget2) ? 2 : 1;
-    constexpr int fixed = STAGES * TILE + 128 + 2 * stage_bytes<NQ>() + RG_SM_SLOTS * 16;
+    constexpr int STAGES = (MINB != 3 && 2 * TILE + 128 + 2 * stage_bytes<LPS>() + RG_SM_SLOTS * 16 + 1024 * 16 <= budget2) ? 2 : 1;
+    constexpr int fixed = STAGES * TILE + 128 + 2 * stage_bytes<LPS>() + RG_SM_SLOTS * 16;
     constexpr int smem = MINB == 3 ? budget3 : budget2;
     constexpr int sm_entries = (smem - fixed) / 16;
     static_assert(sm_entries >= 256, "no room for the tile tables");
-    auto kern = agf_k1_regional<T, NL, DIAG, KINDS, NB, NQ, R_GL, TT, STAGES, MINB>;
+    auto kern = agf_k1_regional<T, NL, DIAG, KINDS, NB, LPS, R_GL, TT, STAGES, MINB>;
 
     static int ctas_per_sm = 0;  // per instantiation
     int sms = 148;
@@ -68,14 +68,13 @@ int launch_regional(const RegionalLaunch &a, int mode, RegionalChoice *choice) {
     if (choice) {
         choice->lanes = NL;
         choice->typed_bins = NB;
-        choice->lps = NQ * (NQ <= 4 ? 4 : 2);
-        choice->partial_row_bytes = NQ * 32;
+        choice->lps = LPS;
         choice->smem_bytes = smem;
         choice->ctas_per_sm = ctas_per_sm;
     }
     if (mode != 0) return 0;
     const int64_t n_groups = a.g_end - a.g_begin;
-    const int64_t ws_bytes = (int64_t)plan->n_partial_rows * a.G * NQ * 32;
+    const int64_t ws_bytes = (int64_t)plan->n_partial_rows * a.G * LPS * 16;
     unsigned char *ws = (unsigned char *)(((uintptr_t)a.d_workspace + 255) & ~(uintptr_t)255);
     if (plan->n_partial_rows > 0 && a.workspace_bytes - (ws - (unsigned char *)a.d_workspace) < ws_bytes)
         return agf_fail(AGF_E_INVALID, "workspace of %lld bytes, %lld needed", (long long)a.workspace_bytes, (long long)ws_bytes + 256);
@@ -100,17 +99,18 @@ int launch_regional(const RegionalLaunch &a, int mode, RegionalChoice *choice) {
     q.den_out = a.d_den;
     q.G = a.G;
     q.n_cols = a.out_ncols;
-    for (int i = 0; i < 32; ++i) q.dst_col[i] = -1;
+    q.n_int_units = S::N_INT_UNITS;
+    q.den_unit = (S::N_INT - 1) >> 1;
+    q.den_half = (S::N_INT - 1) & 1;
+    for (int i = 0; i < 32; ++i) q.dst_int[i] = -1;
+    for (int i = 0; i < 16; ++i) q.dst_dbl[i] = -1;
     if constexpr (S::TL) {
-        q.den_col = S::NBL;
-        for (int j = 0; j < S::NBL; ++j) q.dst_col[j] = kp.cols[j].dst;
-        for (int l = 0; l < S::NA; ++l) q.dst_col[S::NBL + 1 + l] = kp.cols[S::NBL + l].dst;
+        for (int j = 0; j < S::NBL; ++j) q.dst_int[j] = kp.cols[j].dst;
+        for (int l = 0; l < S::NA; ++l) q.dst_dbl[l] = kp.cols[S::NBL + l].dst;
     } else if constexpr (DIAG) {
-        q.den_col = 0;
-        for (int l = 0; l < NL; ++l) q.dst_col[1 + l] = l < kp.n_cols ? kp.cols[l].dst : -1;
+        for (int l = 0; l < NL; ++l) q.dst_dbl[l] = l < kp.n_cols ? kp.cols[l].dst : -1;
     } else {
-        q.den_col = 0;
-        for (int c = 0; c < kp.n_cols && 1 + c < 32; ++c) q.dst_col[1 + c] = kp.cols[c].dst;
+        for (int c = 0; c < kp.n_cols && c < 16; ++c) q.dst_dbl[c] = kp.cols[c].dst;
     }
     if (plan->n_empty_regions > 0) {
         agf_regional_fill_empty<<<plan->n_regions, 256, 0, a.k.stream>>>(plan->d_region_slot_ptr, plan->n_regions, q.g_begin,
@@ -149,13 +149,16 @@ int launch_regional(const RegionalLaunch &a, int mode, RegionalChoice *choice) {
         m.den_out = q.den_out;
         m.G = q.G;
         m.n_cols = q.n_cols;
-        m.den_col = q.den_col;
-        memcpy(m.dst_col, q.dst_col, sizeof(m.dst_col));
-        const int per_block = 256 / NQ;
+        m.n_int_units = q.n_int_units;
+        m.den_unit = q.den_unit;
+        m.den_half = q.den_half;
+        memcpy(m.dst_int, q.dst_int, sizeof(m.dst_int));
+        memcpy(m.dst_dbl, q.dst_dbl, sizeof(m.dst_dbl));
+        const int per_block = 256 / LPS;
         const int64_t ychunks = (n_groups + per_block - 1) / per_block;
         if (ychunks > 65535) return agf_fail(AGF_E_UNSUPPORTED, "too many periods in one launch");
         dim3 mgrid((unsigned)plan->n_multi, (unsigned)ychunks);
-        agf_regional_merge<NQ><<<mgrid, 256, 0, a.k.stream>>>(m);
+        agf_regional_merge<LPS><<<mgrid, 256, 0, a.k.stream>>>(m);
         CU(cudaGetLastError());
     }
     return 0;
@@ -166,19 +169,19 @@ int launch_regional(const RegionalLaunch &a, int mode, RegionalChoice *choice) {
 int agf_k1_f32_regional(const RegionalLaunch &a, int mode, RegionalChoice *choice, int *rc) {
     const agf_program *p = a.k.p;
     if (p->desc.n_slots != 0 || p->uniform_gl != R_GL) return 1;
-#define RCASE(NL, DG, KINDS, NB, NQ)                                  \
-    if (regional_fits<NL, DG, KINDS, NB, NQ>(p)) {                    \
-        *rc = launch_regional<NL, DG, KINDS, NB, NQ>(a, mode, choice); \
-        return 0;                                                     \
+#define RCASE(NL, DG, KINDS, NB, LPS)                                  \
+    if (regional_fits<NL, DG, KINDS, NB, LPS>(p)) {                    \
+        *rc = launch_regional<NL, DG, KINDS, NB, LPS>(a, mode, choice); \
+        return 0;                                                      \
     }
-    RCASE(1, false, KIND_SUM, NB_GENERAL, 1)
-    RCASE(1, false, KIND_DD, NB_GENERAL, 1)
-    RCASE(2, true, KIND_MIX_SD, NB_GENERAL, 1)
-    RCASE(4, true, KIND_MIX_SD, NB_GENERAL, 2)
-    RCASE(4, true, KIND_DD, NB_GENERAL, 2)
-    RCASE(8, true, KIND_SUM | KIND_BINS, 6, 4)
-    RCASE(14, true, KIND_SUM | KIND_BINS, 13, 4)
-    RCASE(16, true, KIND_SUM | KIND_BINS, 14, 8)
+    RCASE(1, false, KIND_SUM, NB_GENERAL, 4)
+    RCASE(1, false, KIND_DD, NB_GENERAL, 4)
+    RCASE(2, true, KIND_MIX_SD, NB_GENERAL, 4)
+    RCASE(4, true, KIND_MIX_SD, NB_GENERAL, 8)
+    RCASE(4, true, KIND_DD, NB_GENERAL, 8)
+    RCASE(8, true, KIND_SUM | KIND_BINS, 6, 8)
+    RCASE(14, true, KIND_SUM | KIND_BINS, 13, 8)
+    RCASE(16, true, KIND_SUM | KIND_BINS, 14, 16)
 #undef RCASE
     return 1;
 }

@@ -306,7 +306,7 @@ extern "C" int agf_temporal_regional_plan(const agf_program_t *p, const agf_rpla
     info->kernel_lanes = ch.lanes;
     info->smem_bytes = ch.smem_bytes;
     info->ctas_per_sm = ch.ctas_per_sm;
-    info->workspace_bytes = (int64_t)plan->n_partial_rows * panel_groups * ch.partial_row_bytes + 256;
+    info->workspace_bytes = (int64_t)plan->n_partial_rows * panel_groups * ch.lps * 16 + 256;
     return 0;
 }
 

@@ -230,7 +230,7 @@ class RegionalRunner:
 
     def partial_bytes(self) -> int:
         """Scratch rows of the regions that straddle tiles: written by the scan kernel, read once by the merge kernel."""
-        return max(0, int(self.info.workspace_bytes) - 256)
+        return int(self.plan.info.n_partial_rows) * self.G * int(self.info.lanes_per_slot) * 16
 
     def algorithmic_input_bytes(self) -> int:
         """Raster bytes the kernel must read: the tiles that hold at least one weighted cell (cells no region
