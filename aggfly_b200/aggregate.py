@@ -181,6 +181,9 @@ def _temporal_device(dataset: Dataset, aggregator_dict, target_stripes: int = 0)
         # whose chunks span the whole time axis delivers every row at once: planned like a resident raster.)
         nbytes = int(np.prod(dataset.shape)) * dataset.dtype.itemsize
         target_stripes = -int(min(64, nbytes // (4 * _stream.OPTIONS["chunk_bytes"])))
+        if nbytes > _stream.OPTIONS["device_raster_budget_bytes"]:
+            # a record longer than the device budget goes through a ring of device windows: one stripe per window
+            target_stripes = -int(-(-nbytes // _stream.OPTIONS["ring_slot_bytes"]))
     import time
     t0 = time.perf_counter()
     runner = _engine.StageRunner(stage, n_cells, target_stripes=target_stripes)

@@ -207,7 +207,7 @@ class RegionalRunner:
         self.panel = torch.empty((R, self.G, self.n_cols), dtype=torch.float64, device=self.device)
         self.den = torch.empty((R, self.G), dtype=torch.float64, device=self.device) if self.want_den else None
 
-    def _launch(self, raster, g0: int, g1: int, stream, k1_events=None) -> None:
+    def _launch(self, raster, g0: int, g1: int, stream, k1_events=None, row0: int = 0) -> None:
         torch = _torch()
         if raster.dtype != torch.float32:
             raise TypeError(f"raster dtype {raster.dtype} does not match the planned float32")
@@ -217,7 +217,7 @@ class RegionalRunner:
             ev[0].record(stream)
         with torch.cuda.stream(stream):
             _lib.check(_lib.lib().agf_temporal_regional_run(
-                self.program.handle, self.plan.handle, raster.data_ptr(), self.n_cells, 0, g0, g1,
+                self.program.handle, self.plan.handle, raster.data_ptr(), self.n_cells, int(row0), g0, g1,
                 self.workspace.data_ptr(), self.workspace.numel(), self.panel.data_ptr(), self.G, self.n_cols,
                 self.den.data_ptr() if self.den is not None else None, stream.cuda_stream))
         if ev is not None:
@@ -254,14 +254,24 @@ class RegionalRunner:
         self._buffers()
         self._cursor = 0
 
-    def feed(self, raster, rows_ready: int, stream, k1_events=None) -> int:
+    def window_cuts(self) -> np.ndarray:
+        """Rows at which a device window of the raster may end (stream.feed_and_run's ring mode): ends of whole
+        launch quanta, and the end of the time axis."""
+        q = np.arange(self.GROUP_QUANTUM, self.G, self.GROUP_QUANTUM)
+        return np.unique(np.concatenate([self.b1[q], self.b1[-1:]])).astype(np.int64)
+
+    def feed(self, raster, rows_ready: int, stream, k1_events=None, row0: int = 0, flush: bool = False) -> int:
+        """``raster`` holds rows [row0, rows_ready) of the time axis (row0 = 0: the whole raster so far).  ``flush``:
+        the window ends at rows_ready -- launch every complete period, not only whole quanta."""
         g_ready = int(np.searchsorted(self.b1, rows_ready, side="right")) - 1     # complete periods
         g_ready = min(g_ready, self.G)
-        if g_ready < self.G:
+        if g_ready < self.G and not flush:
             g_ready = self._cursor + (g_ready - self._cursor) // self.GROUP_QUANTUM * self.GROUP_QUANTUM
         if g_ready <= self._cursor:
             return 0
-        self._launch(raster, self._cursor, g_ready, stream, k1_events)
+        if self.b1[self._cursor] < row0:
+            raise RuntimeError("ring window starts past the first row of the next period")
+        self._launch(raster, self._cursor, g_ready, stream, k1_events, row0)
         self._cursor = g_ready
         return 1
 
@@ -444,9 +454,25 @@ class StageRunner:
                 r.V.fill_(1)
             r._ran_token = None
 
-    def feed(self, raster, rows_ready: int, stream, k1_events=None) -> int:
-        """Rows [0, rows_ready) of ``raster`` are (stream-ordered) resident: launch every stripe of
-        every raster-reading program that is now complete.  Returns the number of launches."""
+    def window_cuts(self) -> np.ndarray:
+        """Rows at which a device window of the raster may end (stream.feed_and_run's ring mode): stripe ends shared
+        by EVERY raster-reading program of the stage tree (the end of the time axis always is one).  None: a stage
+        that needs the whole raster at once (an elementwise transform of the raw raster)."""
+        cuts = None
+        for r in self._walk():
+            if r.stage.elementwise is not None and r.stage.elementwise.source is None:
+                return None
+            for p in r.programs:
+                if getattr(p.spec, "_source", None) is not None:
+                    continue
+                ends = np.array([p.stripe_rows(s)[1] for s in range(p.info.n_stripes)], dtype=np.int64)
+                cuts = ends if cuts is None else np.intersect1d(cuts, ends)
+        return cuts
+
+    def feed(self, raster, rows_ready: int, stream, k1_events=None, row0: int = 0, flush: bool = False) -> int:
+        """Rows [row0, rows_ready) of the time axis are (stream-ordered) resident in ``raster`` (row0 = 0: the whole
+        raster so far; otherwise a ring window whose first row is row0): launch every stripe of every raster-reading
+        program that is now complete.  Returns the number of launches."""
         torch = _torch()
         L = _lib.lib()
         n = 0
@@ -467,7 +493,9 @@ class StageRunner:
                 if k1_events is not None:
                     ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
                     ev[0].record(stream)
-                _lib.check(L.agf_temporal_run(prog.handle, raster.data_ptr(), r.n_cells, 0, s0, s1, pptr,
+                if row0 and prog.stripe_rows(s0)[0] < row0:
+                    raise RuntimeError("ring window starts past the first row of the next stripe")
+                _lib.check(L.agf_temporal_run(prog.handle, raster.data_ptr(), r.n_cells, int(row0), s0, s1, pptr,
                                               r.X.data_ptr(), r.V.data_ptr(), n_cols, 1, stream.cuda_stream))
                 if ev is not None:
                     ev[1].record(stream)

@@ -13,9 +13,13 @@ range), so the copy engine and the SMs work at the same time and the call costs
 * pageable source: worker threads memcpy chunks into a small ring of pinned staging buffers
   (numpy releases the GIL), the main thread issues the async copies in order.
 
-The device side holds the whole call's raster (one year of global 0.25deg hourly data is 36.4 GB of
-the 180 GB HBM); longer records are looped by period on the host like the reference's CLI does
-(aggfly/cli/pipeline.py:138-150).
+Device footprint.  A raster up to ``OPTIONS["device_raster_budget_bytes"]`` is held whole on the device (one year
+of global 0.25deg hourly data is 36.4 GB of the 180 GB HBM) and its buffer is kept for the next call.  A longer
+record -- the reference streams any length by time chunk (aggfly/aggregate/spatial.py:189-199) and its CLI loops
+years (aggfly/cli/pipeline.py:138-150) -- goes through a RING of ``ring_slots`` device windows of about
+``ring_slot_bytes``: a window ends where every raster-reading program has a stripe end, its kernels are launched
+with the window as their raster (``row0`` of agf_temporal_run / agf_temporal_regional_run), and its slot is reused
+once they have run.  Device raster memory is then independent of the length of the time axis.
 """
 from __future__ import annotations
 
@@ -33,6 +37,10 @@ OPTIONS = {
     "staging_slots": 8,                # pinned ring depth for pageable sources
     "staging_threads": 8,              # host threads filling the ring
     "keep_device_raster": True,        # keep the device copy's buffer between calls (see _device_raster)
+    # rasters larger than this are streamed through a ring of device windows instead of being held whole
+    "device_raster_budget_bytes": int(float(__import__("os").environ.get("AGF_RASTER_BUDGET_GB", "48")) * (1 << 30)),
+    "ring_slot_bytes": 16 << 30,        # target size of one device window (grown to the largest window the cuts allow)
+    "ring_slots": 3,
     "chunked_ring_bytes": 2 << 30,     # pinned (and device) staging for chunked stores: slots x decoded chunk size
     "device_decompress": True,         # Blosc-LZ4 chunks: inflate on the GPU's decompression engine when it has one
     # The per-chunk tables of the device decode (expected stream lengths, raw-segment table) are uploaded from
@@ -102,6 +110,155 @@ class _Staging:
         self.pool.shutdown(wait=True)
 
 
+def plan_windows(cuts, n_rows: int, slot_rows: int):
+    """[(r0, r1)] covering [0, n_rows): every window ends at one of ``cuts`` (ascending rows, the last one is
+    n_rows) and holds at most ``slot_rows`` rows where the cuts allow it (else the shortest window that reaches the
+    next cut).  Greedy: the farthest cut inside the slot."""
+    cuts = np.unique(np.asarray(cuts, dtype=np.int64))
+    cuts = cuts[(cuts > 0) & (cuts <= n_rows)]
+    if len(cuts) == 0 or cuts[-1] != n_rows:
+        cuts = np.append(cuts, n_rows)
+    out, r0 = [], 0
+    while r0 < n_rows:
+        j = int(np.searchsorted(cuts, r0 + slot_rows, side="right")) - 1
+        r1 = int(cuts[j]) if j >= 0 and cuts[j] > r0 else int(cuts[int(np.searchsorted(cuts, r0, side="right"))])
+        out.append((r0, r1))
+        r0 = r1
+    return out
+
+
+def _source_breaks(values, n_rows: int):
+    """Rows where a lazily concatenated source changes part (chunks are cut there, so that every chunk is one
+    part's own slice)."""
+    starts = getattr(values, "starts", None)
+    if starts is None:
+        return np.zeros(0, dtype=np.int64)
+    b = np.asarray(starts, dtype=np.int64)
+    return b[(b > 0) & (b < n_rows)]
+
+
+def _chunks_of(r0: int, r1: int, row_bytes: int, chunk_bytes: int, breaks):
+    """Row chunks of [r0, r1) of about chunk_bytes, never straddling a source break."""
+    edges = np.unique(np.concatenate([[r0, r1], breaks[(breaks > r0) & (breaks < r1)]])).astype(np.int64)
+    out = []
+    for a, b in zip(edges[:-1], edges[1:]):
+        out += [(int(a) + x, int(a) + y) for x, y in chunk_rows(int(b - a), row_bytes, chunk_bytes)]
+    return out
+
+
+_RING_RASTERS = {}       # (device, dtype, slot elements, slots) -> device windows, kept across calls like _DEVICE_RASTERS
+
+
+def _pinned_piece(torch, piece, tdtype):
+    """A pinned torch view of a host chunk that can be copied from in place, else None."""
+    if type(piece).__module__.startswith("torch"):
+        t = piece
+    elif isinstance(piece, np.ndarray) and piece.flags.c_contiguous and piece.dtype.isnative and piece.flags.writeable:
+        t = torch.from_numpy(piece)
+    else:
+        return None
+    if t.dtype != tdtype or not t.is_contiguous():
+        return None
+    try:
+        return t if t.is_pinned() else None
+    except Exception:
+        return None
+
+
+def _feed_ring(torch, runner, values, host, host_np, T: int, n_cells: int, tdtype, cuts, comp, copy, k1_events, chunk_bytes):
+    """feed_and_run for a record longer than the device budget: windows of the time axis go through a ring of
+    device slots (module docstring).  Returns (result, ring tensor, stats)."""
+    dev = runner.device
+    item = torch.empty(0, dtype=tdtype).element_size()
+    row_bytes = n_cells * item
+    slot_rows = max(1, int(OPTIONS["ring_slot_bytes"] // row_bytes))
+    windows = plan_windows(cuts, T, slot_rows)
+    slot_rows = max(r1 - r0 for r0, r1 in windows)
+    n_slots = int(max(2, min(OPTIONS["ring_slots"], len(windows))))
+    key = (dev.index, str(tdtype), slot_rows * n_cells, n_slots)
+    ring = _RING_RASTERS.get(key)
+    if ring is None:
+        _RING_RASTERS.clear()
+        _DEVICE_RASTERS.clear()
+        ring = torch.empty((n_slots, slot_rows, n_cells), dtype=tdtype, device=dev)
+        _RING_RASTERS[key] = ring
+    pinned = host is not None
+    cb = chunk_bytes or OPTIONS["chunk_bytes" if pinned else "staging_chunk_bytes"]
+    breaks = _source_breaks(values, T)
+    staging = None
+    if not pinned:
+        staging = _Staging(torch, tdtype, max(1, int(cb // row_bytes)) * n_cells, OPTIONS["staging_slots"], OPTIONS["staging_threads"])
+    work = []                                                  # (window index, r0, r1, last chunk of its window)
+    for k, (w0, w1) in enumerate(windows):
+        cs = _chunks_of(w0, w1, row_bytes, cb, breaks)
+        work += [(k, a, b, j == len(cs) - 1) for j, (a, b) in enumerate(cs)]
+    consumed = [None] * n_slots                                # last kernel that read the slot
+    copy.wait_stream(comp)
+    ev_first, ev_last = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev_first.record(copy)
+    runner.begin_streamed(comp)
+    launches = direct = 0
+    try:
+        futs = {}
+        ahead = len(staging.slots) if staging else 0
+        n_staged = 0
+
+        def submit(i):
+            nonlocal n_staged
+            _, a, b, _last = work[i]
+            piece = host_np[a:b]
+            t = _pinned_piece(torch, piece, tdtype)
+            if t is not None:
+                futs[i] = ("direct", t)
+            else:
+                futs[i] = ("staged", staging.pool.submit(staging.fill, n_staged % ahead, piece), n_staged % ahead)
+                n_staged += 1
+
+        if staging:
+            for i in range(min(ahead, len(work))):
+                submit(i)
+        for i, (k, a, b, last) in enumerate(work):
+            slot = k % n_slots
+            w0 = windows[k][0]
+            sslot = None
+            if staging:
+                got = futs.pop(i)
+                if got[0] == "direct":
+                    src = got[1].view(b - a, n_cells)
+                    direct += 1
+                else:
+                    src, sslot = got[1].result().view(b - a, n_cells), got[2]
+            else:
+                src = host[a:b]
+            with torch.cuda.stream(copy):
+                if a == w0 and consumed[slot] is not None:
+                    copy.wait_event(consumed[slot])            # the slot's previous window has been scanned
+                ring[slot, a - w0:b - w0].copy_(src, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy)
+            if staging:
+                if sslot is not None:
+                    staging.events[sslot] = ev
+                if i + ahead < len(work):
+                    submit(i + ahead)
+            comp.wait_event(ev)
+            launches += runner.feed(ring[slot], b, comp, k1_events, row0=w0, flush=last)
+            if last:
+                ce = torch.cuda.Event()
+                ce.record(comp)
+                consumed[slot] = ce
+        ev_last.record(copy)
+        res = runner.finish_streamed(None, comp)
+    finally:
+        if staging:
+            staging.close()
+    ring.record_stream(comp)
+    stats = dict(chunks=len(work), pinned=bool(pinned), h2d_bytes=T * row_bytes, k1_launches=launches,
+                 copy_events=(ev_first, ev_last), ring=True, ring_slots=n_slots, ring_slot_rows=slot_rows,
+                 ring_bytes=int(ring.numel() * item), windows=len(windows), direct_chunks=direct)
+    return res, ring, stats
+
+
 def feed_and_run(runner, values, n_cells: int, stream=None, k1_events: Optional[list] = None,
                  chunk_bytes: Optional[int] = None, stats: Optional[dict] = None):
     """Run ``runner`` (an ``engine.StageRunner``) over a HOST raster ``values[T, ...cells]``.
@@ -124,6 +281,15 @@ def feed_and_run(runner, values, n_cells: int, stream=None, k1_events: Optional[
     dev = runner.device
     comp = torch.cuda.current_stream(dev) if stream is None else stream
     copy = _copy_stream(dev)
+    global LAST_STATS
+    if T * n_cells * (8 if tdtype == torch.float64 else 4) > OPTIONS["device_raster_budget_bytes"]:
+        cuts = runner.window_cuts() if hasattr(runner, "window_cuts") else None
+        if cuts is not None:
+            res, ring, LAST_STATS = _feed_ring(torch, runner, values, host, host_np, T, n_cells, tdtype, cuts, comp, copy,
+                                               k1_events, chunk_bytes)
+            if stats is not None:
+                stats.update(LAST_STATS)
+            return res, ring
     raster = _device_raster(torch, dev, tdtype, T, n_cells)
     row_bytes = n_cells * raster.element_size()
     chunks = chunk_rows(T, row_bytes, chunk_bytes or OPTIONS["chunk_bytes" if pinned else "staging_chunk_bytes"])
@@ -169,7 +335,6 @@ def feed_and_run(runner, values, n_cells: int, stream=None, k1_events: Optional[
         if staging:
             staging.close()
     raster.record_stream(comp)
-    global LAST_STATS
     LAST_STATS = dict(chunks=len(chunks), pinned=bool(pinned), h2d_bytes=T * row_bytes, k1_launches=launches,
                       copy_events=(ev_first, ev_last))      # elapsed_time() once the caller has synchronised
     if stats is not None:
@@ -438,6 +603,7 @@ def _device_raster(torch, dev, tdtype, T: int, n_cells: int):
 def release_device_rasters() -> None:
     """Give the cached device raster (and the pinned staging ring) back."""
     _DEVICE_RASTERS.clear()
+    _RING_RASTERS.clear()
     _RINGS.clear()
     _CHUNK_RINGS.clear()
 

@@ -379,6 +379,56 @@ def test_streamed_feed_is_bitwise_the_device_resident_result(name, feed):
     _close(streamed[vals].values, want[vals].values, 1e-11)
 
 
+# ---- records longer than the device budget: a ring of device windows (stream._feed_ring) ---------------------
+@pytest.mark.parametrize("feed", ["pinned", "pageable", "concat_pinned_parts"])
+@pytest.mark.parametrize("name", ["c3_bins_and_poly", "c3b_daily", "monthly_mix", "three_levels"])
+def test_ring_of_device_windows_is_bitwise_the_device_resident_result(name, feed):
+    """The device holds two windows of about 100 rows at a time; the panel is bit for bit the one of the
+    device-resident raster (same stripes, so the same merge order)."""
+    import torch
+    from aggfly_b200 import stream
+    from aggfly_b200.dataset import TimeConcat
+    arr, t, lat, lon = _raster("float32", True, T=24 * 40 + 5, seed=17)
+    rng = np.random.default_rng(5)
+    wdf, shp = _weights_case(lat, lon, rng)
+
+    def run(values):
+        ds = af.Dataset.from_arrays(values, t, lat, lon, True)
+        w = af.weights_from_objects(ds, af.GeoRegions(shp, "geoid"), zero_weight="nan")
+        w.weights = wdf
+        return af.aggregate_dataset(weights=w, dataset=ds, aggregator_dict=SPECS[name])
+
+    engine.OPTIONS["target_stripes"] = 11
+    old = dict(stream.OPTIONS)
+    row = arr[0].nbytes
+    try:
+        resident = run(torch.from_numpy(arr).cuda())
+        stream.OPTIONS.update(chunk_bytes=13 * row, staging_chunk_bytes=13 * row, staging_slots=3, staging_threads=2,
+                              device_raster_budget_bytes=1, ring_slot_bytes=100 * row, ring_slots=2)
+        if feed == "pinned":
+            host = torch.from_numpy(arr).pin_memory()
+        elif feed == "pageable":
+            host = arr
+        else:               # three pinned "year buffers" concatenated lazily: their chunks are copied from in place
+            cuts = [0, 24 * 13 + 7, 24 * 29, arr.shape[0]]
+            keep = [torch.from_numpy(arr[a:b]).pin_memory() for a, b in zip(cuts[:-1], cuts[1:])]
+            host = TimeConcat([k.numpy() for k in keep])
+        streamed = run(host)
+        st = stream.LAST_STATS
+        assert st.get("ring") and st["ring_slots"] == 2 and st["windows"] >= 4
+        assert st["ring_bytes"] < arr.nbytes / 3
+        if feed == "concat_pinned_parts":
+            assert st["direct_chunks"] == st["chunks"]
+        if feed == "pageable":
+            assert st["direct_chunks"] == 0
+    finally:
+        stream.OPTIONS.update(old)
+        stream.release_device_rasters()
+    vals = [c for c in resident.columns if c not in ("geoid", "time")]
+    assert list(streamed.columns) == list(resident.columns) and len(streamed) == len(resident)
+    _exact(streamed[vals].values, resident[vals].values)
+
+
 # ---- daily rasters: single-row inner groups collapse to one pass (spec.Planner._collapsed_lane) ----------
 DAILY_SPECS = {
     "gdd_month": dict(gdd=[("aggregate", {"calc": "dd", "groupby": "date", "ddargs": [10, 30, 0]}),

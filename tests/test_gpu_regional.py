@@ -238,3 +238,31 @@ def test_full_size_daily_panel_is_repeatable_and_matches_the_two_kernel_path():
     assert torch.equal(torch.isnan(first), torch.isnan(p2))
     ok = ~torch.isnan(p2)
     assert float(((first[ok] - p2[ok]).abs() / p2[ok].abs().clamp_min(1e-2)).max()) <= 1e-12
+
+
+@pytest.mark.parametrize("feed", ["pinned", "pageable"])
+def test_ring_of_device_windows_feeds_the_one_kernel_path_bit_identically(feed):
+    """A host record longer than the device budget: the one-kernel path scans it window by window (row0 of
+    agf_temporal_regional_run); same association per period, so the panel is bit for bit the resident one."""
+    import torch
+    from aggfly_b200 import stream
+    spec = SPECS["daily_bins_mean"]
+    arr, t, lat, lon, ds, w = _case(21, 100, days=50, seed=77)
+    engine.OPTIONS["regional"] = True
+    dres = af.Dataset.from_arrays(torch.from_numpy(arr).cuda(), t, lat, lon, lon_is_360=True)
+    resident = af.aggregate_dataset(weights=w, dataset=dres, aggregator_dict=spec)
+    old = dict(stream.OPTIONS)
+    row = arr[0].nbytes
+    try:
+        stream.OPTIONS.update(chunk_bytes=31 * row, staging_chunk_bytes=31 * row, staging_slots=3, staging_threads=2,
+                              device_raster_budget_bytes=1, ring_slot_bytes=24 * 17 * row, ring_slots=2)
+        host = torch.from_numpy(arr).pin_memory() if feed == "pinned" else arr
+        dh = af.Dataset.from_arrays(host, t, lat, lon, lon_is_360=True)
+        streamed = af.aggregate_dataset(weights=w, dataset=dh, aggregator_dict=spec)
+        assert any(k.startswith("temporal + regional") for k in agg_mod.LAST_TRACE["phases_ms"]), agg_mod.LAST_TRACE
+        st = stream.LAST_STATS
+        assert st.get("ring") and st["windows"] >= 3 and st["ring_bytes"] < arr.nbytes
+    finally:
+        stream.OPTIONS.update(old)
+        stream.release_device_rasters()
+    _same_frame(streamed, resident, 0.0)
