@@ -59,6 +59,32 @@ __global__ void __launch_bounds__(256) agf_tile_rows(const TS *__restrict__ src,
     }
 }
 
+// Whole raster rows stored contiguously (a row chunk of a time-major source, dataset.PackedRaster): the source and the
+// destination are the same linear index apart, so no div / mod per element; 16 bytes of source per thread and trip.
+template <typename TS, typename TD>
+__global__ void __launch_bounds__(256) agf_tile_linear(const TS *__restrict__ src, TD *__restrict__ dst, long long n, TileArgs a) {
+    constexpr int V = 16 / (int)sizeof(TS);
+    const long long nv = n / V;
+    const long long step = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += step) {
+        const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(src) + i);
+        TS v[V];
+        memcpy(v, &raw, 16);
+        TD o[V];
+#pragma unroll
+        for (int k = 0; k < V; ++k) o[k] = tile_decode<TS, TD>(v[k], a);
+        constexpr int OV = 16 / (int)sizeof(TD);   // destination elements per 16-byte store
+#pragma unroll
+        for (int k = 0; k < V / OV; ++k) {
+            uint4 w;
+            memcpy(&w, o + k * OV, 16);
+            reinterpret_cast<uint4 *>(dst + i * V)[k] = w;
+        }
+    }
+    for (long long i = nv * V + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step)
+        dst[i] = tile_decode<TS, TD>(src[i], a);
+}
+
 // The stride-1 source axis is f in {t, y}; o is the remaining axis.  Block (32, 8) moves a 32 (f) x 32 (x)
 // tile; blockIdx.z strides over o.
 template <typename TS, typename TD>
@@ -92,7 +118,13 @@ template <typename TS, typename TD>
 int launch_tile(const void *d_src, void *d_dst, const TileArgs &a, int sms, cudaStream_t st) {
     const long long n = a.nt * a.ny * a.nx;
     const int f_is_t = a.st == 1 && a.nt > 1, f_is_y = a.sy == 1 && a.ny > 1;
-    if (a.sx == 1 || a.nx == 1 || (!f_is_t && !f_is_y)) {
+    TD *dbase = (TD *)d_dst + a.t0 * a.ld;
+    if (a.sx == 1 && a.sy == a.nx && a.st == a.ny * a.nx && a.x0 == 0 && a.y0 == 0 && a.nx == a.n_lon && a.ny * a.n_lon == a.ld &&
+        sizeof(TS) <= sizeof(TD) && (uintptr_t)d_src % 16 == 0 && (uintptr_t)dbase % 16 == 0) {
+        constexpr int V = 16 / (int)sizeof(TS);
+        const unsigned blocks = (unsigned)std::min<long long>((n / V + 255) / 256 + 1, (long long)sms * 16);
+        agf_tile_linear<TS, TD><<<blocks, 256, 0, st>>>((const TS *)d_src, dbase, n, a);
+    } else if (a.sx == 1 || a.nx == 1 || (!f_is_t && !f_is_y)) {
         const unsigned blocks = (unsigned)std::min<long long>((n + 255) / 256, (long long)sms * 32);
         agf_tile_rows<TS, TD><<<blocks, 256, 0, st>>>((const TS *)d_src, (TD *)d_dst, a);
     } else {

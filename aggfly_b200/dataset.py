@@ -125,6 +125,61 @@ class TimeConcat:
         return f"<TimeConcat {self.shape} {self.dtype} of {len(self.parts)} parts>"
 
 
+class PackedRaster:
+    """CF-packed integers ``stored[T, lat, lon]`` (int16 / int32 / uint8 ...) in HOST memory with their
+    ``scale_factor`` / ``add_offset`` / ``_FillValue`` -- what an ERA5 NetCDF variable is on disk, and what
+    ``xr.open_dataset(..., mask_and_scale=True)`` decodes lazily for the reference (aggfly/dataset/dataset.py:700-707).
+    Here the stored integers cross PCIe as they are (2 bytes per value instead of 4) and are decoded ON THE DEVICE by
+    ``agf_tile_place_run`` (``stored * scale_factor + add_offset`` in double, then rounded to ``dtype``; fill -> NaN)
+    while the next chunk is copied (stream.feed_packed).  ``stored`` may be a NumPy array or a (pinned) CPU torch
+    tensor; slicing along time stays lazy."""
+
+    is_packed_raster = True
+    ndim = 3
+
+    def __init__(self, stored, scale_factor: float = 1.0, add_offset: float = 0.0, fill_value=None, dtype=np.float32):
+        self.stored = stored
+        self.scale, self.offset = float(scale_factor), float(add_offset)
+        self.fill = None if fill_value is None else float(fill_value)
+        self.dtype = np.dtype(dtype)
+        if self.dtype not in (np.float32, np.float64):
+            raise TypeError("decoded dtype must be float32 or float64")
+        if len(stored.shape) != 3:
+            raise ValueError("stored values must be [time, lat, lon]")
+
+    @property
+    def shape(self):
+        return tuple(int(v) for v in self.stored.shape)
+
+    @property
+    def size(self) -> int:
+        return int(np.prod(self.shape))
+
+    def __len__(self):
+        return self.shape[0]
+
+    def stored_numpy(self) -> np.ndarray:
+        return self.stored.numpy() if _is_torch(self.stored) else np.asarray(self.stored)
+
+    def __getitem__(self, key):
+        k0 = key[0] if isinstance(key, tuple) else key
+        rest = key[1:] if isinstance(key, tuple) else ()
+        if isinstance(k0, slice) and k0.step in (None, 1) and all(isinstance(k, slice) and k == slice(None) for k in rest):
+            return PackedRaster(self.stored[k0], self.scale, self.offset, self.fill, self.dtype)
+        return np.asarray(self)[key]
+
+    def __array__(self, dtype=None, copy=None):
+        """Host materialisation (tests, small cases): the arithmetic agf_tile_place_run does on the device."""
+        raw = self.stored_numpy()
+        out = (raw.astype(np.float64) * self.scale + self.offset).astype(self.dtype)
+        if self.fill is not None:
+            out[raw.astype(np.float64) == self.fill] = np.nan
+        return out if dtype is None else out.astype(dtype, copy=False)
+
+    def __repr__(self):
+        return f"<PackedRaster {self.shape} {self.stored.dtype} -> {self.dtype} scale={self.scale} offset={self.offset}>"
+
+
 def time_selection(time, time_sel):
     """Row range [a, b) of ``.sel(time=time_sel)`` on a sorted axis: a partial date string ("2001",
     "2001-06", "2001-06-15"), a timestamp, or a slice of those (both ends inclusive, like pandas/xarray)."""
@@ -198,7 +253,8 @@ class Dataset:
                 order = np.argsort(time.values, kind="stable")
             time = time[order]
             values = values[order] if not _is_torch(values) else values[list(order)]
-        if not _is_torch(values) and not getattr(values, "is_chunked_raster", False) and not getattr(values, "lazy_rows", False):
+        if (not _is_torch(values) and not getattr(values, "is_chunked_raster", False) and not getattr(values, "lazy_rows", False)
+                and not getattr(values, "is_packed_raster", False)):
             values = np.asarray(values)
             if values.dtype not in (np.float32, np.float64):
                 values = values.astype(np.float64)

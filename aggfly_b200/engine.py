@@ -54,6 +54,12 @@ def to_device(values, device=None):
         torch.cuda.current_stream(device).synchronize()
         _stream.check_device_decompress()
         return raster.view(T, Y, X).clone()                         # the streamed buffer is recycled by the next feed
+    if getattr(values, "is_packed_raster", False):                 # packed integers: copied as stored, decoded on the device
+        from . import stream as _stream
+        T, Y, X = values.shape
+        _, raster = _stream.feed_packed(None, values, Y * X, device=device)
+        torch.cuda.current_stream(device).synchronize()
+        return raster.view(T, Y, X).clone()
     if getattr(values, "lazy_rows", False):
         values = np.asarray(values)
     if isinstance(values, np.ndarray):

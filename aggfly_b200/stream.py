@@ -67,6 +67,9 @@ def _host_source(values):
         arr = np.asarray(values)
         if arr.dtype not in (np.float32, np.float64) or not arr.dtype.isnative:
             arr = arr.astype(np.float64 if arr.dtype.itemsize > 4 or arr.dtype.kind != "f" else np.float32)
+        t = _pinned_piece(torch, arr, torch.float64 if arr.dtype == np.float64 else torch.float32)
+        if t is not None:                      # a NumPy view of page-locked memory (tensor.numpy() of a pinned tensor)
+            return t, None
         return None, arr
     t = values
     if t.dtype not in (torch.float32, torch.float64):
@@ -268,6 +271,8 @@ def feed_and_run(runner, values, n_cells: int, stream=None, k1_events: Optional[
     import torch
     if getattr(values, "is_chunked_raster", False):
         return feed_chunked(runner, values, n_cells, stream, k1_events, stats)
+    if getattr(values, "is_packed_raster", False):
+        return feed_packed(runner, values, n_cells, stream, k1_events, stats)
     host, host_np = _host_source(values)
     pinned = host is not None
     T = int(host.shape[0] if pinned else host_np.shape[0])
@@ -580,6 +585,107 @@ def feed_chunked(runner, src, n_cells: int, stream=None, k1_events: Optional[lis
     return res, raster
 
 
+# ---------------------------------------------------------------------------------------------
+# packed integers in host memory (dataset.PackedRaster): copied as stored, decoded on the device
+# ---------------------------------------------------------------------------------------------
+_PACKED_DEV = {}         # (device, dtype, slot elements, slots) -> device staging for stored chunks
+
+
+def feed_packed(runner, src, n_cells: int, stream=None, k1_events: Optional[list] = None, stats: Optional[dict] = None,
+                device=None):
+    """``feed_and_run`` for a ``dataset.PackedRaster``: row chunks of the STORED integers go to a small device ring
+    (pinned sources are copied from in place, pageable ones through the pinned staging ring), ``agf_tile_place_run``
+    unpacks them into the float raster on the compute stream (CF scale / offset in double, fill -> NaN), and the
+    temporal kernels of a stripe start as soon as its rows are decoded.  Half the PCIe bytes of a float32 raster for
+    int16 data.  ``runner=None`` only builds the device raster."""
+    import torch
+    from . import _lib
+    L = _lib.lib()
+    T, Y, X = src.shape
+    if Y * X != n_cells:
+        raise ValueError(f"raster of shape {src.shape} does not have {n_cells} cells per step")
+    dev = runner.device if runner is not None else (device or torch.device("cuda", torch.cuda.current_device()))
+    comp = torch.cuda.current_stream(dev) if stream is None else stream
+    copy = _copy_stream(dev)
+    tdtype = torch.float64 if src.dtype == np.float64 else torch.float32
+    dst_code = _lib.F64 if tdtype == torch.float64 else _lib.F32
+    stored = src.stored
+    is_t = type(stored).__module__.startswith("torch")
+    sdt = np.dtype(str(stored.dtype).replace("torch.", "")) if is_t else np.dtype(stored.dtype).newbyteorder("=")
+    code = _TILE_DTYPES.get(sdt.str[1:])
+    if code is None or (not is_t and not np.dtype(stored.dtype).isnative):
+        raise NotImplementedError(f"no tile decoder for stored dtype {stored.dtype}")
+    st_tdtype = getattr(torch, sdt.name)
+    pinned = bool(is_t and stored.is_pinned() and stored.is_contiguous())
+    host = stored.reshape(T, n_cells) if pinned else None
+    host_np = None if pinned else (stored.numpy() if is_t else stored).reshape(T, n_cells)
+    raster = _device_raster(torch, dev, tdtype, T, n_cells)
+    row_bytes = n_cells * sdt.itemsize
+    chunks = chunk_rows(T, row_bytes, OPTIONS["chunk_bytes" if pinned else "staging_chunk_bytes"])
+    slot_rows = max(r1 - r0 for r0, r1 in chunks)
+    n_dev = 3
+    key = (dev.index, sdt.str, slot_rows * n_cells, n_dev)
+    if key not in _PACKED_DEV:
+        _PACKED_DEV.clear()
+        _PACKED_DEV[key] = [torch.empty(slot_rows * n_cells, dtype=st_tdtype, device=dev) for _ in range(n_dev)]
+    dslots = _PACKED_DEV[key]
+    staging = None if pinned else _Staging(torch, st_tdtype, slot_rows * n_cells, OPTIONS["staging_slots"], OPTIONS["staging_threads"])
+    placed = [None] * n_dev
+    copy.wait_stream(comp)
+    ev_first, ev_last = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev_first.record(copy)
+    if runner is not None:
+        runner.begin_streamed(comp)
+    launches = 0
+    try:
+        futs = {}
+        ahead = len(staging.slots) if staging else 0
+
+        def submit(i):
+            r0, r1 = chunks[i]
+            futs[i] = staging.pool.submit(staging.fill, i % ahead, host_np[r0:r1])
+
+        if staging:
+            for i in range(min(ahead, len(chunks))):
+                submit(i)
+        for i, (r0, r1) in enumerate(chunks):
+            slot = i % n_dev
+            n = (r1 - r0) * n_cells
+            hsrc = futs.pop(i).result()[:n] if staging else host[r0:r1].reshape(-1)
+            with torch.cuda.stream(copy):
+                if placed[slot] is not None:
+                    copy.wait_event(placed[slot])              # the unpack kernel that last read this device slot
+                dslots[slot][:n].copy_(hsrc, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy)
+            if staging:
+                staging.events[i % ahead] = ev
+                if i + ahead < len(chunks):
+                    submit(i + ahead)
+            comp.wait_event(ev)
+            _lib.check(L.agf_tile_place_run(
+                dslots[slot].data_ptr(), code, r1 - r0, Y, X, n_cells, X, 1, raster.data_ptr(), dst_code, n_cells, X, r0, 0, 0,
+                1, float(src.scale), float(src.offset), int(src.fill is not None),
+                float(src.fill if src.fill is not None else 0.0), comp.cuda_stream))
+            pe = torch.cuda.Event()
+            pe.record(comp)
+            placed[slot] = pe
+            if runner is not None:
+                launches += runner.feed(raster, r1, comp, k1_events)
+        ev_last.record(copy)
+        res = runner.finish_streamed(raster, comp) if runner is not None else None
+    finally:
+        if staging:
+            staging.close()
+    raster.record_stream(comp)
+    global LAST_STATS
+    LAST_STATS = dict(chunks=len(chunks), pinned=pinned, packed=True, h2d_bytes=T * row_bytes, k1_launches=launches,
+                      place_launches=len(chunks), copy_events=(ev_first, ev_last))
+    if stats is not None:
+        stats.update(LAST_STATS)
+    return res, raster
+
+
 _DEVICE_RASTERS = {}     # (device, dtype, elements) -> the device copy of the last host raster of that shape
 
 
@@ -606,6 +712,7 @@ def release_device_rasters() -> None:
     _RING_RASTERS.clear()
     _RINGS.clear()
     _CHUNK_RINGS.clear()
+    _PACKED_DEV.clear()
 
 
 _COPY_STREAMS = {}

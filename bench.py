@@ -257,6 +257,170 @@ def main_reference(args, rank, world):
 
 
 # ------------------------------------------------------------------------------------------------
+# the other configurations of BASELINE.json, device resident (extra key "workloads" of the N = 1 line)
+# ------------------------------------------------------------------------------------------------
+def resident_workload(torch, name, dev, seed, steps, warmup, shared=None):
+    """A few device-resident steps of one workload: {workload, path, ms_per_step, value, k1_ms, roofline}.  ``shared`` =
+    (workload, raster, dataset, weights, csr) of a workload on the same grid / time axis whose raster and weights are reused."""
+    from aggfly_b200 import engine, synthetic as syn
+    from aggfly_b200.aggregate import _device_csr, _plan
+    wl = syn.make_workload(name)
+    if shared is not None:
+        _, raster, ds, w, csr = shared
+        ds = wl.dataset(raster)
+    else:
+        raster = wl.raster(dev, seed=seed)
+        ds = wl.dataset(raster)
+        w = wl.weights(ds)
+        csr = _device_csr(w, ds)
+    names, stage = _plan(ds, wl.spec)
+    flat = raster.reshape(wl.n_time, wl.n_cells)
+    n_lat, n_lon = len(wl.grid.latitude), len(wl.grid.longitude)
+    k1_events = []
+    regional = None
+    if engine.regional_candidate(stage, n_lon):
+        regional = engine.RegionalRunner(stage, csr, n_lat, n_lon, dev)
+        if not regional.supported:
+            regional.close()
+            regional = None
+    if regional is not None:
+        runner, path = regional, "one kernel: temporal scan + regional average (agf_k1_regional + merge)"
+        step = lambda rec: runner.run(flat, k1_events=k1_events if rec else None).panel          # noqa: E731
+        launches = runner.launches_per_run
+    else:
+        runner, path = engine.StageRunner(stage, wl.n_cells, dev), "two kernels: temporal scan -> X -> CSR regional average"
+        step = lambda rec: engine.run_spmm(csr, runner.run(flat, k1_events=k1_events if rec else None))   # noqa: E731
+        launches = runner.launches_per_run + 1
+    for _ in range(max(3, warmup)):
+        step(False)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step(True)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    k1_ms = float(np.sum([a.elapsed_time(b) for a, b in k1_events])) / steps
+    peak, peak_src = measured_peak()
+    in_b, out_b = runner.algorithmic_input_bytes(), runner.algorithmic_output_bytes()
+    ach = (in_b + out_b) / (k1_ms * 1e-3) / 1e9
+    out = {"workload": wl.name, "description": wl.description, "path": path, "steps": steps, "ms_per_step": ms,
+           "value": wl.cell_steps / (ms * 1e-3), "unit": UNIT, "k1_ms": k1_ms, "gpu_launches_per_step": launches,
+           "regions": int(csr.host.n_regions), "periods": len(stage.labels), "columns": len(names),
+           "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                        "algorithmic_read_bytes": in_b, "algorithmic_write_bytes": out_b,
+                        "traffic": recorded_traffic(wl.name + ("__regional" if regional is not None else ""))}}
+    if regional is not None:
+        out["roofline"]["scratch_bytes_written_and_read_back"] = regional.partial_bytes()
+        out["roofline"]["note"] = ("read bytes = the 8 x 32 cell tiles that hold a weighted cell (ocean tiles are never loaded); "
+                                   "cell-hours/s counts the whole grid")
+    runner.close()
+    return out
+
+
+def run_c4(torch, dist, af, wl, w, host, years, world, rank, dev, one_year_df):
+    """``years`` synthetic years as ONE Dataset (the rank's pinned year buffer cycled along a noleap hourly axis, so the
+    host holds one year while the record is ``years`` long), aggregated by ONE call: ``aggregate_dataset`` at N = 1,
+    ``aggregate_dataset_sharded`` (years split over the ranks, one panel all-gather) at N > 1.  The device holds a ring of
+    windows, not the record (stream._feed_ring).  Checked: every year of the panel equals the one-year call's panel."""
+    from aggfly_b200 import stream as _stream, timeaxis
+    from aggfly_b200.dataset import Dataset, TimeConcat
+    T = years * wl.n_time
+    t_long = timeaxis.CalendarIndex.range("noleap", 2001, T, "h")
+    year_np = host.numpy()
+    ds_long = Dataset.from_arrays(TimeConcat([year_np] * years), t_long, wl.grid.latitude, wl.grid.longitude,
+                                  lon_is_360=wl.grid.lon_is_360, name=wl.name + "_c4")
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.reset_peak_memory_stats(dev)
+    t0 = time.perf_counter()
+    if world > 1:
+        df = af.aggregate_dataset_sharded(w, ds_long, wl.spec)
+    else:
+        df = af.aggregate_dataset(weights=w, dataset=ds_long, aggregator_dict=wl.spec)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    st = dict(_stream.LAST_STATS)
+    tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    dt = float(tt[0])
+    h2d_ms = st["copy_events"][0].elapsed_time(st["copy_events"][1]) if "copy_events" in st else None
+    # parity with the per-year loop: this rank-0 process knows its own year buffer; the years rank 0 aggregated come first
+    from aggfly_b200 import shard as _shard
+    r0, r1 = _shard.plan_time_shards(t_long, world)[0] if world > 1 else (0, T)
+    my_years = (r1 - r0) // wl.n_time
+    rid = one_year_df.columns[0]
+    cols = [c for c in one_year_df.columns if c not in (rid, "time")]
+    nreg = int(one_year_df[rid].nunique())
+    g1 = len(one_year_df) // max(1, nreg)
+    ok, n_checked = False, 0
+    if nreg and len(one_year_df) == nreg * g1 and len(df) == nreg * g1 * years:
+        ref = one_year_df[cols].to_numpy(float).reshape(nreg, 1, g1, len(cols))
+        got = df[cols].to_numpy(float).reshape(nreg, years, g1, len(cols))[:, :my_years]
+        ok = bool(np.array_equal(np.asarray(df[rid]).reshape(nreg, -1)[:, 0], np.asarray(one_year_df[rid]).reshape(nreg, -1)[:, 0])
+                  and np.allclose(got, ref, rtol=1e-11, atol=0, equal_nan=True))
+        n_checked = int(my_years)
+    return {"workload": "c4: %d synthetic years of %s as one record" % (years, wl.name), "years": years,
+            "seconds": dt, "years_per_s": years / dt, "value": years * wl.cell_steps / dt, "unit": UNIT,
+            "api": "aggregate_dataset_sharded (years over ranks)" if world > 1 else "aggregate_dataset",
+            "h2d_bytes_per_rank": st.get("h2d_bytes"), "h2d_gbs_per_rank": (st.get("h2d_bytes", 0) / (h2d_ms * 1e-3) / 1e9) if h2d_ms else None,
+            "ring": {k: st.get(k) for k in ("ring", "ring_slots", "ring_slot_rows", "ring_bytes", "windows", "chunks", "direct_chunks")},
+            "record_bytes": int(T) * wl.n_cells * 4, "device_peak_bytes": int(torch.cuda.max_memory_allocated(dev)),
+            "host_year_buffers": 1, "panel_rows": int(len(df)),
+            "equals_one_year_call": {"ok": bool(ok), "years_checked": n_checked, "rtol": 1e-11}}
+
+
+def run_packed(torch, dist, af, wl, w, host, q_dev, pack, world, dev, steps, R, G, NC):
+    """The workload's year as CF-packed int16 in pinned host memory (dataset.PackedRaster): the stored integers cross PCIe
+    (2 bytes per value) and agf_tile_place_run unpacks them on the device behind the copy."""
+    from aggfly_b200 import stream as _stream
+    from aggfly_b200.dataset import PackedRaster
+    if world > 1:       # N ranks share the host: reuse (half of) the pinned float32 year, which nothing reads after this
+        q_host = host.view(torch.int16).view(-1)[: q_dev.numel()].view(q_dev.shape)
+    else:
+        q_host = torch.empty(q_dev.shape, dtype=torch.int16, pin_memory=True)
+    q_host.copy_(q_dev)
+    torch.cuda.synchronize()
+    packed = PackedRaster(q_host, pack["scale"], pack["offset"], pack["fill"], np.float32)
+    hds = wl.dataset(packed)
+    df = af.aggregate_dataset(weights=w, dataset=hds, aggregator_dict=wl.spec)        # warm-up
+    torch.cuda.synchronize()
+    # the device raster of that call against NumPy's decode of the same integers (first and last day)
+    ras = next(iter(_stream._DEVICE_RASTERS.values())).view(q_dev.shape[0], -1)
+    same = True
+    for r0 in (0, q_dev.shape[0] - 24):
+        want = np.asarray(packed[r0:r0 + 24]).reshape(24, -1)
+        same &= bool(np.array_equal(ras[r0:r0 + 24].cpu().numpy(), want, equal_nan=True))
+    if world > 1:
+        dist.barrier()
+    step_ms = []
+    for _ in range(steps):
+        ts = time.perf_counter()
+        df = af.aggregate_dataset(weights=w, dataset=hds, aggregator_dict=wl.spec)
+        step_ms.append((time.perf_counter() - ts) * 1e3)
+    torch.cuda.synchronize()
+    dt = float(np.median(step_ms)) * 1e-3
+    tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    dt = float(tt[0])
+    st = dict(_stream.LAST_STATS)
+    h2d_ms = st["copy_events"][0].elapsed_time(st["copy_events"][1]) if "copy_events" in st else None
+    return {"value": world * wl.cell_steps / dt, "unit": UNIT, "ms_per_step": dt * 1e3, "steps": steps,
+            "statistic": f"median of {steps} calls (max over ranks)", "step_ms": [round(x, 1) for x in step_ms],
+            "source": "int16 with scale_factor / add_offset / _FillValue in pinned host memory (dataset.PackedRaster), unpacked on "
+                      "the device by agf_tile_place_run",
+            "h2d_bytes_per_step": int(q_dev.numel() * 2), "d2h_bytes_per_step": int(R * G * NC * 8),
+            "feed": {"chunks": st.get("chunks"), "h2d_ms": h2d_ms,
+                     "h2d_gbs": (st.get("h2d_bytes", 0) / (h2d_ms * 1e-3) / 1e9) if h2d_ms else None,
+                     "unpack_launches": st.get("place_launches")},
+            "device_raster_equals_numpy_decode": bool(same), "panel_rows": int(len(df))}
+
+
+# ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
 def main_ours(args, rank, world, local_rank):
@@ -333,6 +497,34 @@ def main_ours(args, rank, world, local_rank):
                 "algorithmic_read_bytes": in_bytes, "algorithmic_write_bytes": out_bytes, "k1_ms": k1_ms,
                 "frac_of_8TBps_nominal": achieved / 8000.0}
 
+    # ---- the other configurations, and the public API on the device-resident raster (N = 1) ----------
+    workloads, e2e_resident = None, None
+    if world == 1 and not args.no_extras:
+        workloads = []
+        for name in [n for n in args.extra_workloads.split(",") if n and n != wl.name]:
+            same_grid = (wl.name, raster, ds, w, csr) if (name.startswith("c3") and wl.name.startswith("c3")) else None
+            try:
+                workloads.append(resident_workload(torch, name, dev, args.seed, max(3, min(args.steps, 5)), args.warmup, same_grid))
+            except Exception as exc:                                   # never lose the headline line to an extra
+                workloads.append({"workload": name, "error": f"{type(exc).__name__}: {exc}"})
+            torch.cuda.empty_cache()
+        # af.aggregate_dataset on the raster that is ALREADY on the device: plan cache, runner construction, X / V
+        # allocation, kernels, panel D2H and the pandas frame -- everything a user's call pays except the host feed
+        times = []
+        for i in range(1 + 5):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            rdf = af.aggregate_dataset(weights=w, dataset=ds, aggregator_dict=wl.spec)
+            torch.cuda.synchronize()
+            if i:
+                times.append(time.perf_counter() - t0)
+        from aggfly_b200 import aggregate as _agg0
+        e2e_resident = {"value": wl.cell_steps / float(np.median(times)), "unit": UNIT, "ms_per_step": float(np.median(times)) * 1e3,
+                        "step_ms": [round(x * 1e3, 2) for x in times], "statistic": "median of 5 calls after 1 warm-up",
+                        "phases_ms": {k: round(v, 2) for k, v in _agg0.LAST_TRACE.get("phases_ms", {}).items()},
+                        "d2h_bytes_per_step": int(R * G * NC * 8), "panel_rows": int(len(rdf)),
+                        "api": "aggfly_b200.aggregate_dataset(weights, Dataset(CUDA tensor), aggregator_dict)"}
+
     # ---- end to end through the public API, raster in pinned host memory ---------------------------
     e2e = None
     e2e_note = None
@@ -341,9 +533,24 @@ def main_ours(args, rank, world, local_rank):
         e2e_note = (f"skipped: {world} pinned host rasters need {need_gb:.0f} GB, "
                     f"{host_mem_available_gb():.0f} GB of host memory available")
         args.no_e2e = True
+    c4 = e2e_packed = None
     if not args.no_e2e:
         host = torch.empty(raster.shape, dtype=raster.dtype, pin_memory=True)
         host.copy_(raster)
+        q_dev = pack = None
+        if not args.no_packed and raster.dtype == torch.float32:
+            # the same year as CF-packed int16 (what an ERA5 NetCDF variable is on disk): quantised on the device now,
+            # brought to pinned host memory once the float32 copy is no longer needed
+            lo, hi = float(torch.nan_to_num(raster[:240], nan=1e30).min()), float(torch.nan_to_num(raster[:240], nan=-1e30).max())
+            lo, hi = lo - 40.0, hi + 40.0
+            pack = {"scale": (hi - lo) / 65000.0, "offset": 0.5 * (hi + lo), "fill": -32768.0}
+            q_dev = torch.empty(raster.shape, dtype=torch.int16, device=dev)
+            for r0 in range(0, raster.shape[0], 96):
+                blk = raster[r0:r0 + 96]
+                qq = torch.clamp(torch.round((blk - pack["offset"]) / pack["scale"]), -32767, 32767)
+                q_dev[r0:r0 + 96] = torch.nan_to_num(qq, nan=-32768.0).to(torch.int16)
+            del blk, qq
+        same_grid = rdf = None
         del flat, ds, raster, runner
         torch.cuda.empty_cache()
         hds = wl.dataset(host)
@@ -385,6 +592,21 @@ def main_ours(args, rank, world, local_rank):
                "d2h_bytes_per_step": int(R * G * NC * 8), "ms_per_step": dt * 1e3, "steps": e2e_steps,
                "api": "aggfly_b200.aggregate_dataset(weights, Dataset(pinned host tensor), aggregator_dict)",
                "panel_rows": int(len(df))}
+        # ---- C4 (north_star configs[3]): a record of many years, streamed through a bounded ring of device windows --------
+        if args.c4_years > 0 and wl.hourly and wl.n_time == 8760 and host_mem_available_gb() > 8.0:
+            try:
+                c4 = run_c4(torch, dist, af, wl, w, host, args.c4_years, world, rank, dev, df)
+            except Exception as exc:
+                c4 = {"error": f"{type(exc).__name__}: {exc}"}
+            _stream.release_device_rasters()
+            torch.cuda.empty_cache()
+        # ---- the same year, host-fed as packed int16 and unpacked on the device -------------------------------------
+        if q_dev is not None:
+            try:
+                e2e_packed = run_packed(torch, dist, af, wl, w, host, q_dev, pack, world, dev, e2e_steps, R, G, NC)
+            except Exception as exc:
+                e2e_packed = {"error": f"{type(exc).__name__}: {exc}"}
+            del q_dev
         raster_for_cpu = host
     else:
         raster_for_cpu = raster
@@ -413,6 +635,7 @@ def main_ours(args, rank, world, local_rank):
                        "parallelism": f"time-sharded x{world} (one year per GPU), replicated CSR, panel all-gather",
                        "l2_policy": f"inputs ({in_bytes / 1e9:.2f} GB per step) are larger than the 126 MB L2; no flush needed"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_note": e2e_note,
+            "e2e_resident": e2e_resident, "e2e_packed": e2e_packed, "c4": c4, "workloads": workloads,
             "gpu_launches": launches * args.steps,
             "gpu_launches_per_step": launches, "clocks": clocks,
         }))
@@ -433,6 +656,11 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the extra keys 'workloads' and 'e2e_resident' (N = 1)")
+    ap.add_argument("--no-packed", action="store_true", help="skip the packed-int16 host feed ('e2e_packed')")
+    ap.add_argument("--extra-workloads", default="c3b_global_daily,c1_conus_tavg,c2_conus_gdd,c5_cmip_gdd")
+    ap.add_argument("--c4-years", type=int, default=40,
+                    help="years of the streamed multi-year record ('c4'; time-sharded over the ranks; 0: skip)")
     args = ap.parse_args()
     if args.cpu_rows <= 0:
         args.cpu_rows = int(min(192, max(24, os.cpu_count() or 24)))

@@ -429,6 +429,53 @@ def test_ring_of_device_windows_is_bitwise_the_device_resident_result(name, feed
     _exact(streamed[vals].values, resident[vals].values)
 
 
+# ---- CF-packed integers in host memory: copied as stored, unpacked on the device (stream.feed_packed) -------------
+@pytest.mark.parametrize("feed", ["pinned", "pageable"])
+@pytest.mark.parametrize("stored,dtype", [("int16", "float32"), ("int16", "float64"), ("uint8", "float32"), ("int32", "float64")])
+@pytest.mark.parametrize("name", ["c3_bins_and_poly", "c3b_daily"])
+def test_packed_host_raster_is_unpacked_on_the_device(name, stored, dtype, feed):
+    import torch
+    from aggfly_b200 import stream
+    from aggfly_b200.dataset import PackedRaster
+    arr, t, lat, lon = _raster("float32", False, T=24 * 21 + 3, seed=23)
+    info = np.iinfo(stored)
+    scale, offset = (float(arr.max()) - float(arr.min())) / (info.max - info.min - 2), 3.25
+    q = np.clip(np.rint((arr.astype(np.float64) - offset) / scale), info.min + 1, info.max).astype(stored)
+    fill = float(info.min)
+    q[5:9, 2, 3] = info.min                                        # _FillValue -> NaN
+    rng = np.random.default_rng(9)
+    wdf, shp = _weights_case(lat, lon, rng)
+
+    def run(values):
+        ds = af.Dataset.from_arrays(values, t, lat, lon, True)
+        w = af.weights_from_objects(ds, af.GeoRegions(shp, "geoid"), zero_weight="nan")
+        w.weights = wdf
+        return af.aggregate_dataset(weights=w, dataset=ds, aggregator_dict=SPECS[name])
+
+    decoded = (q.astype(np.float64) * scale + offset).astype(dtype)
+    decoded[q == info.min] = np.nan
+    host = torch.from_numpy(q).pin_memory() if feed == "pinned" else q
+    packed = PackedRaster(host, scale, offset, fill, dtype)
+    assert packed.shape == arr.shape and packed.dtype == np.dtype(dtype)
+    assert np.array_equal(np.asarray(packed), decoded, equal_nan=True)
+    assert np.array_equal(np.asarray(packed[24:48]), decoded[24:48], equal_nan=True)
+    engine.OPTIONS["target_stripes"] = 7
+    old = dict(stream.OPTIONS)
+    try:
+        stream.OPTIONS.update(chunk_bytes=17 * q[0].nbytes, staging_chunk_bytes=17 * q[0].nbytes, staging_slots=3, staging_threads=2)
+        want = run(torch.from_numpy(decoded).cuda())
+        got = run(packed)
+        st = stream.LAST_STATS
+        assert st.get("packed") and st["pinned"] == (feed == "pinned") and st["h2d_bytes"] == q.nbytes
+        dev = engine.to_device(packed)                             # the device-resident route decodes the same way
+        assert np.array_equal(dev.cpu().numpy(), decoded, equal_nan=True)
+    finally:
+        stream.OPTIONS.update(old)
+    vals = [c for c in want.columns if c not in ("geoid", "time")]
+    assert list(got.columns) == list(want.columns) and len(got) == len(want)
+    _exact(got[vals].values, want[vals].values)
+
+
 # ---- daily rasters: single-row inner groups collapse to one pass (spec.Planner._collapsed_lane) ----------
 DAILY_SPECS = {
     "gdd_month": dict(gdd=[("aggregate", {"calc": "dd", "groupby": "date", "ddargs": [10, 30, 0]}),
