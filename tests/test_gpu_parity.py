@@ -415,8 +415,10 @@ def test_ring_of_device_windows_is_bitwise_the_device_resident_result(name, feed
             host = TimeConcat([k.numpy() for k in keep])
         streamed = run(host)
         st = stream.LAST_STATS
-        assert st.get("ring") and st["ring_slots"] == 2 and st["windows"] >= 4
-        assert st["ring_bytes"] < arr.nbytes / 3
+        assert st.get("ring") and st["ring_slots"] == 2
+        if name.startswith("c3"):             # daily level-1 groups: many common stripe ends, windows of <= 100 rows
+            assert st["windows"] >= 4 and st["ring_bytes"] < arr.nbytes / 3
+        # (a month-level program next to a date-level one shares few stripe ends: the windows grow to what the cuts allow)
         if feed == "concat_pinned_parts":
             assert st["direct_chunks"] == st["chunks"]
         if feed == "pageable":
