@@ -91,7 +91,8 @@ SYMBOLS = ("agf_version", "agf_last_error", "agf_program_create", "agf_program_d
            "agf_temporal_finalize", "agf_csr_create", "agf_csr_destroy", "agf_spmm_run",
            "agf_valid_mask_run", "agf_elementwise_run", "agf_tile_place_run", "agf_decompress_caps", "agf_decompress_lz4_run",
            "agf_unshuffle_run", "agf_copy_segments_run", "agf_overlap_create", "agf_overlap_fetch", "agf_overlap_destroy",
-           "agf_rplan_create", "agf_rplan_destroy", "agf_rplan_info", "agf_rplan_tables", "agf_temporal_regional_plan",
+           "agf_rplan_create", "agf_rplan_destroy", "agf_rplan_info", "agf_rplan_tables", "agf_rplan_check_segments",
+           "agf_temporal_regional_plan",
            "agf_temporal_regional_run")
 
 
@@ -135,6 +136,7 @@ def lib() -> C.CDLL:
     L.agf_rplan_destroy.argtypes = [vp]
     L.agf_rplan_tables.argtypes = [i32, i32, i32, i64, vp, vp, vp, C.POINTER(RPlanInfo)] + [vp] * 9
     L.agf_rplan_info.argtypes = [vp, C.POINTER(RPlanInfo)]
+    L.agf_rplan_check_segments.argtypes = [i32, i32, i32, i64, vp, vp, vp, i32, vp]
     L.agf_temporal_regional_plan.argtypes = [vp, vp, i64, C.POINTER(RegionalInfo)]
     L.agf_temporal_regional_run.argtypes = [vp, vp, vp, i64, i64, i64, i64, vp, i64, vp, i64, i32, vp, u64]
     for name in SYMBOLS:

@@ -73,7 +73,26 @@ struct agf_rplan {
     int *d_region_slot_ptr = nullptr, *d_region_slots = nullptr, *d_multi_regions = nullptr;
     void *d_entries = nullptr;
     int64_t table_bytes = 0;
+    // Balanced walk tables, one set per lanes-per-slot variant of the kernel (256 / LPS lane groups per tile), built on
+    // first use from the host copies below (agf_rplan_segments).
+    struct SegTables {
+        int ng = 0;                       // lane groups per tile (0: not built yet)
+        int max_segs = 0, max_pent = 0;   // largest tile: segments / padded entries
+        int64_t n_segs = 0, n_pent = 0;
+        int *d_tile_seg_ptr = nullptr;    // [n_active + 1] segments of the tile
+        int *d_tile_pent_ptr = nullptr;   // [n_active + 1] padded entries of the tile
+        int *d_grp = nullptr;             // [n_active][ng + 1][2]: (first segment record, first padded entry), tile-relative
+        int *d_seg = nullptr;             // [n_segs][2]: (end of the segment in the tile's padded entries, segment id), group-major
+        int *d_slot_q = nullptr;          // [n_gslots][2]: segment ids [q0, q1) of the slot (slot-major numbering)
+        void *d_pent = nullptr;           // [n_pent] RgEntry, group-major; pads have w = 0 and cell = -1
+    };
+    mutable SegTables seg[3];             // LPS 4, 8, 16
+    std::vector<int32_t> h_tile_slot_ptr, h_slot_ent_ptr;
+    std::vector<double> h_ent_w;
+    std::vector<int32_t> h_ent_cell;
 };
+// Builds (once) and returns the balanced walk tables for `lps` lanes per slot; nullptr + agf_fail on error.
+const agf_rplan::SegTables *agf_rplan_segments(const agf_rplan *plan, int lps);
 
 struct RegionalLaunch {
     K1Launch k;              // program, raster view, stream (stripe / X / V fields unused)

@@ -40,17 +40,17 @@ int launch_regional(const RegionalLaunch &a, int mode, RegionalChoice *choice) {
     constexpr int MINB0 = state_regs <= 30 ? 3 : (state_regs <= 48 ? 2 : 1);
     constexpr int TT = R_GL;
     constexpr int TILE = TT * TMA_CW * (int)sizeof(T);
-    // Shared memory: ring + barriers + two buffers of staged rows + the tile's slot / entry tables.  One ring stage is
-    // enough for three CTAs per SM: a stage is handed back as soon as its 24 values per thread sit in registers, and the
-    // scan is bound by instruction issue, not by bytes in flight (13.5 KB per SM cover DRAM latency at 2 TB/s).
+    // Shared memory: ring + barriers + the staged rows (+ the zero row) + the segment sums + the tile's tables.  One ring
+    // stage is enough for three CTAs per SM: a stage is handed back as soon as its 24 values per thread sit in registers,
+    // and the scan is bound by instruction issue, not by bytes in flight (13.5 KB per SM cover DRAM latency at 2 TB/s).
     constexpr int budget3 = 74 * 1024, budget2 = 110 * 1024;
-    constexpr int fixed1 = TILE + 128 + 2 * stage_bytes<LPS>() + RG_SM_SLOTS * 16;
-    constexpr int MINB = (MINB0 == 3 && fixed1 + 256 * 16 <= budget3) ? 3 : (MINB0 >= 2 ? 2 : 1);
-    constexpr int STAGES = (MINB != 3 && 2 * TILE + 128 + 2 * stage_bytes<LPS>() + RG_SM_SLOTS * 16 + 1024 * 16 <= budget2) ? 2 : 1;
-    constexpr int fixed = STAGES * TILE + 128 + 2 * stage_bytes<LPS>() + RG_SM_SLOTS * 16;
+    constexpr int rest = 128 + stage_bytes<LPS>() + rg_part_bytes<LPS>() + rg_table_bytes<LPS>();
+    constexpr int MINB = (MINB0 == 3 && TILE + rest + 512 * 16 <= budget3) ? 3 : (MINB0 >= 2 ? 2 : 1);
+    constexpr int STAGES = (MINB != 3 && 2 * TILE + rest + 1024 * 16 <= budget2) ? 2 : 1;
+    constexpr int fixed = STAGES * TILE + rest;
     constexpr int smem = MINB == 3 ? budget3 : budget2;
     constexpr int sm_entries = (smem - fixed) / 16;
-    static_assert(sm_entries >= 256, "no room for the tile tables");
+    static_assert(sm_entries >= 512, "no room for the tile tables");
     auto kern = agf_k1_regional<T, NL, DIAG, KINDS, NB, LPS, R_GL, TT, STAGES, MINB>;
 
     static int ctas_per_sm = 0;  // per instantiation
@@ -88,6 +88,14 @@ int launch_regional(const RegionalLaunch &a, int mode, RegionalChoice *choice) {
     q.slot_dst = plan->d_slot_dst;
     q.slot_ent_ptr = plan->d_slot_ent_ptr;
     q.entries = (const RgEntry *)plan->d_entries;
+    const agf_rplan::SegTables *sg = agf_rplan_segments(plan, LPS);
+    if (!sg) return AGF_E_INVALID;
+    q.tile_seg_ptr = sg->d_tile_seg_ptr;
+    q.tile_pent_ptr = sg->d_tile_pent_ptr;
+    q.grp = (const int2 *)sg->d_grp;
+    q.seg = (const int2 *)sg->d_seg;
+    q.slot_q = (const int2 *)sg->d_slot_q;
+    q.pent = (const RgEntry *)sg->d_pent;
     q.n_active = plan->n_active;
     q.tiles_x = plan->tiles_x;
     q.sm_entries = sm_entries;

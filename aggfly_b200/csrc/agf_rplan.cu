@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <vector>
 
 #include <cuda.h>
@@ -36,6 +37,14 @@ extern "C" int agf_rplan_destroy(agf_rplan_t *p) {
     cudaFree(p->d_region_slot_ptr);
     cudaFree(p->d_region_slots);
     cudaFree(p->d_entries);
+    for (auto &sg : p->seg) {
+        cudaFree(sg.d_tile_seg_ptr);
+        cudaFree(sg.d_tile_pent_ptr);
+        cudaFree(sg.d_grp);
+        cudaFree(sg.d_seg);
+        cudaFree(sg.d_slot_q);
+        cudaFree(sg.d_pent);
+    }
     delete p;
     return 0;
 }
@@ -210,7 +219,212 @@ extern "C" int agf_rplan_create(agf_rplan_t **out, int32_t n_regions, int32_t n_
         agf_rplan_destroy(p);
         return rc;
     }
+    p->h_tile_slot_ptr = t.tile_slot_ptr;
+    p->h_slot_ent_ptr = t.slot_ent_ptr;
+    p->h_ent_w.resize(t.entries.size());
+    p->h_ent_cell.resize(t.entries.size());
+    for (size_t k = 0; k < t.entries.size(); ++k) {
+        p->h_ent_w[k] = t.entries[k].w;
+        p->h_ent_cell[k] = t.entries[k].cell;
+    }
     *out = p;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Balanced walk: the entries of a tile dealt to its lane groups
+// ------------------------------------------------------------------------------------------
+// The kernel walks a tile's entries once per period with 256 / LPS lane groups.  Handing whole slots to the groups left
+// most of them idle behind the longest slot (ncu r2m: 15 % of all stall samples on the per-period barrier).  Here every
+// slot is cut into SEGMENTS of at most c entries, c ~ entries / groups, the segments are dealt to the groups longest
+// first onto the least loaded group, and each group's segments are laid out back to back (each padded to a multiple of
+// four entries with zero-weight pads, so the kernel's loop has no remainder).  Segment sums are added in ascending
+// segment order afterwards: the association is fixed by these tables, results do not depend on scheduling.
+namespace {
+struct SegHost {
+    std::vector<int32_t> tile_seg_ptr, tile_pent_ptr, grp, seg, slot_q;
+    std::vector<RgEntry> pent;
+    int max_segs = 0, max_pent = 0;
+};
+
+void build_segments(const agf_rplan *p, int ng, SegHost &o) {
+    const int n_active = p->n_active;
+    o.tile_seg_ptr.assign(1, 0);
+    o.tile_pent_ptr.assign(1, 0);
+    o.grp.reserve((size_t)n_active * (ng + 1) * 2);
+    o.slot_q.resize((size_t)p->n_gslots * 2);
+    struct Seg { int e0, n, sid; };
+    std::vector<Seg> segs;
+    std::vector<int> order, load;
+    std::vector<std::vector<int>> mine(ng);
+    for (int ti = 0; ti < n_active; ++ti) {
+        const int s0 = p->h_tile_slot_ptr[ti], s1 = p->h_tile_slot_ptr[ti + 1];
+        const int total = p->h_slot_ent_ptr[s1] - p->h_slot_ent_ptr[s0];
+        const int c = std::max(4, ((total + ng - 1) / ng + 3) / 4 * 4);
+        segs.clear();
+        for (int s = s0; s < s1; ++s) {
+            const int e0 = p->h_slot_ent_ptr[s], n = p->h_slot_ent_ptr[s + 1] - e0;
+            const int k = std::max(1, (n + c - 1) / c);
+            o.slot_q[2 * (size_t)s] = (int)segs.size();
+            for (int i = 0; i < k; ++i) {   // even split: pieces differ by at most one entry
+                const int a = (int)((int64_t)n * i / k), b = (int)((int64_t)n * (i + 1) / k);
+                segs.push_back(Seg{e0 + a, b - a, (int)segs.size()});
+            }
+            o.slot_q[2 * (size_t)s + 1] = (int)segs.size();
+        }
+        order.resize(segs.size());
+        for (size_t i = 0; i < segs.size(); ++i) order[i] = (int)i;
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return segs[a].n > segs[b].n; });
+        load.assign(ng, 0);
+        for (auto &m : mine) m.clear();
+        for (int i : order) {
+            int g = 0;
+            for (int k = 1; k < ng; ++k)
+                if (load[k] < load[g]) g = k;
+            load[g] += (segs[i].n + 3) / 4 * 4;
+            mine[g].push_back(i);
+        }
+        const int seg_base = o.tile_seg_ptr.back(), pent_base = o.tile_pent_ptr.back();
+        int n_seg = 0, n_pent = 0;
+        for (int g = 0; g < ng; ++g) {
+            o.grp.push_back(n_seg);
+            o.grp.push_back(n_pent);
+            std::sort(mine[g].begin(), mine[g].end());
+            for (int i : mine[g]) {
+                const Seg &sg = segs[i];
+                for (int e = 0; e < sg.n; ++e) {
+                    RgEntry en;
+                    en.w = p->h_ent_w[sg.e0 + e];
+                    en.cell = p->h_ent_cell[sg.e0 + e];
+                    en.pad = 0;
+                    o.pent.push_back(en);
+                }
+                for (int e = sg.n; e % 4 != 0; ++e) o.pent.push_back(RgEntry{0.0, -1, 0});
+                n_pent += (sg.n + 3) / 4 * 4;
+                o.seg.push_back(n_pent);
+                o.seg.push_back(sg.sid);
+                ++n_seg;
+            }
+        }
+        o.grp.push_back(n_seg);
+        o.grp.push_back(n_pent);
+        o.tile_seg_ptr.push_back(seg_base + n_seg);
+        o.tile_pent_ptr.push_back(pent_base + n_pent);
+        o.max_segs = std::max(o.max_segs, n_seg);
+        o.max_pent = std::max(o.max_pent, n_pent);
+    }
+}
+}  // namespace
+
+const agf_rplan::SegTables *agf_rplan_segments(const agf_rplan *p, int lps) {
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
+    const int idx = lps == 4 ? 0 : (lps == 8 ? 1 : (lps == 16 ? 2 : -1));
+    if (idx < 0) {
+        agf_fail(AGF_E_INVALID, "lanes per slot %d", lps);
+        return nullptr;
+    }
+    agf_rplan::SegTables &sg = p->seg[idx];
+    if (sg.ng != 0) return &sg;
+    if ((int64_t)p->n_entries * 2 > 0x7fffffff) {
+        agf_fail(AGF_E_UNSUPPORTED, "too many entries for the balanced walk tables");
+        return nullptr;
+    }
+    SegHost h;
+    build_segments(p, 256 / lps, h);
+    int64_t bytes = 0;
+    auto up = [&]() -> int {
+        int rc;
+        if ((rc = upload_vec(&sg.d_tile_seg_ptr, h.tile_seg_ptr, &bytes)) || (rc = upload_vec(&sg.d_tile_pent_ptr, h.tile_pent_ptr, &bytes)) ||
+            (rc = upload_vec(&sg.d_grp, h.grp, &bytes)) || (rc = upload_vec(&sg.d_seg, h.seg, &bytes)) ||
+            (rc = upload_vec(&sg.d_slot_q, h.slot_q, &bytes)) || (rc = upload_vec((RgEntry **)&sg.d_pent, h.pent, &bytes)))
+            return rc;
+        return 0;
+    };
+    if (up()) return nullptr;
+    sg.max_segs = h.max_segs;
+    sg.max_pent = h.max_pent;
+    sg.n_segs = (int64_t)h.seg.size() / 2;
+    sg.n_pent = (int64_t)h.pent.size();
+    sg.ng = 256 / lps;
+    return &sg;
+}
+
+// host-only: build the balanced walk tables for `lps` lanes per slot and check them against the slot tables --
+// walking every group's segments must visit every entry of every slot exactly once, in the slot's own order when the
+// segments are taken by ascending id.  stats: segments, padded entries, largest / mean group load (entries), tiles.
+extern "C" int agf_rplan_check_segments(int32_t n_regions, int32_t n_lat, int32_t n_lon, int64_t nnz, const int32_t *row_ptr,
+                                        const int32_t *cell_idx, const double *w, int32_t lps, int64_t *stats) {
+    if (lps != 4 && lps != 8 && lps != 16) return agf_fail(AGF_E_INVALID, "lanes per slot %d", lps);
+    HostTables t;
+    int rc = build_tables(t, n_regions, n_lat, n_lon, nnz, row_ptr, cell_idx, w);
+    if (rc) return rc;
+    agf_rplan plan;
+    plan.n_active = (int)t.tile_ids.size();
+    plan.n_gslots = (int)t.slot_region.size();
+    plan.h_tile_slot_ptr = t.tile_slot_ptr;
+    plan.h_slot_ent_ptr = t.slot_ent_ptr;
+    for (const RgEntry &e : t.entries) {
+        plan.h_ent_w.push_back(e.w);
+        plan.h_ent_cell.push_back(e.cell);
+    }
+    const int ng = 256 / lps;
+    SegHost h;
+    build_segments(&plan, ng, h);
+    int64_t max_load = 0, sum_load = 0;
+    for (int ti = 0; ti < plan.n_active; ++ti) {
+        const int s0 = t.tile_slot_ptr[ti], s1 = t.tile_slot_ptr[ti + 1];
+        const int sb = h.tile_seg_ptr[ti], nseg = h.tile_seg_ptr[ti + 1] - sb;
+        const int pb = h.tile_pent_ptr[ti], npent = h.tile_pent_ptr[ti + 1] - pb;
+        const int32_t *grp = &h.grp[(size_t)ti * (ng + 1) * 2];
+        if (grp[0] != 0 || grp[1] != 0 || grp[2 * ng] != nseg || grp[2 * ng + 1] != npent)
+            return agf_fail(AGF_E_STATE, "tile %d: group table does not span the tile", ti);
+        // segment id -> (first padded entry, end)
+        std::vector<int> first(nseg, -1), last(nseg, -1);
+        for (int g = 0; g < ng; ++g) {
+            int e = grp[2 * g + 1];
+            if (grp[2 * g] > grp[2 * g + 2] || e > grp[2 * g + 3]) return agf_fail(AGF_E_STATE, "tile %d: group table not monotonic", ti);
+            for (int j = grp[2 * g]; j < grp[2 * g + 2]; ++j) {
+                const int end = h.seg[2 * (size_t)(sb + j)], sid = h.seg[2 * (size_t)(sb + j) + 1];
+                if (sid < 0 || sid >= nseg || first[sid] != -1 || end <= e || (end - e) % 4 != 0)
+                    return agf_fail(AGF_E_STATE, "tile %d: bad segment record", ti);
+                first[sid] = e;
+                last[sid] = end;
+                e = end;
+            }
+            if (e != grp[2 * g + 3]) return agf_fail(AGF_E_STATE, "tile %d: group %d entries do not end at the next group", ti, g);
+            max_load = std::max<int64_t>(max_load, grp[2 * g + 3] - grp[2 * g + 1]);
+        }
+        sum_load += npent;
+        for (int s = s0; s < s1; ++s) {
+            int e = t.slot_ent_ptr[s];
+            for (int sid = h.slot_q[2 * (size_t)s]; sid < h.slot_q[2 * (size_t)s + 1]; ++sid) {
+                if (sid < 0 || sid >= nseg || first[sid] < 0) return agf_fail(AGF_E_STATE, "tile %d: slot segment missing", ti);
+                bool pad = false;
+                for (int k = first[sid]; k < last[sid]; ++k) {
+                    const RgEntry &pe = h.pent[(size_t)pb + k];
+                    if (pe.cell < 0) {
+                        if (pe.w != 0.0) return agf_fail(AGF_E_STATE, "pad with a weight");
+                        pad = true;
+                        continue;
+                    }
+                    if (pad || e >= t.slot_ent_ptr[s + 1] || pe.cell != t.entries[e].cell || pe.w != t.entries[e].w)
+                        return agf_fail(AGF_E_STATE, "tile %d slot %d: entries out of order", ti, s);
+                    ++e;
+                }
+            }
+            if (e != t.slot_ent_ptr[s + 1]) return agf_fail(AGF_E_STATE, "tile %d slot %d: entries missing", ti, s);
+        }
+    }
+    if (stats) {
+        stats[0] = (int64_t)h.seg.size() / 2;
+        stats[1] = (int64_t)h.pent.size();
+        stats[2] = max_load;
+        stats[3] = plan.n_active ? sum_load / ((int64_t)plan.n_active * ng) : 0;
+        stats[4] = plan.n_active;
+        stats[5] = h.max_segs;
+        stats[6] = h.max_pent;
+    }
     return 0;
 }
 

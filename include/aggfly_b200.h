@@ -278,6 +278,12 @@ int agf_rplan_tables(int32_t n_regions, int32_t n_lat, int32_t n_lon, int64_t nn
                      int32_t *tile_slot_ptr, int32_t *slot_region, int32_t *slot_ent_ptr, int32_t *entry_cell,
                      double *entry_w, int32_t *region_slot_ptr, int32_t *region_slots, int32_t *slot_dst);
 int agf_rplan_info(const agf_rplan_t *plan, agf_rplan_info_t *info);
+/* Host-only self check of the balanced walk tables the kernel variant with `lps` (4 | 8 | 16) lanes per slot uses: builds
+ * them from the CSR and verifies that the lane groups' segments visit every entry of every (tile, region) slot exactly
+ * once and in the slot's own order.  stats (int64[7], may be NULL): segments, padded entries, largest group load,
+ * mean group load, active tiles, most segments / padded entries in one tile. */
+int agf_rplan_check_segments(int32_t n_regions, int32_t n_lat, int32_t n_lon, int64_t nnz, const int32_t *row_ptr,
+                             const int32_t *cell_idx, const double *w, int32_t lps, int64_t *stats);
 
 typedef struct {
     int32_t supported;        /* 0: this program has no regional instantiation -- use agf_temporal_run + agf_spmm_run */

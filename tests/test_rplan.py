@@ -130,3 +130,27 @@ def test_bad_arguments_are_rejected():
     rp2 = np.array([0, 1], np.int32)
     with pytest.raises(_lib.AgfError, match="row_ptr"):
         _lib.check(L.agf_rplan_tables(1, 4, 8, 2, rp2.ctypes.data, ci.ctypes.data, w.ctypes.data, C.byref(info), *([None] * 9)))
+
+
+@pytest.mark.parametrize("lps", [4, 8, 16])
+@pytest.mark.parametrize("shape,R,mean_len", [((16, 64), 37, 14), ((21, 100), 90, 6), ((8, 32), 300, 2), ((40, 236), 25, 120),
+                                              ((5, 20), 3, 60)])
+def test_balanced_walk_tables_visit_every_entry_once_and_in_order(shape, R, mean_len, lps):
+    """agf_rplan_check_segments builds the per-lane-group segment tables of the kernel variant with ``lps`` lanes per slot
+    and verifies them in the library; the loads of the lane groups must be close to the mean."""
+    n_lat, n_lon = shape
+    rng = np.random.default_rng(n_lat * 77 + R + lps)
+    row_ptr, cell_idx, w = _random_csr(rng, R, n_lat, n_lon, mean_len, empty=(1,))
+    stats = np.zeros(7, np.int64)
+    rp, ci, ww = np.ascontiguousarray(row_ptr, np.int32), np.ascontiguousarray(cell_idx, np.int32), np.ascontiguousarray(w)
+    _lib.check(_lib.lib().agf_rplan_check_segments(R, n_lat, n_lon, len(ci), rp.ctypes.data, ci.ctypes.data, ww.ctypes.data,
+                                                   lps, stats.ctypes.data))
+    n_segs, n_pent, max_load, mean_load, n_tiles, max_segs, max_pent = (int(v) for v in stats)
+    assert n_pent >= len(ci) and n_pent % 4 == 0 and n_pent <= len(ci) + 3 * n_segs
+    assert n_segs >= 1 and max_segs <= n_segs and max_pent <= n_pent
+    # no group carries more than the mean plus one maximal segment (LPT bound), segments are at most ~ entries / groups
+    info, t = _tables(R, n_lat, n_lon, row_ptr, cell_idx, w)
+    per_tile = np.diff(t["slot_ent_ptr"][t["tile_slot_ptr"]])
+    ng = 256 // lps
+    c_max = max(4, int(-(-(-(-int(per_tile.max()) // ng)) // 4) * 4))
+    assert max_load <= int(np.ceil(1.2 * per_tile.max() / ng)) + c_max + 8
