@@ -2,6 +2,8 @@
 // Rows are RCASE(kernel lanes, diagonal, lane kinds, NB, lanes per slot), tried in order, cheapest first.
 #define AGF_T float
 #include <algorithm>
+#include <cmath>
+#include <cstdlib>
 
 #include "agf_k1_inst.cuh"
 #include "agf_regional.cuh"
@@ -43,13 +45,15 @@ int launch_regional(const RegionalLaunch &a, int mode, RegionalChoice *choice) {
     // Shared memory: ring + barriers + the staged rows (+ the zero row) + the segment sums + the tile's tables.  One ring
     // stage is enough for three CTAs per SM: a stage is handed back as soon as its 24 values per thread sit in registers,
     // and the scan is bound by instruction issue, not by bytes in flight (13.5 KB per SM cover DRAM latency at 2 TB/s).
-    constexpr int budget3 = 74 * 1024, budget2 = 110 * 1024;
+    // (228 KB per SM, 1 KB reserved per CTA: three CTAs get 75 KB each, two 113 KB)
+    constexpr int budget3 = 75 * 1024, budget2 = 113 * 1024, budget1 = 200 * 1024;
     constexpr int rest = 128 + stage_bytes<LPS>() + rg_part_bytes<LPS>() + rg_table_bytes<LPS>();
-    constexpr int MINB = (MINB0 == 3 && TILE + rest + 512 * 16 <= budget3) ? 3 : (MINB0 >= 2 ? 2 : 1);
-    constexpr int STAGES = (MINB != 3 && 2 * TILE + rest + 1024 * 16 <= budget2) ? 2 : 1;
+    constexpr int MINB = (MINB0 == 3 && TILE + rest + 512 * 16 <= budget3) ? 3 : ((MINB0 >= 2 && TILE + rest + 512 * 16 <= budget2) ? 2 : 1);
+    constexpr int budget = MINB == 3 ? budget3 : (MINB == 2 ? budget2 : budget1);
+    constexpr int STAGES = (MINB != 3 && 2 * TILE + rest + 1024 * 16 <= budget) ? 2 : 1;
     constexpr int fixed = STAGES * TILE + rest;
-    constexpr int smem = MINB == 3 ? budget3 : budget2;
-    constexpr int sm_entries = (smem - fixed) / 16;
+    constexpr int sm_entries = (budget - fixed) / 16 < 4096 ? (budget - fixed) / 16 : 4096;
+    constexpr int smem = fixed + sm_entries * 16;
     static_assert(sm_entries >= 512, "no room for the tile tables");
     auto kern = agf_k1_regional<T, NL, DIAG, KINDS, NB, LPS, R_GL, TT, STAGES, MINB>;
 
@@ -119,6 +123,38 @@ int launch_regional(const RegionalLaunch &a, int mode, RegionalChoice *choice) {
         for (int l = 0; l < NL; ++l) q.dst_dbl[l] = l < kp.n_cols ? kp.cols[l].dst : -1;
     } else {
         for (int c = 0; c < kp.n_cols && c < 16; ++c) q.dst_dbl[c] = kp.cols[c].dst;
+    }
+    if constexpr (S::TL && S::NBL > 4 && S::NA >= 1) {
+        // contiguous ascending bins -> counted through their edges (agf_regional.cuh).  Interior edges that ARE floats
+        // (lo_j+1 == hi_j) need the equality screen: usable when their bit patterns end in >= 16 zero bits.
+        bool ok = true;
+        unsigned low = 0xffffffffu;   // bits that are zero in every representable interior edge
+        bool any_rep = false;
+        for (int j = 0; j + 1 < S::NBL && ok; ++j) {
+            const float hi = kp.lanes[j].hi, lo_next = kp.lanes[j + 1].lo;
+            if (!(kp.lanes[j].lo < lo_next) || !(hi == hi) || !(lo_next == lo_next)) ok = false;
+            if (lo_next == hi) {
+                unsigned b;
+                memcpy(&b, &hi, 4);
+                low &= ~b;
+                any_rep = true;
+            } else if (lo_next != nextafterf(hi, -INFINITY)) {
+                ok = false;
+            }
+        }
+        const float hi_last = kp.lanes[S::NBL - 1].hi;
+        if (!(kp.lanes[S::NBL - 1].lo < hi_last) || std::isinf(hi_last)) ok = false;
+        unsigned mask = 0xffffffffu;
+        if (any_rep) {
+            int tz = 0;
+            while (tz < 23 && ((low >> tz) & 1u)) ++tz;   // trailing bits that are zero in every such edge
+            mask = (1u << tz) - 1u;
+            if (tz < 16) ok = false;
+        }
+        if (getenv("AGF_BINS_BY_EDGES") && atoi(getenv("AGF_BINS_BY_EDGES")) == 0) ok = false;
+        q.bins_fast = ok ? 1 : 0;
+        q.eq_mask = mask;
+        q.top_edge = nextafterf(hi_last, -INFINITY);
     }
     if (plan->n_empty_regions > 0) {
         agf_regional_fill_empty<<<plan->n_regions, 256, 0, a.k.stream>>>(plan->d_region_slot_ptr, plan->n_regions, q.g_begin,
