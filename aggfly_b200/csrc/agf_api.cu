@@ -652,8 +652,9 @@ extern "C" int agf_spmm_run(const agf_csr_t *c, const void *d_x, int32_t x_dtype
 extern "C" int agf_valid_mask_run(const void *d_x, int32_t x_dtype, int64_t n_groups, int32_t n_cols,
                                   int64_t n_cells, uint8_t *d_valid, uintptr_t stream) {
     if (!d_x || !d_valid) return fail(AGF_E_INVALID, "null argument");
-    if (n_groups <= 0 || n_groups > 65535 || n_cols <= 0 || n_cells <= 0) return fail(AGF_E_INVALID, "bad sizes");
-    dim3 grid((unsigned)((n_cells + 255) / 256), (unsigned)n_groups);
+    if (n_groups <= 0 || n_groups > 0x7fffffff || n_cols <= 0 || n_cells <= 0) return fail(AGF_E_INVALID, "bad sizes");
+    if ((n_cells + 255) / 256 > 65535) return fail(AGF_E_UNSUPPORTED, "more than 16776960 cells per step");
+    dim3 grid((unsigned)n_groups, (unsigned)((n_cells + 255) / 256));
     cudaStream_t st = (cudaStream_t)stream;
     if (x_dtype == AGF_F64)
         agf_valid_mask<double><<<grid, 256, 0, st>>>((const double *)d_x, n_cells, n_cols, d_valid);

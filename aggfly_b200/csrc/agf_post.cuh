@@ -181,9 +181,10 @@ __global__ void __launch_bounds__(256)
 template <typename TX>
 __global__ void __launch_bounds__(256)
     agf_valid_mask(const TX *__restrict__ X, long long n_cells, int n_cols, unsigned char *__restrict__ V) {
-    const long long cell = (long long)blockIdx.x * 256 + threadIdx.x;
+    // blockIdx.y: cell block, blockIdx.x: group (grid.x may hold 2^31 - 1 groups: an un-aggregated hourly series of any length)
+    const long long cell = (long long)blockIdx.y * 256 + threadIdx.x;
     if (cell >= n_cells) return;
-    const size_t g = blockIdx.y;
+    const size_t g = blockIdx.x;
     bool ok = true;
     for (int c = 0; c < n_cols; ++c) {
         const TX v = X[(g * n_cells + cell) * n_cols + c];

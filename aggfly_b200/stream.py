@@ -85,6 +85,17 @@ def chunk_rows(n_rows: int, row_bytes: int, chunk_bytes: int):
     return [(r, min(n_rows, r + step)) for r in range(0, n_rows, step)]
 
 
+def _drop(cache: dict) -> None:
+    """Empty a cache of pinned / device staging buffers.  Copies and kernels of an earlier feed may still be using them
+    (the feeds are asynchronous; ``aggregate_dataset`` synchronises before it returns, a caller that drives ``feed_*`` on
+    its own stream need not have), so the device is synchronised first."""
+    if cache:
+        import torch
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+        cache.clear()
+
+
 _RINGS = {}          # (dtype, slot_elems, n_slots) -> pinned slots, kept across calls: pinning 512 MB costs ~100 ms
 
 
@@ -95,7 +106,7 @@ class _Staging:
         self.torch = torch
         key = (str(dtype), int(slot_elems), int(n_slots))
         if key not in _RINGS:
-            _RINGS.clear()                             # one ring at a time: it is pinned memory
+            _drop(_RINGS)                              # one ring at a time: it is pinned memory
             _RINGS[key] = [torch.empty(slot_elems, dtype=dtype, pin_memory=True) for _ in range(n_slots)]
         self.slots = _RINGS[key]
         self.events = [None] * n_slots                 # copy-done event of the slot's last use
@@ -181,8 +192,8 @@ def _feed_ring(torch, runner, values, host, host_np, T: int, n_cells: int, tdtyp
     key = (dev.index, str(tdtype), slot_rows * n_cells, n_slots)
     ring = _RING_RASTERS.get(key)
     if ring is None:
-        _RING_RASTERS.clear()
-        _DEVICE_RASTERS.clear()
+        _drop(_RING_RASTERS)
+        _drop(_DEVICE_RASTERS)
         ring = torch.empty((n_slots, slot_rows, n_cells), dtype=tdtype, device=dev)
         _RING_RASTERS[key] = ring
     pinned = host is not None
@@ -364,7 +375,7 @@ def _chunk_ring(torch, dev, slot_bytes: int, n_slots: int, de: bool):
     chunks) and two more device buffers hold the inflated and the unshuffled chunk."""
     key = (dev.index, int(slot_bytes), int(n_slots), bool(de))
     if key not in _CHUNK_RINGS:
-        _CHUNK_RINGS.clear()
+        _drop(_CHUNK_RINGS)
         cap = slot_bytes + (slot_bytes // 64 + 65536 if de else 0)
         cap = (cap + 15) // 16 * 16
         ring = {"cap": cap,
@@ -626,7 +637,7 @@ def feed_packed(runner, src, n_cells: int, stream=None, k1_events: Optional[list
     n_dev = 3
     key = (dev.index, sdt.str, slot_rows * n_cells, n_dev)
     if key not in _PACKED_DEV:
-        _PACKED_DEV.clear()
+        _drop(_PACKED_DEV)
         _PACKED_DEV[key] = [torch.empty(slot_rows * n_cells, dtype=st_tdtype, device=dev) for _ in range(n_dev)]
     dslots = _PACKED_DEV[key]
     staging = None if pinned else _Staging(torch, st_tdtype, slot_rows * n_cells, OPTIONS["staging_slots"], OPTIONS["staging_threads"])
@@ -700,19 +711,16 @@ def _device_raster(torch, dev, tdtype, T: int, n_cells: int):
     key = (dev.index, str(tdtype), T * n_cells)
     buf = _DEVICE_RASTERS.get(key)
     if buf is None:
-        _DEVICE_RASTERS.clear()                  # one shape at a time
+        _drop(_DEVICE_RASTERS)                   # one shape at a time
         buf = torch.empty(T * n_cells, dtype=tdtype, device=dev)
         _DEVICE_RASTERS[key] = buf
     return buf.view(T, n_cells)
 
 
 def release_device_rasters() -> None:
-    """Give the cached device raster (and the pinned staging ring) back."""
-    _DEVICE_RASTERS.clear()
-    _RING_RASTERS.clear()
-    _RINGS.clear()
-    _CHUNK_RINGS.clear()
-    _PACKED_DEV.clear()
+    """Give the cached device raster (and the pinned staging rings) back."""
+    for cache in (_DEVICE_RASTERS, _RING_RASTERS, _RINGS, _CHUNK_RINGS, _PACKED_DEV):
+        _drop(cache)
 
 
 _COPY_STREAMS = {}

@@ -289,6 +289,8 @@ def lower_to_csr(wdf: pd.DataFrame, grid_cell_id: np.ndarray, n_lat: int, n_lon:
     rows, pos, w = rows[order], pos[order], w[order]
     row_ptr = np.zeros(len(region_ids) + 1, dtype=np.int64)
     np.cumsum(np.bincount(rows, minlength=len(region_ids)), out=row_ptr[1:])
+    if len(pos) > np.iinfo(np.int32).max or n_lat * n_lon > np.iinfo(np.int32).max:
+        raise ValueError(f"{len(pos)} weight entries / {n_lat * n_lon} cells exceed the 32-bit indices of the device CSR")
     return HostCSR(row_ptr.astype(np.int32), pos.astype(np.int32), np.ascontiguousarray(w),
                    region_ids, n_cells)
 
@@ -324,13 +326,23 @@ def lower_to_csr_cached(wdf: pd.DataFrame, grid_cell_id: np.ndarray, n_lat: int,
     if os.path.exists(path):
         try:
             with np.load(path) as z:
-                return HostCSR(z["row_ptr"], z["cell_idx"], z["w"], z["region_ids"], int(z["n_cells"]))
-        except Exception:
-            pass                                                   # unreadable cache entry: rebuild it
+                rid = z["region_ids"]
+                if "region_ids_object" in z.files and bool(z["region_ids_object"]):
+                    rid = rid.astype(object)                       # string ids come back as the object array they were
+                return HostCSR(z["row_ptr"], z["cell_idx"], z["w"], rid, int(z["n_cells"]))
+        except Exception as exc:                                   # unreadable cache entry: say so and rebuild it
+            import warnings
+            warnings.warn(f"DeviceCSR cache entry {path} is unreadable ({type(exc).__name__}: {exc}); rebuilding it")
     csr = lower_to_csr(wdf, grid_cell_id, n_lat, n_lon, lon_order)
     os.makedirs(d, exist_ok=True)
     tmp = f"{path}.{os.getpid()}.tmp.npz"
-    np.savez(tmp, row_ptr=csr.row_ptr, cell_idx=csr.cell_idx, w=csr.w, region_ids=csr.region_ids,
+    rid = np.asarray(csr.region_ids)
+    as_object = rid.dtype == object
+    if as_object:                                                  # np.savez would pickle an object array (unloadable by default)
+        if not all(isinstance(v, str) for v in rid):
+            return csr                                             # mixed / exotic ids: not cached
+        rid = rid.astype(str)
+    np.savez(tmp, row_ptr=csr.row_ptr, cell_idx=csr.cell_idx, w=csr.w, region_ids=rid, region_ids_object=np.bool_(as_object),
              n_cells=np.int64(csr.n_cells))
     os.replace(tmp, path)                                          # atomic: ranks may race
     return csr

@@ -215,3 +215,17 @@ def test_specs_with_opaque_values_are_never_plan_cached():
     big = {"a": [("aggregate", {"calc": "mean", "groupby": "date"}), ("transform", {"inter": np.zeros((3, 5, 5))})]}
     assert _spec_fingerprint(big) is None
     assert _spec_fingerprint({"a": [("transform", {"inter": object()})]}) is None
+
+
+def test_csr_disk_cache_round_trips_string_region_ids(tmp_path):
+    """np.savez pickles object arrays and np.load refuses them: string ids are stored as unicode and come back as objects."""
+    import pandas as pd
+    from aggfly_b200.weights import lower_to_csr_cached
+    wdf = pd.DataFrame({"cell_id": [0, 1, 2, 3], "index_right": ["b", "b", "a", "c"], "weight": [0.5, 0.5, 1.0, 1.0]})
+    first = lower_to_csr_cached(wdf, np.arange(6), 2, 3, None, str(tmp_path))
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")                         # an unreadable entry would warn
+        again = lower_to_csr_cached(wdf, np.arange(6), 2, 3, None, str(tmp_path))
+    assert list(again.region_ids) == list(first.region_ids) == ["a", "b", "c"]
+    assert np.array_equal(again.row_ptr, first.row_ptr) and np.array_equal(again.cell_idx, first.cell_idx)
