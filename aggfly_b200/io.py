@@ -33,6 +33,7 @@ import pandas as pd
 from .dataset import Dataset
 from .geometry import orient_polygon
 from .weights import GeoRegions, SecondaryWeights
+from . import hdf5io as _hdf5io
 from .zarrio import looks_like_zarr, open_raster, write_dataset
 
 
@@ -98,12 +99,16 @@ def dataset_from_path(path, var: Optional[str] = None, xycoords: Sequence[str] =
         keepalive = f                                                # the raster is a view of the mapped file
     elif kwargs.get("engine") in (None, "zarr") and looks_like_zarr(path):      # dataset.py:697-701
         values, time, lat, lon = open_raster(path, var, xycoords, timecoord)
+    elif kwargs.get("engine") in (None, "netcdf4", "h5netcdf") and os.path.isfile(path) and _hdf5io.looks_like_hdf5(path):
+        # NetCDF-4 = HDF5: chunks are read, inflated and un-shuffled by host threads into pinned slots and placed /
+        # unpacked on the device (hdf5io.py); no xarray / netCDF4 / h5py needed
+        values, time, lat, lon = _hdf5io.open_raster(path, var, xycoords, timecoord)
     else:
         try:
             import xarray as xr                                      # optional dependency
         except Exception as exc:
             raise ImportError(f"{path}: reading this format needs xarray (not installed); natively supported: "
-                              ".npz, .npy (+ .axes.npz), NetCDF-3 .nc, zarr directory stores") from exc
+                              ".npz, .npy (+ .axes.npz), NetCDF-3 and NetCDF-4 .nc, zarr directory stores") from exc
         kwargs.pop("chunks", None)
         dsx = xr.open_dataset(path, **kwargs)
         return Dataset(dsx[var], xycoords=xycoords, timecoord=timecoord, time_sel=time_sel, lon_is_360=lon_is_360,

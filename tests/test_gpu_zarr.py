@@ -331,3 +331,58 @@ def test_multi_file_dataset_matches_single_array(tmp_path):
     assert len(got) == len(want) > 0
     _exact(got[vals].values, want[vals].values)                       # same host feed, same stripes
     _exact(engine.to_device(ds.values).cpu().numpy(), arr)
+
+
+# ---- NetCDF-4 (HDF5) files: chunks inflated + un-shuffled by host threads, placed / unpacked on the device (hdf5io.py) ----
+@pytest.mark.parametrize("layout", ["time_major_packed_deflate", "lat_lon_time_packed_deflate", "float32_contiguous",
+                                    "float32_chunked_shuffle"])
+@pytest.mark.parametrize("name", ["c3_bins_and_poly", "c3b_daily"])
+def test_netcdf4_file_matches_in_memory_result(tmp_path, name, layout):
+    import torch
+    from aggfly_b200 import hdf5io
+    arr, t, lat, lon = _raster("float32", False, T=24 * 21 + 3, seed=41)
+    T, Y, X = arr.shape
+    hours = ((t - t[0]) / np.timedelta64(1, "h")).astype(np.int32)
+    units = f"hours since {t[0]:%Y-%m-%d %H:%M:%S}"
+    path = str(tmp_path / "era5.nc")
+    if "packed" in layout:
+        scale, offset = 0.002, float(np.nanmean(arr))
+        q = np.clip(np.rint((arr.astype(np.float64) - offset) / scale), -32000, 32000).astype(np.int16)
+        q[7:11, 1, 2] = -32767
+        decoded = q.astype(np.float64) * scale + offset
+        decoded[q == -32767] = np.nan
+        attrs = {"scale_factor": scale, "add_offset": offset, "_FillValue": np.int16(-32767), "units": "K"}
+        if layout.startswith("time_major"):
+            hdf5io.write_netcdf4(path, q, hours, units, lat, lon, var="t2m", chunks=(24, Y, X), attrs=attrs)
+        else:
+            hdf5io.write_netcdf4(path, np.ascontiguousarray(np.transpose(q, (1, 2, 0))), hours, units, lat, lon, var="t2m",
+                                 dims=("latitude", "longitude", "time"), chunks=(3, 5, T), attrs=attrs)
+    else:
+        decoded = arr
+        hdf5io.write_netcdf4(path, arr, hours, units, lat, lon, var="t2m", chunks=None if "contiguous" in layout else (48, 4, X),
+                             deflate=None, shuffle="shuffle" in layout)
+    rng = np.random.default_rng(12)
+    wdf, shp = _weights_case(lat, lon, rng)
+
+    def run(ds):
+        w = af.weights_from_objects(ds, af.GeoRegions(shp, "geoid"), zero_weight="nan")
+        w.weights = wdf
+        return af.aggregate_dataset(weights=w, dataset=ds, aggregator_dict=SPECS[name])
+
+    engine.OPTIONS["target_stripes"] = 5                       # same stripes (same merge order) in both runs
+    old = dict(stream.OPTIONS)
+    try:
+        stream.OPTIONS.update(staging_slots=3, staging_threads=2)
+        resident = run(af.Dataset.from_arrays(torch.from_numpy(decoded).cuda(), t, lat, lon, True))
+        ds = af.dataset_from_path(path, var="t2m")
+        assert getattr(ds.values, "is_chunked_raster", False) and ds.dtype == decoded.dtype
+        assert len(ds.time) == T and ds.time[0] == t[0] and ds.time[-1] == t[-1]
+        got = run(ds)
+        assert stream.LAST_STATS.get("chunked") and stream.LAST_STATS["chunks"] >= 1
+        dev_raster = engine.to_device(ds.values).cpu().numpy()
+    finally:
+        stream.OPTIONS.update(old)
+    _exact(dev_raster, decoded)
+    vals = [c for c in resident.columns if c not in ("geoid", "time")]
+    assert len(got) == len(resident) > 0
+    _exact(got[vals].values, resident[vals].values)
