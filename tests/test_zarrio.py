@@ -469,3 +469,22 @@ def test_multi_file_dataset_is_a_lazy_time_concat(tmp_path):
     for r0, r1 in stream.chunk_rows(full.shape[0], 35 * 4, 40 * 35 * 4):
         got = ring.fill(0, src[r0:r1]).view(r1 - r0, 35).numpy()
         assert np.array_equal(got, full[r0:r1].reshape(r1 - r0, 35))
+
+
+def test_decode_dtype_policy_is_pinned(tmp_path):
+    """Integer and packed sources decode to float64, float sources keep their width.  xarray's CF decoding (which the
+    reference reads through) picks float32 for integers of <= 2 bytes in older releases and follows the dtype of
+    ``scale_factor`` in newer ones; this engine always takes the widest of those choices, so a panel from a packed store is
+    computed at least as precisely as the reference's ("Decode dtype").  ``dataset.PackedRaster`` lets the caller
+    choose float32 explicitly."""
+    t = pd.date_range("2001-01-01", periods=6, freq="h")
+    lat, lon = np.array([1.0, 0.0]), np.array([10.0, 11.0, 12.0])
+    cases = {"int16_packed": (np.arange(36, dtype=np.int16).reshape(6, 2, 3), {"scale_factor": 0.5, "add_offset": 1.0}, np.float64),
+             "int16_plain": (np.arange(36, dtype=np.int16).reshape(6, 2, 3), {}, np.float64),
+             "uint8_fill_only": (np.arange(36, dtype=np.uint8).reshape(6, 2, 3), {"_FillValue": 7}, np.float64),
+             "float32": (np.arange(36, dtype=np.float32).reshape(6, 2, 3), {}, np.float32),
+             "float32_packed": (np.arange(36, dtype=np.float32).reshape(6, 2, 3), {"scale_factor": 2.0}, np.float64)}
+    for name, (vals, attrs, want) in cases.items():
+        store = zarrio.write_dataset(str(tmp_path / f"{name}.zarr"), vals, t, lat, lon, var="v", attrs=attrs, compressor=None)
+        ds = af.dataset_from_path(store, var="v")
+        assert ds.dtype == np.dtype(want), name
