@@ -357,10 +357,13 @@ def run_c4(torch, dist, af, wl, w, host, years, world, rank, dev, one_year_df):
     nreg = int(one_year_df[rid].nunique())
     g1 = len(one_year_df) // max(1, nreg)
     ok, n_checked = False, 0
-    if nreg and len(one_year_df) == nreg * g1 and len(df) == nreg * g1 * years:
+    # rows of the years this rank aggregated (other ranks' years hold other rasters, with other NaN rows dropped)
+    yr = np.fromiter((getattr(t, "year", 0) for t in df["time"]), dtype=np.int64, count=len(df))
+    mine = df[(yr - 2001) < my_years]
+    if nreg and len(one_year_df) == nreg * g1 and len(mine) == nreg * g1 * my_years:
         ref = one_year_df[cols].to_numpy(float).reshape(nreg, 1, g1, len(cols))
-        got = df[cols].to_numpy(float).reshape(nreg, years, g1, len(cols))[:, :my_years]
-        ok = bool(np.array_equal(np.asarray(df[rid]).reshape(nreg, -1)[:, 0], np.asarray(one_year_df[rid]).reshape(nreg, -1)[:, 0])
+        got = mine[cols].to_numpy(float).reshape(nreg, my_years, g1, len(cols))
+        ok = bool(np.array_equal(np.asarray(mine[rid]).reshape(nreg, -1)[:, 0], np.asarray(one_year_df[rid]).reshape(nreg, -1)[:, 0])
                   and np.allclose(got, ref, rtol=1e-11, atol=0, equal_nan=True))
         n_checked = int(my_years)
     return {"workload": "c4: %d synthetic years of %s as one record" % (years, wl.name), "years": years,
