@@ -12,7 +12,7 @@ from typing import Optional
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libaggfly_b200.so")
 
-ABI_VERSION = 4                      # AGF_ABI_VERSION of include/aggfly_b200.h
+ABI_VERSION = 5                      # AGF_ABI_VERSION of include/aggfly_b200.h
 MAX_LANES, MAX_SLOTS, MAX_COLS = 32, 32, 64
 E_INVALID, E_UNSUPPORTED, E_NOMEM, E_STATE = -1, -2, -3, -4
 
@@ -123,7 +123,7 @@ def lib() -> C.CDLL:
     L.agf_valid_mask_run.argtypes = [vp, i32, i64, i32, i64, vp, u64]
     L.agf_elementwise_run.argtypes = [vp, i32, vp, i32, i64, i32, C.c_double, vp, i32, vp, i32, C.POINTER(Pre), u64]
     L.agf_tile_place_run.argtypes = [vp, i32, i64, i64, i64, i64, i64, i64, vp, i32, i64, i64, i64, i64, i64,
-                                     i32, C.c_double, C.c_double, i32, C.c_double, u64]
+                                     i32, C.c_double, C.c_double, i32, C.c_double, i64, u64]
     L.agf_decompress_caps.argtypes = [C.POINTER(i32), C.POINTER(i64)]
     L.agf_decompress_lz4_run.argtypes = [vp, C.POINTER(i64), C.POINTER(i64), vp, C.POINTER(i64), C.POINTER(i64), i64, vp, u64]
     L.agf_unshuffle_run.argtypes = [vp, vp, i64, i32, i64, u64]

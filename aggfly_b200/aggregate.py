@@ -331,7 +331,36 @@ def _assemble_panel(panel: np.ndarray, names: List[str], labels, region_ids: np.
 
 
 def _panel_frame(panel, names: List[str], labels, region_ids: np.ndarray, weights: GridWeights) -> pd.DataFrame:
-    """Device panel ``[R, G, n_cols]`` (torch, float64) -> the frame ``aggregate_dataset`` returns: the long frame of
+    """The frame ``aggregate_dataset`` returns, from the columns of ``_panel_columns`` (no copies)."""
+    got = _panel_columns(panel, names, labels, region_ids, weights)
+    if isinstance(got, pd.DataFrame):
+        return got
+    data, index = got
+    return pd.DataFrame(data, index=index, copy=False)
+
+
+def _panel_table(panel, names: List[str], labels, region_ids: np.ndarray, weights: GridWeights):
+    """The same rows as a ``pyarrow.Table`` built straight from the gathered columns (no pandas frame in between): what the
+    panel writer takes (aggfly/cli/pipeline.py:150, 159-172 concatenates and writes pandas frames).  Labels of a
+    non-standard calendar are written as ISO strings, like ``io.write_output`` does."""
+    import pyarrow as pa
+    got = _panel_columns(panel, names, labels, region_ids, weights)
+    if isinstance(got, pd.DataFrame):                                  # literal route (duplicated region index, no device room)
+        df = got.copy()
+        if len(df) and not isinstance(df["time"].iloc[0], (pd.Timestamp, np.datetime64)):
+            df["time"] = df["time"].map(lambda t: t.isoformat() if hasattr(t, "isoformat") else str(t))
+        return pa.Table.from_pandas(df, preserve_index=False)
+    data, _index = got
+    cols = {}
+    for k, v in data.items():
+        if k == "time" and getattr(v, "dtype", None) == object:
+            v = np.array([t.isoformat() if hasattr(t, "isoformat") else str(t) for t in v], dtype=object)
+        cols[k] = pa.array(v)
+    return pa.table(cols)
+
+
+def _panel_columns(panel, names: List[str], labels, region_ids: np.ndarray, weights: GridWeights):
+    """Device panel ``[R, G, n_cols]`` (torch, float64) -> ({column name: array}, index) of the long frame of
     spatial.py:136-153 with its row-drop rules, already joined with the region ids (aggregate.py:276-280).
 
     Same rows, order, columns and index as ``_assemble_panel`` + ``shp[[rid]].merge(...)``, but the row selection, the
@@ -384,7 +413,7 @@ def _panel_frame(panel, names: List[str], labels, region_ids: np.ndarray, weight
     data = {rid: reg_col, "time": time_col}
     for c, nm in enumerate(names):
         data[nm] = cols[c]
-    return pd.DataFrame(data, index=index, copy=False)
+    return data, index
 
 
 class SpatialAggregator:
@@ -445,6 +474,7 @@ def aggregate_dataset(weights: GridWeights, dataset: Dataset = None,
             f"aggregate_dataset no longer builds a Dask cluster; {sorted(stale)} is/are ignored. "
             "aggfly_b200 runs on the CUDA engine of the current device.",
             DeprecationWarning, stacklevel=2)
+    as_table = bool(kwargs.pop("_as_arrow_table", False))
     if aggregator_dict is None and kwargs:
         aggregator_dict = kwargs
     if aggregator_dict is None and dataset_dict is not None:
@@ -458,7 +488,9 @@ def aggregate_dataset(weights: GridWeights, dataset: Dataset = None,
     if fused is not None:
         names, pres = fused
         tr.mark("temporal + regional, one kernel (+ host feed)")
-        if _engine.OPTIONS.get("device_panel_frame", False):
+        if as_table:
+            df = _panel_table(pres.panel, names, pres.labels, csr.host.region_ids, weights)
+        elif _engine.OPTIONS.get("device_panel_frame", False):
             df = _panel_frame(pres.panel, names, pres.labels, csr.host.region_ids, weights)
         else:
             df = _assemble_panel(pres.panel.cpu().numpy(), names, pres.labels, csr.host.region_ids, weights)
@@ -469,7 +501,12 @@ def aggregate_dataset(weights: GridWeights, dataset: Dataset = None,
         return df
     names, res, raster = _temporal_device(dataset, aggregator_dict)
     tr.mark("temporal (+ host feed)")
-    if _engine.OPTIONS.get("device_panel_frame", False):
+    if as_table:
+        panel = _engine.run_spmm(csr, res)
+        tr.mark("spmm (issue)")
+        df = _panel_table(panel, names, res.labels, csr.host.region_ids, weights)
+        tr.mark("panel table (row selection on the device, d2h, arrow columns)")
+    elif _engine.OPTIONS.get("device_panel_frame", False):
         panel = _engine.run_spmm(csr, res)
         tr.mark("spmm (issue)")
         df = _panel_frame(panel, names, res.labels, csr.host.region_ids, weights)
@@ -484,6 +521,15 @@ def aggregate_dataset(weights: GridWeights, dataset: Dataset = None,
         tr.mark("merge")
     tr.done()
     return df
+
+
+def aggregate_dataset_table(weights: GridWeights, dataset: Dataset = None, aggregator_dict=None, engine: str = "auto", **kwargs):
+    """``aggregate_dataset`` whose result is a ``pyarrow.Table`` with the same rows and columns, built straight from the
+    panel's gathered columns -- what ``aggfly run`` concatenates and hands to the parquet / feather / csv writer
+    (``io.write_table``) without a pandas frame in between (aggfly/cli/pipeline.py:150, 159-172)."""
+    if aggregator_dict is None and not kwargs:
+        raise ValueError("aggregate_dataset_table needs an aggregator_dict")
+    return aggregate_dataset(weights, dataset, aggregator_dict, engine=engine, _as_arrow_table=True, **kwargs)
 
 
 class _Trace:

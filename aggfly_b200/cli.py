@@ -96,9 +96,12 @@ def compute_weights(config: _cfg.RunConfig, log=lambda m: None):
     return w, georegions, sample
 
 
-def run_pipeline(config: _cfg.RunConfig, log=lambda m: None) -> Optional[pd.DataFrame]:
-    """The panel (on rank 0; None on the other ranks of a distributed job)."""
-    from .aggregate import aggregate_dataset
+def run_pipeline(config: _cfg.RunConfig, log=lambda m: None, as_table: bool = False):
+    """The panel (on rank 0; None on the other ranks of a distributed job): a DataFrame, or with ``as_table`` a
+    ``pyarrow.Table`` whose yearly parts were built straight from the device panels' columns (what ``aggfly run`` writes)."""
+    from .aggregate import aggregate_dataset, aggregate_dataset_table
+    if as_table:
+        aggregate_dataset = aggregate_dataset_table                      # noqa: F811 -- same signature, Arrow result
     rank, world = _dist_info()
     weights, georegions, sample = compute_weights(config, log)
     paths = config.resolved_paths()
@@ -118,6 +121,9 @@ def run_pipeline(config: _cfg.RunConfig, log=lambda m: None) -> Optional[pd.Data
         if rank != 0:
             return None
     frames = [f for _, f in sorted(frames, key=lambda t: t[0])]
+    if as_table:
+        import pyarrow as pa
+        return pa.concat_tables(frames) if len(frames) > 1 else frames[0]
     return pd.concat(frames, ignore_index=True) if len(frames) > 1 else frames[0]
 
 
@@ -243,14 +249,14 @@ def run(config, output, engine, years, project_dir, backend, n_workers, verbose)
     except _pp.PreprocessError as e:
         raise click.ClickException(f"preprocess: {e}")
     try:
-        df = run_pipeline(cfg, log=_log_fn(verbose))
+        table = run_pipeline(cfg, log=_log_fn(verbose), as_table=True)
     except Exception as e:
         if verbose:
             raise
         raise click.ClickException(f"{type(e).__name__}: {e}")
-    if df is not None:
-        _io.write_output(df, cfg.output_path, cfg.output_format)
-        click.echo(f"Wrote {len(df)} rows to {cfg.output_path} ({cfg.output_format}).")
+    if table is not None:
+        _io.write_table(table, cfg.output_path, cfg.output_format)        # Arrow columns -> file, no pandas frame
+        click.echo(f"Wrote {table.num_rows} rows to {cfg.output_path} ({cfg.output_format}).")
 
 
 # ---------------------------------------------------------------------------------------------

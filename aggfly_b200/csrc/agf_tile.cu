@@ -141,13 +141,16 @@ int launch_tile(const void *d_src, void *d_dst, const TileArgs &a, int sms, cuda
 extern "C" int agf_tile_place_run(const void *d_src, int32_t src_dtype, int64_t nt, int64_t ny, int64_t nx,
                                   int64_t st, int64_t sy, int64_t sx, void *d_dst, int32_t dst_dtype, int64_t ld,
                                   int64_t n_lon, int64_t t0, int64_t y0, int64_t x0, int32_t packed, double scale,
-                                  double offset, int32_t has_fill, double fill, uintptr_t stream) {
+                                  double offset, int32_t has_fill, double fill, int64_t dst_rows, uintptr_t stream) {
     if (!d_src || !d_dst) return agf_fail(AGF_E_INVALID, "null argument");
     if (nt < 0 || ny < 0 || nx < 0 || st < 0 || sy < 0 || sx < 0) return agf_fail(AGF_E_INVALID, "negative extent / stride");
     if (t0 < 0 || y0 < 0 || x0 < 0 || n_lon <= 0 || x0 + nx > n_lon || (y0 + ny) * n_lon > ld)
         return agf_fail(AGF_E_INVALID, "tile [%lld+%lld, %lld+%lld] does not fit a row of %lld x %lld cells (pitch %lld)",
                         (long long)y0, (long long)ny, (long long)x0, (long long)nx, (long long)(ld / n_lon),
                         (long long)n_lon, (long long)ld);
+    if (dst_rows <= 0 || t0 + nt > dst_rows)
+        return agf_fail(AGF_E_INVALID, "tile rows [%lld, %lld) do not fit a raster of %lld rows", (long long)t0, (long long)(t0 + nt),
+                        (long long)dst_rows);
     if (dst_dtype != AGF_F32 && dst_dtype != AGF_F64) return agf_fail(AGF_E_INVALID, "destination dtype %d", dst_dtype);
     if (nt == 0 || ny == 0 || nx == 0) return 0;
     TileArgs a{nt, ny, nx, st, sy, sx, ld, n_lon, t0, y0, x0, scale, offset, fill, has_fill != 0, packed != 0};

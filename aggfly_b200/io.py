@@ -518,6 +518,26 @@ def crop_weights_from_path(path: str, crop: str = "corn", feed: Optional[str] = 
 # ---------------------------------------------------------------------------------------------
 # panels
 # ---------------------------------------------------------------------------------------------
+def write_table(table, path: str, fmt: Optional[str] = None) -> str:
+    """``write_output`` for a ``pyarrow.Table`` (``aggregate_dataset_table``): parquet / feather / csv written by Arrow itself."""
+    import pyarrow as pa
+    fmt = fmt or {"pq": "parquet"}.get(os.path.splitext(path)[1].lstrip(".").lower(),
+                                       os.path.splitext(path)[1].lstrip(".").lower())
+    os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+    if fmt == "parquet":
+        import pyarrow.parquet as pq
+        pq.write_table(table, path)
+    elif fmt == "feather":
+        import pyarrow.feather as pf
+        pf.write_feather(table, path)
+    elif fmt == "csv":
+        import pyarrow.csv as pc
+        pc.write_csv(table, path)
+    else:
+        raise ValueError(f"output format {fmt!r} not in ['csv', 'feather', 'parquet']")
+    return path
+
+
 def write_output(df: pd.DataFrame, path: str, fmt: Optional[str] = None) -> str:
     """aggfly/cli/pipeline.py:159-172: parquet / feather / csv by ``fmt`` or the extension."""
     fmt = fmt or {"pq": "parquet"}.get(os.path.splitext(path)[1].lstrip(".").lower(),

@@ -474,7 +474,7 @@ def feed_chunked(runner, src, n_cells: int, stream=None, k1_events: Optional[lis
         _lib.check(L.agf_tile_place_run(
             ptr + tile.offset * sdt.itemsize, code, nt, ny, nx, tile.st, tile.sy, tile.sx, raster.data_ptr(), dst_code,
             n_cells, X, tile.t0, tile.y0, tile.x0, int(src.packed), float(src.scale), float(src.offset),
-            int(src.fill is not None), float(src.fill if src.fill is not None else 0.0), comp.cuda_stream))
+            int(src.fill is not None), float(src.fill if src.fill is not None else 0.0), T, comp.cuda_stream))
 
     i64p = C.POINTER(C.c_int64)
     align = int(OPTIONS.get("device_decompress_align", 0) or 0)
@@ -677,7 +677,7 @@ def feed_packed(runner, src, n_cells: int, stream=None, k1_events: Optional[list
             _lib.check(L.agf_tile_place_run(
                 dslots[slot].data_ptr(), code, r1 - r0, Y, X, n_cells, X, 1, raster.data_ptr(), dst_code, n_cells, X, r0, 0, 0,
                 1, float(src.scale), float(src.offset), int(src.fill is not None),
-                float(src.fill if src.fill is not None else 0.0), comp.cuda_stream))
+                float(src.fill if src.fill is not None else 0.0), T, comp.cuda_stream))
             pe = torch.cuda.Event()
             pe.record(comp)
             placed[slot] = pe

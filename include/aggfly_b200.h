@@ -47,7 +47,7 @@
 extern "C" {
 #endif
 
-#define AGF_ABI_VERSION 4
+#define AGF_ABI_VERSION 5
 
 #define AGF_MAX_LANES 32  /* level-1 reducers per program */
 #define AGF_MAX_SLOTS 32  /* level-2 reducers per program */
@@ -328,11 +328,12 @@ int agf_elementwise_run(const void *d_in, int32_t in_dtype, void *d_out, int32_t
  * decode: if has_fill and src == fill -> NaN; if packed -> (double)src * scale + offset (CF
  * scale_factor / add_offset, what xarray's decode_cf does on open, aggfly/dataset/dataset.py:700-707);
  * then converted to dst_dtype (AGF_F32 | AGF_F64).  src_dtype: any AGF_* dtype; float64 sources need a
- * float64 raster.  d_src and d_dst are caller-owned device buffers. */
+ * float64 raster.  d_src and d_dst are caller-owned device buffers; dst_rows = rows of the raster d_dst points at
+ * (t0 + nt must not exceed it: a wrong time offset is rejected instead of writing past the raster, ABI 5). */
 int agf_tile_place_run(const void *d_src, int32_t src_dtype, int64_t nt, int64_t ny, int64_t nx,
                        int64_t st, int64_t sy, int64_t sx, void *d_dst, int32_t dst_dtype, int64_t ld,
                        int64_t n_lon, int64_t t0, int64_t y0, int64_t x0, int32_t packed, double scale,
-                       double offset, int32_t has_fill, double fill, uintptr_t stream);
+                       double offset, int32_t has_fill, double fill, int64_t dst_rows, uintptr_t stream);
 
 /* ---- compressed chunks: Blackwell decompression engine --------------------------------------------- */
 

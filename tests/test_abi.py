@@ -19,7 +19,7 @@ def test_library_exports_every_declared_symbol():
     L = _lib.lib()
     for name in declared:
         assert hasattr(L, name), name
-    assert L.agf_version() == 4          # AGF_ABI_VERSION
+    assert L.agf_version() == 5          # AGF_ABI_VERSION
 
 
 def test_struct_layouts_match_the_header_as_gcc_sees_it(tmp_path):

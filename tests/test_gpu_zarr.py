@@ -44,7 +44,7 @@ def _place(chunk, perm, ext, off, dst_shape, dst_off, dst_dtype, packed=False, s
     rc = _lib.lib().agf_tile_place_run(src.data_ptr() + elem_off * chunk.dtype.itemsize, _CODES[str(chunk.dtype)],
                                       ext[0], ext[1], ext[2], strides[0], strides[1], strides[2], dst.data_ptr(),
                                       _CODES[dst_dtype], Y * X, X, dst_off[0], dst_off[1], dst_off[2], int(packed),
-                                      scale, offset, int(fill is not None), 0.0 if fill is None else float(fill),
+                                      scale, offset, int(fill is not None), 0.0 if fill is None else float(fill), T,
                                       torch.cuda.current_stream().cuda_stream)
     _lib.check(rc)
     torch.cuda.synchronize()
@@ -87,12 +87,15 @@ def test_tile_place_rejects_bad_arguments():
     a = torch.zeros(64, device="cuda")
     L = _lib.lib()
     s = torch.cuda.current_stream().cuda_stream
-    assert L.agf_tile_place_run(a.data_ptr(), 0, 1, 2, 9, 16, 8, 1, a.data_ptr(), 0, 16, 8, 0, 0, 0, 0, 1.0, 0.0, 0, 0.0, s) == -1
+    assert L.agf_tile_place_run(a.data_ptr(), 0, 1, 2, 9, 16, 8, 1, a.data_ptr(), 0, 16, 8, 0, 0, 0, 0, 1.0, 0.0, 0, 0.0, 1, s) == -1
     assert b"does not fit" in L.agf_last_error()
-    assert L.agf_tile_place_run(a.data_ptr(), 1, 1, 1, 1, 1, 1, 1, a.data_ptr(), 0, 16, 8, 0, 0, 0, 0, 1.0, 0.0, 0, 0.0, s) == -1
-    assert L.agf_tile_place_run(a.data_ptr(), 9, 1, 1, 1, 1, 1, 1, a.data_ptr(), 0, 16, 8, 0, 0, 0, 0, 1.0, 0.0, 0, 0.0, s) == -1
-    assert L.agf_tile_place_run(None, 0, 1, 1, 1, 1, 1, 1, a.data_ptr(), 0, 16, 8, 0, 0, 0, 0, 1.0, 0.0, 0, 0.0, s) == -1
-    assert L.agf_tile_place_run(a.data_ptr(), 0, 0, 1, 1, 1, 1, 1, a.data_ptr(), 0, 16, 8, 0, 0, 0, 0, 1.0, 0.0, 0, 0.0, s) == 0
+    assert L.agf_tile_place_run(a.data_ptr(), 1, 1, 1, 1, 1, 1, 1, a.data_ptr(), 0, 16, 8, 0, 0, 0, 0, 1.0, 0.0, 0, 0.0, 1, s) == -1
+    assert L.agf_tile_place_run(a.data_ptr(), 9, 1, 1, 1, 1, 1, 1, a.data_ptr(), 0, 16, 8, 0, 0, 0, 0, 1.0, 0.0, 0, 0.0, 1, s) == -1
+    assert L.agf_tile_place_run(None, 0, 1, 1, 1, 1, 1, 1, a.data_ptr(), 0, 16, 8, 0, 0, 0, 0, 1.0, 0.0, 0, 0.0, 1, s) == -1
+    assert L.agf_tile_place_run(a.data_ptr(), 0, 0, 1, 1, 1, 1, 1, a.data_ptr(), 0, 16, 8, 0, 0, 0, 0, 1.0, 0.0, 0, 0.0, 1, s) == 0
+    # a time offset past the raster's rows is rejected instead of written (ABI 5)
+    assert L.agf_tile_place_run(a.data_ptr(), 0, 2, 1, 1, 1, 1, 1, a.data_ptr(), 0, 16, 8, 3, 0, 0, 0, 1.0, 0.0, 0, 0.0, 4, s) == -1
+    assert b"do not fit a raster of 4 rows" in L.agf_last_error()
 
 
 LAYOUTS = {

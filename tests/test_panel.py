@@ -68,3 +68,37 @@ def test_panel_frame_edge_cases():
     pd.testing.assert_frame_equal(_panel_frame(torch.from_numpy(holes), names, labels, rids, dup), _literal(holes, names, labels, rids, dup))
     one = _panel_frame(torch.from_numpy(full[:, :1]), names, labels[:1], rids, w)                   # yearly panel: one period
     assert len(one) == R and one["time"].nunique() == 1
+
+
+@pytest.mark.parametrize("zero_weight", ["nan", "area"])
+@pytest.mark.parametrize("string_ids", [True, False])
+@pytest.mark.parametrize("calendar", [False, True])
+def test_panel_table_holds_the_frames_rows_and_round_trips_through_the_writers(tmp_path, zero_weight, string_ids, calendar):
+    """``_panel_table`` (the Arrow route ``aggfly run`` writes from) == ``_panel_frame`` row for row; parquet / feather / csv
+    written by ``io.write_table`` read back like the files ``io.write_output`` writes from the frame."""
+    from aggfly_b200 import io as aio
+    from aggfly_b200.aggregate import _panel_table
+    from aggfly_b200.timeaxis import CalendarIndex
+    rng = np.random.default_rng(7 + string_ids + 2 * calendar)
+    R, G, NC = 25, 6, 2
+    panel = rng.random((R, G, NC))
+    panel[rng.random(R) < 0.15] = np.nan
+    rids = np.arange(R) * 3
+    shp_ids = rng.permutation(rids[:-2])
+    vals = [f"g{v}" for v in shp_ids] if string_ids else (shp_ids * 10).astype(np.int64)
+    w = _weights(rids, shp_ids, vals, zero_weight, 0.2, rng)
+    names = ["a", "b"]
+    labels = CalendarIndex.range("noleap", 2001, G) if calendar else pd.date_range("2001-01-01", periods=G, freq="D")
+    frame = _panel_frame(torch.from_numpy(panel), names, labels, rids, w)
+    table = _panel_table(torch.from_numpy(panel), names, labels, rids, w)
+    assert table.column_names == list(frame.columns) and table.num_rows == len(frame)
+    got = table.to_pandas()
+    want = frame.reset_index(drop=True)
+    if calendar:
+        want = want.assign(time=want["time"].map(lambda t: t.isoformat()))
+    pd.testing.assert_frame_equal(got, want, check_dtype=False)
+    read_csv = pd.read_csv if calendar else (lambda p: pd.read_csv(p, parse_dates=["time"]))     # Arrow prints the time of day too
+    for fmt, read in (("parquet", pd.read_parquet), ("feather", pd.read_feather), ("csv", read_csv)):
+        a = aio.write_table(table, str(tmp_path / f"t.{fmt}"), fmt)
+        b = aio.write_output(frame, str(tmp_path / f"f.{fmt}"), fmt)
+        pd.testing.assert_frame_equal(read(a), read(b), check_dtype=False)
