@@ -129,3 +129,99 @@ def test_unsupported_structures_are_named(tmp_path):
     assert not hdf5io.looks_like_hdf5(str(p))
     with pytest.raises(IOError, match="not an HDF5 file"):
         hdf5io.Hdf5File(str(p))
+
+
+def _v2_header(messages, flags=0x04 | 0x20 | 0x10 | 0x01):
+    """A version-2 object header ("OHDR") as the specification lays it out: optional timestamps (bit 5), attribute phase
+    change values (bit 4), creation order per message (bit 2), 2-byte chunk size (bits 0-1 = 1); checksum left zero."""
+    body = b""
+    for k, (mtype, data) in enumerate(messages):
+        body += struct.pack("<BHB", mtype, len(data), 0) + (struct.pack("<H", k) if flags & 0x04 else b"") + data
+    body += bytes(5)                                                    # a gap the parser must not read as a message
+    head = b"OHDR" + struct.pack("<BB", 2, flags)
+    if flags & 0x20:
+        head += struct.pack("<IIII", 1, 2, 3, 4)
+    if flags & 0x10:
+        head += struct.pack("<HH", 8, 6)
+    head += struct.pack("<H", len(body))
+    return head + body + bytes(4)
+
+
+def test_new_style_dataset_headers_filters_attributes_and_vlen_strings(tmp_path):
+    """What libhdf5 >= 1.8 writes for a NetCDF-4 variable, assembled by hand: "OHDR" headers with timestamps and creation
+    order, dataspace v2, fill value v3, filter pipeline v2 (no names for predefined filters), attribute v3 -- one of them a
+    variable-length string kept in a global heap collection -- over the v1 B-tree chunk index of the fixture writer."""
+    import zlib
+    rng = np.random.default_rng(11)
+    T, Y, X = 50, 6, 8
+    q = rng.integers(-2000, 2000, (T, Y, X)).astype(np.int16)
+    chunks = (24, 3, 8)
+    path = str(tmp_path / "new_style.nc")
+    out = hdf5io._Out(path)
+    # chunks: shuffle + deflate, the last time chunk partial
+    entries = []
+    for idx in np.ndindex(*[-(-s // c) for s, c in zip(q.shape, chunks)]):
+        block = np.full(chunks, -32767, "<i2")
+        sl = tuple(slice(i * c, min(s, (i + 1) * c)) for i, c, s in zip(idx, chunks, q.shape))
+        block[tuple(slice(0, s.stop - s.start) for s in sl)] = q[sl]
+        raw = zlib.compress(np.frombuffer(block.tobytes(), np.uint8).reshape(-1, 2).T.tobytes(), 5)
+        entries.append((tuple(i * c for i, c in zip(idx, chunks)), len(raw), out.put(raw)))
+    btree = hdf5io._write_chunk_btree(out, entries, q.shape, chunks)
+    # a global heap collection holding the string of a variable-length attribute
+    text = b"2 metre temperature"
+    gcol_body = struct.pack("<HHIQ", 1, 1, 0, len(text)) + text + bytes(hdf5io._pad8(len(text)) - len(text)) + struct.pack("<HHIQ", 0, 0, 0, 0)
+    gcol = out.put(b"GCOL" + struct.pack("<B3xQ", 1, 16 + len(gcol_body)) + gcol_body)
+
+    def attr_v3(name, dt, space, data):
+        nm = name.encode() + b"\0"
+        return struct.pack("<BBHHHB", 3, 0, len(nm), len(dt), len(space), 0) + nm + dt + space + data
+
+    scalar = struct.pack("<BBBB", 2, 0, 0, 0)                           # dataspace v2, scalar
+    f64 = hdf5io._dt_message(np.dtype("<f8"))
+    vlen_str = struct.pack("<BBBBI", 0x19, 0x01, 0, 0, 16) + hdf5io._dt_message(np.dtype("S1"))
+    msgs = [
+        (0x01, struct.pack("<BBBB", 2, 3, 0, 1) + b"".join(struct.pack("<Q", s) for s in q.shape)),      # dataspace v2, simple
+        (0x03, hdf5io._dt_message(np.dtype("<i2"))),
+        (0x05, struct.pack("<BBI", 3, 0x20 | 0x09, 2) + np.int16(-32767).tobytes()),                       # fill value v3, defined
+        (0x08, struct.pack("<BBBQ", 3, 2, 4, btree) + b"".join(struct.pack("<I", c) for c in chunks) + struct.pack("<I", 2)),
+        (0x0B, struct.pack("<BB", 2, 2) + struct.pack("<HHHI", 2, 0, 1, 2) + struct.pack("<HHHI", 1, 0, 1, 5)),   # shuffle(2), deflate(5)
+        (0x0C, attr_v3("scale_factor", f64, scalar, struct.pack("<d", 0.01))),
+        (0x0C, attr_v3("add_offset", f64, scalar, struct.pack("<d", 273.15))),
+        (0x0C, attr_v3("_FillValue", hdf5io._dt_message(np.dtype("<i2")), scalar, np.int16(-32767).tobytes())),
+        (0x0C, attr_v3("long_name", vlen_str, scalar, struct.pack("<IQI", len(text), gcol, 1))),
+    ]
+    var_addr = out.put(_v2_header(msgs))
+    addrs = {"t2m": var_addr}
+    coords = {"time": np.arange(T, dtype="<i4"), "latitude": np.linspace(50, 49, Y), "longitude": np.linspace(10, 12, X)}
+    for name, vals in coords.items():
+        vals = np.ascontiguousarray(vals)
+        data = out.put(vals.tobytes())
+        m = [(0x01, struct.pack("<BBBB", 2, 1, 0, 1) + struct.pack("<Q", len(vals))), (0x03, hdf5io._dt_message(vals.dtype)),
+             (0x05, struct.pack("<BB", 3, 0x10 | 0x05)),                                                    # fill value v3, undefined
+             (0x08, struct.pack("<BBQQ", 3, 1, data, vals.nbytes))]
+        if name == "time":
+            units = b"hours since 2001-01-01 00:00:00\0"
+            m.append((0x0C, attr_v3("units", hdf5io._dt_message(np.dtype(f"S{len(units)}")), scalar, units)))
+        addrs[name] = out.put(_v2_header(m, flags=0x01))                                                    # plain flags on these
+    links = []
+    for k, (name, addr) in enumerate(sorted(addrs.items())):
+        nm = name.encode()
+        links.append((0x06, struct.pack("<BB", 1, 0x04 | 0x08 | 0x10) + struct.pack("<B", 0) + struct.pack("<Q", k) + struct.pack("<B", 1)
+                      + struct.pack("<B", len(nm)) + nm + struct.pack("<Q", addr)))
+    root = out.put(_v2_header([(0x02, struct.pack("<BBQ", 0, 0x01, 3) + struct.pack("<QQ", hdf5io.UNDEF, hdf5io.UNDEF))] + links))
+    eof = out.f.tell()
+    out.f.seek(0)
+    out.f.write(hdf5io.SIGNATURE + struct.pack("<BBBB", 3, 8, 8, 0) + struct.pack("<QQQQ", 0, hdf5io.UNDEF, eof, root) + bytes(4))
+    out.f.close()
+
+    f = hdf5io.Hdf5File(path)
+    assert f.names() == ["latitude", "longitude", "t2m", "time"]
+    a = f["t2m"]
+    assert a.shape == q.shape and a.chunks == chunks and a.dtype == np.dtype("<i2") and a.fill_value == -32767
+    assert [fid for fid, _ in a.filters] == [2, 1]
+    assert a.attrs["scale_factor"] == 0.01 and a.attrs["add_offset"] == 273.15 and a.attrs["_FillValue"] == -32767
+    assert a.attrs["long_name"] == "2 metre temperature"
+    assert np.array_equal(a.read(), q)
+    raster, time, lat, lon = hdf5io.open_raster(path, "t2m")
+    assert raster.packed and raster.fill == -32767.0 and len(time) == T and time[1] == pd.Timestamp("2001-01-01 01:00")
+    assert np.array_equal(np.asarray(raster), q.astype(np.float64) * 0.01 + 273.15)
