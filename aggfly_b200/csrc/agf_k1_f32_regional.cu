@@ -2,7 +2,6 @@
 // Rows are RCASE(kernel lanes, diagonal, lane kinds, NB, lanes per slot), tried in order, cheapest first.
 #define AGF_T float
 #include <algorithm>
-#include <cuda_fp16.h>
 #include <cmath>
 #include <cstdlib>
 
@@ -156,30 +155,6 @@ int launch_regional(const RegionalLaunch &a, int mode, RegionalChoice *choice) {
         q.bins_fast = ok ? 1 : 0;
         q.eq_mask = mask;
         q.top_edge = nextafterf(hi_last, -INFINITY);
-        // float16 compares: every edge (the lower thresholds and the last upper one) exact in half, every interior
-        // edge a float (no open gaps), and the last upper threshold covered by the equality screen too
-        bool half_ok = ok && S::NBL + 1 <= 16 && !(getenv("AGF_BINS_HALF") && atoi(getenv("AGF_BINS_HALF")) == 0);
-        unsigned low_h = low;
-        for (int k = 0; k <= S::NBL && half_ok; ++k) {
-            const float e = k < S::NBL ? kp.lanes[k].lo : hi_last;
-            const __half eh = __float2half_rn(e);
-            if (!(__half2float(eh) == e) || fabsf(e) > 60000.0f) half_ok = false;
-            if (k > 0 && k < S::NBL && kp.lanes[k].lo != kp.lanes[k - 1].hi) half_ok = false;
-            unsigned short hb;
-            memcpy(&hb, &eh, 2);
-            q.edge_h2[k] = (unsigned)hb | ((unsigned)hb << 16);
-        }
-        if (half_ok) {
-            unsigned b;
-            memcpy(&b, &hi_last, 4);
-            low_h &= ~b;
-            int tz = 0;
-            while (tz < 23 && ((low_h >> tz) & 1u)) ++tz;
-            if (tz < 16) half_ok = false;
-            else q.eq_mask = (1u << tz) - 1u;
-        }
-        q.bins_half = half_ok ? 1 : 0;
-        q.last_hi = hi_last;
     }
     if (plan->n_empty_regions > 0) {
         agf_regional_fill_empty<<<plan->n_regions, 256, 0, a.k.stream>>>(plan->d_region_slot_ptr, plan->n_regions, q.g_begin,
