@@ -59,7 +59,7 @@ def _host_source(values):
     everything else -- numpy arrays (any strides: memory maps, clipped views), pageable tensors -- goes
     through the pinned staging ring chunk by chunk, so no whole-raster host copy is ever made."""
     import torch
-    if getattr(values, "lazy_rows", False):
+    if getattr(values, "lazy_rows", False) or getattr(values, "is_packed_raster", False):
         # dataset.TimeConcat (several files along time): row slices are NumPy views / lazy windows of the parts, turned
         # into arrays by np.copyto inside the staging threads -- the whole raster is never materialised on the host
         return None, values
@@ -212,6 +212,7 @@ def _feed_ring(torch, runner, values, host, host_np, T: int, n_cells: int, tdtyp
     ev_first.record(copy)
     runner.begin_streamed(comp)
     launches = direct = 0
+    pk_dev, pk_placed, n_packed, h2d_saved = [None] * 3, [None] * 3, 0, 0     # device staging of packed pieces
     try:
         futs = {}
         ahead = len(staging.slots) if staging else 0
@@ -221,6 +222,14 @@ def _feed_ring(torch, runner, values, host, host_np, T: int, n_cells: int, tdtyp
             nonlocal n_staged
             _, a, b, _last = work[i]
             piece = host_np[a:b]
+            if getattr(piece, "is_packed_raster", False):
+                # CF-packed integers: a pinned piece is copied as stored and unpacked into the window on the device
+                st = piece.stored
+                sdt = np.dtype(str(st.dtype).replace("torch.", ""))
+                ts = _pinned_piece(torch, st, getattr(torch, sdt.name, None)) if sdt.str[1:] in _TILE_DTYPES else None
+                if ts is not None:
+                    futs[i] = ("packed", ts, piece, sdt)
+                    return
             t = _pinned_piece(torch, piece, tdtype)
             if t is not None:
                 futs[i] = ("direct", t)
@@ -235,21 +244,49 @@ def _feed_ring(torch, runner, values, host, host_np, T: int, n_cells: int, tdtyp
             slot = k % n_slots
             w0 = windows[k][0]
             sslot = None
+            packed_piece = None
             if staging:
                 got = futs.pop(i)
                 if got[0] == "direct":
                     src = got[1].view(b - a, n_cells)
+                    direct += 1
+                elif got[0] == "packed":
+                    src, packed_piece, sdt = got[1].reshape(-1), got[2], got[3]
                     direct += 1
                 else:
                     src, sslot = got[1].result().view(b - a, n_cells), got[2]
             else:
                 src = host[a:b]
             with torch.cuda.stream(copy):
-                if a == w0 and consumed[slot] is not None:
-                    copy.wait_event(consumed[slot])            # the slot's previous window has been scanned
-                ring[slot, a - w0:b - w0].copy_(src, non_blocking=True)
+                if packed_piece is not None:
+                    j = n_packed % len(pk_placed)
+                    if pk_dev[j] is None or pk_dev[j].dtype != src.dtype or pk_dev[j].numel() < src.numel():
+                        if pk_placed[j] is not None:
+                            pk_placed[j].synchronize()
+                        pk_dev[j] = torch.empty(max(src.numel(), max(1, int(cb // row_bytes)) * n_cells), dtype=src.dtype, device=dev)
+                    if pk_placed[j] is not None:
+                        copy.wait_event(pk_placed[j])          # the unpack kernel that last read this staging buffer
+                    pk_dev[j][: src.numel()].copy_(src, non_blocking=True)
+                else:
+                    if a == w0 and consumed[slot] is not None:
+                        copy.wait_event(consumed[slot])        # the slot's previous window has been scanned
+                    ring[slot, a - w0:b - w0].copy_(src, non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(copy)
+            if packed_piece is not None:
+                comp.wait_event(ev)                            # (comp runs behind the kernels of the slot's previous window)
+                _, Yp, Xp = packed_piece.shape
+                from . import _lib
+                _lib.check(_lib.lib().agf_tile_place_run(
+                    pk_dev[j].data_ptr(), _TILE_DTYPES[sdt.str[1:]], b - a, Yp, Xp, n_cells, Xp, 1, ring[slot].data_ptr(),
+                    _lib.F64 if tdtype == torch.float64 else _lib.F32, n_cells, Xp, a - w0, 0, 0, 1, float(packed_piece.scale),
+                    float(packed_piece.offset), int(packed_piece.fill is not None),
+                    float(packed_piece.fill if packed_piece.fill is not None else 0.0), slot_rows, comp.cuda_stream))
+                pe = torch.cuda.Event()
+                pe.record(comp)
+                pk_placed[j] = pe
+                n_packed += 1
+                h2d_saved += (b - a) * row_bytes - src.numel() * src.element_size()
             if staging:
                 if sslot is not None:
                     staging.events[sslot] = ev
@@ -267,9 +304,9 @@ def _feed_ring(torch, runner, values, host, host_np, T: int, n_cells: int, tdtyp
         if staging:
             staging.close()
     ring.record_stream(comp)
-    stats = dict(chunks=len(work), pinned=bool(pinned), h2d_bytes=T * row_bytes, k1_launches=launches,
+    stats = dict(chunks=len(work), pinned=bool(pinned), h2d_bytes=T * row_bytes - h2d_saved, k1_launches=launches,
                  copy_events=(ev_first, ev_last), ring=True, ring_slots=n_slots, ring_slot_rows=slot_rows,
-                 ring_bytes=int(ring.numel() * item), windows=len(windows), direct_chunks=direct)
+                 ring_bytes=int(ring.numel() * item), windows=len(windows), direct_chunks=direct, unpacked_chunks=n_packed)
     return res, ring, stats
 
 
@@ -283,7 +320,9 @@ def feed_and_run(runner, values, n_cells: int, stream=None, k1_events: Optional[
     if getattr(values, "is_chunked_raster", False):
         return feed_chunked(runner, values, n_cells, stream, k1_events, stats)
     if getattr(values, "is_packed_raster", False):
-        return feed_packed(runner, values, n_cells, stream, k1_events, stats)
+        over = int(np.prod(values.shape)) * values.dtype.itemsize > OPTIONS["device_raster_budget_bytes"]
+        if not (over and hasattr(runner, "window_cuts") and runner.window_cuts() is not None):
+            return feed_packed(runner, values, n_cells, stream, k1_events, stats)
     host, host_np = _host_source(values)
     pinned = host is not None
     T = int(host.shape[0] if pinned else host_np.shape[0])

@@ -319,7 +319,7 @@ def resident_workload(torch, name, dev, seed, steps, warmup, shared=None):
     return out
 
 
-def run_c4(torch, dist, af, wl, w, host, years, world, rank, dev, one_year_df):
+def run_c4(torch, dist, af, wl, w, host, years, world, rank, dev, one_year_df, packed=None):
     """``years`` synthetic years as ONE Dataset (the rank's pinned year buffer cycled along a noleap hourly axis, so the
     host holds one year while the record is ``years`` long), aggregated by ONE call: ``aggregate_dataset`` at N = 1,
     ``aggregate_dataset_sharded`` (years split over the ranks, one panel all-gather) at N > 1.  The device holds a ring of
@@ -328,7 +328,7 @@ def run_c4(torch, dist, af, wl, w, host, years, world, rank, dev, one_year_df):
     from aggfly_b200.dataset import Dataset, TimeConcat
     T = years * wl.n_time
     t_long = timeaxis.CalendarIndex.range("noleap", 2001, T, "h")
-    year_np = host.numpy()
+    year_np = host.numpy() if packed is None else packed          # packed: a dataset.PackedRaster of the year (int16, pinned)
     ds_long = Dataset.from_arrays(TimeConcat([year_np] * years), t_long, wl.grid.latitude, wl.grid.longitude,
                                   lon_is_360=wl.grid.lon_is_360, name=wl.name + "_c4")
     torch.cuda.synchronize()
@@ -366,11 +366,13 @@ def run_c4(torch, dist, af, wl, w, host, years, world, rank, dev, one_year_df):
         ok = bool(np.array_equal(np.asarray(mine[rid]).reshape(nreg, -1)[:, 0], np.asarray(one_year_df[rid]).reshape(nreg, -1)[:, 0])
                   and np.allclose(got, ref, rtol=1e-11, atol=0, equal_nan=True))
         n_checked = int(my_years)
-    return {"workload": "c4: %d synthetic years of %s as one record" % (years, wl.name), "years": years,
+    return {"workload": "c4: %d synthetic years of %s as one record%s" % (years, wl.name, "" if packed is None else " (CF-packed int16)"),
+            "years": years,
             "seconds": dt, "years_per_s": years / dt, "value": years * wl.cell_steps / dt, "unit": UNIT,
             "api": "aggregate_dataset_sharded (years over ranks)" if world > 1 else "aggregate_dataset",
             "h2d_bytes_per_rank": st.get("h2d_bytes"), "h2d_gbs_per_rank": (st.get("h2d_bytes", 0) / (h2d_ms * 1e-3) / 1e9) if h2d_ms else None,
-            "ring": {k: st.get(k) for k in ("ring", "ring_slots", "ring_slot_rows", "ring_bytes", "windows", "chunks", "direct_chunks")},
+            "ring": {k: st.get(k) for k in ("ring", "ring_slots", "ring_slot_rows", "ring_bytes", "windows", "chunks", "direct_chunks",
+                                            "unpacked_chunks")},
             "record_bytes": int(T) * wl.n_cells * 4, "device_peak_bytes": int(torch.cuda.max_memory_allocated(dev)),
             "host_year_buffers": 1, "panel_rows": int(len(df)),
             "equals_one_year_call": {"ok": bool(ok), "years_checked": n_checked, "rtol": 1e-11}}
@@ -420,7 +422,7 @@ def run_packed(torch, dist, af, wl, w, host, q_dev, pack, world, dev, steps, R, 
             "feed": {"chunks": st.get("chunks"), "h2d_ms": h2d_ms,
                      "h2d_gbs": (st.get("h2d_bytes", 0) / (h2d_ms * 1e-3) / 1e9) if h2d_ms else None,
                      "unpack_launches": st.get("place_launches")},
-            "device_raster_equals_numpy_decode": bool(same), "panel_rows": int(len(df))}
+            "device_raster_equals_numpy_decode": bool(same), "panel_rows": int(len(df))}, df, packed
 
 
 # ------------------------------------------------------------------------------------------------
@@ -536,7 +538,7 @@ def main_ours(args, rank, world, local_rank):
         e2e_note = (f"skipped: {world} pinned host rasters need {need_gb:.0f} GB, "
                     f"{host_mem_available_gb():.0f} GB of host memory available")
         args.no_e2e = True
-    c4 = e2e_packed = None
+    c4 = c4_packed = e2e_packed = None
     if not args.no_e2e:
         host = torch.empty(raster.shape, dtype=raster.dtype, pin_memory=True)
         host.copy_(raster)
@@ -605,11 +607,21 @@ def main_ours(args, rank, world, local_rank):
             torch.cuda.empty_cache()
         # ---- the same year, host-fed as packed int16 and unpacked on the device -------------------------------------
         if q_dev is not None:
+            pdf = praster = None
             try:
-                e2e_packed = run_packed(torch, dist, af, wl, w, host, q_dev, pack, world, dev, e2e_steps, R, G, NC)
+                e2e_packed, pdf, praster = run_packed(torch, dist, af, wl, w, host, q_dev, pack, world, dev, e2e_steps, R, G, NC)
             except Exception as exc:
                 e2e_packed = {"error": f"{type(exc).__name__}: {exc}"}
             del q_dev
+            # ... and the multi-year record from the packed year: half the bytes per rank through the same ring
+            if praster is not None and c4 is not None and "error" not in c4:
+                _stream.release_device_rasters()
+                torch.cuda.empty_cache()
+                try:
+                    c4_packed = run_c4(torch, dist, af, wl, w, host, args.c4_years, world, rank, dev, pdf, packed=praster)
+                except Exception as exc:
+                    c4_packed = {"error": f"{type(exc).__name__}: {exc}"}
+                _stream.release_device_rasters()
         raster_for_cpu = host
     else:
         raster_for_cpu = raster
@@ -638,7 +650,7 @@ def main_ours(args, rank, world, local_rank):
                        "parallelism": f"time-sharded x{world} (one year per GPU), replicated CSR, panel all-gather",
                        "l2_policy": f"inputs ({in_bytes / 1e9:.2f} GB per step) are larger than the 126 MB L2; no flush needed"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_note": e2e_note,
-            "e2e_resident": e2e_resident, "e2e_packed": e2e_packed, "c4": c4, "workloads": workloads,
+            "e2e_resident": e2e_resident, "e2e_packed": e2e_packed, "c4": c4, "c4_packed": c4_packed, "workloads": workloads,
             "gpu_launches": launches * args.steps,
             "gpu_launches_per_step": launches, "clocks": clocks,
         }))

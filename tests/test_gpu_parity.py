@@ -478,6 +478,59 @@ def test_packed_host_raster_is_unpacked_on_the_device(name, stored, dtype, feed)
     _exact(got[vals].values, want[vals].values)
 
 
+@pytest.mark.parametrize("source", ["one_packed_raster", "concat_of_packed_years", "pageable_packed"])
+def test_packed_record_longer_than_the_device_goes_through_the_ring(source):
+    """Packed integers + a record over the device budget: pinned pieces are copied as stored and unpacked straight into the
+    ring windows; the panel is bit for bit that of the decoded raster held on the device."""
+    import torch
+    from aggfly_b200 import stream
+    from aggfly_b200.dataset import PackedRaster, TimeConcat
+    arr, t, lat, lon = _raster("float32", False, T=24 * 30 + 7, seed=29)
+    scale, offset = 0.004, 11.5
+    q = np.clip(np.rint((arr.astype(np.float64) - offset) / scale), -32000, 32000).astype(np.int16)
+    q[40:44, 0, 1] = -32767
+    decoded = (q.astype(np.float64) * scale + offset).astype(np.float32)
+    decoded[q == -32767] = np.nan
+    rng = np.random.default_rng(2)
+    wdf, shp = _weights_case(lat, lon, rng)
+    name = "c3_bins_and_poly"
+
+    def run(values):
+        ds = af.Dataset.from_arrays(values, t, lat, lon, True)
+        w = af.weights_from_objects(ds, af.GeoRegions(shp, "geoid"), zero_weight="nan")
+        w.weights = wdf
+        return af.aggregate_dataset(weights=w, dataset=ds, aggregator_dict=SPECS[name])
+
+    engine.OPTIONS["target_stripes"] = 9
+    old = dict(stream.OPTIONS)
+    row = decoded[0].nbytes
+    try:
+        want = run(torch.from_numpy(decoded).cuda())
+        stream.OPTIONS.update(chunk_bytes=11 * row, staging_chunk_bytes=11 * row, staging_slots=3, staging_threads=2,
+                              device_raster_budget_bytes=1, ring_slot_bytes=120 * row, ring_slots=2)
+        if source == "one_packed_raster":
+            values = PackedRaster(torch.from_numpy(q).pin_memory(), scale, offset, -32767.0)
+        elif source == "pageable_packed":
+            values = PackedRaster(q, scale, offset, -32767.0)
+        else:
+            cuts = [0, 24 * 11, 24 * 19 + 5, q.shape[0]]
+            keep = [torch.from_numpy(q[a:b]).pin_memory() for a, b in zip(cuts[:-1], cuts[1:])]
+            values = TimeConcat([PackedRaster(k, scale, offset, -32767.0) for k in keep])
+        got = run(values)
+        st = stream.LAST_STATS
+        assert st.get("ring") and st["windows"] >= 3
+        if source == "pageable_packed":
+            assert st["unpacked_chunks"] == 0                          # decoded by the staging threads on the host
+        else:
+            assert st["unpacked_chunks"] == st["chunks"] and st["h2d_bytes"] == q.nbytes
+    finally:
+        stream.OPTIONS.update(old)
+        stream.release_device_rasters()
+    vals = [c for c in want.columns if c not in ("geoid", "time")]
+    assert len(got) == len(want) > 0
+    _exact(got[vals].values, want[vals].values)
+
+
 # ---- daily rasters: single-row inner groups collapse to one pass (spec.Planner._collapsed_lane) ----------
 DAILY_SPECS = {
     "gdd_month": dict(gdd=[("aggregate", {"calc": "dd", "groupby": "date", "ddargs": [10, 30, 0]}),

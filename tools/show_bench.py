@@ -15,6 +15,7 @@ for k in ("e2e", "e2e_resident", "e2e_packed"):
     else:
         print(k, e)
 print("c4", d.get("c4"))
+print("c4_packed", d.get("c4_packed"))
 for w in d.get("workloads") or []:
     if "error" in w:
         print("  ", w)
