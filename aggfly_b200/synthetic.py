@@ -98,9 +98,11 @@ def tessellation(gd: GridDef, regionid: str = "geoid") -> GeoRegions:
 
 
 def synth_raster(gd: GridDef, n_time: int, seed: int, device, hourly: bool = True, ocean_frac: float = 0.0,
-                 dtype="float32", chunk_days: int = 8):
+                 dtype="float32", chunk_days: int = 8, noise_sigma: float = 3.0):
     """values[T, lat, lon] on ``device`` (torch tensor):
-    27 cos(lat) - 6 + 9 sign(lat) sin(2 pi (doy - 110) / 365) + 4 sin(2 pi (hour - 9) / 24) + 3 N(0, 1) [deg C]."""
+    27 cos(lat) - 6 + 9 sign(lat) sin(2 pi (doy - 110) / 365) + 4 sin(2 pi (hour - 9) / 24) + 3 N(0, 1) [deg C].
+    ``noise_sigma`` (default 3: every hour and cell independent -- much rougher than a reanalysis field) is only varied
+    by the sensitivity runs of tools/regional_bench.py."""
     import torch
     tdt = torch.float32 if dtype == "float32" else torch.float64
     ny, nx = len(gd.latitude), len(gd.longitude)
@@ -121,7 +123,7 @@ def synth_raster(gd: GridDef, n_time: int, seed: int, device, hourly: bool = Tru
         if hourly:
             v = v + 4.0 * torch.sin(2 * np.pi * ((t % 24) - 9.0) / 24.0)[:, None, None]
         noise = torch.randn((t1 - t0, ny, nx), generator=gen, device=device, dtype=torch.float32)
-        out[t0:t1] = (v + 3.0 * noise).to(tdt)
+        out[t0:t1] = (v + float(noise_sigma) * noise).to(tdt)
     if ocean_frac > 0:
         g2 = torch.Generator(device=device)
         g2.manual_seed(int(seed) + 7919)
@@ -157,8 +159,9 @@ class Workload:
         """cell-hours (cell-days for daily inputs) one pass aggregates"""
         return self.n_time * self.n_cells
 
-    def raster(self, device, seed: int):
-        return synth_raster(self.grid, self.n_time, seed, device, hourly=self.hourly, ocean_frac=self.ocean_frac)
+    def raster(self, device, seed: int, noise_sigma: float = 3.0):
+        return synth_raster(self.grid, self.n_time, seed, device, hourly=self.hourly, ocean_frac=self.ocean_frac,
+                            noise_sigma=noise_sigma)
 
     def dataset(self, values) -> Dataset:
         return Dataset.from_arrays(values, self.time, self.grid.latitude, self.grid.longitude,

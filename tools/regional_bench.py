@@ -17,13 +17,14 @@ def main():
     ap.add_argument("--workload", default="c3b_global_daily")
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--no-two", action="store_true")
+    ap.add_argument("--noise", type=float, default=3.0, help="sigma of the field's iid hourly noise (bench default 3.0)")
     args = ap.parse_args()
     import torch
     from aggfly_b200 import engine, synthetic as syn
     from aggfly_b200.aggregate import _device_csr, _plan
     dev = torch.device("cuda", 0)
     wl = syn.make_workload(args.workload)
-    raster = wl.raster(dev, seed=1218)
+    raster = wl.raster(dev, seed=1218, noise_sigma=args.noise)
     ds = wl.dataset(raster)
     w = wl.weights(ds)
     csr = _device_csr(w, ds)
@@ -58,7 +59,7 @@ def main():
         print(json.dumps({"path": "regional", "supported": False}))
         return
     ms = timed(lambda: rr.run(flat))
-    out = {"path": "one kernel (+ merge)", "ms": ms, "workspace_GB": rr.info.workspace_bytes / 1e9,
+    out = {"path": "one kernel (+ merge)", "noise_sigma": args.noise, "ms": ms, "workspace_GB": rr.info.workspace_bytes / 1e9,
            "lps": int(rr.info.lanes_per_slot), "ctas_per_sm": int(rr.info.ctas_per_sm), "smem": int(rr.info.smem_bytes),
            "active_tiles": int(rr.plan.info.n_active_tiles), "tiles": int(rr.plan.info.n_tiles), "slots": int(rr.plan.info.n_slots),
            "partial_rows": int(rr.plan.info.n_partial_rows), "max_slots_per_tile": int(rr.plan.info.max_slots_per_tile),
