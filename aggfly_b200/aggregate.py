@@ -218,6 +218,11 @@ def _temporal_regional(dataset: Dataset, aggregator_dict, csr):
     try:
         if not runner.supported:
             return None
+        # scratch rows of the regions that straddle tiles + the panel must fit next to the raster (a very long daily
+        # record): otherwise the two-kernel path decides (it streams X per call and fails loudly if that does not fit either)
+        need = int(runner.info.workspace_bytes) + csr.host.n_regions * len(stage.labels) * len(names) * 8
+        if need > 0.9 * torch.cuda.mem_get_info()[0]:
+            return None
         try:
             if _is_device_tensor(dataset.values):
                 raster = _DeviceRaster(dataset)
@@ -452,9 +457,11 @@ def _panel_columns(panel, names: List[str], labels, region_ids: np.ndarray, weig
             idx = cand[keep[cand]]
             index = (torch.cumsum(keep.to(torch.int64), 0) - 1)[idx].cpu().numpy()     # the row's number in the un-joined frame
         cols = _to_host(flat.index_select(0, idx).t().contiguous())
-        idx_h = _to_host(idx)
-        reg_col, time_col = region_col.take(shp_row_of_region[idx_h // G]), tvals[idx_h % G]
-        index = pd.RangeIndex(len(idx_h)) if index is None else pd.Index(index)
+        # region / period of every kept row, split on the device (two int32 columns instead of an int64 one + host div / mod)
+        r_h = _to_host(torch.div(idx, G, rounding_mode="floor").to(torch.int32))
+        g_h = _to_host((idx % G).to(torch.int32))
+        reg_col, time_col = region_col.take(shp_row_of_region[r_h]), tvals[g_h]
+        index = pd.RangeIndex(len(r_h)) if index is None else pd.Index(index)
     data = {rid: reg_col, "time": time_col}
     for c, nm in enumerate(names):
         data[nm] = cols[c]
