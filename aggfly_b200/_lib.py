@@ -10,7 +10,9 @@ import os
 from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libaggfly_b200.so")
+# AGF_B200_LIB: a developer switch -- tools/build_variant.sh builds the same sources with extra -D flags into
+# csrc/variants/ so that one GPU visit can time several builds side by side.
+LIB_PATH = os.environ.get("AGF_B200_LIB") or os.path.join(_HERE, "csrc", "libaggfly_b200.so")
 
 ABI_VERSION = 5                      # AGF_ABI_VERSION of include/aggfly_b200.h
 MAX_LANES, MAX_SLOTS, MAX_COLS = 32, 32, 64

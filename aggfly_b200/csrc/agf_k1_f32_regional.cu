@@ -4,6 +4,9 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
+
+#include <cuda_fp16.h>
 
 #include "agf_k1_inst.cuh"
 #include "agf_regional.cuh"
@@ -151,10 +154,80 @@ int launch_regional(const RegionalLaunch &a, int mode, RegionalChoice *choice) {
             mask = (1u << tz) - 1u;
             if (tz < 16) ok = false;
         }
-        if (getenv("AGF_BINS_BY_EDGES") && atoi(getenv("AGF_BINS_BY_EDGES")) == 0) ok = false;
-        q.bins_fast = ok ? 1 : 0;
+        int want = 2;
+        if (getenv("AGF_BINS_BY_EDGES")) want = atoi(getenv("AGF_BINS_BY_EDGES"));
+        q.bins_fast = (ok && want > 0) ? 1 : 0;
         q.eq_mask = mask;
-        q.top_edge = nextafterf(hi_last, -INFINITY);
+        for (int j = 0; j < S::NBL; ++j) q.edge_f[j] = kp.lanes[j].lo;
+        q.edge_f[S::NBL] = nextafterf(hi_last, -INFINITY);
+        // Packed form: every edge representable in the packed type (interior edges: hi_j == lo_j+1), none a NaN; the
+        // screen then covers the first lower and the last upper threshold too.
+#if !AGF_RG_F32_EDGES
+        q.bins_fast = 0;
+#endif
+        if (ok && want >= 2) {
+            bool pk_ok = true;
+            unsigned low_all = 0xffffffffu;
+            float e[17];
+            for (int j = 0; j < S::NBL; ++j) e[j] = kp.lanes[j].lo;
+            e[S::NBL] = hi_last;
+            for (int j = 0; j + 1 < S::NBL; ++j)
+                if (kp.lanes[j + 1].lo != kp.lanes[j].hi) pk_ok = false;
+            unsigned epk[17], emul[17];
+            for (int k = 0; k <= S::NBL && pk_ok; ++k) {
+                unsigned b;
+                memcpy(&b, &e[k], 4);
+                if (e[k] != e[k]) pk_ok = false;
+                low_all &= ~b;
+                epk[k] = emul[k] = 0u;
+#if AGF_RG_PACK == 3
+                if (std::isinf(e[k]) || e[k] == 0.0f) continue;       // never in range / counted by signs
+                const __half h = __float2half_rn(e[k]);
+                if (__half2float(h) != e[k]) { pk_ok = false; break; }
+                unsigned short hb;
+                memcpy(&hb, &h, 2);
+                if (e[k] > 0.0f) hb -= 1;                            // v >= e  <=>  trunc(v) > the float16 below e
+                __half hp;
+                memcpy(&hp, &hb, 2);
+                const double ep = (double)__half2float(hp);
+                if (ep == 0.0) { pk_ok = false; break; }
+                const int kexp = std::ilogb(ep);
+                const double big = std::ldexp(1.0, std::min(15, 14 - kexp));
+                // gap between e' and the next float16 above it (towards zero for a negative e')
+                unsigned short hn = (ep > 0.0) ? (unsigned short)(hb + 1) : (unsigned short)(hb - 1);
+                __half hnh;
+                memcpy(&hnh, &hn, 2);
+                const double gap = (double)__half2float(hnh) - ep;
+                if (!(gap * big >= 1.0) || !(std::fabs(ep) * big <= 65504.0)) { pk_ok = false; break; }
+                const __half hm = __float2half_rn((float)big), hc = __float2half_rn((float)(-ep * big));
+                if ((double)__half2float(hm) != big || (double)__half2float(hc) != -ep * big) { pk_ok = false; break; }
+                unsigned short mb, cb;
+                memcpy(&mb, &hm, 2);
+                memcpy(&cb, &hc, 2);
+                emul[k] = (unsigned)mb | ((unsigned)mb << 16);
+                epk[k] = (unsigned)cb | ((unsigned)cb << 16);
+#else
+                if ((b & 0xffffu) != 0u) { pk_ok = false; break; }
+                unsigned h = b >> 16;
+                if (e[k] > 0.0f) h -= 1u;   // v >= e  <=>  trunc(v) > the bfloat16 below e
+                epk[k] = h | (h << 16);
+#endif
+            }
+            if (pk_ok) {
+                int tz = 0;
+                while (tz < 23 && ((low_all >> tz) & 1u)) ++tz;
+                if (tz < 13) pk_ok = false;   // the screen would send most periods to the slow path
+                if (pk_ok) {
+                    q.eq_mask = (1u << tz) - 1u;
+                    for (int k = 0; k <= S::NBL; ++k) {
+                        q.edge_f[k] = e[k];
+                        q.edge_pk[k] = epk[k];
+                        q.edge_mul[k] = emul[k];
+                    }
+                    q.bins_fast = 2;
+                }
+            }
+        }
     }
     if (plan->n_empty_regions > 0) {
         agf_regional_fill_empty<<<plan->n_regions, 256, 0, a.k.stream>>>(plan->d_region_slot_ptr, plan->n_regions, q.g_begin,
@@ -202,7 +275,13 @@ int launch_regional(const RegionalLaunch &a, int mode, RegionalChoice *choice) {
         const int64_t ychunks = (n_groups + per_block - 1) / per_block;
         if (ychunks > 65535) return agf_fail(AGF_E_UNSUPPORTED, "too many periods in one launch");
         dim3 mgrid((unsigned)plan->n_multi, (unsigned)ychunks);
-        agf_regional_merge<LPS><<<mgrid, 256, 0, a.k.stream>>>(m);
+        cudaStream_t ms = a.k.stream;
+        if (a.merge_stream != nullptr) {
+            CU(cudaEventRecord(a.k_done, a.k.stream));
+            CU(cudaStreamWaitEvent(a.merge_stream, a.k_done, 0));
+            ms = a.merge_stream;
+        }
+        agf_regional_merge<LPS><<<mgrid, 256, 0, ms>>>(m);
         CU(cudaGetLastError());
     }
     return 0;

@@ -112,6 +112,48 @@ def test_one_kernel_path_matches_two_kernel_path_and_oracle(name, shape):
     _same_frame(one.reset_index(drop=True), want.reset_index(drop=True), 1e-11)
 
 
+def _adversarial_bits(rng, shape):
+    """float32 bit patterns within +-70000 ulps of the 14 edges of BINS13 (0.0 is one of them: +-0, denormals of both
+    signs): every value sits next to a threshold, on either side of the bfloat16 grid points around it."""
+    edges = np.array([b[0] for b in BINS13] + [BINS13[-1][1]], dtype=np.float32)
+    e = edges[rng.integers(0, len(edges), shape)]
+    k = rng.integers(-70000, 70001, shape)
+    k[rng.random(shape) < 0.3] //= 4096                      # a third of them within a few ulps
+    bits = e.view(np.uint32).astype(np.int64)
+    mag, sign = bits & 0x7FFFFFFF, bits >> 31
+    zero = mag == 0
+    sign = np.where(zero, rng.integers(0, 2, shape), sign)   # around 0.0 the offset is a magnitude, the sign is drawn
+    mag = np.where(zero, np.abs(k), np.maximum(mag + k, 0))
+    return ((sign << 31) | mag).astype(np.uint32).view(np.float32)
+
+
+@pytest.mark.parametrize("mode", ["near_edges", "with_equal_values", "nan_payloads"])
+def test_packed_edge_counting_is_exact_next_to_the_thresholds(mode):
+    """The bfloat16-packed edge compares of the daily-bins kernel (rg_count_above_packed) against the two-kernel path and
+    the oracle on values chosen to break a truncating compare: a miscounted value moves a bin's average by >= 1e-3."""
+    rng = np.random.default_rng(77)
+    n_lat, n_lon, days = 24, 64, 6
+    arr, t, lat, lon, ds, w = _case(n_lat, n_lon, days=days, seed=5, ocean=0.0)
+    vals = _adversarial_bits(rng, arr.shape)
+    low = vals.view(np.uint32) & 0xFFFF
+    keep = np.zeros(vals.shape, dtype=bool)
+    if mode == "with_equal_values":
+        keep[:, :8, :] = True                                 # values equal to an edge (slow path) in the first tile row only
+    vals = np.where((low == 0) & ~keep, np.float32(7.3), vals)   # elsewhere nothing the equality screen would catch
+    if mode == "nan_payloads":
+        for (y, x, pat) in [(3, 5, 0x7F800001), (3, 6, 0xFF800001), (9, 40, 0x7FFFFFFF), (10, 41, 0x7FC00000), (11, 1, 0xFFC00000)]:
+            vals[:, y, x] = np.array([pat], dtype=np.uint32).view(np.float32)[0]     # all-NaN cells (fast path)
+        vals[24:30, 15, 20] = np.nan                                                  # a partly-NaN period (slow path)
+    ds = af.Dataset.from_arrays(vals, t, lat, lon, lon_is_360=True)
+    spec = SPECS["daily_bins_mean"]
+    one, two = _frames(ds, w, spec)
+    _same_frame(one, two, 1e-12)
+    rid = w.georegions.regionid
+    want = orc.aggregate_dataset(orc.OWeights(w.weights, w.grid.cell_id, w.georegions.shp, rid, w.zero_weight),
+                                 orc.ODataset(vals, t, lat, lon, True), aggregator_dict=spec)
+    _same_frame(one.reset_index(drop=True), want.reset_index(drop=True), 1e-11)
+
+
 @pytest.mark.parametrize("zero_weight", ["nan", "area"])
 def test_host_fed_raster_and_zero_weight_rows(zero_weight):
     """The streamed feed (pageable NumPy raster -> staging ring -> launches per period range) and the row-drop rules."""
