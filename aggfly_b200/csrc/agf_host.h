@@ -103,10 +103,6 @@ struct RegionalLaunch {
     double *d_panel, *d_den;
     int64_t G;               // periods of the whole panel (row pitch)
     int out_ncols;
-    // merge_stream != nullptr: agf_regional_merge goes to that stream behind k_done (recorded on k.stream after the scan
-    // kernel), so that the scan of the next period block overlaps it (agf_temporal_regional_run)
-    cudaStream_t merge_stream;
-    cudaEvent_t k_done;
 };
 
 struct RegionalChoice {

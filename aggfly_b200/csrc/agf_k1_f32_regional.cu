@@ -56,7 +56,9 @@ int launch_regional(const RegionalLaunch &a, int mode, RegionalChoice *choice) {
     constexpr int STAGES = (MINB != 3 && 2 * TILE + rest + 1024 * 16 <= budget) ? 2 : 1;
     constexpr int fixed = STAGES * TILE + rest;
     constexpr int sm_entries = (budget - fixed) / 16 < 4096 ? (budget - fixed) / 16 : 4096;
-    constexpr int smem = fixed + sm_entries * 16;
+    constexpr int smem0 = fixed + sm_entries * 16;
+    static int smem_pad = getenv("AGF_RG_SMEM_PAD") ? atoi(getenv("AGF_RG_SMEM_PAD")) : 0;   // timing experiments: fewer CTAs per SM
+    const int smem = smem0 + smem_pad;
     static_assert(sm_entries >= 512, "no room for the tile tables");
     auto kern = agf_k1_regional<T, NL, DIAG, KINDS, NB, LPS, R_GL, TT, STAGES, MINB>;
 
@@ -181,6 +183,7 @@ int launch_regional(const RegionalLaunch &a, int mode, RegionalChoice *choice) {
                 low_all &= ~b;
                 epk[k] = emul[k] = 0u;
 #if AGF_RG_PACK == 3
+                if (e[k] == 0.0f) epk[k] = 0xffffffffu;               // counted by signs
                 if (std::isinf(e[k]) || e[k] == 0.0f) continue;       // never in range / counted by signs
                 const __half h = __float2half_rn(e[k]);
                 if (__half2float(h) != e[k]) { pk_ok = false; break; }
@@ -211,6 +214,7 @@ int launch_regional(const RegionalLaunch &a, int mode, RegionalChoice *choice) {
                 unsigned h = b >> 16;
                 if (e[k] > 0.0f) h -= 1u;   // v >= e  <=>  trunc(v) > the bfloat16 below e
                 epk[k] = h | (h << 16);
+                if (e[k] == 0.0f) epk[k] = 0xffffffffu;   // the edge 0.0 is counted by signs
 #endif
             }
             if (pk_ok) {
@@ -275,13 +279,7 @@ int launch_regional(const RegionalLaunch &a, int mode, RegionalChoice *choice) {
         const int64_t ychunks = (n_groups + per_block - 1) / per_block;
         if (ychunks > 65535) return agf_fail(AGF_E_UNSUPPORTED, "too many periods in one launch");
         dim3 mgrid((unsigned)plan->n_multi, (unsigned)ychunks);
-        cudaStream_t ms = a.k.stream;
-        if (a.merge_stream != nullptr) {
-            CU(cudaEventRecord(a.k_done, a.k.stream));
-            CU(cudaStreamWaitEvent(a.merge_stream, a.k_done, 0));
-            ms = a.merge_stream;
-        }
-        agf_regional_merge<LPS><<<mgrid, 256, 0, ms>>>(m);
+        agf_regional_merge<LPS><<<mgrid, 256, 0, a.k.stream>>>(m);
         CU(cudaGetLastError());
     }
     return 0;

@@ -5,9 +5,9 @@
 // (weights-frame order); the tables below keep that order inside every (tile, region) slot, so the in-kernel sums add
 // the same terms in the same order as np.add.at for every region that lies inside one tile.
 #include <algorithm>
+#include <mutex>
 #include <cstdlib>
 #include <cstring>
-#include <mutex>
 #include <vector>
 
 #include <cuda.h>
@@ -558,55 +558,7 @@ extern "C" int agf_temporal_regional_run(const agf_program_t *p, const agf_rplan
     a.G = panel_groups;
     a.out_ncols = out_ncols;
     int krc = 0;
-    // Period blocks: the merge of block b (memory-bound: partial rows in, panel rows out) runs on a side stream while the
-    // scan kernel of block b + 1 (issue-bound) is on the device; the scans alternate between two streams so that one
-    // block's last CTAs overlap the next block's first.  Everything joins the caller's stream again before returning.
-    const int64_t n_groups = group_end - group_begin;
-    int blocks = 4;
-    if (const char *e = getenv("AGF_RG_BLOCKS")) blocks = atoi(e);
-    blocks = (int)std::min<int64_t>(blocks, n_groups / 64);
-    if (blocks <= 1 || plan->n_multi == 0) {
-        if (agf_k1_f32_regional(a, 0, nullptr, &krc))
-            return agf_fail(AGF_E_UNSUPPORTED, "no regional instantiation for this program");
-        return krc;
-    }
-    static std::mutex mu;
-    std::lock_guard<std::mutex> lock(mu);
-    constexpr int MAXB = 16;
-    static int fork_dev = -1;
-    static cudaStream_t s_scan[2], s_merge;
-    static cudaEvent_t ev_fork, ev_k[MAXB], ev_join[3];
-    int dev = -1;
-    CU(cudaGetDevice(&dev));
-    if (fork_dev != dev) {   // one process drives one device (streams of an earlier device are left to the driver)
-        int lo_prio = 0, hi_prio = 0;
-        CU(cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio));
-        for (int i = 0; i < 2; ++i) CU(cudaStreamCreateWithPriority(&s_scan[i], cudaStreamNonBlocking, lo_prio));
-        CU(cudaStreamCreateWithPriority(&s_merge, cudaStreamNonBlocking, hi_prio));
-        CU(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
-        for (int i = 0; i < MAXB; ++i) CU(cudaEventCreateWithFlags(&ev_k[i], cudaEventDisableTiming));
-        for (int i = 0; i < 3; ++i) CU(cudaEventCreateWithFlags(&ev_join[i], cudaEventDisableTiming));
-        fork_dev = dev;
-    }
-    blocks = std::min(blocks, MAXB);
-    cudaStream_t caller = (cudaStream_t)stream;
-    CU(cudaEventRecord(ev_fork, caller));
-    CU(cudaStreamWaitEvent(s_scan[0], ev_fork, 0));
-    CU(cudaStreamWaitEvent(s_scan[1], ev_fork, 0));
-    CU(cudaStreamWaitEvent(s_merge, ev_fork, 0));
-    for (int b = 0; b < blocks && krc == 0; ++b) {
-        a.g_begin = group_begin + n_groups * b / blocks;
-        a.g_end = group_begin + n_groups * (b + 1) / blocks;
-        a.k.stream = s_scan[b & 1];
-        a.merge_stream = s_merge;
-        a.k_done = ev_k[b];
-        if (agf_k1_f32_regional(a, 0, nullptr, &krc)) krc = agf_fail(AGF_E_UNSUPPORTED, "no regional instantiation for this program");
-    }
-    // join even after an error: the caller's stream must not run ahead of work already queued
-    cudaStream_t side[3] = {s_scan[0], s_scan[1], s_merge};
-    for (int i = 0; i < 3; ++i) {
-        CU(cudaEventRecord(ev_join[i], side[i]));
-        CU(cudaStreamWaitEvent(caller, ev_join[i], 0));
-    }
+    if (agf_k1_f32_regional(a, 0, nullptr, &krc))
+        return agf_fail(AGF_E_UNSUPPORTED, "no regional instantiation for this program");
     return krc;
 }
