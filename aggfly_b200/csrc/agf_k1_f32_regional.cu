@@ -6,7 +6,6 @@
 #include <cstdlib>
 #include <cstring>
 
-#include <cuda_fp16.h>
 
 #include "agf_k1_inst.cuh"
 #include "agf_regional.cuh"
@@ -175,47 +174,18 @@ int launch_regional(const RegionalLaunch &a, int mode, RegionalChoice *choice) {
             e[S::NBL] = hi_last;
             for (int j = 0; j + 1 < S::NBL; ++j)
                 if (kp.lanes[j + 1].lo != kp.lanes[j].hi) pk_ok = false;
-            unsigned epk[17], emul[17];
+            unsigned epk[17];
             for (int k = 0; k <= S::NBL && pk_ok; ++k) {
                 unsigned b;
                 memcpy(&b, &e[k], 4);
                 if (e[k] != e[k]) pk_ok = false;
                 low_all &= ~b;
-                epk[k] = emul[k] = 0u;
-#if AGF_RG_PACK == 3
-                if (e[k] == 0.0f) epk[k] = 0xffffffffu;               // counted by signs
-                if (std::isinf(e[k]) || e[k] == 0.0f) continue;       // never in range / counted by signs
-                const __half h = __float2half_rn(e[k]);
-                if (__half2float(h) != e[k]) { pk_ok = false; break; }
-                unsigned short hb;
-                memcpy(&hb, &h, 2);
-                if (e[k] > 0.0f) hb -= 1;                            // v >= e  <=>  trunc(v) > the float16 below e
-                __half hp;
-                memcpy(&hp, &hb, 2);
-                const double ep = (double)__half2float(hp);
-                if (ep == 0.0) { pk_ok = false; break; }
-                const int kexp = std::ilogb(ep);
-                const double big = std::ldexp(1.0, std::min(15, 14 - kexp));
-                // gap between e' and the next float16 above it (towards zero for a negative e')
-                unsigned short hn = (ep > 0.0) ? (unsigned short)(hb + 1) : (unsigned short)(hb - 1);
-                __half hnh;
-                memcpy(&hnh, &hn, 2);
-                const double gap = (double)__half2float(hnh) - ep;
-                if (!(gap * big >= 1.0) || !(std::fabs(ep) * big <= 65504.0)) { pk_ok = false; break; }
-                const __half hm = __float2half_rn((float)big), hc = __float2half_rn((float)(-ep * big));
-                if ((double)__half2float(hm) != big || (double)__half2float(hc) != -ep * big) { pk_ok = false; break; }
-                unsigned short mb, cb;
-                memcpy(&mb, &hm, 2);
-                memcpy(&cb, &hc, 2);
-                emul[k] = (unsigned)mb | ((unsigned)mb << 16);
-                epk[k] = (unsigned)cb | ((unsigned)cb << 16);
-#else
+                epk[k] = 0u;
                 if ((b & 0xffffu) != 0u) { pk_ok = false; break; }
                 unsigned h = b >> 16;
                 if (e[k] > 0.0f) h -= 1u;   // v >= e  <=>  trunc(v) > the bfloat16 below e
                 epk[k] = h | (h << 16);
                 if (e[k] == 0.0f) epk[k] = 0xffffffffu;   // the edge 0.0 is counted by signs
-#endif
             }
             if (pk_ok) {
                 int tz = 0;
@@ -223,10 +193,11 @@ int launch_regional(const RegionalLaunch &a, int mode, RegionalChoice *choice) {
                 if (tz < 13) pk_ok = false;   // the screen would send most periods to the slow path
                 if (pk_ok) {
                     q.eq_mask = (1u << tz) - 1u;
+                    q.zero_k = -1;
                     for (int k = 0; k <= S::NBL; ++k) {
+                        if (e[k] == 0.0f) q.zero_k = k;
                         q.edge_f[k] = e[k];
                         q.edge_pk[k] = epk[k];
-                        q.edge_mul[k] = emul[k];
                     }
                     q.bins_fast = 2;
                 }
@@ -275,10 +246,7 @@ int launch_regional(const RegionalLaunch &a, int mode, RegionalChoice *choice) {
         m.den_half = q.den_half;
         memcpy(m.dst_int, q.dst_int, sizeof(m.dst_int));
         memcpy(m.dst_dbl, q.dst_dbl, sizeof(m.dst_dbl));
-        const int per_block = 256 / LPS;
-        const int64_t ychunks = (n_groups + per_block - 1) / per_block;
-        if (ychunks > 65535) return agf_fail(AGF_E_UNSUPPORTED, "too many periods in one launch");
-        dim3 mgrid((unsigned)plan->n_multi, (unsigned)ychunks);
+        dim3 mgrid((unsigned)plan->n_multi);
         agf_regional_merge<LPS><<<mgrid, 256, 0, a.k.stream>>>(m);
         CU(cudaGetLastError());
     }
