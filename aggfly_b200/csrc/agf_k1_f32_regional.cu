@@ -212,7 +212,8 @@ int launch_regional(const RegionalLaunch &a, int mode, RegionalChoice *choice) {
     if (plan->n_active == 0) return 0;
     // periods per CTA: enough CTAs for ~8 waves of the resident grid, at least 8 periods each (the ring's ramp-up
     // and the tile's tables are paid once per CTA)
-    const int64_t want_ctas = 8LL * ctas_per_sm * sms;
+    static const int waves = getenv("AGF_RG_WAVES") ? std::max(1, atoi(getenv("AGF_RG_WAVES"))) : 8;
+    const int64_t want_ctas = (int64_t)waves * ctas_per_sm * sms;
     int64_t stripes = std::max<int64_t>(1, std::min<int64_t>((want_ctas + plan->n_active - 1) / plan->n_active, n_groups / 8));
     stripes = std::min<int64_t>(stripes, 65535);
     q.groups_per_cta = (int)((n_groups + stripes - 1) / stripes);
