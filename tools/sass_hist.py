@@ -12,7 +12,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 KEY = ["UTMALDG", "UTMACCTL", "SYNCS", "BAR", "LDS", "STS", "LDG", "STG", "DADD", "DMUL", "DFMA", "F2F", "MUFU", "FSETP", "FADD",
-       "FMNMX", "FMNMX3", "SHFL", "IMAD", "LOP3", "ATOM", "RED", "HMMA", "UTCHMMA", "UTCMMA", "DMMA"]
+       "FMNMX", "FMNMX3", "SHFL", "CREDUX", "HSET2", "HADD2", "HFMA2", "PRMT", "IDP", "VOTE", "POPC", "IMAD", "LOP3", "ATOM", "RED", "HMMA", "UTCHMMA", "UTCMMA", "DMMA"]
 
 
 def main():
