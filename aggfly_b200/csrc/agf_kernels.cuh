@@ -532,10 +532,20 @@ __device__ __forceinline__ void l1_acc_group(const K1Params<T, NL, NS> &p, ST &s
             mn = fmin(mn, v[r]);
             mx = fmax(mx, v[r]);
         }
+        if constexpr (sizeof(T) == 4) {
+            // warp reductions (sm_100a: CREDUX.MIN / MAX.F32; NaNs are skipped like fmin / fmax skip them) instead of a
+            // butterfly of ten dependent shuffles
+            float rn, rx;
+            asm volatile("redux.sync.min.f32 %0, %1, 0xffffffff;" : "=f"(rn) : "f"((float)mn));
+            asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(rx) : "f"((float)mx));
+            mn = (T)rn;
+            mx = (T)rx;
+        } else {
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, off));
-            mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+            for (int off = 16; off > 0; off >>= 1) {
+                mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, off));
+                mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+            }
         }
 #pragma unroll
         for (int j = 0; j < NBL; ++j) {
