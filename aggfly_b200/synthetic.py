@@ -46,6 +46,9 @@ SPECS: Dict[str, dict] = {
     # C3b: daily panel (hourly bins per date + daily mean); write traffic is not negligible
     "daily_bins_mean": dict(hbins=[("aggregate", {"calc": "bins", "groupby": "date", "ddargs": BINS13})],
                             tavg=[("aggregate", {"calc": "mean", "groupby": "date"})]),
+    # bins of the HOURLY values by year (SURVEY a-1: "[bins(multi) on hourly]"): one ragged 8760-row group per cell
+    "hourly_bins_year": dict(hbins=[("aggregate", {"calc": "bins", "groupby": "year", "ddargs": BINS13})],
+                             tavg=[("aggregate", {"calc": "mean", "groupby": "year"})]),
     # configs[4]: degree-days by month (daily input)
     "gdd_month": dict(gdd=[("aggregate", {"calc": "dd", "groupby": "date", "ddargs": [10, 30, 0]}),
                            ("aggregate", {"calc": "sum", "groupby": "month"})]),
@@ -201,6 +204,9 @@ def make_workload(name: str) -> Workload:
     if name == "c3b_global_daily":
         return Workload(name, global_grid(), "daily_bins_mean", 8760, _hourly_year(),
                         description="global 0.25deg hourly year, daily panel: 13 hourly bins per date + daily mean")
+    if name == "c3d_global_hourly_bins":
+        return Workload(name, global_grid(), "hourly_bins_year", 8760, _hourly_year(),
+                        description="global 0.25deg hourly year: 13 bins of the hourly values per year + annual mean")
     if name == "c5_cmip_gdd":
         n = 365 * 150
         return Workload(name, cmip_grid(), "gdd_month", n, CalendarIndex.range("noleap", 1950, n), hourly=False,

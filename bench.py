@@ -673,7 +673,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the extra keys 'workloads' and 'e2e_resident' (N = 1)")
     ap.add_argument("--no-packed", action="store_true", help="skip the packed-int16 host feed ('e2e_packed')")
-    ap.add_argument("--extra-workloads", default="c3b_global_daily,c1_conus_tavg,c2_conus_gdd,c5_cmip_gdd")
+    ap.add_argument("--extra-workloads", default="c3b_global_daily,c3d_global_hourly_bins,c1_conus_tavg,c2_conus_gdd,c5_cmip_gdd")
     ap.add_argument("--c4-years", type=int, default=40,
                     help="years of the streamed multi-year record ('c4'; time-sharded over the ranks; 0: skip)")
     args = ap.parse_args()
