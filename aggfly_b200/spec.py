@@ -289,6 +289,9 @@ def _xf_fields(xfs: List[Node]):
     return x.xf, (x.xparam if x.xf == "pow" else 0.0), x
 
 
+MAX_TYPED_BINS = 28
+
+
 def _lane_index(lanes: List[LaneSpec], calc, dd) -> int:
     for i, l in enumerate(lanes):
         if l.calc == calc and l.dd == dd:
@@ -344,7 +347,8 @@ class Planner:
         return ("outer", a.src.key, a.freq)     # single-level program over the materialised a.src
 
     def _collapsed_lane(self, s1: Node, a: Node):
-        """``a(s1(raw))`` where every group of ``s1`` is exactly ONE row (daily data grouped by date):
+        """``a(s1(raw))`` where every group of ``s1`` is exactly ONE row (daily data grouped by date), or a sum of bin
+        counts over non-empty inner groups of any length:
         the inner step is the identity (mean / sum / min / max / nanmean of one value), a 0/1 bin
         indicator, or one degree-day term, so the pair is a single-level reduction of the raster
         over the composed bounds.  Returns the (calc, ddargs) of that lane, or None.
@@ -354,6 +358,13 @@ class Planner:
         step stores its result in the input dtype, nb_kernels.py:260)."""
         b1, _ = self.g.axis(s1)
         n_rows = len(self.g.labels(self.g.raw))
+        if s1.calc == "bins" and a.calc == "sum" and len(b1) > 1 and np.all(np.diff(b1) >= 1):
+            # Counts of counts: ``bins / date -> sum / year`` (the chain of the reference's own golden matrix,
+            # tests/test_aggregate.py:275-280) adds exact small integers, so it is the bin count over the composed
+            # group whatever the inner group length -- as long as no inner group is EMPTY (an empty group's bins are
+            # NaN, nb_kernels.py:197-199, and would poison the outer sum).  One single-level pass with typed bin lanes
+            # instead of sixteen general lanes feeding sixteen slots (C3-size year: 67 ms -> 10 ms).
+            return ("bins", s1.dd)
         if len(b1) - 1 != n_rows or (n_rows and not np.all(np.diff(b1) == 1)):
             return None
         if s1.calc in ("mean", "sum", "min", "max", "nanmean"):
@@ -426,7 +437,12 @@ class Planner:
             xf, xparam, xnode = (None, 0.0, None) if identity else _xf_fields(tail)
             calc, dd = ("mean", None) if identity else (lane_of(a) if lane_of is not None else (a.calc, a.dd))
             need = (1 if calc != "sine_dd" else 4)
-            if prog is None or len(prog.lanes) + need > _lib.MAX_LANES or len(prog.cols) + 1 > _lib.MAX_COLS:
+            # the typed-lane kernels hold at most 28 bin counters (csrc/agf_k1_*: NB = 6 / 14 / 28): a 29th bin lane would
+            # send the whole program to the general per-value dispatch
+            bins_full = (calc == "bins" and prog is not None and (calc, dd) not in [(l.calc, l.dd) for l in prog.lanes]
+                         and sum(l.calc == "bins" for l in prog.lanes) >= MAX_TYPED_BINS)
+            if (prog is None or bins_full or len(prog.lanes) + need > _lib.MAX_LANES
+                    or len(prog.cols) + 1 > _lib.MAX_COLS):
                 prog = ProgramSpec(input=input_node, in_dtype=input_node.dtype, bounds1=b1, bounds2=None,
                                    freq1=freq, n_time=n_time, pre=self.g.pre_ops if source is None else [])
                 prog._source = source

@@ -49,6 +49,15 @@ SPECS: Dict[str, dict] = {
     # bins of the HOURLY values by year (SURVEY a-1: "[bins(multi) on hourly]"): one ragged 8760-row group per cell
     "hourly_bins_year": dict(hbins=[("aggregate", {"calc": "bins", "groupby": "year", "ddargs": BINS13})],
                              tavg=[("aggregate", {"calc": "mean", "groupby": "year"})]),
+    # the reference tests' own chain shape (tests/test_aggregate.py:275-280): hourly bins per date summed over the year,
+    # next to the polynomial of the daily mean
+    "bins_date_year_poly": dict(hbins=[("aggregate", {"calc": "bins", "groupby": "date", "ddargs": BINS13}),
+                                       ("aggregate", {"calc": "sum", "groupby": "year"})],
+                                tavg=[("aggregate", {"calc": "mean", "groupby": "date"}),
+                                      ("transform", {"transform": "power", "exp": np.arange(1, 3)}),
+                                      ("aggregate", {"calc": "sum", "groupby": "year"})]),
+    "bins_date_year": dict(hbins=[("aggregate", {"calc": "bins", "groupby": "date", "ddargs": BINS13}),
+                                  ("aggregate", {"calc": "sum", "groupby": "year"})]),
     # configs[4]: degree-days by month (daily input)
     "gdd_month": dict(gdd=[("aggregate", {"calc": "dd", "groupby": "date", "ddargs": [10, 30, 0]}),
                            ("aggregate", {"calc": "sum", "groupby": "month"})]),
@@ -207,6 +216,12 @@ def make_workload(name: str) -> Workload:
     if name == "c3d_global_hourly_bins":
         return Workload(name, global_grid(), "hourly_bins_year", 8760, _hourly_year(),
                         description="global 0.25deg hourly year: 13 bins of the hourly values per year + annual mean")
+    if name == "c3e_global_bins_date_year":
+        return Workload(name, global_grid(), "bins_date_year_poly", 8760, _hourly_year(),
+                        description="global 0.25deg hourly year: hourly bins per date -> year sum, + daily mean -> power 1..2 -> year sum")
+    if name == "c3f_global_bins_date_year_only":
+        return Workload(name, global_grid(), "bins_date_year", 8760, _hourly_year(),
+                        description="global 0.25deg hourly year: hourly bins per date -> year sum")
     if name == "c5_cmip_gdd":
         n = 365 * 150
         return Workload(name, cmip_grid(), "gdd_month", n, CalendarIndex.range("noleap", 1950, n), hourly=False,

@@ -96,8 +96,15 @@ def test_many_lanes_split_into_several_programs():
     dd = [[i, i + 1, 0] for i in range(40)]
     g, outs, stage = _plan(dict(b=[("aggregate", {"calc": "bins", "groupby": "date", "ddargs": dd}),
                                    ("aggregate", {"calc": "sum", "groupby": "year"})]))
-    assert len(outs) == 40 and len(stage.programs) == 3                 # 16 + 16 + 8 (diagonal form)
+    # a sum of bin counts over non-empty inner groups is the bin count over the composed groups: single-level programs
+    # with typed bin lanes, at most 28 of them each
+    assert len(outs) == 40 and [len(p.lanes) for p in stage.programs] == [28, 12]
+    assert all(not p.two_level and p.input is g.raw for p in stage.programs)
     assert sorted(c.out_col for p in stage.programs for c in p.cols) == list(range(40))
+    # ... but not when an inner group is empty (its bins are NaN and poison the outer sum): the two-level form stays
+    g2, outs2, stage2 = _plan(dict(b=[("aggregate", {"calc": "bins", "groupby": "date", "ddargs": dd}),
+                                      ("aggregate", {"calc": "sum", "groupby": "year"})]), t=T_HOURLY.delete(slice(48, 72)))       # a whole day missing: an empty date group
+    assert len(outs2) == 40 and len(stage2.programs) == 3 and all(p.two_level for p in stage2.programs)   # 16 + 16 + 8
 
 
 def test_errors_match_reference():
@@ -139,9 +146,12 @@ def test_single_row_inner_groups_collapse_to_one_level():
     p = stage.programs[0]
     assert [(l.calc, l.dd) for l in p.lanes] == [("dd_r", (10.0, 30.0, 0.0)), ("mean", None), ("bins", (30.0, 99.0, 0.0))]
     assert len(p.bounds1) == 37 and list(p.bounds1[:4]) == [0, 31, 59, 90] and p.bounds1[-1] == 365 * 3
-    # hourly data: groups of 24 rows do not collapse
+    # hourly data: groups of 24 rows do not collapse -- except the sum of bin counts, which is the bin count over the
+    # month whatever the inner group length (typed bin lanes in a pass of their own)
     _, _, stage = _plan(spec)
-    assert all(q.two_level for q in stage.programs)
+    assert sorted(q.two_level for q in stage.programs) == [False, True]
+    single = [q for q in stage.programs if not q.two_level][0]
+    assert [(l.calc, l.dd) for l in single.lanes] == [("bins", (30.0, 99.0, 0.0))] and len(single.bounds1) == 4
     # a transform between the steps keeps the two-level form (the power applies to the daily value)
     _, _, stage = _plan(dict(a=[("aggregate", {"calc": "mean", "groupby": "date"}),
                                 ("transform", {"transform": "power", "exp": np.arange(1, 3)}),
