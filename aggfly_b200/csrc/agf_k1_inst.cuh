@@ -30,6 +30,45 @@ static inline void set_thresholds(LaneP<double> &L, double t0, double t1) {
 }
 
 // descriptor + launch arguments -> the kernel's parameter block (lane / slot / column tables in KERNEL order)
+// Typed bin lanes of a float program -> BinEdgesP (agf_kernels.cuh): the edge form needs contiguous ascending bins whose
+// thresholds are all bfloat16s (>= 16 trailing zero bits; +-inf qualify), so that hi_j == lo_j+1 exactly and a value can
+// equal an edge only if its low mantissa bits are zero.  AGF_BINS_BY_EDGES=0 keeps the bin-by-bin count.
+template <typename LANE>
+static void k1_fill_bin_edges(agf::BinEdgesP &be, const LANE *lanes, int n_bins) {
+    memset(&be, 0, sizeof(be));
+    be.zero_k = -1;
+    for (int k = 0; k <= AGF_MAX_LANES; ++k) be.edge_f[k] = INFINITY;
+    if (n_bins < 1 || n_bins > AGF_MAX_LANES) return;
+    if (getenv("AGF_BINS_BY_EDGES") && atoi(getenv("AGF_BINS_BY_EDGES")) == 0) return;
+    float e[AGF_MAX_LANES + 1];
+    for (int j = 0; j < n_bins; ++j) e[j] = (float)lanes[j].lo;
+    e[n_bins] = (float)lanes[n_bins - 1].hi;
+    for (int j = 0; j + 1 < n_bins; ++j)
+        if ((float)lanes[j + 1].lo != (float)lanes[j].hi) return;   // a gap, an overlap or a threshold that is not a float
+    unsigned low_all = 0xffffffffu;
+    for (int k = 0; k <= n_bins; ++k) {
+        unsigned b;
+        memcpy(&b, &e[k], 4);
+        if (e[k] != e[k] || (b & 0xffffu) != 0u) return;
+        if (k > 0 && !(e[k - 1] < e[k])) return;
+        low_all &= ~b;
+    }
+    int tz = 0;
+    while (tz < 23 && ((low_all >> tz) & 1u)) ++tz;
+    be.eq_mask = (1u << tz) - 1u;
+    be.n_edges = n_bins + 1;
+    for (int k = 0; k <= n_bins; ++k) {
+        unsigned b;
+        memcpy(&b, &e[k], 4);
+        unsigned h = b >> 16;
+        if (e[k] > 0.0f) h -= 1u;   // v >= e  <=>  trunc(v) > the bfloat16 below e
+        if (e[k] == 0.0f) be.zero_k = k;
+        be.edge_f[k] = e[k];
+        be.edge_pk[k] = h | (h << 16);
+    }
+    be.fast = 1;
+}
+
 template <typename T, int NL, int NS, bool DIAG, unsigned KINDS, int NB>
 static void k1_fill_params(K1Params<T, NL, NS> &kp, const K1Launch &a) {
     const agf_program *p = a.p;
@@ -144,6 +183,12 @@ static void k1_fill_params(K1Params<T, NL, NS> &kp, const K1Launch &a) {
         L.base_f = (float)L.base;
         L.base_is_f32 = (sizeof(T) == 4 && (double)L.base_f == L.base) ? 1 : 0;
         set_thresholds(L, L.t0, L.t1);
+    }
+    kp.be.fast = 0;
+    if constexpr (TL && sizeof(T) == 4) {
+        int n_bins = 0;
+        for (int l = 0; l < d.n_lanes; ++l) n_bins += d.lanes[l].calc == AGF_CALC_BINS;
+        if (NB > 4) k1_fill_bin_edges(kp.be, kp.lanes, n_bins);   // kernel lanes [0, n_bins): the bins in program order
     }
     if (NS > 0) {
         auto fill = [&](SlotP &S, int j) {

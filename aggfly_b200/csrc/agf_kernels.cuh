@@ -139,6 +139,17 @@ struct PreP {  // one preprocess operation (AGF_PRE_*), constant already in the 
     T c;
 };
 
+// Contiguous ascending bins counted through their EDGES, two values per instruction (l1_acc_group, agf_regional.cuh):
+// set by the launcher (k1_fill_bin_edges) when every edge of a typed-lane program is a bfloat16.
+struct BinEdgesP {
+    int fast;           // 0: bins are counted one by one
+    unsigned eq_mask;   // a value can equal an edge only if (bits & eq_mask) == 0
+    int zero_k;         // index of the edge 0.0 (-1: none)
+    int n_edges;        // real bins + 1
+    float edge_f[AGF_MAX_LANES + 1];     // lo_0 .. lo_{n-1}, hi_{n-1}; +inf behind them
+    unsigned edge_pk[AGF_MAX_LANES + 1]; // what the packed compare tests against, in both halves
+};
+
 template <typename T, int NL, int NS>
 struct K1Params {
     const T *x;
@@ -166,6 +177,7 @@ struct K1Params {
     LaneP<T> lanes[NL];
     SlotP slots[NS > 0 ? NS : 1];
     ColP cols[AGF_MAX_COLS];  // NS == 0: columns read lanes; NS > 0 (direct output only): src = KERNEL slot index
+    BinEdgesP be;
 };
 
 // ------------------------------------------------------------------------------------------
@@ -516,6 +528,69 @@ __device__ __forceinline__ void l1_acc(const K1Params<T, NL, NS> &p, ST &s, T v)
     }
 }
 
+// ---- counting the values of a period above an edge, two values per instruction ----
+// The 24 floats of a period are TRUNCATED to bfloat16 once (one PRMT packs the high halves of two values) and every edge
+// inside the warp's range is tested with 12 HSET2.BF16 + 12 HADD2.BF16 instead of 24 FSETP + 24 predicated FADD.  That is
+// exact, not approximate, on the fast path (no value equals an edge, no NaN next to a number):
+//   * e < 0:  v > e  <=>  trunc(v) > e.   A negative v is truncated towards zero, i.e. UP onto the bfloat16 grid the edge
+//     lies on, so it cannot cross e from below (v < e => trunc(v) <= e would need trunc(v) == e only for v in (e - ulp, e):
+//     truncation moves such a v to the grid point ABOVE it only if that point is e itself -- and then v > e was false
+//     and trunc(v) > e is false); a non-negative v stays non-negative.
+//   * e > 0:  v > e  <=>  v >= e (screen)  <=>  trunc(v) >= e  <=>  trunc(v) > pred(e), pred(e) the bfloat16 below e:
+//     a positive v is truncated DOWN onto the grid; a negative v stays <= -0 < pred(e) or == pred(e) = +0 (false).
+//   * e == 0: truncation takes tiny values to +-0, so the SIGNS are counted instead (no value is +-0 on the fast path):
+//     one PRMT replicates the sign bits of four values into bytes, one IDP4A adds the four -1 / 0.
+// An all-NaN cell (a NaN may truncate to an infinity) is zeroed by the caller; partly-NaN cells never get here.
+__device__ __forceinline__ unsigned rg_pack_hi(float a, float b) {  // (bfloat16 trunc(a), bfloat16 trunc(b))
+    unsigned d;
+    asm("prmt.b32 %0, %1, %2, 0x7632;" : "=r"(d) : "r"(__float_as_uint(a)), "r"(__float_as_uint(b)));
+    return d;
+}
+__device__ __forceinline__ unsigned rg_bf2_gt(unsigned a, unsigned e) {  // per half: 1.0 if a > e else 0.0
+    unsigned d;
+    asm("set.gt.bf16x2.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(e));
+    return d;
+}
+__device__ __forceinline__ unsigned rg_bf2_add(unsigned a, unsigned b) {
+    unsigned d;
+    asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
+// g += (v > edge): one compare (ALU pipe) + one predicated add (FMA pipe) -- the float32 form, for edges that are not
+// bfloat16s (bins_fast == 1).
+__device__ __forceinline__ void count_above(float &g, float v, float edge) {
+    asm("{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.gt.f32 p, %1, %2;\n\t"
+        "@p add.f32 %0, %0, 0f3F800000;\n\t"
+        "}"
+        : "+f"(g)
+        : "f"(v), "f"(edge));
+}
+template <int NP>
+__device__ __forceinline__ float rg_count_above_packed(const unsigned (&pk)[NP], unsigned epk) {
+    static_assert(NP >= 4, "four chains");
+    unsigned a[4];  // four chains of exact small integers (<= NP / 4 per half)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a[i] = rg_bf2_gt(pk[i], epk);
+#pragma unroll
+    for (int i = 4; i < NP; ++i) a[i & 3] = rg_bf2_add(a[i & 3], rg_bf2_gt(pk[i], epk));
+    const unsigned s = rg_bf2_add(rg_bf2_add(a[0], a[1]), rg_bf2_add(a[2], a[3]));
+    return __uint_as_float(s << 16) + __uint_as_float(s & 0xffff0000u);
+}
+template <int NP>
+__device__ __forceinline__ float rg_count_positive_packed(const unsigned (&pk)[NP]) {
+    static_assert(NP % 2 == 0, "pairs of packed registers");
+    int c = 2 * NP;
+#pragma unroll
+    for (int i = 0; i < NP; i += 2) {
+        unsigned sg;
+        asm("prmt.b32 %0, %1, %2, 0xfdb9;" : "=r"(sg) : "r"(pk[i]), "r"(pk[i + 1]));  // 0xff per negative value
+        asm("dp4a.s32.s32 %0, %1, %2, %0;" : "+r"(c) : "r"(sg), "r"(0x01010101));
+    }
+    return __uint_as_float(0x4B000000u + (unsigned)c) - 8388608.0f;
+}
+
 // A whole level-1 group held in registers (uniform-group kernel).  Typed lanes with many bins: the
 // bins a warp can possibly hit are bounded by the min / max of its 32 x N values, and neighbouring
 // cells at the same hours are close in value, so each bin's N x (2 compares + add) block is guarded
@@ -532,6 +607,25 @@ __device__ __forceinline__ void l1_acc_group(const K1Params<T, NL, NS> &p, ST &s
             mn = fmin(mn, v[r]);
             mx = fmax(mx, v[r]);
         }
+        // Edge form (float rasters, every edge a bfloat16): this lane can take it unless one of its values could equal
+        // an edge (low mantissa bits all zero) or only SOME of them are NaN (a float sum of the batch is NaN then; an
+        // overflow to infinities only costs the slow path)
+        constexpr bool EDGES = sizeof(T) == 4 && N % 4 == 0;
+        bool fast = false, all_nan = false;
+        if constexpr (EDGES) {
+            if (p.be.fast) {
+                unsigned em = 0xffffffffu;
+                float f4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+                for (int r = 0; r < N; ++r) {
+                    em = min(em, __float_as_uint((float)v[r]) & p.be.eq_mask);
+                    f4[r & 3] += (float)v[r];
+                }
+                const float fs = (f4[0] + f4[1]) + (f4[2] + f4[3]);
+                all_nan = mn != mn;
+                fast = !__any_sync(0xffffffffu, !all_nan && (em == 0u || fs != fs));
+            }
+        }
         if constexpr (sizeof(T) == 4) {
             // warp reductions (sm_100a: CREDUX.MIN / MAX.F32; NaNs are skipped like fmin / fmax skip them) instead of a
             // butterfly of ten dependent shuffles
@@ -547,11 +641,37 @@ __device__ __forceinline__ void l1_acc_group(const K1Params<T, NL, NS> &p, ST &s
                 mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, off));
             }
         }
+        if (fast) {
+            if constexpr (EDGES) {
+                // G(e) = #(v > e) for the edges inside the warp's range (below it G = the lane's valid values, above it
+                // 0), bin j += G(lo_j) - G(lo_j+1): one packed compare + add per TWO values and edge instead of two compares
+                // + an add per value and bin (see rg_count_above_packed for why the truncated compare is exact)
+                unsigned pk[N / 2];
 #pragma unroll
-        for (int j = 0; j < NBL; ++j) {
-            if (mx > p.lanes[j].lo && mn < p.lanes[j].hi) {  // warp-uniform
+                for (int i = 0; i < N / 2; ++i) pk[i] = rg_pack_hi((float)v[2 * i], (float)v[2 * i + 1]);
+                const float n_valid = all_nan ? 0.0f : (float)N;
+                float gprev = 0.0f;
 #pragma unroll
-                for (int r = 0; r < N; ++r) count_in_range(s.cf[j], v[r], p.lanes[j].lo, p.lanes[j].hi);
+                for (int k = 0; k <= NBL; ++k) {
+                    const float edge = p.be.edge_f[k];
+                    float gk;
+                    if (edge >= (float)mn && edge < (float)mx) {  // warp-uniform
+                        gk = (k == p.be.zero_k) ? rg_count_positive_packed(pk) : rg_count_above_packed(pk, p.be.edge_pk[k]);
+                        if (all_nan) gk = 0.0f;
+                    } else {
+                        gk = (edge < (float)mn) ? n_valid : 0.0f;
+                    }
+                    if (k > 0) s.cf[k - 1] += gprev - gk;
+                    gprev = gk;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < NBL; ++j) {
+                if (mx > p.lanes[j].lo && mn < p.lanes[j].hi) {  // warp-uniform
+#pragma unroll
+                    for (int r = 0; r < N; ++r) count_in_range(s.cf[j], v[r], p.lanes[j].lo, p.lanes[j].hi);
+                }
             }
         }
 #pragma unroll

@@ -154,6 +154,36 @@ def test_packed_edge_counting_is_exact_next_to_the_thresholds(mode):
     _same_frame(one.reset_index(drop=True), want.reset_index(drop=True), 1e-11)
 
 
+@pytest.mark.parametrize("groupby", ["date", "month"])
+def test_edge_form_of_the_two_kernel_path_is_exact_next_to_the_thresholds(groupby):
+    """The same adversarial values through the temporal kernels of the two-kernel path (l1_acc_group's edge form: the
+    per-date kernel for ``date``, the ragged-group kernel with its tile / eight-row batches and per-value tails for
+    ``month``) against the oracle."""
+    rng = np.random.default_rng(78)
+    n_lat, n_lon, days = 16, 64, 40                                # 1 March .. 9 April: two ragged month groups
+    arr, t, lat, lon, ds, w = _case(n_lat, n_lon, days=days, seed=6, ocean=0.0)
+    vals = _adversarial_bits(rng, arr.shape)
+    low = vals.view(np.uint32) & 0xFFFF
+    keep = np.zeros(vals.shape, dtype=bool)
+    keep[:, :4, :] = True                                          # values equal to an edge in the first rows only
+    vals = np.where((low == 0) & ~keep, np.float32(7.3), vals)
+    for (y, x, pat) in [(8, 5, 0x7F800001), (8, 6, 0xFF800001), (9, 40, 0x7FFFFFFF), (10, 41, 0x7FC00000)]:
+        vals[:, y, x] = np.array([pat], dtype=np.uint32).view(np.float32)[0]          # all-NaN cells
+    vals[24:30, 12, 20] = np.nan                                                       # partly-NaN batches
+    vals[100, 13, 21] = np.nan
+    ds = af.Dataset.from_arrays(vals, t, lat, lon, lon_is_360=True)
+    spec = dict(hbins=[("aggregate", {"calc": "bins", "groupby": groupby, "ddargs": BINS13})],
+                tavg=[("aggregate", {"calc": "mean", "groupby": groupby})])
+    engine.OPTIONS["regional"] = False
+    import torch
+    d = af.Dataset.from_arrays(torch.from_numpy(vals).cuda(), t, lat, lon, lon_is_360=True)
+    got = af.aggregate_dataset(weights=w, dataset=d, aggregator_dict=spec)
+    rid = w.georegions.regionid
+    want = orc.aggregate_dataset(orc.OWeights(w.weights, w.grid.cell_id, w.georegions.shp, rid, w.zero_weight),
+                                 orc.ODataset(vals, t, lat, lon, True), aggregator_dict=spec)
+    _same_frame(got.reset_index(drop=True), want.reset_index(drop=True), 1e-11)
+
+
 @pytest.mark.parametrize("zero_weight", ["nan", "area"])
 def test_host_fed_raster_and_zero_weight_rows(zero_weight):
     """The streamed feed (pageable NumPy raster -> staging ring -> launches per period range) and the row-drop rules."""
