@@ -1,6 +1,8 @@
 // K1 instantiations of this unit: float raster, TMA ring, UNIFORM level-1 groups (agf_k1_tma_uni:
 // every group has GL rows; GL = 24 hourly -> date, 8 / 4 three- / six-hourly -> date, 1 daily data by date).  Rows are
-// K1CASE(lanes, slots, diag, lane kinds, NB, GL); tried in order, cheapest first.
+// K1CASE(lanes, slots, diag, lane kinds, NB, GL); tried in order, cheapest first.  (KIND_SUM | KIND_MINMAX: daily minimum /
+// maximum / mean of hourly values -- tmin, tmax, tavg -- per date or averaged over months / years: 35 ms on the general
+// ragged-group kernel for a global year.)
 #define AGF_T float
 #define AGF_TMA 1
 #define AGF_FN agf_k1_f32_tma_uni
@@ -21,6 +23,8 @@
     K1CASE(4, 0, true, KIND_MIX_SD, NB_GENERAL, 24)     \
     K1CASE(4, 4, false, KIND_MIX_SD, 0, 24)             \
     K1CASE(4, 20, false, KIND_MIX_SD, 16, 24)           \
+    K1CASE(4, 0, false, KIND_SUM | KIND_MINMAX, NB_GENERAL, 24) \
+    K1CASE(4, 4, false, KIND_SUM | KIND_MINMAX, 0, 24)  \
     K1CASE(8, 0, true, KIND_SUM | KIND_BINS, 6, 24)     \
     K1CASE(16, 0, true, KIND_SUM | KIND_BINS, 14, 24)   \
     K1CASE(32, 0, true, KIND_SUM | KIND_BINS, 28, 24)   \

@@ -143,7 +143,20 @@ static void k1_fill_params(K1Params<T, NL, NS> &kp, const K1Launch &a) {
     int lane_of[AGF_MAX_LANES];
     constexpr bool TL = typed_lanes<NS, NB>();
     constexpr bool MIX = !TL && KINDS == KIND_MIX_SD;  // lane 0 = the mean / sum lane, 1.. = the dd lanes
-    if constexpr (MIX) {
+    constexpr bool MMS = !TL && KINDS == KIND_MMS && NL >= 3;   // lane 0 = mean / sum, 1 = min, 2 = max
+    if constexpr (MMS) {
+        for (int l = 0; l < d.n_lanes; ++l)
+            lane_of[l] = d.lanes[l].calc == AGF_CALC_MIN ? 1 : (d.lanes[l].calc == AGF_CALC_MAX ? 2 : 0);
+        for (int l = 0; l < NL; ++l) {  // inert pads: accumulators nobody reads
+            LaneP<T> &L = kp.lanes[l];
+            L.calc = l == 1 ? AGF_CALC_MIN : (l == 2 ? AGF_CALC_MAX : AGF_CALC_SUM);
+            L.lo = (T)INFINITY;
+            L.hi = (T)-INFINITY;
+            L.t0 = INFINITY;
+            L.t1 = -INFINITY;
+        }
+        kp.n_lanes = NL;
+    } else if constexpr (MIX) {
         int nd = 1;
         for (int l = 0; l < d.n_lanes; ++l)
             lane_of[l] = (kind_of_calc(d.lanes[l].calc) == KIND_SUM) ? 0 : nd++;
@@ -237,7 +250,7 @@ static void k1_fill_params(K1Params<T, NL, NS> &kp, const K1Launch &a) {
         for (int c = 0; c < d.n_cols; ++c) {
             // typed lanes are diagonal (column c reads lane c): the column moves with its lane
             ColP &C = kp.cols[(TL || MIX) ? lane_of[d.cols[c].src] : c];
-            C.src = (TL || MIX) ? lane_of[d.cols[c].src] : d.cols[c].src;
+            C.src = (TL || MIX || MMS) ? lane_of[d.cols[c].src] : d.cols[c].src;
             C.xform = d.cols[c].xform;
             C.xparam = d.cols[c].xparam;
             C.x_f64 = d.cols[c].x_f64;
@@ -322,6 +335,16 @@ static inline bool k1_fits(const agf_program *p, int NL, int NS, bool DG, unsign
     if ((NS == 0) != (d.n_slots == 0) || d.n_slots > NS) return false;
     if (DG && !p->diag_ok) return false;
     if (NS > 0 && NL > 4 && !DG) return false;  // select-chain form only for <= 4 lanes
+    if (KINDS == KIND_MMS && NL >= 3 && !(NS == 0 && NB >= 0)) {  // fixed layout: one mean / sum lane, one min, one max
+        int nsum = 0, nmin = 0, nmax = 0;
+        for (int l = 0; l < d.n_lanes; ++l) {
+            nsum += kind_of_calc(d.lanes[l].calc) == KIND_SUM;
+            nmin += d.lanes[l].calc == AGF_CALC_MIN;
+            nmax += d.lanes[l].calc == AGF_CALC_MAX;
+        }
+        if ((p->kinds & ~KIND_MMS) || nsum > 1 || nmin > 1 || nmax > 1 || nsum + nmin + nmax != d.n_lanes) return false;
+        if (DG) return false;  // columns / slots pick their lane through the select chain
+    }
     if (KINDS == KIND_MIX_SD && !(NS == 0 && NB >= 0)) {  // mixed layout: at most one mean / sum lane + dd lanes
         int nsum = 0;
         for (int l = 0; l < d.n_lanes; ++l) nsum += kind_of_calc(d.lanes[l].calc) == KIND_SUM;

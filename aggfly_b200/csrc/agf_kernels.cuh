@@ -45,6 +45,11 @@ enum : unsigned {
 // plus degree days -> annual sum, examples/era5_counties_area.yaml) would otherwise run the generic
 // switch-per-value kernel.
 constexpr unsigned KIND_MIX_SD = KIND_SUM | KIND_DD;
+// KIND_SUM | KIND_MINMAX as a compile-time set means the FIXED layout of daily minimum / maximum / mean programs (tmin,
+// tmax, tavg): kernel lane 0 = the program's one mean / sum lane, lane 1 = its min lane, lane 2 = its max lane (inert
+// pads where the program has none), so the per-value code is one add and two compare-selects instead of a dispatch on
+// the lane's calc per lane and value (tmin + tmax + tavg by date -> year means of a global hourly year: 35 ms before, profiles/README.md).
+constexpr unsigned KIND_MMS = KIND_SUM | KIND_MINMAX;
 
 __host__ __device__ constexpr unsigned kind_of_calc(int calc) {
     return (calc == AGF_CALC_MEAN || calc == AGF_CALC_SUM)  ? KIND_SUM
@@ -452,6 +457,13 @@ __device__ __forceinline__ void l1_acc(const K1Params<T, NL, NS> &p, ST &s, T v)
 #pragma unroll
         for (int l = 1; l < NL; ++l)
             if (v > p.lanes[l].lo && v < p.lanes[l].hi) s.a[l] += fabs(vd - p.lanes[l].base);
+        return;
+    }
+    if constexpr (KINDS == KIND_MMS && !ST::TL && NL >= 3) {  // lane 0: mean / sum, lane 1: min, lane 2: max (launcher)
+        s.nan |= (v != v);
+        s.a[0] += vd;
+        if (vd < s.a[1]) s.a[1] = vd;
+        if (vd > s.a[2]) s.a[2] = vd;
         return;
     }
     if constexpr (ST::TL) {  // typed lanes: straight-line, no per-lane dispatch

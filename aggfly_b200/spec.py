@@ -497,6 +497,11 @@ class Planner:
 def _fits_two_level(lanes: List[LaneSpec], slots: List[SlotSpec]) -> bool:
     if len(lanes) <= 4 and len(slots) <= _lib.MAX_SLOTS:
         return True
+    # Degree-day / mean / sum lanes have specialised kernels for up to four lanes (csrc/agf_k1_f32_tma_uni.cu: KIND_DD,
+    # KIND_MIX_SD); the sixteen-lane diagonal form below runs on the general ragged-group kernel, which is slower than
+    # several passes of those (six dd thresholds of a global hourly year: 154 ms in one pass, 11 ms in two)
+    if all(l.calc in ("dd", "mean", "sum") for l in lanes):
+        return False
     # diagonal form: lane j feeds slot j only
     if len(lanes) <= 16 and len(slots) == len(lanes):
         return all(s.src == j for j, s in enumerate(slots))

@@ -58,6 +58,24 @@ SPECS: Dict[str, dict] = {
                                       ("aggregate", {"calc": "sum", "groupby": "year"})]),
     "bins_date_year": dict(hbins=[("aggregate", {"calc": "bins", "groupby": "date", "ddargs": BINS13}),
                                   ("aggregate", {"calc": "sum", "groupby": "year"})]),
+    # probes of other chain shapes at the global size (tools/gpu_r2_probe.sh)
+    "probe_minmaxmean": dict(tmin=[("aggregate", {"calc": "min", "groupby": "date"}), ("aggregate", {"calc": "mean", "groupby": "year"})],
+                             tmax=[("aggregate", {"calc": "max", "groupby": "date"}), ("aggregate", {"calc": "mean", "groupby": "year"})],
+                             tavg=[("aggregate", {"calc": "mean", "groupby": "date"}), ("aggregate", {"calc": "mean", "groupby": "year"})]),
+    "probe_dd6": dict(dd=[("aggregate", {"calc": "dd", "groupby": "date",
+                                         "ddargs": [[0, 10, 0], [10, 20, 0], [20, 30, 0], [30, 99, 0], [-99, 0, 1], [10, 30, 0]]}),
+                          ("aggregate", {"calc": "sum", "groupby": "year"})]),
+    "probe_bins_mean": dict(hbins=[("aggregate", {"calc": "bins", "groupby": "date", "ddargs": BINS13}),
+                                   ("aggregate", {"calc": "mean", "groupby": "year"})]),
+    "probe_golden": dict(bins=[("aggregate", {"calc": "bins", "groupby": "date", "ddargs": [[-99, 20, 0], [20, 99, 0]]}),
+                               ("aggregate", {"calc": "sum", "groupby": "year"})],
+                         cooling_dday=[("aggregate", {"calc": "dd", "groupby": "date", "ddargs": [20, 99, 0]}),
+                                       ("aggregate", {"calc": "sum", "groupby": "year"})],
+                         tavg=[("aggregate", {"calc": "mean", "groupby": "date"}),
+                               ("transform", {"transform": "power", "exp": np.arange(1, 3)}),
+                               ("aggregate", {"calc": "sum", "groupby": "year"})]),
+    "probe_sine": dict(sdd=[("aggregate", {"calc": "sine_dd", "groupby": "date", "ddargs": [10, 30, 0]}),
+                            ("aggregate", {"calc": "sum", "groupby": "year"})]),
     # configs[4]: degree-days by month (daily input)
     "gdd_month": dict(gdd=[("aggregate", {"calc": "dd", "groupby": "date", "ddargs": [10, 30, 0]}),
                            ("aggregate", {"calc": "sum", "groupby": "month"})]),
@@ -222,6 +240,8 @@ def make_workload(name: str) -> Workload:
     if name == "c3f_global_bins_date_year_only":
         return Workload(name, global_grid(), "bins_date_year", 8760, _hourly_year(),
                         description="global 0.25deg hourly year: hourly bins per date -> year sum")
+    if name.startswith("probe_") and name in SPECS:
+        return Workload(name, global_grid(), name, 8760, _hourly_year(), description="global hourly year, chain-shape probe " + name)
     if name == "c5_cmip_gdd":
         n = 365 * 150
         return Workload(name, cmip_grid(), "gdd_month", n, CalendarIndex.range("noleap", 1950, n), hourly=False,

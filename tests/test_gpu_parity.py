@@ -147,6 +147,21 @@ SPECS = {
              ("aggregate", {"calc": "sum", "groupby": "month"})],
         direct=[("aggregate", {"calc": "mean", "groupby": "month"})]),
     "weekly": dict(w=[("aggregate", {"calc": "sum", "groupby": "date"}), ("aggregate", {"calc": "max", "groupby": "week"})]),
+    # daily minimum / maximum / mean of the hourly values (fixed lane layout KIND_MMS): two-level, per date, without a mean
+    "tmin_tmax_tavg_monthly": dict(
+        tmin=[("aggregate", {"calc": "min", "groupby": "date"}), ("aggregate", {"calc": "mean", "groupby": "month"})],
+        tmax=[("aggregate", {"calc": "max", "groupby": "date"}), ("aggregate", {"calc": "max", "groupby": "month"})],
+        tavg=[("aggregate", {"calc": "mean", "groupby": "date"}), ("aggregate", {"calc": "mean", "groupby": "month"})]),
+    "tmin_tmax_tavg_daily": dict(tmax=[("aggregate", {"calc": "max", "groupby": "date"})],
+                                 tavg=[("aggregate", {"calc": "mean", "groupby": "date"})],
+                                 tmin=[("aggregate", {"calc": "min", "groupby": "date"})]),
+    "tmin_tmax_yearly": dict(
+        tmax=[("aggregate", {"calc": "max", "groupby": "date"}), ("aggregate", {"calc": "mean", "groupby": "year"})],
+        tmin=[("aggregate", {"calc": "min", "groupby": "date"}), ("aggregate", {"calc": "mean", "groupby": "year"})]),
+    # more degree-day thresholds than one four-lane program holds (several passes instead of the sixteen-lane general form)
+    "dd6": dict(dd=[("aggregate", {"calc": "dd", "groupby": "date",
+                                   "ddargs": [[0, 10, 0], [10, 20, 0], [20, 30, 0], [30, 99, 0], [-99, 0, 1], [10, 30, 0]]}),
+                    ("aggregate", {"calc": "sum", "groupby": "year"})]),
     "spline_and_pow": dict(
         s=[("aggregate", {"calc": "mean", "groupby": "date"}), ("transform", {"transform": "spline"}),
            ("aggregate", {"calc": "sum", "groupby": "month"})],
