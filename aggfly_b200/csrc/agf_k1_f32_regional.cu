@@ -266,6 +266,7 @@ int agf_k1_f32_regional(const RegionalLaunch &a, int mode, RegionalChoice *choic
     }
     RCASE(1, false, KIND_SUM, NB_GENERAL, 4)
     RCASE(1, false, KIND_DD, NB_GENERAL, 4)
+    RCASE(4, false, KIND_MMS, NB_GENERAL, 4)
     RCASE(2, true, KIND_MIX_SD, NB_GENERAL, 4)
     RCASE(4, true, KIND_MIX_SD, NB_GENERAL, 8)
     RCASE(4, true, KIND_DD, NB_GENERAL, 8)

@@ -34,6 +34,9 @@ SPECS = {
                                                "ddargs": [[-99, -20, 0]] + BINS13})],
                             tavg=[("aggregate", {"calc": "mean", "groupby": "date"})],
                             tsum=[("aggregate", {"calc": "sum", "groupby": "date"})]),
+    "tmin_tmax_tavg": dict(tmax=[("aggregate", {"calc": "max", "groupby": "date"})],             # fixed min / max / mean layout
+                           tavg=[("aggregate", {"calc": "mean", "groupby": "date"})],
+                           tmin=[("aggregate", {"calc": "min", "groupby": "date"})]),
     "tavg_poly": dict(tavg=[("aggregate", {"calc": "mean", "groupby": "date"}),                   # columns transformed from one lane
                             ("transform", {"transform": "power", "exp": np.arange(1, 4)})]),
 }
@@ -273,10 +276,14 @@ def test_unsupported_programs_fall_back_to_the_two_kernel_path():
     ds64 = af.Dataset.from_arrays(arr.astype(np.float64), t, lat, lon, lon_is_360=True)
     df = af.aggregate_dataset(weights=w, dataset=ds64, aggregator_dict=SPECS["tavg"])
     assert len(df) > 0 and not any(k.startswith("temporal + regional") for k in agg_mod.LAST_TRACE["phases_ms"])
-    # min / max lanes have no regional instantiation: the library says so, the host falls back
-    spec = dict(tmin=[("aggregate", {"calc": "min", "groupby": "date"})])
+    # nanmean lanes have no regional instantiation: the library says so, the host falls back
+    spec = dict(tnm=[("aggregate", {"calc": "nanmean", "groupby": "date"})])
     df = af.aggregate_dataset(weights=w, dataset=ds, aggregator_dict=spec)
     assert len(df) > 0 and not any(k.startswith("temporal + regional") for k in agg_mod.LAST_TRACE["phases_ms"])
+    # ... a daily minimum alone has one (the fixed min / max / mean layout)
+    spec = dict(tmin=[("aggregate", {"calc": "min", "groupby": "date"})])
+    df = af.aggregate_dataset(weights=w, dataset=ds, aggregator_dict=spec)
+    assert len(df) > 0 and any(k.startswith("temporal + regional") for k in agg_mod.LAST_TRACE["phases_ms"])
 
 
 def test_full_size_daily_panel_is_repeatable_and_matches_the_two_kernel_path():
