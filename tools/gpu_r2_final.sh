@@ -6,7 +6,7 @@ TAG=${1:-r2final}
 O=gpurun_out
 mkdir -p $O
 timeout 200 python -c "import __graft_entry__ as g; g.build(); g.smoke()" > $O/${TAG}_smoke.log 2>&1; echo "smoke rc=$? t=$SECONDS"; tail -1 $O/${TAG}_smoke.log
-timeout 1500 python -m pytest tests -m gpu -x -q --durations=5 > $O/${TAG}_pytest.log 2>&1; echo "pytest rc=$? t=$SECONDS"; tail -9 $O/${TAG}_pytest.log
+timeout 1500 python -m pytest tests -m gpu -q --durations=5 > $O/${TAG}_pytest.log 2>&1; echo "pytest rc=$? t=$SECONDS"; tail -9 $O/${TAG}_pytest.log
 timeout 300 python tools/regional_bench.py --steps 5 > $O/${TAG}_regional_c3b.jsonl 2> $O/${TAG}_regional_c3b.err; echo "regional rc=$? t=$SECONDS"; cut -c1-160 $O/${TAG}_regional_c3b.jsonl; grep -o '"max_rel_vs_two.*' $O/${TAG}_regional_c3b.jsonl; tail -2 $O/${TAG}_regional_c3b.err
 for S in 1.0 0.3; do timeout 300 python tools/regional_bench.py --steps 5 --no-two --noise $S 2>/dev/null | cut -c1-100 | tee -a $O/${TAG}_regional_noise.jsonl; done
 CMD="python tools/regional_bench.py --steps 2 --no-two"
