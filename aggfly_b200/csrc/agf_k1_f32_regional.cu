@@ -55,9 +55,7 @@ int launch_regional(const RegionalLaunch &a, int mode, RegionalChoice *choice) {
     constexpr int STAGES = (MINB != 3 && 2 * TILE + rest + 1024 * 16 <= budget) ? 2 : 1;
     constexpr int fixed = STAGES * TILE + rest;
     constexpr int sm_entries = (budget - fixed) / 16 < 4096 ? (budget - fixed) / 16 : 4096;
-    constexpr int smem0 = fixed + sm_entries * 16;
-    static int smem_pad = getenv("AGF_RG_SMEM_PAD") ? atoi(getenv("AGF_RG_SMEM_PAD")) : 0;   // timing experiments: fewer CTAs per SM
-    const int smem = smem0 + smem_pad;
+    constexpr int smem = fixed + sm_entries * 16;
     static_assert(sm_entries >= 512, "no room for the tile tables");
     auto kern = agf_k1_regional<T, NL, DIAG, KINDS, NB, LPS, R_GL, TT, STAGES, MINB>;
 
@@ -163,9 +161,6 @@ int launch_regional(const RegionalLaunch &a, int mode, RegionalChoice *choice) {
         q.edge_f[S::NBL] = nextafterf(hi_last, -INFINITY);
         // Packed form: every edge representable in the packed type (interior edges: hi_j == lo_j+1), none a NaN; the
         // screen then covers the first lower and the last upper threshold too.
-#if !AGF_RG_F32_EDGES
-        q.bins_fast = 0;
-#endif
         if (ok && want >= 2) {
             bool pk_ok = true;
             unsigned low_all = 0xffffffffu;
@@ -212,8 +207,8 @@ int launch_regional(const RegionalLaunch &a, int mode, RegionalChoice *choice) {
     if (plan->n_active == 0) return 0;
     // periods per CTA: enough CTAs for ~8 waves of the resident grid, at least 8 periods each (the ring's ramp-up
     // and the tile's tables are paid once per CTA)
-    static const int waves = getenv("AGF_RG_WAVES") ? std::max(1, atoi(getenv("AGF_RG_WAVES"))) : 8;
-    const int64_t want_ctas = (int64_t)waves * ctas_per_sm * sms;
+    // (16 / 32 / 64 waves measured: flat up to 48, slower beyond, profiles/r2_k1r_steps.jsonl)
+    const int64_t want_ctas = 8LL * ctas_per_sm * sms;
     int64_t stripes = std::max<int64_t>(1, std::min<int64_t>((want_ctas + plan->n_active - 1) / plan->n_active, n_groups / 8));
     stripes = std::min<int64_t>(stripes, 65535);
     q.groups_per_cta = (int)((n_groups + stripes - 1) / stripes);

@@ -1191,15 +1191,8 @@ __global__ void __launch_bounds__(TMA_THREADS, MINB)
     // at a time through l1_acc_group, which tests only the bins inside the warp's min / max of the batch instead of every
     // bin for every value (13 bins: 39 instructions per value otherwise; C3-size hourly bins by year 16.9 -> 10.8 ms with
     // batches of eight).
-#ifndef AGF_K1_GROUP_ROWS
-#define AGF_K1_GROUP_ROWS 24
-#endif
-#ifdef AGF_K1_NO_GROUPED
-    constexpr bool GROUPED = false;
-#else
     constexpr bool GROUPED = typed_lanes<NS, NB>() && NB > 4;
-#endif
-    constexpr int UNROLL = GROUPED ? AGF_K1_GROUP_ROWS : (NL <= 4 ? 8 : (NL <= 16 ? 2 : 1));
+    constexpr int UNROLL = GROUPED ? 24 : (NL <= 4 ? 8 : (NL <= 16 ? 2 : 1));
     extern __shared__ __align__(128) unsigned char smem_raw[];
     T *tiles = reinterpret_cast<T *>(smem_raw);
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + TMA_STAGES * TMA_TILE_BYTES);

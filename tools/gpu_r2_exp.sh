@@ -1,5 +1,6 @@
 #!/bin/bash
-# Timing experiments on C3b (AGF_RG_EXP builds give wrong results on purpose; AGF_RG_SMEM_PAD lowers the occupancy).
+# Timing experiments on C3b as they were run (profiles/r2_k1r_steps.jsonl): AGF_RG_EXP builds compiled parts of the kernel out
+# (wrong results on purpose) and AGF_RG_SMEM_PAD lowered the occupancy; both switches were removed from the final sources.
 # usage: tools/gpu_r2_exp.sh <tag> "<pads>" <variant> ...
 set -u
 TAG=$1; PADS=$2; shift 2

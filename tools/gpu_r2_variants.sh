@@ -1,6 +1,7 @@
 #!/bin/bash
 # One visit, several builds of the library side by side (tools/build_variant.sh): regional tests on the default build,
-# C3b timings for period-block counts (AGF_RG_BLOCKS) and for every variant named on the command line.
+# C3b timings for the values of an environment knob (AGF_RG_BLOCKS: the period-block experiment, since removed) and for
+# every variant named on the command line.
 # usage: tools/gpu_r2_variants.sh <tag> "<blocks list>" <variant> [<variant> ...]     (a variant suffixed with +t also runs the tests)
 set -u
 TAG=$1; BLOCKS=$2; shift 2
