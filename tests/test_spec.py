@@ -107,6 +107,23 @@ def test_many_lanes_split_into_several_programs():
     assert len(outs2) == 40 and len(stage2.programs) == 3 and all(p.two_level for p in stage2.programs)   # 16 + 16 + 8
 
 
+def test_degree_day_lanes_stay_within_the_four_lane_kernels():
+    """Six dd thresholds: two two-level programs of <= 4 lanes (the specialised kernels), not one sixteen-lane diagonal
+    program on the general ragged-group kernel; a mean lane shares a program with dd lanes up to four in total."""
+    dd = [[0, 10, 0], [10, 20, 0], [20, 30, 0], [30, 99, 0], [-99, 0, 1], [10, 30, 0]]
+    g, outs, stage = _plan(dict(dd=[("aggregate", {"calc": "dd", "groupby": "date", "ddargs": dd}),
+                                    ("aggregate", {"calc": "sum", "groupby": "year"})],
+                                tavg=[("aggregate", {"calc": "mean", "groupby": "date"}),
+                                      ("aggregate", {"calc": "mean", "groupby": "year"})]))
+    assert len(outs) == 7 and all(p.two_level for p in stage.programs)
+    assert [len(p.lanes) for p in stage.programs] == [4, 3]
+    assert sorted(c.out_col for p in stage.programs for c in p.cols) == list(range(7))
+    # bins that feed a MEAN keep the diagonal form (the mean of daily counts is not a count)
+    g, outs, stage = _plan(dict(b=[("aggregate", {"calc": "bins", "groupby": "date", "ddargs": dd}),
+                                   ("aggregate", {"calc": "mean", "groupby": "year"})]))
+    assert len(stage.programs) == 1 and stage.programs[0].two_level and len(stage.programs[0].lanes) == 6
+
+
 def test_errors_match_reference():
     with pytest.raises(ValueError, match="multiple ddargs"):
         _plan(dict(a=[("aggregate", {"calc": "mean", "groupby": "date"}),
