@@ -111,6 +111,39 @@ __device__ __forceinline__ double dd_term_rounded(const LaneP<T> &L, T v, double
     }
 }
 
+// acc += (t0 < v < t1) ? |v - base| : 0 -- with the term ZEROED instead of the add predicated.  ``if (in) acc += term``
+// compiles to an unconditional DADD, two FSELs on the halves of the double and two moves (ncu r3: half of the dd_r
+// kernel's instructions per value); selecting on the FLOAT side costs one FSEL, and adding +0.0 to a sum of non-negative
+// terms changes nothing (C5, daily dd by month: K1 2.76 -> 2.35 ms, 0.82 -> 0.96 x measured peak).
+template <typename T>
+__device__ __forceinline__ void dd_add_rounded(const LaneP<T> &L, double &acc, T v, double vd) {
+    if constexpr (sizeof(T) == 4) {
+        if (L.base_is_f32) {
+            float t;  // (one asm block: the compiler would move the select behind the conversion, onto both halves)
+            asm("{\n\t"
+                ".reg .pred p;\n\t"
+                "setp.gt.f32 p, %1, %2;\n\t"
+                "setp.lt.and.f32 p, %1, %3, p;\n\t"
+                "sub.f32 %0, %1, %4;\n\t"
+                "abs.f32 %0, %0;\n\t"
+                "selp.f32 %0, %0, 0f00000000, p;\n\t"
+                "}"
+                : "=f"(t)
+                : "f"((float)v), "f"((float)L.lo), "f"((float)L.hi), "f"(L.base_f));
+            acc += (double)t;
+            return;
+        }
+    }
+    if (v > L.lo && v < L.hi) acc += dd_term_rounded(L, v, vd);
+}
+// The plain dd lane keeps the predicated add: its term is a float64 (|double(v) - base|), and zeroing it through the input
+// (v' = in ? v : base) costs one conversion per LANE and value instead of one per value -- six dd thresholds of a global
+// year went from 29 to 39 ms that way (XU pipe).
+template <typename T>
+__device__ __forceinline__ void dd_add(const LaneP<T> &L, double &acc, T v, double vd) {
+    if (v > L.lo && v < L.hi) acc += fabs(vd - L.base);
+}
+
 struct SlotP {
     int src;
     int xform;
@@ -456,7 +489,7 @@ __device__ __forceinline__ void l1_acc(const K1Params<T, NL, NS> &p, ST &s, T v)
         s.a[0] += vd;
 #pragma unroll
         for (int l = 1; l < NL; ++l)
-            if (v > p.lanes[l].lo && v < p.lanes[l].hi) s.a[l] += fabs(vd - p.lanes[l].base);
+            dd_add(p.lanes[l], s.a[l], v, vd);
         return;
     }
     if constexpr (KINDS == KIND_MMS && !ST::TL && NL >= 3) {  // lane 0: mean / sum, lane 1: min, lane 2: max (launcher)
@@ -487,9 +520,9 @@ __device__ __forceinline__ void l1_acc(const K1Params<T, NL, NS> &p, ST &s, T v)
             } else if constexpr (KINDS == KIND_BINS) {
                 if (v > L.lo && v < L.hi) s.a[l] += 1.0;
             } else if constexpr (KINDS == KIND_DD) {
-                if (v > L.lo && v < L.hi) s.a[l] += fabs(vd - L.base);
+                dd_add(L, s.a[l], v, vd);
             } else if constexpr (KINDS == KIND_DDR) {
-                if (v > L.lo && v < L.hi) s.a[l] += dd_term_rounded(L, v, vd);
+                dd_add_rounded(L, s.a[l], v, vd);
             } else {
                 switch (L.calc) {
                     case AGF_CALC_MEAN:
@@ -522,11 +555,11 @@ __device__ __forceinline__ void l1_acc(const K1Params<T, NL, NS> &p, ST &s, T v)
                         break;
                     case AGF_CALC_DD:
                         if constexpr ((KINDS & KIND_DD) != 0)
-                            if (v > L.lo && v < L.hi) s.a[l] += fabs(vd - L.base);
+                            dd_add(L, s.a[l], v, vd);
                         break;
                     case AGF_CALC_DD_R:
                         if constexpr ((KINDS & KIND_DDR) != 0)
-                            if (v > L.lo && v < L.hi) s.a[l] += dd_term_rounded(L, v, vd);
+                            dd_add_rounded(L, s.a[l], v, vd);
                         break;
                     case AGF_CALC_BINS:
                         if constexpr ((KINDS & KIND_BINS) != 0)
